@@ -1,0 +1,398 @@
+// C-ABI entry points of libadt_b200.so (see include/adt_b200.h).  Host-side launch logic only.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/adt_b200.h"
+#include "kernels_bwd.cuh"
+#include "kernels_embed_opt.cuh"
+#include "kernels_fwd.cuh"
+
+using namespace adt;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* what) {
+  snprintf(g_err, sizeof(g_err), fmt, what);
+  return code;
+}
+static int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return ADT_E_CUDA;
+  }
+  return ADT_OK;
+}
+
+static DropDesc mk_drop(const adt_dropout& d) {
+  DropDesc r;
+  memset(&r, 0, sizeof(r));
+  r.enabled = (d.enabled && d.p > 0.f) ? 1u : 0u;
+  double t = floor((double)d.p * 4294967296.0 + 0.5);
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  r.thr = (uint32_t)t;
+  r.scale = 1.0f / (1.0f - d.p);
+  r.seed_lo = (uint32_t)(d.seed & 0xffffffffull);
+  r.seed_hi = (uint32_t)(d.seed >> 32);
+  r.step = d.step;
+  r.site = d.site;
+  r.base = d.base;
+  r.step_dev = d.step_dev;
+  return r;
+}
+
+static const size_t SMEM_MAX = 227 * 1024 - 2048;   // leave room for the kernels' small static arrays
+
+// rows-per-CTA choice: 64 when the tile set fits, else 32
+static int pick_tm(size_t row_floats, size_t* bytes) {
+  for (int tm = 64; tm >= 32; tm >>= 1) {
+    const size_t b = ((size_t)tm * row_floats + WS_FLOATS) * sizeof(float);
+    if (b <= SMEM_MAX) {
+      *bytes = b;
+      return tm;
+    }
+  }
+  return 0;
+}
+
+template <class K>
+static cudaError_t set_smem(K kern, size_t bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int check_dims(int B, int L, int H, int nh) {
+  if (B <= 0 || L <= 0 || L > 256 || H <= 0 || H > 256 || (H & 3) || nh <= 0 || nh > 8 || H % nh || ((H / nh) & 3))
+    return fail(ADT_E_SHAPE, "%s", "unsupported shape: need 0<L<=256, H%4==0, H<=256, nh<=8, (H/nh)%4==0");
+  return ADT_OK;
+}
+
+#define LAUNCH_TM(tm, KERN, grid, smem, stream, ...)                                   \
+  do {                                                                                 \
+    if ((tm) == 64) {                                                                  \
+      set_smem(KERN<64>, smem);                                                        \
+      KERN<64><<<grid, NT, smem, stream>>>(__VA_ARGS__);                               \
+    } else {                                                                           \
+      set_smem(KERN<32>, smem);                                                        \
+      KERN<32><<<grid, NT, smem, stream>>>(__VA_ARGS__);                               \
+    }                                                                                  \
+  } while (0)
+
+#define LAUNCH_TM2(tm, KERN, FLAG, grid, smem, stream, ...)                            \
+  do {                                                                                 \
+    if ((tm) == 64) {                                                                  \
+      set_smem(KERN<64, FLAG>, smem);                                                  \
+      KERN<64, FLAG><<<grid, NT, smem, stream>>>(__VA_ARGS__);                         \
+    } else {                                                                           \
+      set_smem(KERN<32, FLAG>, smem);                                                  \
+      KERN<32, FLAG><<<grid, NT, smem, stream>>>(__VA_ARGS__);                         \
+    }                                                                                  \
+  } while (0)
+
+extern "C" int adt_version(void) { return 100; }
+extern "C" const char* adt_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int adt_embed_fwd(const adt_embed_fwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (int e = check_dims(a->B, a->L, a->H, 1)) return e;
+  const int M = a->B * a->L;
+  const long long n = (long long)M * (a->H / 4);
+  const int grid = (int)((n + 255) / 256);
+  embed_fwd_kernel<<<grid, 256, 0, s>>>(a->ids, a->item_emb, a->pos_emb, a->x, M, a->L, a->H, (float)sqrt((double)a->H), mk_drop(a->drop));
+  return check_launch("adt_embed_fwd");
+}
+
+// shared launch helpers -------------------------------------------------------------------------------------
+static int launch_pre_fwd(const float* x, const float* ln_w, const float* ln_b, const adt_mha_w& w, float* q, float* k, float* v,
+                          float* norm_out, int M, int H, int nh, int kv_from_norm, cudaStream_t s) {
+  size_t smem;
+  const int tm = pick_tm(2 * (size_t)(H + 4), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "pre_fwd: tile does not fit shared memory");
+  const float qscale = 1.0f / sqrtf((float)(H / nh));
+  const int grid = (M + tm - 1) / tm;
+  LAUNCH_TM(tm, pre_fwd_kernel, grid, smem, s, x, ln_w, ln_b, w.in_w, w.in_b, q, k, v, norm_out, M, H, qscale, kv_from_norm);
+  return check_launch("pre_fwd");
+}
+
+static int launch_attn_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, const int* key_ids, int B, int L,
+                           int H, int nh, int mask_mode, const adt_dropout& d, int training, cudaStream_t s) {
+  const int hd = H / nh;
+  const size_t rowf = (size_t)(hd + 4) + (size_t)(((L + 3) & ~3) + 4);
+  size_t smem;
+  int tm = pick_tm(rowf, &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_fwd: tile does not fit shared memory");
+  if (L <= 32 && tm == 64) { tm = 32; smem = ((size_t)tm * rowf + WS_FLOATS) * sizeof(float); }
+  adt_dropout dd = d;
+  if (!training) dd.enabled = 0;
+  dim3 grid((L + tm - 1) / tm, nh, B);
+  LAUNCH_TM(tm, attn_fwd_kernel, grid, smem, s, q, k, v, ctx, lse, key_ids, L, H, nh, mask_mode, mk_drop(dd));
+  return check_launch("attn_fwd");
+}
+
+static int launch_attn_bwd(const float* q, const float* k, const float* v, const float* dctx, const float* lse, const int* key_ids,
+                           float* dq, float* dk, float* dv, int B, int L, int H, int nh, int mask_mode, const adt_dropout& d,
+                           cudaStream_t s) {
+  const int hd = H / nh;
+  const size_t rowf = 2 * (size_t)(hd + 4) + 2 * (size_t)(((L + 3) & ~3) + 4);
+  size_t smem;
+  int tm = pick_tm(rowf, &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_bwd: tile does not fit shared memory");
+  if (L <= 32 && tm == 64) { tm = 32; smem = ((size_t)tm * rowf + WS_FLOATS) * sizeof(float); }
+  dim3 grid((L + tm - 1) / tm, nh, B);
+  LAUNCH_TM(tm, attn_bwd_kernel, grid, smem, s, q, k, v, dctx, lse, key_ids, dq, dk, dv, L, H, nh, mask_mode, mk_drop(d));
+  return check_launch("attn_bwd");
+}
+
+static adt_dropout row_drop(const adt_dropout& d, int training) {
+  adt_dropout r = d;
+  if (!training) r.enabled = 0;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
+  const int M = a->B * a->L, H = a->H;
+  if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, s)) return e;
+  if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, s))
+    return e;
+  PostFwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.ctx = a->ctx; p.resid = a->x; p.ids = a->ids; p.Wo = a->attn.out_w; p.bo = a->attn.out_b;
+  p.ln1_g = a->ln1_w; p.ln1_b = a->ln1_b; p.ln2_g = a->ln2_w; p.ln2_b = a->ln2_b;
+  p.C1 = a->ffn.w1; p.c1 = a->ffn.b1; p.C2 = a->ffn.w2; p.c2 = a->ffn.b2;
+  p.Wsp = a->sparse_w; p.bsp = a->sparse_b;
+  p.u_save = a->y; p.h1_save = a->h1; p.out = a->out; p.rec = a->rec; p.acc = a->nll_acc;
+  p.M = M; p.H = H; p.nh = a->nh;
+  p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training));
+  p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
+  size_t smem;
+  const int tm = pick_tm(3 * (size_t)(H + 4), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "post_fwd: tile does not fit shared memory");
+  LAUNCH_TM2(tm, post_fwd_kernel, false, (M + tm - 1) / tm, smem, s, p);
+  return check_launch("enc post_fwd");
+}
+
+extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
+  const int M = a->B * a->L, H = a->H;
+  PostBwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.dout = a->dout; p.ids = a->ids; p.ctx = a->ctx; p.u = a->y; p.h1 = a->h1;
+  p.Wo = a->attn.out_w; p.ln2_g = a->ln2_w; p.ln2_b = a->ln2_b; p.C1 = a->ffn.w1; p.C2 = a->ffn.w2;
+  p.Wsp = a->sparse_w; p.bsp = a->sparse_b; p.nll_coef = a->nll_coef; p.drec = a->drec;
+  p.dctx = a->dctx; p.dres = a->dy;
+  p.gWo = a->g_attn.out_w; p.gbo = a->g_attn.out_b; p.gln2_g = a->g_ln2_w; p.gln2_b = a->g_ln2_b;
+  p.gC1 = a->g_ffn.w1; p.gc1 = a->g_ffn.b1; p.gC2 = a->g_ffn.w2; p.gc2 = a->g_ffn.b2;
+  p.gWsp = a->g_sparse_w; p.gbsp = a->g_sparse_b;
+  p.M = M; p.H = H; p.nh = a->nh;
+  p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
+  size_t smem;
+  int tm = pick_tm(4 * (size_t)(H + 4), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
+  LAUNCH_TM2(tm, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p);
+  if (int e = check_launch("enc post_bwd")) return e;
+  if (int e = launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
+                              a->drop_attn, s))
+    return e;
+  PreBwdArgs r;
+  memset(&r, 0, sizeof(r));
+  r.dq = a->dq; r.dk = a->dk; r.dv = a->dv; r.x = a->x; r.dnorm_extra = a->dy; r.dx_extra = a->dx_extra;
+  r.ln_g = a->ln1_w; r.ln_b = a->ln1_b; r.Win = a->attn.in_w; r.dx = a->dx;
+  r.gWin = a->g_attn.in_w; r.gbin = a->g_attn.in_b; r.gln_g = a->g_ln1_w; r.gln_b = a->g_ln1_b;
+  r.M = M; r.H = H; r.qscale = 1.0f / sqrtf((float)(H / a->nh)); r.kv_from_norm = 0;
+  tm = pick_tm(4 * (size_t)(H + 4), &smem);
+  LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r);
+  return check_launch("enc pre_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
+  const int M = a->B * a->L, H = a->H;
+  if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, s)) return e;
+  if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, s))
+    return e;
+  size_t smem;
+  int tm = pick_tm(3 * (size_t)(H + 4), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_fwd: tile does not fit shared memory");
+  const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  LAUNCH_TM(tm, mid_fwd_kernel, (M + tm - 1) / tm, smem, s, a->ctx1, a->feats, a->slf.out_w, a->slf.out_b, a->enc.in_w, a->enc.in_b, a->a,
+            a->q2, a->k2, a->v2, M, H, qscale);
+  if (int e = check_launch("mid_fwd")) return e;
+  if (int e = launch_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, s))
+    return e;
+  PostFwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.ctx = a->ctx2; p.resid = a->d; p.ids = a->ids; p.Wo = a->enc.out_w; p.bo = a->enc.out_b;
+  p.C1 = a->ffn.w1; p.c1 = a->ffn.b1; p.C2 = a->ffn.w2; p.c2 = a->ffn.b2;
+  p.enc_in = a->enc_in; p.u_save = a->c; p.h1_save = a->h1; p.out = a->out; p.acc = a->mse_acc;
+  p.M = M; p.H = H; p.nh = a->nh;
+  p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training));
+  p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
+  LAUNCH_TM2(tm, post_fwd_kernel, true, (M + tm - 1) / tm, smem, s, p);
+  return check_launch("dec post_fwd");
+}
+
+extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
+  const int M = a->B * a->L, H = a->H;
+  const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  PostBwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.dout = a->dout; p.out = a->out; p.enc_in = a->enc_in; p.mse_coef = a->mse_coef; p.denc = a->denc; p.ids = a->ids;
+  p.ctx = a->ctx2; p.u = a->c; p.h1 = a->h1; p.Wo = a->enc.out_w; p.C1 = a->ffn.w1; p.C2 = a->ffn.w2;
+  p.dctx = a->dctx2; p.dres = a->dd;
+  p.gWo = a->g_enc.out_w; p.gbo = a->g_enc.out_b; p.gC1 = a->g_ffn.w1; p.gc1 = a->g_ffn.b1; p.gC2 = a->g_ffn.w2; p.gc2 = a->g_ffn.b2;
+  p.M = M; p.H = H; p.nh = a->nh;
+  p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
+  size_t smem;
+  int tm = pick_tm(4 * (size_t)(H + 4), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
+  LAUNCH_TM2(tm, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p);
+  if (int e = check_launch("dec post_bwd")) return e;
+  // cross attention (keys/values from the encoder features)
+  if (int e = launch_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,
+                              a->drop_enc, s))
+    return e;
+  MidBwdArgs m;
+  memset(&m, 0, sizeof(m));
+  m.dq2 = a->dq2; m.dk2 = a->dk2; m.dv2 = a->dv2; m.a = a->a; m.feats = a->feats; m.ctx1 = a->ctx1;
+  m.Wo1 = a->slf.out_w; m.Win2 = a->enc.in_w; m.dfeats = a->dfeats; m.dctx1 = a->dctx;
+  m.gWo1 = a->g_slf.out_w; m.gbo1 = a->g_slf.out_b; m.gWin2 = a->g_enc.in_w; m.gbin2 = a->g_enc.in_b;
+  m.M = M; m.H = H; m.qscale = qscale;
+  tm = pick_tm(3 * (size_t)(H + 4) + (size_t)(2 * H + 4), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_bwd: tile does not fit shared memory");
+  LAUNCH_TM(tm, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m);
+  if (int e = check_launch("mid_bwd")) return e;
+  if (int e = launch_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
+                              a->drop_slf, s))
+    return e;
+  PreBwdArgs r;
+  memset(&r, 0, sizeof(r));
+  r.dq = a->dq; r.dk = a->dk; r.dv = a->dv; r.x = a->x; r.dnorm_extra = a->dd; r.dx_extra = nullptr;
+  r.ln_g = a->ln_w; r.ln_b = a->ln_b; r.Win = a->slf.in_w; r.dx = a->dx;
+  r.gWin = a->g_slf.in_w; r.gbin = a->g_slf.in_b; r.gln_g = a->g_ln_w; r.gln_b = a->g_ln_b;
+  r.M = M; r.H = H; r.qscale = qscale; r.kv_from_norm = 1;
+  tm = pick_tm(4 * (size_t)(H + 4), &smem);
+  LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r);
+  return check_launch("dec pre_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int adt_final_logits_loss_fwd(const adt_final_fwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (a->H > 256 || (a->H & 3)) return fail(ADT_E_SHAPE, "%s", "final_fwd: H");
+  const int grid = min((a->M + 7) / 8, 148 * 8);
+  final_fwd_kernel<<<grid, NT, 0, s>>>(a->x, a->ln_w, a->ln_b, a->item_emb, a->pos, a->neg, a->feats, a->pos_logits, a->neg_logits, a->acc,
+                                       a->M, a->H);
+  return check_launch("final_fwd");
+}
+
+extern "C" int adt_final_logits_loss_bwd(const adt_final_bwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (a->H > 256 || (a->H & 3)) return fail(ADT_E_SHAPE, "%s", "final_bwd: H");
+  FinalBwdArgs p;
+  p.x = a->x; p.ln_g = a->ln_w; p.E = a->item_emb; p.pos = a->pos; p.neg = a->neg;
+  p.pos_logits = a->pos_logits; p.neg_logits = a->neg_logits; p.dfeats_in = a->dfeats_in; p.n_valid = a->n_valid;
+  p.bce_weight = a->bce_weight; p.dpl_ext = a->dpl_ext; p.dnl_ext = a->dnl_ext;
+  p.dx = a->dx; p.cpos = a->cpos; p.cneg = a->cneg; p.gln_g = a->g_ln_w; p.gln_b = a->g_ln_b; p.M = a->M; p.H = a->H;
+  const int grid = min((a->M + 7) / 8, 148 * 4);
+  final_bwd_kernel<<<grid, NT, 0, s>>>(p);
+  return check_launch("final_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int adt_embed_sort(const adt_embed_sort_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  const int N = 4 * a->M;
+  const int nW = (N + SORT_WCH - 1) / SORT_WCH;
+  int bits = 1;
+  while ((1ll << bits) <= (long long)a->max_id) ++bits;
+  const int passes = (bits + 7) / 8;
+  SortSrc src;
+  src.ids[0] = a->seq; src.ids[1] = a->dec; src.ids[2] = a->pos; src.ids[3] = a->neg; src.M = a->M;
+  const int grid = (nW + 7) / 8;
+  // ping-pong so that the last pass lands in (keys, vals)
+  int* kbuf[2] = {a->keys, a->keys_tmp};
+  int* vbuf[2] = {a->vals, a->vals_tmp};
+  int cur = (passes & 1) ? 0 : 1;   // buffer written by pass 0
+  const int* kin = nullptr;
+  const int* vin = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = 8 * p;
+    if (p == 0) {
+      radix_hist_kernel<true><<<grid, 256, 0, s>>>(src, nullptr, N, shift, a->hist, nW);
+      exclusive_scan_kernel<<<1, 1024, 0, s>>>(a->hist, 256 * nW);
+      radix_scatter_kernel<true><<<grid, 256, 0, s>>>(src, nullptr, nullptr, N, shift, a->hist, nW, kbuf[cur], vbuf[cur]);
+    } else {
+      radix_hist_kernel<false><<<grid, 256, 0, s>>>(src, kin, N, shift, a->hist, nW);
+      exclusive_scan_kernel<<<1, 1024, 0, s>>>(a->hist, 256 * nW);
+      radix_scatter_kernel<false><<<grid, 256, 0, s>>>(src, kin, vin, N, shift, a->hist, nW, kbuf[cur], vbuf[cur]);
+    }
+    kin = kbuf[cur];
+    vin = vbuf[cur];
+    cur ^= 1;
+  }
+  return check_launch("adt_embed_sort");
+}
+
+extern "C" int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (int e = check_dims(a->B, a->L, a->H, 1)) return e;
+  const int M = a->B * a->L;
+  if (NT / (a->H / 4) < 1) return fail(ADT_E_SHAPE, "%s", "embed_bwd: H");
+  if (a->d_pos_emb) {
+    if (a->dx_enc) posgrad_kernel<<<a->L, NT, 0, s>>>(a->dx_enc, a->seq, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_enc));
+    if (a->dx_dec) posgrad_kernel<<<a->L, NT, 0, s>>>(a->dx_dec, a->dec, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_dec));
+  }
+  ScatterArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.keys = a->keys; sa.vals = a->vals; sa.N = 4 * M; sa.M = M; sa.H = a->H;
+  sa.dx_enc = a->dx_enc; sa.dx_dec = a->dx_dec; sa.feats = a->feats; sa.cpos = a->cpos; sa.cneg = a->cneg;
+  sa.scale = (float)sqrt((double)a->H);
+  sa.drop_enc = mk_drop(a->drop_enc); sa.drop_dec = mk_drop(a->drop_dec);
+  sa.dE = a->d_item_emb; sa.head = a->head; sa.tail = a->tail; sa.has_tail = a->has_tail;
+  const int nb = (sa.N + 31) / 32;
+  scatter_phase1_kernel<<<(nb + 7) / 8, 256, 0, s>>>(sa);
+  scatter_phase2_kernel<<<(nb + 7) / 8, 256, 0, s>>>(sa);
+  return check_launch("adt_embed_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int adt_sumsq(const float* x, int64_t n, double* out, adt_stream_t s_) {
+  const int grid = (int)((n / 4 + 255) / 256 < 148 * 8 ? ((n / 4 + 255) / 256 > 0 ? (n / 4 + 255) / 256 : 1) : 148 * 8);
+  sumsq_kernel<<<grid, 256, 0, (cudaStream_t)s_>>>(x, (long long)n, out);
+  return check_launch("adt_sumsq");
+}
+
+extern "C" int adt_norm_decay_grad(float* g, const float* w, int64_t n, float wd, const double* normsq, adt_stream_t s_) {
+  const long long blocks = (n + 255) / 256;
+  norm_decay_grad_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(g, w, (long long)n, wd, normsq);
+  return check_launch("adt_norm_decay_grad");
+}
+
+extern "C" int adt_adam(const adt_adam_args* a, adt_stream_t s_) {
+  AdamArgs k;
+  k.p = a->p; k.g = a->g; k.m = a->m; k.v = a->v; k.n = a->n;
+  k.lr = a->lr; k.beta1 = a->beta1; k.beta2 = a->beta2; k.eps = a->eps; k.weight_decay = a->weight_decay;
+  k.bc1 = (float)(1.0 - pow((double)a->beta1, (double)a->step));
+  k.bc2 = (float)(1.0 - pow((double)a->beta2, (double)a->step));
+  k.max_norm = a->max_norm; k.gnormsq = a->gnormsq; k.step_dev = a->step_dev;
+  const long long blocks = (a->n + 255) / 256;
+  adam_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(k);
+  return check_launch("adt_adam");
+}
+
+extern "C" int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t s_) {
+  const long long blocks = (n + 255) / 256;
+  philox_mask_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(out, (long long)n, mk_drop(*d));
+  return check_launch("adt_philox_mask");
+}

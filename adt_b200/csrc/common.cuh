@@ -1,0 +1,401 @@
+// Shared device building blocks for the ADT hot-path kernels (sm_100a).
+//
+// Every transformer-block kernel in this library is a "row-tile" kernel: one CTA
+// (256 threads) owns TM rows of the flattened [B*L, H] activation matrix, keeps
+// them in shared memory across a chain of fused ops (LayerNorm -> GEMM -> bias
+// -> dropout -> ReLU -> residual -> mask), and streams weight matrices through a
+// double-buffered cp.async staging area.  All arithmetic is fp32 (the reference
+// is fp32 end to end) with fp32 FFMA register tiles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace adt {
+
+constexpr int NT = 256;        // threads per CTA for all row-tile kernels
+constexpr int CH = 64;         // weight chunk edge (rows and cols)
+constexpr int CHP = CH + 4;    // padded chunk row stride in floats (272 B: 16B aligned, LDS.128 conflict free)
+constexpr int WS_FLOATS = 2 * CH * CHP;  // double-buffered staging area
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 dropout (must match oracle/philox.py bit for bit)
+// ---------------------------------------------------------------------------------------------
+struct DropDesc {
+  uint32_t enabled;   // 0: identity
+  uint32_t thr;       // keep iff rnd >= thr
+  float scale;        // 1/(1-p)
+  uint32_t seed_lo, seed_hi, step, site;
+  unsigned long long base;  // element offset added to every index (batch offset b0 * per-sample elements)
+  const uint32_t* step_dev; // optional device-side counter added to step
+};
+__device__ __forceinline__ uint32_t drop_step(const DropDesc& d) { return d.step_dev ? d.step + *d.step_dev : d.step; }
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// multipliers (0 or scale) for the 4 consecutive elements idx4*4 .. idx4*4+3
+__device__ __forceinline__ float4 drop_mul4(const DropDesc& d, unsigned long long idx4) {
+  const uint4 r = philox4x32_10((uint32_t)idx4, (uint32_t)(idx4 >> 32), d.site, drop_step(d), d.seed_lo, d.seed_hi);
+  return make_float4(r.x >= d.thr ? d.scale : 0.f, r.y >= d.thr ? d.scale : 0.f, r.z >= d.thr ? d.scale : 0.f,
+                     r.w >= d.thr ? d.scale : 0.f);
+}
+__device__ __forceinline__ float drop_mul1(const DropDesc& d, unsigned long long idx) {
+  const uint4 r = philox4x32_10((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), d.site, drop_step(d), d.seed_lo, d.seed_hi);
+  const uint32_t lane = (uint32_t)idx & 3u;
+  const uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+  return v >= d.thr ? d.scale : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// CTA-wide sum of one double per thread -> atomicAdd into *dst (thread 0). scratch: >= 8 doubles of smem.
+__device__ __forceinline__ void cta_accumulate(double v, double* dst, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < NT / 32; ++i) s += scratch[i];
+    atomicAdd(dst, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Activation tiles: smem [TM][ld] fp32, ld = C + 4 (C multiple of 4).
+// ---------------------------------------------------------------------------------------------
+// Load rows row0..row0+TM-1 (rows >= M are zero filled) of a row-major [M, ldg] matrix, columns c0..c0+C-1.
+template <int TM>
+__device__ __forceinline__ void load_tile(float* __restrict__ T, int ld, const float* __restrict__ G, long long ldg, int c0,
+                                          int C, int row0, int M) {
+  const int c4n = C >> 2;
+  for (int s = threadIdx.x; s < TM * c4n; s += NT) {
+    const int r = s / c4n, c4 = s - r * c4n;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < M) v = *reinterpret_cast<const float4*>(G + (long long)(row0 + r) * ldg + c0 + 4 * c4);
+    *reinterpret_cast<float4*>(T + r * ld + 4 * c4) = v;
+  }
+}
+template <int TM>
+__device__ __forceinline__ void store_tile(const float* __restrict__ T, int ld, float* __restrict__ G, long long ldg, int c0,
+                                           int C, int row0, int M) {
+  const int c4n = C >> 2;
+  for (int s = threadIdx.x; s < TM * c4n; s += NT) {
+    const int r = s / c4n, c4 = s - r * c4n;
+    if (row0 + r < M)
+      *reinterpret_cast<float4*>(G + (long long)(row0 + r) * ldg + c0 + 4 * c4) = *reinterpret_cast<const float4*>(T + r * ld + 4 * c4);
+  }
+}
+
+// LayerNorm of every row of a tile (warp per row), biased variance, eps inside the sqrt
+// (torch.nn.LayerNorm; reference uses eps=1e-8, sasrec/modules.py:638,640,660 and model.py:29).
+// dst may alias src.  Rows with row0+r >= M are written as zeros.
+template <int TM>
+__device__ __forceinline__ void ln_tile(const float* __restrict__ S, float* __restrict__ D, int ld, int C,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int row0, int M) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int r = w; r < TM; r += NT / 32) {
+    const float* s = S + r * ld;
+    float* d = D + r * ld;
+    if (row0 + r >= M) {
+      for (int c = l; c < C; c += 32) d[c] = 0.f;
+      continue;
+    }
+    float sum = 0.f;
+    for (int c = l; c < C; c += 32) sum += s[c];
+    const float mean = warp_sum(sum) / (float)C;
+    float var = 0.f;
+    for (int c = l; c < C; c += 32) {
+      const float t = s[c] - mean;
+      var += t * t;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(var) / (float)C + eps);
+    for (int c = l; c < C; c += 32) d[c] = (s[c] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+// LayerNorm backward on a tile. X: LN input rows, G: upstream grad rows (dL/d out). Writes dX into DX (may alias G,
+// must not alias X) -- if ACCUM, adds to DX instead.  dgamma/dbeta are accumulated with atomics (one per column per CTA).
+// red: smem scratch of 2*(NT/32)*C floats.
+template <int TM, bool ACCUM>
+__device__ __forceinline__ void ln_bwd_tile(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ DX, int ld,
+                                            int C, const float* __restrict__ gamma, float eps, int row0, int M,
+                                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ red) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  constexpr int NW = NT / 32;
+  float dg[8], db[8];  // C <= 256 -> at most 8 columns per lane
+#pragma unroll
+  for (int u = 0; u < 8; ++u) dg[u] = db[u] = 0.f;
+  for (int r = w; r < TM; r += NW) {
+    if (row0 + r >= M) {
+      if (!ACCUM)
+        for (int c = l; c < C; c += 32) DX[r * ld + c] = 0.f;
+      continue;
+    }
+    const float* x = X + r * ld;
+    const float* g = G + r * ld;
+    float sum = 0.f;
+    for (int c = l; c < C; c += 32) sum += x[c];
+    const float mean = warp_sum(sum) / (float)C;
+    float var = 0.f;
+    for (int c = l; c < C; c += 32) {
+      const float t = x[c] - mean;
+      var += t * t;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(var) / (float)C + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = l + 32 * u;
+      if (c < C) {
+        const float xh = (x[c] - mean) * rstd;
+        const float gg = g[c] * gamma[c];
+        s1 += gg;
+        s2 += gg * xh;
+        dg[u] += g[c] * xh;
+        db[u] += g[c];
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = l + 32 * u;
+      if (c < C) {
+        const float xh = (x[c] - mean) * rstd;
+        const float v = rstd * (g[c] * gamma[c] - s1 - xh * s2);
+        if (ACCUM) DX[r * ld + c] += v; else DX[r * ld + c] = v;
+      }
+    }
+  }
+  // cross-warp reduction of dgamma/dbeta
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = l + 32 * u;
+    if (c < C) {
+      red[w * C + c] = dg[u];
+      red[(NW + w) * C + c] = db[u];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += NT) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < NW; ++i) {
+      a += red[i * C + c];
+      b += red[(NW + i) * C + c];
+    }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight staging: one [64][64] chunk of a row-major matrix -> smem [64][CHP] (zero filled outside).
+// PERM: store global chunk row n at smem row (n>>2) + 16*(n&3) so that the NT micro-kernel's thread tx
+//       reads rows tx+16j (conflict free) while owning the 4 CONTIGUOUS output columns 4tx..4tx+3.
+// ---------------------------------------------------------------------------------------------
+template <bool PERM>
+__device__ __forceinline__ void stage_chunk(float* __restrict__ buf, const float* __restrict__ G, long long ldg, int r0, int c0,
+                                            int nr, int nc) {
+#pragma unroll
+  for (int it = 0; it < (CH * CH / 4) / NT; ++it) {
+    const int s = threadIdx.x + it * NT;
+    const int r = s >> 4, c4 = s & 15;
+    const bool ok = (r < nr) && (4 * c4 < nc);
+    const int rs = PERM ? ((r >> 2) + 16 * (r & 3)) : r;
+    const float* src = ok ? (G + (long long)(r0 + r) * ldg + c0 + 4 * c4) : G;
+    cp_async16(buf + rs * CHP + 4 * c4, src, ok);
+  }
+}
+
+// acc[i][j] += sum_k A[ty+16i][k0+k] * W[n0+4tx+j][k]      (chunk staged with PERM=true)
+template <int RM>
+__device__ __forceinline__ void mma_nt(float (&acc)[RM][4], const float* __restrict__ A, int lda, int k0,
+                                       const float* __restrict__ Wc, int klen) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* a0 = A + ty * lda + k0;
+  const float* w0 = Wc + tx * CHP;
+#pragma unroll 2
+  for (int kk = 0; kk < klen; kk += 4) {
+    float4 a[RM], w[4];
+#pragma unroll
+    for (int i = 0; i < RM; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + 16 * i * lda + kk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(w0 + 16 * j * CHP + kk);
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fmaf(a[i].x, w[j].x, acc[i][j]);
+        acc[i][j] = fmaf(a[i].y, w[j].y, acc[i][j]);
+        acc[i][j] = fmaf(a[i].z, w[j].z, acc[i][j]);
+        acc[i][j] = fmaf(a[i].w, w[j].w, acc[i][j]);
+      }
+  }
+}
+
+// acc[i][c] += sum_n A[ty+16i][n0+n] * W[n][c0+4tx+c]       (chunk staged with PERM=false)
+template <int RM>
+__device__ __forceinline__ void mma_nn(float (&acc)[RM][4], const float* __restrict__ A, int lda, int n0,
+                                       const float* __restrict__ Wc, int nlen) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* a0 = A + ty * lda + n0;
+  const float* w0 = Wc + 4 * tx;
+#pragma unroll 2
+  for (int nn = 0; nn < nlen; nn += 4) {
+    float4 a[RM], w[4];
+#pragma unroll
+    for (int i = 0; i < RM; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + 16 * i * lda + nn);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) w[u] = *reinterpret_cast<const float4*>(w0 + (nn + u) * CHP);
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      acc[i][0] = fmaf(a[i].x, w[0].x, acc[i][0]); acc[i][1] = fmaf(a[i].x, w[0].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].x, w[0].z, acc[i][2]); acc[i][3] = fmaf(a[i].x, w[0].w, acc[i][3]);
+      acc[i][0] = fmaf(a[i].y, w[1].x, acc[i][0]); acc[i][1] = fmaf(a[i].y, w[1].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].y, w[1].z, acc[i][2]); acc[i][3] = fmaf(a[i].y, w[1].w, acc[i][3]);
+      acc[i][0] = fmaf(a[i].z, w[2].x, acc[i][0]); acc[i][1] = fmaf(a[i].z, w[2].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].z, w[2].z, acc[i][2]); acc[i][3] = fmaf(a[i].z, w[2].w, acc[i][3]);
+      acc[i][0] = fmaf(a[i].w, w[3].x, acc[i][0]); acc[i][1] = fmaf(a[i].w, w[3].y, acc[i][1]);
+      acc[i][2] = fmaf(a[i].w, w[3].z, acc[i][2]); acc[i][3] = fmaf(a[i].w, w[3].w, acc[i][3]);
+    }
+  }
+}
+
+// Row-tile GEMM driver.
+//   NN == false:  Y[r][n] = sum_k A[r][k] * W[n][k]     W is [Nout][Kred] row-major (nn.Linear weight), ld = ldw
+//   NN == true :  Y[r][c] = sum_n A[r][n] * W[n][c]     W is [Kred][Nout] row-major, ld = ldw
+// A is an smem tile [TM][lda] whose reduction extent is Kred (columns beyond Kred are never read because the staged
+// chunk is zero there -- but they must be finite, so tiles are allocated with zeroed padding).
+// epi(i, row_local, col, float4 v) is called once per thread per (row ty+16i, columns col..col+3); col < Nout guaranteed
+// (Nout is a multiple of 4).  Ends with a __syncthreads(): tile writes made by epi are visible on return.
+template <int TM, bool NN, class Epi>
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ A, int lda, int Kred, const float* __restrict__ W, long long ldw,
+                                          int Nout, float* __restrict__ Ws, Epi epi) {
+  constexpr int RM = TM / 16;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int noc = (Nout + CH - 1) / CH, nrc = (Kred + CH - 1) / CH;
+  const int total = noc * nrc;
+  auto stage = [&](int t) {
+    const int oc = t / nrc, rc = t - oc * nrc;
+    float* buf = Ws + (t & 1) * CH * CHP;
+    if (!NN)
+      stage_chunk<true>(buf, W, ldw, oc * CH, rc * CH, min(CH, Nout - oc * CH), min(CH, Kred - rc * CH));
+    else
+      stage_chunk<false>(buf, W, ldw, rc * CH, oc * CH, min(CH, Kred - rc * CH), min(CH, Nout - oc * CH));
+    cp_async_commit();
+  };
+  stage(0);
+  float acc[RM][4];
+  for (int t = 0; t < total; ++t) {
+    const int oc = t / nrc, rc = t - oc * nrc;
+    if (rc == 0) {
+#pragma unroll
+      for (int i = 0; i < RM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    }
+    if (t + 1 < total) {
+      stage(t + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* buf = Ws + (t & 1) * CH * CHP;
+    // round the reduction length up to 4 (staged zeros make the tail harmless)
+    const int rlen = min(CH, Kred - rc * CH);
+    if (!NN) mma_nt<RM>(acc, A, lda, rc * CH, buf, rlen);
+    else mma_nn<RM>(acc, A, lda, rc * CH, buf, rlen);
+    if (rc == nrc - 1) {
+      const int col = oc * CH + 4 * tx;
+      if (col < Nout) {
+#pragma unroll
+        for (int i = 0; i < RM; ++i) epi(i, ty + 16 * i, col, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Weight gradient of a row tile:  dW[n][k] += sum_{r<rows} dY[r][n] * X[r][k]  (vector fp32 atomics into global dW).
+// dY: smem tile [.][ldy] (N columns), X: smem tile [.][ldx] (K columns).  dW is [N][K] row-major with ld ldw.
+__device__ __forceinline__ void wgrad_tile(const float* __restrict__ dY, int ldy, int N, const float* __restrict__ X, int ldx, int K,
+                                           int rows, float* __restrict__ dW, long long ldw) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int n0 = 0; n0 < N; n0 += CH)
+    for (int k0 = 0; k0 < K; k0 += CH) {
+      const int n = n0 + 4 * ty, k = k0 + 4 * tx;
+      if (n >= N || k >= K) continue;
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      const float* yp = dY + n;
+      const float* xp = X + k;
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+        const float4 y = *reinterpret_cast<const float4*>(yp + r * ldy);
+        const float4 x = *reinterpret_cast<const float4*>(xp + r * ldx);
+        acc[0][0] = fmaf(y.x, x.x, acc[0][0]); acc[0][1] = fmaf(y.x, x.y, acc[0][1]); acc[0][2] = fmaf(y.x, x.z, acc[0][2]); acc[0][3] = fmaf(y.x, x.w, acc[0][3]);
+        acc[1][0] = fmaf(y.y, x.x, acc[1][0]); acc[1][1] = fmaf(y.y, x.y, acc[1][1]); acc[1][2] = fmaf(y.y, x.z, acc[1][2]); acc[1][3] = fmaf(y.y, x.w, acc[1][3]);
+        acc[2][0] = fmaf(y.z, x.x, acc[2][0]); acc[2][1] = fmaf(y.z, x.y, acc[2][1]); acc[2][2] = fmaf(y.z, x.z, acc[2][2]); acc[2][3] = fmaf(y.z, x.w, acc[2][3]);
+        acc[3][0] = fmaf(y.w, x.x, acc[3][0]); acc[3][1] = fmaf(y.w, x.y, acc[3][1]); acc[3][2] = fmaf(y.w, x.z, acc[3][2]); acc[3][3] = fmaf(y.w, x.w, acc[3][3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (n + i < N)
+          atomicAdd(reinterpret_cast<float4*>(dW + (long long)(n + i) * ldw + k), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+}
+
+// db[n] += sum_{r<rows} dY[r][n]
+__device__ __forceinline__ void colsum_atomic(const float* __restrict__ dY, int ldy, int N, int rows, float* __restrict__ db) {
+  for (int n = threadIdx.x; n < N; n += NT) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += dY[r * ldy + n];
+    atomicAdd(db + n, s);
+  }
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+}  // namespace adt

@@ -1,0 +1,519 @@
+// Backward kernels of the SASRec-ADT hot path (hand-derived adjoints of kernels_fwd.cuh).
+// Weight gradients are reduced over the CTA's row tile in registers and added to the global gradient
+// buffers with 128-bit vector atomics (red.global.add.v4.f32).
+#pragma once
+#include "common.cuh"
+#include "kernels_fwd.cuh"
+
+namespace adt {
+
+// elementwise helper over a [TM][C] tile (one float4 per thread step): f(row_local, col)
+template <int TM, class F>
+__device__ __forceinline__ void tile_foreach4(int C, F f) {
+  const int c4n = C >> 2;
+  for (int s = threadIdx.x; s < TM * c4n; s += NT) {
+    const int r = s / c4n, c4 = s - r * c4n;
+    f(r, 4 * c4);
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// -------------------------------------------------------------------------------------------------
+// post_bwd: adjoint of post_fwd.
+// -------------------------------------------------------------------------------------------------
+struct PostBwdArgs {
+  const float* dout;      // upstream grad wrt block output (nullable == 0)
+  const float* out;       // dec: saved block output (for the MSE term)
+  const float* enc_in;    // dec: reconstruction target (nullable)
+  float mse_coef;         // dec: lambda1 * 2 / (M_total*H)
+  float* denc;            // dec: grad wrt enc_in written here (nullable)
+  const int* ids;
+  const float* ctx; const float* u; const float* h1;   // saved: attention context, y (enc) / c (dec), FFN hidden
+  const float* Wo; const float* ln2_g; const float* ln2_b; const float* C1; const float* C2; const float* Wsp; const float* bsp;
+  float nll_coef;         // enc: lambda2 / (M_total*nh)   (0 -> no fused NLL grad)
+  const float* drec;      // enc: external grad wrt rec [M][nh][nh] (compat mode, nullable)
+  float* dctx;            // out: grad wrt attention context
+  float* dres;            // out: enc -> dy (grad reaching Qn through the residual) ; dec -> dd (grad wrt d)
+  float* gWo; float* gbo; float* gln2_g; float* gln2_b; float* gC1; float* gc1; float* gC2; float* gc2; float* gWsp; float* gbsp;
+  int M, H, nh;
+  DropDesc drop1, drop2;
+};
+
+template <int TM, bool IS_DEC>
+__global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, M = p.M;
+  const int ld = H + 4;
+  float* G = smem;            // dO -> (enc) dy
+  float* A = G + TM * ld;     // a = relu(h1*m1) -> dh1 -> ctx
+  float* Bt = A + TM * ld;    // dh2 -> z -> dz/dc -> dctx
+  float* Y = Bt + TM * ld;    // enc: y ; dec: c
+  float* Ws = Y + TM * ld;    // weight staging; reused as LN-bwd / sparse-head scratch
+  const int row0 = blockIdx.x * TM;
+  const int rows = min(TM, M - row0);
+
+  // 1./2. dO = (dout + mse_coef*(out-enc_in)) * keep ; y/c ; a = relu(h1*m1) ; dh2 = dO*m2
+  tile_foreach4<TM>(H, [&](int r, int c) {
+    float4 g = zero4(), a = zero4(), y = zero4(), d2 = zero4();
+    if (row0 + r < M) {
+      const long long gi = (long long)(row0 + r) * H + c;
+      if (p.dout) g = ld4(p.dout + gi);
+      if (IS_DEC && p.enc_in) {
+        const float4 o = ld4(p.out + gi), e = ld4(p.enc_in + gi);
+        const float4 d = make_float4(p.mse_coef * (o.x - e.x), p.mse_coef * (o.y - e.y), p.mse_coef * (o.z - e.z), p.mse_coef * (o.w - e.w));
+        g = f4_add(g, d);
+        if (p.denc) st4(p.denc + gi, make_float4(-d.x, -d.y, -d.z, -d.w));
+      }
+      if (p.ids[row0 + r] == 0) g = zero4();
+      y = ld4(p.u + gi);
+      float4 h = ld4(p.h1 + gi);
+      if (p.drop1.enabled) h = f4_mul(h, drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)gi) >> 2));
+      a = make_float4(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
+      d2 = g;
+      if (p.drop2.enabled) d2 = f4_mul(d2, drop_mul4(p.drop2, (p.drop2.base + (unsigned long long)gi) >> 2));
+    }
+    st4(G + r * ld + c, g);
+    st4(A + r * ld + c, a);
+    st4(Y + r * ld + c, y);
+    st4(Bt + r * ld + c, d2);
+  });
+  __syncthreads();
+  // 3. dC2 += dh2^T a ; dc2 += colsum(dh2)
+  wgrad_tile(Bt, ld, H, A, ld, H, rows, p.gC2, H);
+  colsum_atomic(Bt, ld, H, rows, p.gc2);
+  // 4. da = dh2 C2 ; dh1 = da * [a>0] * m1   (element-wise overwrite of A; A is not this GEMM's operand)
+  gemm_tile<TM, true>(Bt, ld, H, p.C2, H, H, Ws, [&](int, int r, int col, float4 acc) {
+    const float4 a = ld4(A + r * ld + col);
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.drop1.enabled) m = drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)(row0 + r) * H + col) >> 2);
+    st4(A + r * ld + col, make_float4(a.x > 0.f ? acc.x * m.x : 0.f, a.y > 0.f ? acc.y * m.y : 0.f,
+                                      a.z > 0.f ? acc.z * m.z : 0.f, a.w > 0.f ? acc.w * m.w : 0.f));
+  });
+  // 5. z = FFN input (enc: LN2(y) -> Bt ; dec: c == Y) ; dC1 += dh1^T z ; dc1 += colsum(dh1)
+  const float* Z = Y;
+  if (!IS_DEC) {
+    ln_tile<TM>(Y, Bt, ld, H, p.ln2_g, p.ln2_b, 1e-8f, row0, M);
+    __syncthreads();
+    Z = Bt;
+  }
+  wgrad_tile(A, ld, H, Z, ld, H, rows, p.gC1, H);
+  colsum_atomic(A, ld, H, rows, p.gc1);
+  // 6. dz (enc) / dc (dec) = dO + dh1 C1  -> Bt
+  gemm_tile<TM, true>(A, ld, H, p.C1, H, H, Ws, [&](int, int r, int col, float4 acc) {
+    st4(Bt + r * ld + col, f4_add(acc, ld4(G + r * ld + col)));
+  });
+  if (!IS_DEC) {
+    // 7. dy = LN2^T(dz) -> G
+    ln_bwd_tile<TM, false>(Y, Bt, G, ld, H, p.ln2_g, 1e-8f, row0, M, p.gln2_g, p.gln2_b, Ws);
+    // 8. dres = dy ; dWo += dy^T ctx
+    store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
+    load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
+    __syncthreads();
+    wgrad_tile(G, ld, H, A, ld, H, rows, p.gWo, H);
+    colsum_atomic(G, ld, H, rows, p.gbo);
+    // 9. dctx = dy Wo (+ independence-head adjoint) -> Bt -> global
+    gemm_tile<TM, true>(G, ld, H, p.Wo, H, H, Ws, [&](int, int r, int col, float4 acc) { st4(Bt + r * ld + col, acc); });
+    if (p.nll_coef != 0.f || p.drec) {
+      const int nh = p.nh, hd = H / nh;
+      float* sp = Ws;  // [nh*hd] dWsp partial + [nh] dbsp partial
+      for (int i = threadIdx.x; i < nh * hd + nh; i += NT) sp[i] = 0.f;
+      __syncthreads();
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      for (int r = w; r < rows; r += NT / 32) {
+        for (int c = 0; c < nh; ++c) {
+          float lg[8];
+          float mx = -INFINITY;
+          for (int j = 0; j < nh; ++j) {
+            float s = 0.f;
+            for (int dd = l; dd < hd; dd += 32) s = fmaf(A[r * ld + c * hd + dd], p.Wsp[j * hd + dd], s);
+            s = warp_sum(s) + p.bsp[j];
+            lg[j] = s;
+            mx = fmaxf(mx, s);
+          }
+          float se = 0.f;
+          for (int j = 0; j < nh; ++j) { lg[j] = expf(lg[j] - mx); se += lg[j]; }
+          float gsum = 0.f;
+          if (p.drec)
+            for (int j = 0; j < nh; ++j) gsum += p.drec[((long long)(row0 + r) * nh + c) * nh + j];
+          for (int j = 0; j < nh; ++j) {
+            const float pj = lg[j] / se;
+            float dl = p.nll_coef * (pj - (j == c ? 1.f : 0.f));
+            if (p.drec) dl += p.drec[((long long)(row0 + r) * nh + c) * nh + j] - pj * gsum;
+            lg[j] = dl;
+            if (l == 0) atomicAdd(sp + nh * hd + j, dl);
+          }
+          for (int dd = l; dd < hd; dd += 32) {
+            const float cv = A[r * ld + c * hd + dd];
+            float add = 0.f;
+            for (int j = 0; j < nh; ++j) {
+              add = fmaf(lg[j], p.Wsp[j * hd + dd], add);
+              atomicAdd(sp + j * hd + dd, lg[j] * cv);
+            }
+            Bt[r * ld + c * hd + dd] += add;
+          }
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < nh * hd; i += NT) atomicAdd(p.gWsp + i, sp[i]);
+      for (int i = threadIdx.x; i < nh; i += NT) atomicAdd(p.gbsp + i, sp[nh * hd + i]);
+    }
+    store_tile<TM>(Bt, ld, p.dctx, H, 0, H, row0, M);
+  } else {
+    // 7. dres = dd = dO ; dWo += dc^T ctx ; dctx = dc Wo
+    store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
+    load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
+    __syncthreads();
+    wgrad_tile(Bt, ld, H, A, ld, H, rows, p.gWo, H);
+    colsum_atomic(Bt, ld, H, rows, p.gbo);
+    gemm_tile<TM, true>(Bt, ld, H, p.Wo, H, H, Ws, [&](int, int r, int col, float4 acc) {
+      if (row0 + r < M) st4(p.dctx + (long long)(row0 + r) * H + col, acc);
+    });
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// attn_bwd: adjoint of attn_fwd for one (query tile, head, sequence).  Recomputes P from q,k and the saved
+// log-sum-exp; dq is owned by the CTA (plain stores), dk/dv are accumulated with vector atomics because
+// several query tiles of a sequence contribute to the same keys.
+// -------------------------------------------------------------------------------------------------
+template <int TM>
+__global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                      const float* __restrict__ v, const float* __restrict__ dctx,
+                                                      const float* __restrict__ lse, const int* __restrict__ key_ids,
+                                                      float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int L,
+                                                      int H, int nh, int mask_mode, DropDesc drop) {
+  extern __shared__ __align__(16) float smem[];
+  const int hd = H / nh;
+  const int ldq = hd + 4;
+  const int lds = ((L + 3) & ~3) + 4;
+  float* Qs = smem;
+  float* dCs = Qs + TM * ldq;
+  float* Ps = dCs + TM * ldq;
+  float* dPs = Ps + TM * lds;
+  float* Ws = dPs + TM * lds;
+  const int i0 = blockIdx.x * TM, h = blockIdx.y, b = blockIdx.z;
+  const long long seq_off = (long long)b * L * H + (long long)h * hd;
+  const int Lk = mask_mode == 0 ? min(L, i0 + TM) : L;
+  const int Lk4 = (Lk + 3) & ~3;
+  const int rows = min(TM, L - i0);
+
+  load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
+  load_tile<TM>(dCs, ldq, dctx + seq_off, H, 0, hd, i0, L);
+  __syncthreads();
+  gemm_tile<TM, false>(Qs, ldq, hd, k + seq_off, H, Lk, Ws, [&](int, int r, int col, float4 a) { st4(Ps + r * lds + col, a); });
+  gemm_tile<TM, false>(dCs, ldq, hd, v + seq_off, H, Lk, Ws, [&](int, int r, int col, float4 a) { st4(dPs + r * lds + col, a); });
+
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int r = w; r < TM; r += NT / 32) {
+    const int i = i0 + r;
+    float* prow = Ps + r * lds;
+    float* drow = dPs + r * lds;
+    if (i >= L) {
+      for (int j = l; j < Lk4; j += 32) prow[j] = drow[j] = 0.f;
+      continue;
+    }
+    const int nj = mask_mode == 0 ? i + 1 : L;
+    const float ls = lse[((long long)b * nh + h) * L + i];
+    const unsigned long long rbase = drop.base + (((unsigned long long)b * nh + h) * L + i) * (unsigned long long)L;
+    float pv[8], dpv[8], mv[8];
+    float delta = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = l + 32 * u;
+      float pj = 0.f, dp = 0.f, m = 1.f;
+      if (j < nj) {
+        float s = prow[j];
+        if (mask_mode == 1 && key_ids[b * L + j] == 0) s = -1e9f;
+        pj = expf(s - ls);
+        if (drop.enabled) m = drop_mul1(drop, rbase + j);
+        dp = drow[j] * m;
+        delta = fmaf(dp, pj, delta);
+      }
+      pv[u] = pj; dpv[u] = dp; mv[u] = m;
+    }
+    delta = warp_sum(delta);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = l + 32 * u;
+      if (j < Lk4) {
+        prow[j] = pv[u] * mv[u];                 // dropped probabilities (for dV)
+        drow[j] = pv[u] * (dpv[u] - delta);      // dS
+      }
+    }
+  }
+  __syncthreads();
+  // dq = dS k
+  gemm_tile<TM, true>(dPs, lds, Lk, k + seq_off, H, hd, Ws, [&](int, int r, int col, float4 a) {
+    if (i0 + r < L) st4(dq + seq_off + (long long)(i0 + r) * H + col, a);
+  });
+  // dk += dS^T q ; dv += Pd^T dctx
+  wgrad_tile(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
+  wgrad_tile(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
+}
+
+// -------------------------------------------------------------------------------------------------
+// mid_bwd (decoder): adjoint of mid_fwd.
+// -------------------------------------------------------------------------------------------------
+struct MidBwdArgs {
+  const float* dq2; const float* dk2; const float* dv2;
+  const float* a; const float* feats; const float* ctx1;
+  const float* Wo1; const float* Win2;
+  float* dfeats;   // accumulated (+=) : several decoder layers and the logits feed the same encoder features
+  float* dctx1;
+  float* gWo1; float* gbo1; float* gWin2; float* gbin2;
+  int M, H; float qscale;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, M = p.M;
+  const int ld = H + 4, ld2 = 2 * H + 4;
+  float* T0 = smem;              // dq2*scale
+  float* T1 = T0 + TM * ld;      // a -> feats -> ctx1
+  float* DA = T1 + TM * ld;      // grad wrt a
+  float* KV = DA + TM * ld;      // [dk2 | dv2]
+  float* Ws = KV + TM * ld2;
+  const int row0 = blockIdx.x * TM;
+  const int rows = min(TM, M - row0);
+  tile_foreach4<TM>(H, [&](int r, int c) {
+    float4 g = zero4(), a = zero4();
+    if (row0 + r < M) {
+      const long long gi = (long long)(row0 + r) * H + c;
+      g = f4_scale(ld4(p.dq2 + gi), p.qscale);
+      a = ld4(p.a + gi);
+    }
+    st4(T0 + r * ld + c, g);
+    st4(T1 + r * ld + c, a);
+  });
+  __syncthreads();
+  wgrad_tile(T0, ld, H, T1, ld, H, rows, p.gWin2, H);
+  colsum_atomic(T0, ld, H, rows, p.gbin2);
+  gemm_tile<TM, true>(T0, ld, H, p.Win2, H, H, Ws, [&](int, int r, int col, float4 acc) { st4(DA + r * ld + col, acc); });
+  load_tile<TM>(KV, ld2, p.dk2, H, 0, H, row0, M);
+  load_tile<TM>(KV + H, ld2, p.dv2, H, 0, H, row0, M);
+  load_tile<TM>(T1, ld, p.feats, H, 0, H, row0, M);
+  __syncthreads();
+  wgrad_tile(KV, ld2, 2 * H, T1, ld, H, rows, p.gWin2 + (long long)H * H, H);
+  colsum_atomic(KV, ld2, 2 * H, rows, p.gbin2 + H);
+  gemm_tile<TM, true>(KV, ld2, 2 * H, p.Win2 + (long long)H * H, H, H, Ws, [&](int, int r, int col, float4 acc) {
+    if (row0 + r < M) {
+      float* d = p.dfeats + (long long)(row0 + r) * H + col;
+      st4(d, f4_add(ld4(d), acc));
+    }
+  });
+  load_tile<TM>(T1, ld, p.ctx1, H, 0, H, row0, M);
+  __syncthreads();
+  wgrad_tile(DA, ld, H, T1, ld, H, rows, p.gWo1, H);
+  colsum_atomic(DA, ld, H, rows, p.gbo1);
+  gemm_tile<TM, true>(DA, ld, H, p.Wo1, H, H, Ws, [&](int, int r, int col, float4 acc) {
+    if (row0 + r < M) st4(p.dctx1 + (long long)(row0 + r) * H + col, acc);
+  });
+}
+
+// -------------------------------------------------------------------------------------------------
+// pre_bwd: adjoint of pre_fwd.
+//   dx = LN^T( dnorm_extra + dq*s Wq [+ dk Wk + dv Wv if kv_from_norm] ) [+ dk Wk + dv Wv if !kv_from_norm] + dx_extra
+// -------------------------------------------------------------------------------------------------
+struct PreBwdArgs {
+  const float* dq; const float* dk; const float* dv;
+  const float* x;
+  const float* dnorm_extra;   // enc: dy from post_bwd ; dec: dd from post_bwd (nullable)
+  const float* dx_extra;      // extra grad added to dx (enc: MSE grad wrt enc_in), nullable
+  const float* ln_g; const float* ln_b; const float* Win;
+  float* dx;
+  float* gWin; float* gbin; float* gln_g; float* gln_b;
+  int M, H; float qscale; int kv_from_norm;
+};
+
+template <int TM>
+__global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, M = p.M;
+  const int ld = H + 4;
+  float* X = smem;
+  float* N = X + TM * ld;
+  float* T = N + TM * ld;
+  float* D = T + TM * ld;
+  float* Ws = D + TM * ld;
+  const int row0 = blockIdx.x * TM;
+  const int rows = min(TM, M - row0);
+  tile_foreach4<TM>(H, [&](int r, int c) {
+    float4 xv = zero4(), g = zero4();
+    if (row0 + r < M) {
+      const long long gi = (long long)(row0 + r) * H + c;
+      xv = ld4(p.x + gi);
+      g = f4_scale(ld4(p.dq + gi), p.qscale);
+    }
+    st4(X + r * ld + c, xv);
+    st4(T + r * ld + c, g);
+  });
+  __syncthreads();
+  ln_tile<TM>(X, N, ld, H, p.ln_g, p.ln_b, 1e-8f, row0, M);
+  __syncthreads();
+  wgrad_tile(T, ld, H, N, ld, H, rows, p.gWin, H);
+  colsum_atomic(T, ld, H, rows, p.gbin);
+  gemm_tile<TM, true>(T, ld, H, p.Win, H, H, Ws, [&](int, int r, int col, float4 acc) {
+    if (p.dnorm_extra && row0 + r < M) acc = f4_add(acc, ld4(p.dnorm_extra + (long long)(row0 + r) * H + col));
+    st4(D + r * ld + col, acc);
+  });
+  if (!p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, Ws);
+  const float* Xkv = p.kv_from_norm ? N : X;
+  for (int which = 0; which < 2; ++which) {
+    load_tile<TM>(T, ld, which == 0 ? p.dk : p.dv, H, 0, H, row0, M);
+    __syncthreads();
+    wgrad_tile(T, ld, H, Xkv, ld, H, rows, p.gWin + (long long)(1 + which) * H * H, H);
+    colsum_atomic(T, ld, H, rows, p.gbin + (1 + which) * H);
+    gemm_tile<TM, true>(T, ld, H, p.Win + (long long)(1 + which) * H * H, H, H, Ws, [&](int, int r, int col, float4 acc) {
+      st4(D + r * ld + col, f4_add(acc, ld4(D + r * ld + col)));
+    });
+  }
+  if (p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, Ws);
+  tile_foreach4<TM>(H, [&](int r, int c) {
+    if (row0 + r < M) {
+      const long long gi = (long long)(row0 + r) * H + c;
+      float4 d = ld4(D + r * ld + c);
+      if (p.dx_extra) d = f4_add(d, ld4(p.dx_extra + gi));
+      st4(p.dx + gi, d);
+    }
+  });
+}
+
+// -------------------------------------------------------------------------------------------------
+// final_bwd: adjoint of final_fwd (+ BCE).  Warp per row.
+//   dpl = -sigmoid(-pl)/n * [pos!=0] (+ ext) ; dnl = sigmoid(nl)/n * [pos!=0] (+ ext)
+//   dfeats = dfeats_in + dpl*E[pos] + dnl*E[neg] ; dx = LN^T(dfeats)
+//   cpos/cneg (the per-row coefficients of the item-table gradient rows dpl*feats, dnl*feats) are written for
+//   the scatter-add kernel.
+// -------------------------------------------------------------------------------------------------
+struct FinalBwdArgs {
+  const float* x; const float* ln_g; const float* E; const int* pos; const int* neg;
+  const float* pos_logits; const float* neg_logits;
+  const float* dfeats_in;      // nullable
+  const double* n_valid;       // device scalar: number of valid (pos != 0) positions of the GLOBAL batch
+  float bce_weight;            // 1 for the fused loss, 0 when only external grads are given
+  const float* dpl_ext; const float* dnl_ext;   // compat-mode external grads (nullable)
+  float* dx; float* cpos; float* cneg; float* gln_g; float* gln_b;
+  int M, H;
+};
+
+__global__ void __launch_bounds__(NT) final_bwd_kernel(FinalBwdArgs p) {
+  __shared__ float red[2 * (NT / 32) * 256];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int H = p.H;
+  constexpr int NW = NT / 32;
+  float dg[8], db[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) dg[u] = db[u] = 0.f;
+  const float inv_n = p.bce_weight != 0.f ? (float)(1.0 / fmax(*p.n_valid, 1.0)) * p.bce_weight : 0.f;
+  for (int row = blockIdx.x * NW + w; row < p.M; row += gridDim.x * NW) {
+    const int pi = p.pos[row], ni = p.neg[row];
+    float dpl = 0.f, dnl = 0.f;
+    if (pi != 0) {
+      const float pl = p.pos_logits[row], nl = p.neg_logits[row];
+      dpl = -inv_n / (1.f + expf(pl));
+      dnl = inv_n / (1.f + expf(-nl));
+    }
+    if (p.dpl_ext) dpl += p.dpl_ext[row];
+    if (p.dnl_ext) dnl += p.dnl_ext[row];
+    if (l == 0) { p.cpos[row] = dpl; p.cneg[row] = dnl; }
+    const float* xr = p.x + (long long)row * H;
+    float xv[8], gv[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = l + 32 * u;
+      xv[u] = c < H ? xr[c] : 0.f;
+      sum += xv[u];
+      float g = 0.f;
+      if (c < H) {
+        if (p.dfeats_in) g = p.dfeats_in[(long long)row * H + c];
+        g = fmaf(dpl, p.E[(long long)pi * H + c], g);
+        g = fmaf(dnl, p.E[(long long)ni * H + c], g);
+      }
+      gv[u] = g;
+    }
+    if (!p.ln_g) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (l + 32 * u < H) p.dx[(long long)row * H + l + 32 * u] = gv[u];
+      continue;
+    }
+    const float mean = warp_sum(sum) / (float)H;
+    float var = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (l + 32 * u < H) { const float t = xv[u] - mean; var += t * t; }
+    const float rstd = 1.0f / sqrtf(warp_sum(var) / (float)H + 1e-8f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = l + 32 * u;
+      if (c < H) {
+        const float xh = (xv[u] - mean) * rstd;
+        const float gg = gv[u] * p.ln_g[c];
+        s1 += gg; s2 += gg * xh;
+        dg[u] += gv[u] * xh; db[u] += gv[u];
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = l + 32 * u;
+      if (c < H) {
+        const float xh = (xv[u] - mean) * rstd;
+        p.dx[(long long)row * H + c] = rstd * (gv[u] * p.ln_g[c] - s1 - xh * s2);
+      }
+    }
+  }
+  if (p.ln_g) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = l + 32 * u;
+      if (c < H) { red[w * H + c] = dg[u]; red[(NW + w) * H + c] = db[u]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += NT) {
+      float a = 0.f, b = 0.f;
+      for (int i = 0; i < NW; ++i) { a += red[i * H + c]; b += red[(NW + i) * H + c]; }
+      atomicAdd(p.gln_g + c, a);
+      atomicAdd(p.gln_b + c, b);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// pos_emb gradient: dP[t][c] += sum_b dx[b][t][c] * m(b,t,c) * [id != 0]    (adjoint of K1 wrt pos_emb)
+// grid = L CTAs; thread (c4, bs) strides over the batch; plain block reduction, one atomic per element.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) posgrad_kernel(const float* __restrict__ dx, const int* __restrict__ ids, float* __restrict__ gP,
+                                                     int B, int L, int H, DropDesc drop) {
+  __shared__ float4 red[NT];
+  const int t = blockIdx.x;
+  const int h4 = H >> 2;
+  const int c4 = threadIdx.x % h4, bs = threadIdx.x / h4, nbs = NT / h4;
+  float4 acc = zero4();
+  if (bs < nbs) {
+    for (int b = bs; b < B; b += nbs) {
+      const int row = b * L + t;
+      if (ids[row] == 0) continue;
+      const long long gi = (long long)row * H + 4 * c4;
+      float4 g = ld4(dx + gi);
+      if (drop.enabled) g = f4_mul(g, drop_mul4(drop, (drop.base + (unsigned long long)gi) >> 2));
+      acc = f4_add(acc, g);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < h4) {
+    float4 s = zero4();
+    for (int i = 0; i < nbs; ++i) s = f4_add(s, red[i * h4 + threadIdx.x]);
+    atomicAdd(reinterpret_cast<float4*>(gP + (long long)t * H) + threadIdx.x, s);
+  }
+}
+
+}  // namespace adt

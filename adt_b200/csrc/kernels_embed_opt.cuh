@@ -1,0 +1,281 @@
+// Embedding backward (K2: stable radix sort by item id + segmented scatter-add) and the fused
+// table/dense optimiser pass (K6).  Reference semantics: torch embedding_dense_backward with padding_idx=0
+// for the four lookups of one step (sasrec/model.py:34,53,72,73), main.py:170-173 (||E|| weight decay,
+// clip_grad_norm_, Adam).
+#pragma once
+#include "common.cuh"
+#include "kernels_bwd.cuh"
+
+namespace adt {
+
+constexpr int SORT_WCH = 256;   // sorted-array elements owned by one warp per radix pass
+
+// key/value of logical element e of the concatenated lookup list: src = e / M (0 seq, 1 dec, 2 pos, 3 neg)
+struct SortSrc {
+  const int* ids[4];
+  int M;
+};
+
+template <bool FIRST>
+__device__ __forceinline__ int sort_key(const SortSrc& s, const int* keys_in, int e) {
+  if (FIRST) {
+    const int src = e / s.M;
+    return s.ids[src][e - src * s.M];
+  }
+  return keys_in[e];
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256) radix_hist_kernel(SortSrc s, const int* __restrict__ keys_in, int N, int shift,
+                                                         int* __restrict__ hist, int nW) {
+  __shared__ int cnt[8][256];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + w;
+  for (int d = l; d < 256; d += 32) cnt[w][d] = 0;
+  __syncwarp();
+  if (gw < nW) {
+    const int end = min(N, (gw + 1) * SORT_WCH);
+    for (int e = gw * SORT_WCH + l; e < end; e += 32) atomicAdd(&cnt[w][(sort_key<FIRST>(s, keys_in, e) >> shift) & 255], 1);
+    __syncwarp();
+    for (int d = l; d < 256; d += 32) hist[d * nW + gw] = cnt[w][d];
+  }
+}
+
+// in-place exclusive scan of n ints, single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int* __restrict__ data, int n) {
+  __shared__ int wsum[32];
+  const int per = (n + 1023) / 1024;
+  const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
+  int s = 0;
+  for (int i = beg; i < end; ++i) s += data[i];
+  const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (l >= o) incl += t;
+  }
+  if (l == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[l];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (l >= o) v += t;
+    }
+    wsum[l] = v;
+  }
+  __syncthreads();
+  int run = incl - s + (w > 0 ? wsum[w - 1] : 0);
+  for (int i = beg; i < end; ++i) {
+    const int t = data[i];
+    data[i] = run;
+    run += t;
+  }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256) radix_scatter_kernel(SortSrc s, const int* __restrict__ keys_in, const int* __restrict__ vals_in,
+                                                            int N, int shift, const int* __restrict__ hist, int nW,
+                                                            int* __restrict__ keys_out, int* __restrict__ vals_out) {
+  __shared__ int off[8][256];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + w;
+  if (gw >= nW) return;
+  for (int d = l; d < 256; d += 32) off[w][d] = hist[d * nW + gw];
+  __syncwarp();
+  const int end = min(N, (gw + 1) * SORT_WCH);
+  for (int base = gw * SORT_WCH; base < end; base += 32) {
+    const int e = base + l;
+    const bool ok = e < end;
+    const int key = ok ? sort_key<FIRST>(s, keys_in, e) : 0;
+    const int val = ok ? (FIRST ? e : vals_in[e]) : 0;
+    const int d = ok ? ((key >> shift) & 255) : (256 + l);   // invalid lanes never match anybody
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << l) - 1u));
+    int dst = 0;
+    if (ok) dst = off[w][d] + rank;
+    __syncwarp();
+    if (ok && rank == 0) off[w][d] += __popc(peers);
+    __syncwarp();
+    if (ok) {
+      keys_out[dst] = key;
+      vals_out[dst] = val;
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Segmented scatter-add over the sorted (id, element) list.
+// Row value of element e (src = e / M, row = e % M), H floats:
+//   src 0/1: dx_{enc,dec}[row] * m_emb(row, :) * sqrt(H)        (adjoint of K1 wrt the table)
+//   src 2/3: c{pos,neg}[row] * feats[row]                        (adjoint of the pos/neg logits)
+// Phase 1: one warp per 32-entry block of the sorted list, entries summed sequentially in sorted (= original)
+//          order; runs fully inside the block are stored to dE, runs crossing a block edge leave a head/tail partial.
+// Phase 2: one warp per block that opens a crossing run: tail + following heads, in order.  Deterministic.
+// -------------------------------------------------------------------------------------------------
+struct ScatterArgs {
+  const int* keys; const int* vals; int N; int M; int H;
+  const float* dx_enc; const float* dx_dec; const float* feats; const float* cpos; const float* cneg;
+  float scale;
+  DropDesc drop_enc, drop_dec;
+  float* dE; float* head; float* tail; int* has_tail;
+};
+
+__device__ __forceinline__ float4 scatter_row4(const ScatterArgs& a, int e, int c) {
+  const int src = e / a.M, row = e - src * a.M;
+  const long long gi = (long long)row * a.H + c;
+  if (src < 2) {
+    float4 g = ld4((src == 0 ? a.dx_enc : a.dx_dec) + gi);
+    const DropDesc& d = src == 0 ? a.drop_enc : a.drop_dec;
+    if (d.enabled) g = f4_mul(g, drop_mul4(d, (d.base + (unsigned long long)gi) >> 2));
+    return f4_scale(g, a.scale);
+  }
+  const float cf = (src == 2 ? a.cpos : a.cneg)[row];
+  return f4_scale(ld4(a.feats + gi), cf);
+}
+
+__global__ void __launch_bounds__(256) scatter_phase1_kernel(ScatterArgs a) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + w;
+  const int base = g * 32;
+  if (base >= a.N) return;
+  const int cnt = min(32, a.N - base);
+  const int key_l = l < cnt ? a.keys[base + l] : -1;
+  const int val_l = l < cnt ? a.vals[base + l] : 0;
+  const int prev_key = base > 0 ? a.keys[base - 1] : -1;
+  const int next_key = base + 32 < a.N ? a.keys[base + 32] : -2;
+  const int h4 = a.H >> 2;
+  float4 acc[2] = {zero4(), zero4()};   // H <= 256 -> at most 2 float4 per lane
+  int run_start = 0;
+  bool tail_written = false;
+  for (int j = 0; j < cnt; ++j) {
+    const int key = __shfl_sync(0xffffffffu, key_l, j);
+    const int e = __shfl_sync(0xffffffffu, val_l, j);
+    const int key_next = j + 1 < cnt ? __shfl_sync(0xffffffffu, key_l, j + 1) : -3;
+    if (key == 0) { run_start = j + 1; continue; }   // padding_idx rows get no gradient
+    const bool fresh = (j == run_start);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int c4 = l + 32 * s;
+      if (c4 < h4) {
+        const float4 v = scatter_row4(a, e, 4 * c4);
+        acc[s] = fresh ? v : f4_add(acc[s], v);
+      }
+    }
+    if (j == cnt - 1 || key_next != key) {
+      const bool from_before = (run_start == 0) && (key == prev_key);
+      const bool goes_after = (j == cnt - 1) && (key == next_key);
+      float* dst;
+      if (from_before) dst = a.head + (long long)g * a.H;
+      else if (goes_after) { dst = a.tail + (long long)g * a.H; tail_written = true; }
+      else dst = a.dE + (long long)key * a.H;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int c4 = l + 32 * s;
+        if (c4 < h4) st4(dst + 4 * c4, acc[s]);
+      }
+      run_start = j + 1;
+    }
+  }
+  if (l == 0) a.has_tail[g] = tail_written ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) scatter_phase2_kernel(ScatterArgs a) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + w;
+  const int nb = (a.N + 31) / 32;
+  if (g >= nb || !a.has_tail[g]) return;
+  const int key = a.keys[g * 32 + 31];
+  const int h4 = a.H >> 2;
+  float4 acc[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int c4 = l + 32 * s;
+    acc[s] = c4 < h4 ? ld4(a.tail + (long long)g * a.H + 4 * c4) : zero4();
+  }
+  for (int g2 = g + 1; g2 < nb && a.keys[g2 * 32] == key; ++g2) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int c4 = l + 32 * s;
+      if (c4 < h4) acc[s] = f4_add(acc[s], ld4(a.head + (long long)g2 * a.H + 4 * c4));
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int c4 = l + 32 * s;
+    if (c4 < h4) st4(a.dE + (long long)key * a.H + 4 * c4, acc[s]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Optimiser pass (K6).
+// -------------------------------------------------------------------------------------------------
+// out += sum x^2 (double)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += (double)x[i] * (double)x[i];
+  cta_accumulate(s, out, red);
+}
+
+// g += (wd / sqrt(*normsq)) * w     -- gradient of wd*||W||_F  (main.py:170)
+__global__ void __launch_bounds__(256) norm_decay_grad_kernel(float* __restrict__ g, const float* __restrict__ w, long long n, float wd,
+                                                              const double* __restrict__ normsq) {
+  const float coef = wd / (float)sqrt(*normsq);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    g[i] = fmaf(coef, w[i], g[i]);
+}
+
+struct AdamArgs {
+  float* p; float* g; float* m; float* v; long long n;
+  float lr, beta1, beta2, eps, weight_decay;   // weight_decay: classic L2 (evolution.py:111), 0 in main.py
+  float bc1, bc2;                              // 1-beta1^t, 1-beta2^t
+  float max_norm;                              // <=0: no clipping
+  const double* gnormsq;                       // device scalar: sum of squares of ALL grads
+  const int* step_dev;                         // optional device step count (overrides bc1/bc2)
+};
+
+// torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (single tensor semantics), fused.  g is left holding the
+// clipped gradient (like the reference's .grad after clip_grad_norm_).
+__global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
+  float coef = 1.f;
+  if (a.max_norm > 0.f) {
+    const float tn = (float)sqrt(*a.gnormsq);
+    coef = fminf(a.max_norm / (tn + 1e-6f), 1.0f);
+  }
+  float bc1 = a.bc1, bc2 = a.bc2;
+  if (a.step_dev) {
+    const double t = (double)*a.step_dev;
+    bc1 = (float)(1.0 - pow((double)a.beta1, t));
+    bc2 = (float)(1.0 - pow((double)a.beta2, t));
+  }
+  const float step = a.lr / bc1;
+  const float isb2 = 1.0f / sqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    float g = a.g[i] * coef;
+    a.g[i] = g;
+    const float p = a.p[i];
+    if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    a.m[i] = m;
+    a.v[i] = v;
+    a.p[i] = p - step * (m / (sqrtf(v) * isb2 + a.eps));
+  }
+}
+
+// test helper: materialise the dropout keep-multipliers for elements [0, n) of a site
+__global__ void philox_mask_kernel(float* __restrict__ out, long long n, DropDesc d) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = d.enabled ? drop_mul1(d, d.base + (unsigned long long)i) : 1.f;
+}
+
+}  // namespace adt

@@ -1,0 +1,194 @@
+/* libadt_b200.so -- C ABI of the B200-native ADT hot path (SASRec-ADT training step + full-catalog eval).
+ *
+ * The reference (defineZYP/ADT) is pure Python/PyTorch and has no FFI layer of its own; the seam it offers is
+ * the torch.nn.Module (`SASRecADT.forward/predict`, /root/reference/sasrec/model.py:67-97) plus the loss /
+ * optimiser lines of its training loop (/root/reference/sasrec/main.py:146-173).  Each entry point below
+ * replaces the span of reference code it cites; `adt_b200/model.py` binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (fp32 activations/weights, int32 ids), 16-byte aligned;
+ *   - activations are row-major [M = B*L, H]; H % 4 == 0, H <= 256, (H/nh) % 4 == 0, L <= 256, nh <= 8;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t), never synchronise, allocate nothing;
+ *   - return 0 on success, a negative ADT_E_* otherwise; adt_last_error() gives the thread-local message;
+ *   - gradient buffers are ACCUMULATED into (+=, atomics) unless stated: zero them once per step.
+ */
+#ifndef ADT_B200_H
+#define ADT_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* adt_stream_t; /* cudaStream_t */
+
+#define ADT_OK 0
+#define ADT_E_SHAPE (-1)
+#define ADT_E_ALIGN (-2)
+#define ADT_E_ARCH (-3)
+#define ADT_E_CUDA (-4)
+
+/* Counter-based dropout site (replaces torch's global-RNG F.dropout; sasrec/modules.py:61, :626-628,
+ * sasrec/model.py:20).  keep(idx) = philox4x32_10(ctr=(idx>>2, site, step), key=seed)[idx&3] >= p*2^32. */
+typedef struct {
+  int32_t enabled;   /* 0 -> identity (eval mode or p == 0) */
+  float p;
+  uint64_t seed;
+  uint32_t step;
+  uint32_t site;
+  uint64_t base;     /* linear index offset of this rank's first element (data-parallel batch offset) */
+  const uint32_t* step_dev; /* optional DEVICE counter added to `step` at run time (lets a captured CUDA graph advance) */
+} adt_dropout;
+
+int adt_version(void);
+const char* adt_last_error(void);
+
+/* K1. x = dropout(E[ids]*sqrt(H) + P[t]) * (ids != 0)            -- sasrec/model.py:34-41 and :53-58 */
+typedef struct {
+  const int32_t* ids; const float* item_emb; const float* pos_emb; float* x;
+  int32_t B, L, H; adt_dropout drop;
+} adt_embed_fwd_args;
+int adt_embed_fwd(const adt_embed_fwd_args* a, adt_stream_t stream);
+
+/* attention weights of one nn.MultiheadAttention / MultiheadAttentionADT (packed in-projection) */
+typedef struct { const float* in_w; const float* in_b; const float* out_w; const float* out_b; } adt_mha_w;
+typedef struct { float* in_w; float* in_b; float* out_w; float* out_b; } adt_mha_g;
+typedef struct { const float* w1; const float* b1; const float* w2; const float* b2; } adt_ffn_w; /* Conv1d k=1 == [H,H] */
+typedef struct { float* w1; float* b1; float* w2; float* b2; } adt_ffn_g;
+
+/* Encoder block -- EncoderLayer.forward, sasrec/modules.py:644-655 (+ MultiheadAttentionADT :270-527,
+ * PointWiseFeedForward :629-633, SparseInputLinear :696-703).  rec is written in TRUE [B,L,nh,nh] layout. */
+typedef struct {
+  const float* x; const int32_t* ids;                     /* block input [M,H], log_seqs (keep = ids != 0) */
+  const float* ln1_w; const float* ln1_b; adt_mha_w attn; const float* ln2_w; const float* ln2_b; adt_ffn_w ffn;
+  const float* sparse_w; const float* sparse_b;
+  float* q; float* k; float* v; float* ctx; float* lse;    /* saved for backward: [M,H] x4, [B,nh,L] */
+  float* y; float* h1;                                     /* saved for backward (may be NULL when training == 0) */
+  float* out; float* rec;                                  /* outputs: [M,H], [M,nh,nh] (rec may be NULL) */
+  double* nll_acc;                                         /* += -sum_{r,c} rec[r][c][c]   (may be NULL) */
+  int32_t B, L, H, nh, training, mask_mode;                /* mask_mode 0 causal, 1 key-padding (bidirectional) */
+  adt_dropout drop_attn, drop_ffn1, drop_ffn2;
+} adt_enc_block_fwd_args;
+int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t stream);
+
+typedef struct {
+  const float* x; const int32_t* ids;
+  const float* ln1_w; const float* ln1_b; adt_mha_w attn; const float* ln2_w; const float* ln2_b; adt_ffn_w ffn;
+  const float* sparse_w; const float* sparse_b;
+  const float* q; const float* k; const float* v; const float* ctx; const float* lse; const float* y; const float* h1;
+  const float* dout;          /* grad wrt block output (NULL = 0) */
+  const float* dx_extra;      /* extra grad wrt block input, e.g. the reconstruction-MSE grad (NULL = 0) */
+  const float* drec;          /* external grad wrt rec (compat mode, NULL = none) */
+  float nll_coef;             /* fused independence loss: lambda2 / (M_global*nh), 0 = off */
+  float* dq; float* dk; float* dv; float* dctx; float* dy;   /* scratch [M,H] each; dk, dv must be ZEROED by the caller */
+  float* dx;                  /* out: grad wrt block input (overwritten) */
+  float* g_ln1_w; float* g_ln1_b; adt_mha_g g_attn; float* g_ln2_w; float* g_ln2_b; adt_ffn_g g_ffn;
+  float* g_sparse_w; float* g_sparse_b;
+  int32_t B, L, H, nh, mask_mode;
+  adt_dropout drop_attn, drop_ffn1, drop_ffn2;
+} adt_enc_block_bwd_args;
+int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t stream);
+
+/* Decoder block -- DecoderLayer.forward, sasrec/modules.py:666-677 (two stock nn.MultiheadAttention + FFN). */
+typedef struct {
+  const float* x; const float* feats; const int32_t* ids;  /* decoder input, encoder features, dec_seqs */
+  const float* ln_w; const float* ln_b; adt_mha_w slf; adt_mha_w enc; adt_ffn_w ffn;
+  const float* enc_in;                                     /* reconstruction target for the fused MSE (may be NULL) */
+  float* d; float* q1; float* k1; float* v1; float* ctx1; float* lse1; float* a;
+  float* q2; float* k2; float* v2; float* ctx2; float* lse2; float* c; float* h1;
+  float* out;
+  double* mse_acc;                                         /* += sum (enc_in - out)^2   (may be NULL) */
+  int32_t B, L, H, nh, training, mask_mode;
+  adt_dropout drop_slf, drop_enc, drop_ffn1, drop_ffn2;
+} adt_dec_block_fwd_args;
+int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t stream);
+
+typedef struct {
+  const float* x; const float* feats; const int32_t* ids;
+  const float* ln_w; const float* ln_b; adt_mha_w slf; adt_mha_w enc; adt_ffn_w ffn;
+  const float* d; const float* q1; const float* k1; const float* v1; const float* ctx1; const float* lse1; const float* a;
+  const float* q2; const float* k2; const float* v2; const float* ctx2; const float* lse2; const float* c; const float* h1;
+  const float* out; const float* enc_in; float mse_coef;   /* fused MSE: lambda1*2/(M_global*H); enc_in NULL = off */
+  const float* dout;                                       /* grad wrt block output (NULL = 0) */
+  float* denc;                                             /* out: grad wrt enc_in (overwritten; may be NULL) */
+  float* dq; float* dk; float* dv; float* dctx; float* dd; float* dq2; float* dk2; float* dv2; float* dctx2; /* scratch; dk,dv,dk2,dv2 ZEROED by caller */
+  float* dfeats;                                           /* accumulated (+=) */
+  float* dx;                                               /* out: grad wrt decoder block input */
+  float* g_ln_w; float* g_ln_b; adt_mha_g g_slf; adt_mha_g g_enc; adt_ffn_g g_ffn;
+  int32_t B, L, H, nh, mask_mode;
+  adt_dropout drop_slf, drop_enc, drop_ffn1, drop_ffn2;
+} adt_dec_block_bwd_args;
+int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t stream);
+
+/* last LayerNorm + pos/neg logits + BCE sums -- sasrec/model.py:48,72-76 and sasrec/main.py:151-153.
+ * acc[0] += sum softplus(-pos_logit), acc[1] += sum softplus(neg_logit), acc[2] += #valid   over pos != 0.
+ * ln_w == NULL skips the LayerNorm (SuperSASRecModel has none, sasrec/supersasrec.py:56-58).
+ * pos == NULL: only feats are produced (predict path, model.py:83-89). */
+typedef struct {
+  const float* x; const float* ln_w; const float* ln_b; const float* item_emb; const int32_t* pos; const int32_t* neg;
+  float* feats; float* pos_logits; float* neg_logits; double* acc; int32_t M, H;
+} adt_final_fwd_args;
+int adt_final_logits_loss_fwd(const adt_final_fwd_args* a, adt_stream_t stream);
+
+typedef struct {
+  const float* x; const float* ln_w; const float* item_emb; const int32_t* pos; const int32_t* neg;
+  const float* pos_logits; const float* neg_logits; const float* dfeats_in;
+  const double* n_valid; float bce_weight; const float* dpl_ext; const float* dnl_ext;
+  float* dx; float* cpos; float* cneg; float* g_ln_w; float* g_ln_b; int32_t M, H;
+} adt_final_bwd_args;
+int adt_final_logits_loss_bwd(const adt_final_bwd_args* a, adt_stream_t stream);
+
+/* K2. embedding backward for the four lookups of one step (seq, dec, pos, neg): stable LSD radix sort of the
+ * 4*M (id, element) pairs followed by a deterministic segmented scatter-add into d_item_emb (rows touched are
+ * OVERWRITTEN, so d_item_emb must be zeroed once per step), plus the pos_emb gradient.
+ * Replaces torch's embedding_dense_backward for sasrec/model.py:34,37,53,56,72,73.
+ * adt_embed_sort only depends on the ids and may run on a side stream as soon as the batch is on the device. */
+typedef struct {
+  const int32_t* seq; const int32_t* dec; const int32_t* pos; const int32_t* neg; int32_t M; int32_t max_id;
+  int32_t* keys; int32_t* vals;            /* out: sorted ids / element indices, 4*M each */
+  int32_t* keys_tmp; int32_t* vals_tmp;    /* scratch 4*M each */
+  int32_t* hist;                           /* scratch: 256 * ceil(4*M/256) ints */
+} adt_embed_sort_args;
+int adt_embed_sort(const adt_embed_sort_args* a, adt_stream_t stream);
+
+typedef struct {
+  const int32_t* keys; const int32_t* vals; const int32_t* seq; const int32_t* dec; int32_t B, L, H;
+  const float* dx_enc; const float* dx_dec; const float* feats; const float* cpos; const float* cneg;
+  adt_dropout drop_enc, drop_dec;
+  float* d_item_emb; float* d_pos_emb;      /* d_pos_emb accumulated */
+  float* head; float* tail; int32_t* has_tail;   /* scratch: ceil(4*M/32) x H floats (x2), ceil(4*M/32) ints */
+} adt_embed_bwd_args;
+int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t stream);
+
+/* K6. optimiser pieces -- sasrec/main.py:170-173 (wd*||E||, clip_grad_norm_, Adam). */
+int adt_sumsq(const float* x, int64_t n, double* out /* += */, adt_stream_t stream);
+int adt_norm_decay_grad(float* g, const float* w, int64_t n, float wd, const double* normsq, adt_stream_t stream);
+typedef struct {
+  float* p; float* g; float* m; float* v; int64_t n;
+  float lr, beta1, beta2, eps, weight_decay; int32_t step; float max_norm; const double* gnormsq;
+  const int32_t* step_dev;  /* optional DEVICE step count t (overrides `step`; for CUDA-graph replay) */
+} adt_adam_args;
+int adt_adam(const adt_adam_args* a, adt_stream_t stream);
+
+/* K7. full-catalog scoring with fused per-user top-K -- replaces predict(full=True) + the host-side
+ * mask / argpartition / sort of the whole score row (sasrec/model.py:91-96, sasrec/utils.py:718-731,
+ * stosa/trainer.py:604-614).  scores[u][i] = <feats[u], item_emb[i]>, items whose GLOBAL id (item_offset + i) is in
+ * the user's sorted seen-list are skipped; ties are ordered by ascending id.  Item-sharded evaluation calls this
+ * once per shard (item_offset = first global id of the shard) and merges the per-shard lists. */
+typedef struct {
+  const float* feats; int32_t U, H;
+  const float* item_emb; int32_t n_items; int32_t item_offset;
+  const int32_t* seen_indptr; const int32_t* seen_idx;   /* CSR over users, ids ascending (NULL = no mask) */
+  int32_t K;                                             /* <= 64 */
+  int32_t n_splits;                                      /* catalog splits per 64-user tile (<= 256) */
+  float* part_scores; int32_t* part_ids;                 /* scratch [n_splits][U][K] */
+  float* out_scores; int32_t* out_ids;                   /* [U][K], best first; -inf / -1 padded */
+} adt_score_topk_args;
+int adt_score_topk(const adt_score_topk_args* a, adt_stream_t stream);
+
+/* test helper: out[i] = keep-multiplier (0 or 1/(1-p)) of element base+i of a dropout site */
+int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
