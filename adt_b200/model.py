@@ -220,7 +220,7 @@ class Engine:
                        ln2_w=layer.forward_layernorm.weight, ln2_b=layer.forward_layernorm.bias, ffn=_ffn_w(layer.forward_layer),
                        sparse_w=layer.sparse.weight, sparse_b=layer.sparse.bias,
                        q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"],
-                       out=w["x"][l + 1], rec=sv["rec"] if m.num_heads > 1 else None,
+                       out=w["x"][l + 1], rec=sv["rec"],
                        nll_acc=(w["acc"][3 + m.num_layers + l:] if (nll and m.num_heads > 1) else None),
                        B=B, L=Lq, H=m.hidden, nh=m.num_heads, training=int(training), mask_mode=0,
                        drop_attn=self._drop(sa, "attn", training, B, Lq), drop_ffn1=self._drop(s1, "row", training, B, Lq),
@@ -334,9 +334,7 @@ class Engine:
             pre = f"encoder.encoder_layers.{l}."
             sa, s1, s2 = sites[("enc", l)]
             ei = ext.get("denc_in")
-            dout = dx
-            if ei is not None and l + 1 < nl and ei[l + 1] is not None:
-                dout = dx + ei[l + 1]
+            dout = dx   # already contains the external grad wrt x[l+1] (added as dx_extra of block l+1)
             dx_extra = w["denc"][l] if fused else (ei[l] if ei is not None else None)
             dr = ext.get("drec")
             z4[:2].zero_()
@@ -408,9 +406,11 @@ class _CompatForward(torch.autograd.Function):
         seq, dec, pos, neg = ctx.ids
         names = [n for n, _ in model.named_parameters()]
         grads = {n: torch.zeros_like(p) for n, p in model.named_parameters()}
+        H = model.hidden
         c = lambda t: None if t is None else t.contiguous().float()
-        ext = {"dpl": c(gouts[0]), "dnl": c(gouts[1]), "denc_in": [c(t) for t in gouts[2:2 + nl]],
-               "ddec_out": [c(t) for t in gouts[2 + nl:2 + 2 * nl]], "drec": [c(t) for t in gouts[2 + 2 * nl:2 + 3 * nl]]}
+        c2 = lambda t: None if t is None else t.contiguous().float().view(-1, H)
+        ext = {"dpl": c(gouts[0]), "dnl": c(gouts[1]), "denc_in": [c2(t) for t in gouts[2:2 + nl]],
+               "ddec_out": [c2(t) for t in gouts[2 + nl:2 + 2 * nl]], "drec": [c(t) for t in gouts[2 + 2 * nl:2 + 3 * nl]]}
         if model.num_heads == 1:
             ext["drec"] = None
         eng.backward(seq, dec, pos, neg, w, grads, ext=ext)
