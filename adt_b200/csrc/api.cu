@@ -26,6 +26,53 @@ static int check_launch(const char* what) {
   return ADT_OK;
 }
 
+// ---- optional per-kernel CUDA-event timing (bench.py's live roofline measurement) -------------------------
+namespace {
+constexpr int TIMING_MAX = 8192;
+struct TimingRec { const char* name; cudaEvent_t a, b; };
+bool g_timing_on = false;
+int g_timing_n = 0;
+TimingRec g_timing[TIMING_MAX];
+struct TimingScope {
+  int idx; cudaStream_t s;
+  TimingScope(const char* name, cudaStream_t s_) : idx(-1), s(s_) {
+    if (!g_timing_on || g_timing_n >= TIMING_MAX) return;
+    idx = g_timing_n++;
+    TimingRec& r = g_timing[idx];
+    r.name = name;
+    if (!r.a) { cudaEventCreate(&r.a); cudaEventCreate(&r.b); }
+    cudaEventRecord(r.a, s);
+  }
+  ~TimingScope() { if (idx >= 0) cudaEventRecord(g_timing[idx].b, s); }
+};
+}  // namespace
+#define TIMED(name, stream) TimingScope _ts(name, stream)
+
+extern "C" int adt_timing_enable(int on) { g_timing_on = on != 0; g_timing_n = 0; return ADT_OK; }
+
+// Synchronises the device, aggregates the recorded launches by kernel name.  names: '\n'-separated list written into
+// names_buf; total_ms[i] / counts[i] per name.  Returns the number of distinct names (<= max_names).
+extern "C" int adt_timing_collect(char* names_buf, int buf_len, float* total_ms, int* counts, int max_names) {
+  cudaDeviceSynchronize();
+  const char* uniq[64];
+  int nu = 0;
+  for (int i = 0; i < g_timing_n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_timing[i].a, g_timing[i].b) != cudaSuccess) continue;
+    int j = 0;
+    for (; j < nu; ++j) if (uniq[j] == g_timing[i].name || !strcmp(uniq[j], g_timing[i].name)) break;
+    if (j == nu) {
+      if (nu >= max_names || nu >= 64) continue;
+      uniq[nu] = g_timing[i].name; total_ms[nu] = 0.f; counts[nu] = 0; ++nu;
+    }
+    total_ms[j] += ms; counts[j] += 1;
+  }
+  int off = 0;
+  for (int j = 0; j < nu; ++j) off += snprintf(names_buf + off, off < buf_len ? buf_len - off : 0, "%s\n", uniq[j]);
+  g_timing_n = 0;
+  return nu;
+}
+
 static DropDesc mk_drop(const adt_dropout& d) {
   DropDesc r;
   memset(&r, 0, sizeof(r));
@@ -101,6 +148,7 @@ extern "C" int adt_embed_fwd(const adt_embed_fwd_args* a, adt_stream_t s_) {
   const int M = a->B * a->L;
   const long long n = (long long)M * (a->H / 4);
   const int grid = (int)((n + 255) / 256);
+  TIMED("embed_fwd", s);
   embed_fwd_kernel<<<grid, 256, 0, s>>>(a->ids, a->item_emb, a->pos_emb, a->x, M, a->L, a->H, (float)sqrt((double)a->H), mk_drop(a->drop));
   return check_launch("adt_embed_fwd");
 }
@@ -113,6 +161,7 @@ static int launch_pre_fwd(const float* x, const float* ln_w, const float* ln_b, 
   if (!tm) return fail(ADT_E_SHAPE, "%s", "pre_fwd: tile does not fit shared memory");
   const float qscale = 1.0f / sqrtf((float)(H / nh));
   const int grid = (M + tm - 1) / tm;
+  TIMED("pre_fwd", s);
   LAUNCH_TM(tm, pre_fwd_kernel, grid, smem, s, x, ln_w, ln_b, w.in_w, w.in_b, q, k, v, norm_out, M, H, qscale, kv_from_norm);
   return check_launch("pre_fwd");
 }
@@ -128,6 +177,7 @@ static int launch_attn_fwd(const float* q, const float* k, const float* v, float
   adt_dropout dd = d;
   if (!training) dd.enabled = 0;
   dim3 grid((L + tm - 1) / tm, nh, B);
+  TIMED("attn_fwd", s);
   LAUNCH_TM(tm, attn_fwd_kernel, grid, smem, s, q, k, v, ctx, lse, key_ids, L, H, nh, mask_mode, mk_drop(dd));
   return check_launch("attn_fwd");
 }
@@ -142,6 +192,7 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
   if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_bwd: tile does not fit shared memory");
   if (L <= 32 && tm == 64) { tm = 32; smem = ((size_t)tm * rowf + WS_FLOATS) * sizeof(float); }
   dim3 grid((L + tm - 1) / tm, nh, B);
+  TIMED("attn_bwd", s);
   LAUNCH_TM(tm, attn_bwd_kernel, grid, smem, s, q, k, v, dctx, lse, key_ids, dq, dk, dv, L, H, nh, mask_mode, mk_drop(d));
   return check_launch("attn_bwd");
 }
@@ -173,7 +224,7 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   size_t smem;
   const int tm = pick_tm(3 * (size_t)(H + 4), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_fwd: tile does not fit shared memory");
-  LAUNCH_TM2(tm, post_fwd_kernel, false, (M + tm - 1) / tm, smem, s, p);
+  { TIMED("enc_post_fwd", s); LAUNCH_TM2(tm, post_fwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
   return check_launch("enc post_fwd");
 }
 
@@ -195,7 +246,7 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   size_t smem;
   int tm = pick_tm(4 * (size_t)(H + 4), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
-  LAUNCH_TM2(tm, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p);
+  { TIMED("enc_post_bwd", s); LAUNCH_TM2(tm, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
   if (int e = check_launch("enc post_bwd")) return e;
   if (int e = launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
                               a->drop_attn, s))
@@ -207,7 +258,7 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   r.gWin = a->g_attn.in_w; r.gbin = a->g_attn.in_b; r.gln_g = a->g_ln1_w; r.gln_b = a->g_ln1_b;
   r.M = M; r.H = H; r.qscale = 1.0f / sqrtf((float)(H / a->nh)); r.kv_from_norm = 0;
   tm = pick_tm(4 * (size_t)(H + 4), &smem);
-  LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r);
+  { TIMED("pre_bwd", s); LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
   return check_launch("enc pre_bwd");
 }
 
@@ -223,8 +274,9 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   int tm = pick_tm(3 * (size_t)(H + 4), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_fwd: tile does not fit shared memory");
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  { TIMED("mid_fwd", s);
   LAUNCH_TM(tm, mid_fwd_kernel, (M + tm - 1) / tm, smem, s, a->ctx1, a->feats, a->slf.out_w, a->slf.out_b, a->enc.in_w, a->enc.in_b, a->a,
-            a->q2, a->k2, a->v2, M, H, qscale);
+            a->q2, a->k2, a->v2, M, H, qscale); }
   if (int e = check_launch("mid_fwd")) return e;
   if (int e = launch_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, s))
     return e;
@@ -236,7 +288,7 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training));
   p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
-  LAUNCH_TM2(tm, post_fwd_kernel, true, (M + tm - 1) / tm, smem, s, p);
+  { TIMED("dec_post_fwd", s); LAUNCH_TM2(tm, post_fwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
   return check_launch("dec post_fwd");
 }
 
@@ -256,7 +308,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   size_t smem;
   int tm = pick_tm(4 * (size_t)(H + 4), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
-  LAUNCH_TM2(tm, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p);
+  { TIMED("dec_post_bwd", s); LAUNCH_TM2(tm, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
   if (int e = check_launch("dec post_bwd")) return e;
   // cross attention (keys/values from the encoder features)
   if (int e = launch_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,
@@ -270,7 +322,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   m.M = M; m.H = H; m.qscale = qscale;
   tm = pick_tm(3 * (size_t)(H + 4) + (size_t)(2 * H + 4), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_bwd: tile does not fit shared memory");
-  LAUNCH_TM(tm, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m);
+  { TIMED("mid_bwd", s); LAUNCH_TM(tm, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m); }
   if (int e = check_launch("mid_bwd")) return e;
   if (int e = launch_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
                               a->drop_slf, s))
@@ -282,7 +334,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   r.gWin = a->g_slf.in_w; r.gbin = a->g_slf.in_b; r.gln_g = a->g_ln_w; r.gln_b = a->g_ln_b;
   r.M = M; r.H = H; r.qscale = qscale; r.kv_from_norm = 1;
   tm = pick_tm(4 * (size_t)(H + 4), &smem);
-  LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r);
+  { TIMED("pre_bwd", s); LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
   return check_launch("dec pre_bwd");
 }
 
@@ -291,6 +343,7 @@ extern "C" int adt_final_logits_loss_fwd(const adt_final_fwd_args* a, adt_stream
   cudaStream_t s = (cudaStream_t)s_;
   if (a->H > 256 || (a->H & 3)) return fail(ADT_E_SHAPE, "%s", "final_fwd: H");
   const int grid = min((a->M + 7) / 8, 148 * 8);
+  TIMED("final_fwd", s);
   final_fwd_kernel<<<grid, NT, 0, s>>>(a->x, a->ln_w, a->ln_b, a->item_emb, a->pos, a->neg, a->feats, a->pos_logits, a->neg_logits, a->acc,
                                        a->M, a->H);
   return check_launch("final_fwd");
@@ -305,6 +358,7 @@ extern "C" int adt_final_logits_loss_bwd(const adt_final_bwd_args* a, adt_stream
   p.bce_weight = a->bce_weight; p.dpl_ext = a->dpl_ext; p.dnl_ext = a->dnl_ext;
   p.dx = a->dx; p.cpos = a->cpos; p.cneg = a->cneg; p.gln_g = a->g_ln_w; p.gln_b = a->g_ln_b; p.M = a->M; p.H = a->H;
   const int grid = min((a->M + 7) / 8, 148 * 4);
+  TIMED("final_bwd", s);
   final_bwd_kernel<<<grid, NT, 0, s>>>(p);
   return check_launch("final_bwd");
 }
@@ -326,6 +380,7 @@ extern "C" int adt_embed_sort(const adt_embed_sort_args* a, adt_stream_t s_) {
   int cur = (passes & 1) ? 0 : 1;   // buffer written by pass 0
   const int* kin = nullptr;
   const int* vin = nullptr;
+  TIMED("embed_sort", s);
   for (int p = 0; p < passes; ++p) {
     const int shift = 8 * p;
     if (p == 0) {
@@ -349,6 +404,7 @@ extern "C" int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t s_) {
   if (int e = check_dims(a->B, a->L, a->H, 1)) return e;
   const int M = a->B * a->L;
   if (NT / (a->H / 4) < 1) return fail(ADT_E_SHAPE, "%s", "embed_bwd: H");
+  TIMED("embed_bwd", s);
   if (a->d_pos_emb) {
     if (a->dx_enc) posgrad_kernel<<<a->L, NT, 0, s>>>(a->dx_enc, a->seq, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_enc));
     if (a->dx_dec) posgrad_kernel<<<a->L, NT, 0, s>>>(a->dx_dec, a->dec, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_dec));
@@ -369,6 +425,7 @@ extern "C" int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t s_) {
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int adt_sumsq(const float* x, int64_t n, double* out, adt_stream_t s_) {
   const int grid = (int)((n / 4 + 255) / 256 < 148 * 8 ? ((n / 4 + 255) / 256 > 0 ? (n / 4 + 255) / 256 : 1) : 148 * 8);
+  TIMED("sumsq", (cudaStream_t)s_);
   sumsq_kernel<<<grid, 256, 0, (cudaStream_t)s_>>>(x, (long long)n, out);
   return check_launch("adt_sumsq");
 }
@@ -387,6 +444,7 @@ extern "C" int adt_adam(const adt_adam_args* a, adt_stream_t s_) {
   k.bc2 = (float)(1.0 - pow((double)a->beta2, (double)a->step));
   k.max_norm = a->max_norm; k.gnormsq = a->gnormsq; k.step_dev = a->step_dev;
   const long long blocks = (a->n + 255) / 256;
+  TIMED("adam", (cudaStream_t)s_);
   adam_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(k);
   return check_launch("adt_adam");
 }

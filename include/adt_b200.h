@@ -188,6 +188,10 @@ int adt_score_topk(const adt_score_topk_args* a, adt_stream_t stream);
 /* test helper: out[i] = keep-multiplier (0 or 1/(1-p)) of element base+i of a dropout site */
 int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t stream);
 
+/* optional per-kernel CUDA-event timing (used by bench.py for the live roofline number; off by default) */
+int adt_timing_enable(int on);
+int adt_timing_collect(char* names_buf, int buf_len, float* total_ms, int* counts, int max_names);
+
 #ifdef __cplusplus
 }
 #endif
