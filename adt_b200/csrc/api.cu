@@ -192,6 +192,10 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
   if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_bwd: tile does not fit shared memory");
   if (L <= 32 && tm == 64) { tm = 32; smem = ((size_t)tm * rowf + WS_FLOATS) * sizeof(float); }
   dim3 grid((L + tm - 1) / tm, nh, B);
+  if (grid.x > 1) {   // several query tiles accumulate into the same keys -> atomics on zeroed buffers
+    cudaMemsetAsync(dk, 0, (size_t)B * L * H * sizeof(float), s);
+    cudaMemsetAsync(dv, 0, (size_t)B * L * H * sizeof(float), s);
+  }
   TIMED("attn_bwd", s);
   LAUNCH_TM(tm, attn_bwd_kernel, grid, smem, s, q, k, v, dctx, lse, key_ids, dq, dk, dv, L, H, nh, mask_mode, mk_drop(d));
   return check_launch("attn_bwd");

@@ -357,6 +357,7 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ A, int lda, 
 
 // Weight gradient of a row tile:  dW[n][k] += sum_{r<rows} dY[r][n] * X[r][k]  (vector fp32 atomics into global dW).
 // dY: smem tile [.][ldy] (N columns), X: smem tile [.][ldx] (K columns).  dW is [N][K] row-major with ld ldw.
+template <bool ATOMIC = true>
 __device__ __forceinline__ void wgrad_tile(const float* __restrict__ dY, int ldy, int N, const float* __restrict__ X, int ldx, int K,
                                            int rows, float* __restrict__ dW, long long ldw) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -380,8 +381,11 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ dY, int ldy
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (n + i < N)
-          atomicAdd(reinterpret_cast<float4*>(dW + (long long)(n + i) * ldw + k), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        if (n + i < N) {
+          float4* dst = reinterpret_cast<float4*>(dW + (long long)(n + i) * ldw + k);
+          const float4 val = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          if (ATOMIC) atomicAdd(dst, val); else *dst = val;
+        }
     }
 }
 

@@ -117,48 +117,64 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     // 9. dctx = dy Wo (+ independence-head adjoint) -> Bt -> global
     gemm_tile<TM, true>(G, ld, H, p.Wo, H, H, Ws, [&](int, int r, int col, float4 acc) { st4(Bt + r * ld + col, acc); });
     if (p.nll_coef != 0.f || p.drec) {
-      const int nh = p.nh, hd = H / nh;
-      float* sp = Ws;  // [nh*hd] dWsp partial + [nh] dbsp partial
-      for (int i = threadIdx.x; i < nh * hd + nh; i += NT) sp[i] = 0.f;
+      const int nh = p.nh, hd = H / nh, n2 = nh * nh;
+      float* lgs = Ws;                 // [TM][nh*nh] logits -> dlogits
+      float* dbs = Ws + TM * n2;       // [nh] bias-grad partial
+      for (int i = threadIdx.x; i < nh; i += NT) dbs[i] = 0.f;
+      for (int i = threadIdx.x; i < TM * n2; i += NT) {
+        const int r = i / n2, cj = i - r * n2, c = cj / nh, j = cj - c * nh;
+        const float* xr = A + r * ld + c * hd;
+        const float* wr = p.Wsp + j * hd;
+        float sacc = 0.f;
+        for (int dd = 0; dd < hd; dd += 4) {
+          const float4 x4 = ld4(xr + dd);
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + dd));
+          sacc = fmaf(x4.x, w4.x, sacc); sacc = fmaf(x4.y, w4.y, sacc); sacc = fmaf(x4.z, w4.z, sacc); sacc = fmaf(x4.w, w4.w, sacc);
+        }
+        lgs[i] = sacc + p.bsp[j];
+      }
       __syncthreads();
-      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-      for (int r = w; r < rows; r += NT / 32) {
-        for (int c = 0; c < nh; ++c) {
-          float lg[8];
-          float mx = -INFINITY;
-          for (int j = 0; j < nh; ++j) {
-            float s = 0.f;
-            for (int dd = l; dd < hd; dd += 32) s = fmaf(A[r * ld + c * hd + dd], p.Wsp[j * hd + dd], s);
-            s = warp_sum(s) + p.bsp[j];
-            lg[j] = s;
-            mx = fmaxf(mx, s);
-          }
-          float se = 0.f;
-          for (int j = 0; j < nh; ++j) { lg[j] = expf(lg[j] - mx); se += lg[j]; }
-          float gsum = 0.f;
-          if (p.drec)
-            for (int j = 0; j < nh; ++j) gsum += p.drec[((long long)(row0 + r) * nh + c) * nh + j];
-          for (int j = 0; j < nh; ++j) {
-            const float pj = lg[j] / se;
-            float dl = p.nll_coef * (pj - (j == c ? 1.f : 0.f));
-            if (p.drec) dl += p.drec[((long long)(row0 + r) * nh + c) * nh + j] - pj * gsum;
-            lg[j] = dl;
-            if (l == 0) atomicAdd(sp + nh * hd + j, dl);
-          }
-          for (int dd = l; dd < hd; dd += 32) {
-            const float cv = A[r * ld + c * hd + dd];
-            float add = 0.f;
-            for (int j = 0; j < nh; ++j) {
-              add = fmaf(lg[j], p.Wsp[j * hd + dd], add);
-              atomicAdd(sp + j * hd + dd, lg[j] * cv);
-            }
-            Bt[r * ld + c * hd + dd] += add;
-          }
+      for (int i = threadIdx.x; i < TM * nh; i += NT) {
+        const int r = i / nh, c = i - r * nh;
+        float* lg = lgs + r * n2 + c * nh;
+        if (r >= rows) {
+          for (int j = 0; j < nh; ++j) lg[j] = 0.f;
+          continue;
+        }
+        float mx = lg[0];
+        for (int j = 1; j < nh; ++j) mx = fmaxf(mx, lg[j]);
+        float se = 0.f;
+        for (int j = 0; j < nh; ++j) se += expf(lg[j] - mx);
+        const float* dr = p.drec ? p.drec + ((long long)(row0 + r) * nh + c) * nh : nullptr;
+        float gsum = 0.f;
+        if (dr) for (int j = 0; j < nh; ++j) gsum += dr[j];
+        for (int j = 0; j < nh; ++j) {
+          const float pj = expf(lg[j] - mx) / se;
+          float dl = p.nll_coef * (pj - (j == c ? 1.f : 0.f));
+          if (dr) dl += dr[j] - pj * gsum;
+          lg[j] = dl;
+          atomicAdd(dbs + j, dl);
         }
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < nh * hd; i += NT) atomicAdd(p.gWsp + i, sp[i]);
-      for (int i = threadIdx.x; i < nh; i += NT) atomicAdd(p.gbsp + i, sp[nh * hd + i]);
+      // dctx[r][c*hd+d] += sum_j dl[r][c][j] * Wsp[j][d]
+      for (int i = threadIdx.x; i < TM * H; i += NT) {
+        const int r = i / H, col = i - r * H, c = col / hd, dd = col - c * hd;
+        const float* dl = lgs + r * n2 + c * nh;
+        float add = 0.f;
+        for (int j = 0; j < nh; ++j) add = fmaf(dl[j], p.Wsp[j * hd + dd], add);
+        Bt[r * ld + col] += add;
+      }
+      // dWsp[j][d] += sum_{r,c} dl[r][c][j] * ctx[r][c*hd+d]
+      for (int i = threadIdx.x; i < nh * hd; i += NT) {
+        const int j = i / hd, dd = i - j * hd;
+        float accw = 0.f;
+        for (int r = 0; r < rows; ++r)
+          for (int c = 0; c < nh; ++c) accw = fmaf(lgs[r * n2 + c * nh + j], A[r * ld + c * hd + dd], accw);
+        atomicAdd(p.gWsp + i, accw);
+      }
+      for (int i = threadIdx.x; i < nh; i += NT) atomicAdd(p.gbsp + i, dbs[i]);
+      __syncthreads();
     }
     store_tile<TM>(Bt, ld, p.dctx, H, 0, H, row0, M);
   } else {
@@ -221,26 +237,36 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
     float pv[8], dpv[8], mv[8];
     float delta = 0.f;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = l + 32 * u;
-      float pj = 0.f, dp = 0.f, m = 1.f;
-      if (j < nj) {
-        float s = prow[j];
-        if (mask_mode == 1 && key_ids[b * L + j] == 0) s = -1e9f;
-        pj = expf(s - ls);
-        if (drop.enabled) m = drop_mul1(drop, rbase + j);
-        dp = drow[j] * m;
-        delta = fmaf(dp, pj, delta);
+    for (int u = 0; u < 2; ++u) {
+      const int j0 = 4 * l + 128 * u;
+      float4 s4 = zero4(), d4 = zero4(), m4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (j0 < nj) {
+        s4 = ld4(prow + j0);
+        d4 = ld4(drow + j0);
+        if (drop.enabled) m4 = drop_mul4_unaligned(drop, rbase + j0);
       }
-      pv[u] = pj; dpv[u] = dp; mv[u] = m;
+      const float st[4] = {s4.x, s4.y, s4.z, s4.w}, dt[4] = {d4.x, d4.y, d4.z, d4.w}, mt[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float pj = 0.f, dp = 0.f;
+        if (j0 + c < nj) {
+          float sc = st[c];
+          if (mask_mode == 1 && key_ids[b * L + j0 + c] == 0) sc = -1e9f;
+          pj = expf(sc - ls);
+          dp = dt[c] * mt[c];
+          delta = fmaf(dp, pj, delta);
+        }
+        pv[4 * u + c] = pj; dpv[4 * u + c] = dp; mv[4 * u + c] = mt[c];
+      }
     }
     delta = warp_sum(delta);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = l + 32 * u;
-      if (j < Lk4) {
-        prow[j] = pv[u] * mv[u];                 // dropped probabilities (for dV)
-        drow[j] = pv[u] * (dpv[u] - delta);      // dS
+    for (int u = 0; u < 2; ++u) {
+      const int j0 = 4 * l + 128 * u;
+      if (j0 < Lk4) {
+        st4(prow + j0, make_float4(pv[4 * u] * mv[4 * u], pv[4 * u + 1] * mv[4 * u + 1], pv[4 * u + 2] * mv[4 * u + 2], pv[4 * u + 3] * mv[4 * u + 3]));
+        st4(drow + j0, make_float4(pv[4 * u] * (dpv[4 * u] - delta), pv[4 * u + 1] * (dpv[4 * u + 1] - delta),
+                                   pv[4 * u + 2] * (dpv[4 * u + 2] - delta), pv[4 * u + 3] * (dpv[4 * u + 3] - delta)));
       }
     }
   }
@@ -249,9 +275,14 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
   gemm_tile<TM, true>(dPs, lds, Lk, k + seq_off, H, hd, Ws, [&](int, int r, int col, float4 a) {
     if (i0 + r < L) st4(dq + seq_off + (long long)(i0 + r) * H + col, a);
   });
-  // dk += dS^T q ; dv += Pd^T dctx
-  wgrad_tile(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
-  wgrad_tile(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
+  // dk += dS^T q ; dv += Pd^T dctx   (plain stores when this CTA is the only query tile of the sequence)
+  if (gridDim.x == 1) {
+    wgrad_tile<false>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
+    wgrad_tile<false>(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
+  } else {
+    wgrad_tile<true>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
+    wgrad_tile<true>(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
+  }
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@
 
 namespace adt {
 
-constexpr int SORT_WCH = 256;   // sorted-array elements owned by one warp per radix pass
+constexpr int SORT_WCH = 512;   // sorted-array elements owned by one warp per radix pass
 
 // key/value of logical element e of the concatenated lookup list: src = e / M (0 seq, 1 dec, 2 pos, 3 neg)
 struct SortSrc {
@@ -41,37 +41,47 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(SortSrc s, const int* _
   }
 }
 
-// in-place exclusive scan of n ints, single CTA of 1024 threads
+// in-place exclusive scan of n ints, single CTA of 1024 threads, coalesced tiles of 4096 with a running carry
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(int* __restrict__ data, int n) {
   __shared__ int wsum[32];
-  const int per = (n + 1023) / 1024;
-  const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
-  int s = 0;
-  for (int i = beg; i < end; ++i) s += data[i];
+  __shared__ int carry_s;
   const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (l >= o) incl += t;
-  }
-  if (l == 31) wsum[w] = incl;
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  if (w == 0) {
-    int v = wsum[l];
+  for (int base = 0; base < n; base += 4096) {
+    const int i0 = base + 4 * threadIdx.x;
+    int v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = (i0 + c < n) ? data[i0 + c] : 0;
+    const int s = v[0] + v[1] + v[2] + v[3];
+    int incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, v, o);
-      if (l >= o) v += t;
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (l >= o) incl += t;
     }
-    wsum[l] = v;
-  }
-  __syncthreads();
-  int run = incl - s + (w > 0 ? wsum[w - 1] : 0);
-  for (int i = beg; i < end; ++i) {
-    const int t = data[i];
-    data[i] = run;
-    run += t;
+    if (l == 31) wsum[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int x = wsum[l];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, x, o);
+        if (l >= o) x += t;
+      }
+      wsum[l] = x;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int run = carry + incl - s + (w > 0 ? wsum[w - 1] : 0);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (i0 + c < n) data[i0 + c] = run;
+      run += v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + wsum[31];
+    __syncthreads();
   }
 }
 

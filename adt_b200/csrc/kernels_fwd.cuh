@@ -80,8 +80,9 @@ __device__ __forceinline__ float4 drop_mul4_unaligned(const DropDesc& d, unsigne
   const float4 a = drop_mul4(d, idx0 >> 2);
   if (off == 0) return a;
   const float4 b = drop_mul4(d, (idx0 >> 2) + 1);
-  const float va[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  return make_float4(va[off], va[off + 1], va[off + 2], va[off + 3]);
+  if (off == 1) return make_float4(a.y, a.z, a.w, b.x);
+  if (off == 2) return make_float4(a.z, a.w, b.x, b.y);
+  return make_float4(a.w, b.x, b.y, b.z);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -124,24 +125,27 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
       continue;
     }
     const int nj = mask_mode == 0 ? i + 1 : L;
-    float sv[8];
+    float sv[8];      // lane owns keys 4l..4l+3 and 128+4l..128+4l+3
     float mx = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = l + 32 * u;
-      float s = -INFINITY;
-      if (j < nj) {
-        s = srow[j];
-        if (mask_mode == 1 && key_ids[b * L + j] == 0) s = -1e9f;
+    for (int u = 0; u < 2; ++u) {
+      const int j0 = 4 * l + 128 * u;
+      float4 s4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (j0 < nj) s4 = *reinterpret_cast<const float4*>(srow + j0);
+      float t[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float sc = (j0 + c < nj) ? t[c] : -INFINITY;
+        if (mask_mode == 1 && j0 + c < nj && key_ids[b * L + j0 + c] == 0) sc = -1e9f;
+        sv[4 * u + c] = sc;
+        mx = fmaxf(mx, sc);
       }
-      sv[u] = s;
-      mx = fmaxf(mx, s);
     }
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float e = (l + 32 * u < nj) ? expf(sv[u] - mx) : 0.f;
+      const float e = sv[u] == -INFINITY ? 0.f : expf(sv[u] - mx);
       sv[u] = e;
       sum += e;
     }
@@ -150,12 +154,13 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
     if (lse && l == 0) lse[((long long)b * nh + h) * L + i] = mx + logf(sum);
     const unsigned long long rbase = drop.base + (((unsigned long long)b * nh + h) * L + i) * (unsigned long long)L;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = l + 32 * u;
-      if (j < Lk4) {
-        float p = sv[u] * inv;
-        if (drop.enabled && j < nj) p *= drop_mul1(drop, rbase + j);
-        srow[j] = p;
+    for (int u = 0; u < 2; ++u) {
+      const int j0 = 4 * l + 128 * u;
+      if (j0 < Lk4) {
+        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (drop.enabled && j0 < nj) m = drop_mul4_unaligned(drop, rbase + j0);
+        *reinterpret_cast<float4*>(srow + j0) =
+            make_float4(sv[4 * u] * inv * m.x, sv[4 * u + 1] * inv * m.y, sv[4 * u + 2] * inv * m.z, sv[4 * u + 3] * inv * m.w);
       }
     }
   }
@@ -253,32 +258,37 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     if (p.u_save && row0 + r < M) *reinterpret_cast<float4*>(p.u_save + (long long)(row0 + r) * H + col) = o;
   });
   if (!IS_DEC) {
-    // independence head on the per-head context slices (warp per row, lanes over the head dim)
+    // independence head on the per-head context slices: one thread per (row, head c, class j) dot product of length
+    // hd, logits parked in the (idle) weight staging area, then one thread per (row, c) log-softmax.
     if (p.rec || p.acc) {
-      const int nh = p.nh, hd = H / nh;
-      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-      double nll = 0.0;
-      for (int r = w; r < TM; r += NT / 32) {
-        if (row0 + r >= M) continue;
-        for (int c = 0; c < nh; ++c) {
-          float lg[8];
-          float mx = -INFINITY;
-          for (int j = 0; j < nh; ++j) {
-            float s = 0.f;
-            for (int dd = l; dd < hd; dd += 32) s = fmaf(T0[r * ld + c * hd + dd], p.Wsp[j * hd + dd], s);
-            s = warp_sum(s) + p.bsp[j];
-            lg[j] = s;
-            mx = fmaxf(mx, s);
-          }
-          float se = 0.f;
-          for (int j = 0; j < nh; ++j) se += expf(lg[j] - mx);
-          const float lz = mx + logf(se);
-          if (l == 0) {
-            if (p.rec)
-              for (int j = 0; j < nh; ++j) p.rec[((long long)(row0 + r) * nh + c) * nh + j] = lg[j] - lz;
-            nll -= (double)(lg[c] - lz);
-          }
+      const int nh = p.nh, hd = H / nh, n2 = nh * nh;
+      float* lgs = Ws;
+      for (int i = threadIdx.x; i < TM * n2; i += NT) {
+        const int r = i / n2, cj = i - r * n2, c = cj / nh, j = cj - c * nh;
+        const float* xr = T0 + r * ld + c * hd;
+        const float* wr = p.Wsp + j * hd;
+        float s = 0.f;
+        for (int dd = 0; dd < hd; dd += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(xr + dd);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(wr + dd));
+          s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
         }
+        lgs[i] = s + p.bsp[j];
+      }
+      __syncthreads();
+      double nll = 0.0;
+      for (int i = threadIdx.x; i < TM * nh; i += NT) {
+        const int r = i / nh, c = i - r * nh;
+        if (row0 + r >= M) continue;
+        const float* lg = lgs + r * n2 + c * nh;
+        float mx = lg[0];
+        for (int j = 1; j < nh; ++j) mx = fmaxf(mx, lg[j]);
+        float se = 0.f;
+        for (int j = 0; j < nh; ++j) se += expf(lg[j] - mx);
+        const float lz = mx + logf(se);
+        if (p.rec)
+          for (int j = 0; j < nh; ++j) p.rec[((long long)(row0 + r) * nh + c) * nh + j] = lg[j] - lz;
+        nll -= (double)(lg[c] - lz);
       }
       if (p.acc) cta_accumulate(nll, p.acc, red);
     }

@@ -101,6 +101,7 @@ class Engine:
         self.batch_offset = 0      # first global sample index of this rank (data parallel)
         self.global_rows = None    # M of the global batch (None -> local)
         self.gflat = None
+        self.step_dev = None       # optional int32 device tensor: [0] is added to the dropout step at run time
 
     # ------------------------------------------------------------------ parameters / flat buffers
     def dev(self):
@@ -160,7 +161,7 @@ class Engine:
         w["feats"], w["pos_logits"], w["neg_logits"] = f(M, H), f(M), f(M)
         w["acc"] = torch.zeros(8 + 2 * nl, dtype=torch.float64, device=dev)
         # backward scratch
-        w["zero4"] = torch.zeros(4, M, H, dtype=torch.float32, device=dev)   # dk, dv, dk2, dv2 (zeroed per block)
+        w["zero4"] = torch.empty(4, M, H, dtype=torch.float32, device=dev)   # dk, dv, dk2, dv2 scratch
         for k in ("dq", "dctx", "dres", "dq2", "dctx2", "dfeats", "dxa", "dxb", "dxd_a", "dxd_b"):
             w[k] = f(M, H)
         w["denc"] = [f(M, H) for _ in range(nl)]
@@ -168,7 +169,7 @@ class Engine:
         N = 4 * M
         i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
         w["keys"], w["vals"], w["keys_tmp"], w["vals_tmp"] = i32(N), i32(N), i32(N), i32(N)
-        w["hist"] = i32(256 * ((N + 255) // 256))
+        w["hist"] = i32(256 * ((N + 255) // 256))   # >= 256 * ceil(N / SORT_WCH)
         nb = (N + 31) // 32
         w["head"], w["tail"], w["has_tail"] = f(nb, H), f(nb, H), i32(nb)
         self.ws[key] = w
@@ -182,6 +183,7 @@ class Engine:
         d.p = float(m.dropout_p)
         d.seed = int(self.drop_seed)
         d.step = int(self.drop_step)
+        d.step_dev = self.step_dev.data_ptr() if self.step_dev is not None else None
         d.site = int(site)
         per = m.num_heads * Lq * Lq if kind == "attn" else Lq * m.hidden
         d.base = int(self.batch_offset) * per
@@ -300,7 +302,6 @@ class Engine:
             if eo is not None and eo[j] is not None:
                 dout = eo[j] if dout is None else dout + eo[j]
             i_enc = nl - 1 - j
-            z4.zero_()
             out_dx = bufs[j % 2]
             a = L.fill(L.adt_dec_block_bwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec,
                        ln_w=layer.layer_norm.weight, ln_b=layer.layer_norm.bias, slf=_mha_w(layer.slf_attn), enc=_mha_w(layer.enc_attn),
@@ -337,7 +338,6 @@ class Engine:
             dout = dx   # already contains the external grad wrt x[l+1] (added as dx_extra of block l+1)
             dx_extra = w["denc"][l] if fused else (ei[l] if ei is not None else None)
             dr = ext.get("drec")
-            z4[:2].zero_()
             a = L.fill(L.adt_enc_block_bwd_args(), x=w["x"][l], ids=seq,
                        ln1_w=layer.attention_layernorm.weight, ln1_b=layer.attention_layernorm.bias, attn=_mha_w(layer.attention_layer),
                        ln2_w=layer.forward_layernorm.weight, ln2_b=layer.forward_layernorm.bias, ffn=_ffn_w(layer.forward_layer),

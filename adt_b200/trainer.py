@@ -21,7 +21,7 @@ from .model import _as_ids
 
 class FusedTrainer:
     def __init__(self, model, lambdas1, lambdas2, weight_decay=0.0, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, clip=5.0,
-                 adam_weight_decay=0.0, seed=0, process_group=None, use_norm_decay=True):
+                 adam_weight_decay=0.0, seed=0, process_group=None, use_norm_decay=True, use_graph=False):
         self.model = model
         self.eng = model.engine
         self.l1, self.l2 = [float(x) for x in lambdas1], [float(x) for x in lambdas2]
@@ -38,29 +38,33 @@ class FusedTrainer:
         self.eng.drop_seed = int(seed)
         self.t = 0
         self._w = None
+        self.use_graph = use_graph
+        self._graphs = {}
+        self.step_dev = None
+        self._counter_t = None
         self.lib = L.lib()
 
     def _stream(self):
         return self.eng._stream()
 
-    def step(self, seq, dec, pos, neg):
-        """One optimisation step on this rank's shard of the batch.  ids: [B_local, L] host arrays or device tensors.
-        Asynchronous; call loss() to read the step's (global) loss."""
+    # ------------------------------------------------------------------------------------------
+    def _step_impl(self, seq, dec, pos, neg):
+        """the device work of one step on int32 device ids; every launch goes to the current stream (capturable)."""
         eng, m = self.eng, self.model
-        dev = eng.dev()
-        seq, dec, pos, neg = (_as_ids(a, dev) for a in (seq, dec, pos, neg))
         B, Lq = seq.shape
-        eng.ensure_flat()
         grads = {n: eng.grad_view(n) for n, _ in eng.order}
-        eng.batch_offset = self.rank * B
-        eng.global_rows = self.world * B * Lq
-        eng.drop_step = self.t
-        self.t += 1
+        self.step_dev.add_(1)
         eng.gflat.zero_()
+        cur = torch.cuda.current_stream()
+        w = eng.workspace(B, Lq)
+        # the radix sort of the lookup ids only depends on the batch: run it beside the forward pass
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            eng.sort_ids(seq, dec, pos, neg, w)
         w = eng.forward(seq, dec, pos, neg, training=True, fused_loss=True)
-        eng.sort_ids(seq, dec, pos, neg, w)
         if self.world > 1:
             torch.distributed.all_reduce(w["acc"], group=self.pg)
+        cur.wait_stream(self.side)
         eng.backward(seq, dec, pos, neg, w, grads, lambdas1=self.l1, lambdas2=self.l2)
         if self.world > 1:
             torch.distributed.all_reduce(eng.gflat, group=self.pg)
@@ -76,11 +80,69 @@ class FusedTrainer:
         gn = acc[4 + 2 * nl:]
         n = eng.gflat.numel()
         L.check(self.lib.adt_sumsq(L.ptr(eng.gflat), ctypes.c_int64(n), L.ptr(gn), s), "adt_sumsq")
-        eng.adam_t += 1
         a = L.fill(L.adt_adam_args(), p=eng.pflat, g=eng.gflat, m=eng.adam_m, v=eng.adam_v, n=n, lr=self.lr, beta1=self.betas[0],
-                   beta2=self.betas[1], eps=self.eps, weight_decay=self.adam_wd, step=eng.adam_t, max_norm=self.clip, gnormsq=gn,
-                   step_dev=None)
+                   beta2=self.betas[1], eps=self.eps, weight_decay=self.adam_wd, step=0, max_norm=self.clip, gnormsq=gn,
+                   step_dev=self.step_dev[1:])
         L.check(self.lib.adt_adam(ctypes.byref(a), s), "adt_adam")
+        return w
+
+    def _prepare(self, B, Lq):
+        eng = self.eng
+        dev = eng.dev()
+        eng.ensure_flat()
+        if self.step_dev is None or self.step_dev.device != dev:
+            # [0] dropout stream counter (step index of the NEXT step minus one), [1] Adam step count
+            self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.side = torch.cuda.Stream(device=dev)
+        eng.batch_offset = self.rank * B
+        eng.global_rows = self.world * B * Lq
+        eng.drop_step = 0
+        eng.step_dev = self.step_dev
+
+    def step(self, seq, dec, pos, neg):
+        """One optimisation step on this rank's shard of the batch.  ids: [B_local, L] host arrays or device tensors.
+        Asynchronous; call loss() to read the step's (global) loss."""
+        eng = self.eng
+        dev = eng.dev()
+        B, Lq = seq.shape
+        self._prepare(B, Lq)
+        # device counters: dropout step = self.t (pre-increment inside _step_impl), Adam t = number of steps taken + 1
+        if self._counter_t != self.t:
+            self.step_dev.copy_(torch.tensor([self.t - 1, eng.adam_t], dtype=torch.int32), non_blocking=False)
+        self.t += 1
+        eng.adam_t += 1
+        self._counter_t = self.t
+        if not self.use_graph:
+            ids = [_as_ids(a, dev) for a in (seq, dec, pos, neg)]
+            self._w = self._step_impl(*ids)
+            return self._w
+        key = (B, Lq)
+        if key not in self._graphs:
+            static = [torch.zeros(B, Lq, dtype=torch.int32, device=dev) for _ in range(4)]
+            for dst, src in zip(static, (seq, dec, pos, neg)):
+                dst.copy_(_as_ids(src, dev))
+            saved = self.step_dev.clone()
+            # warm-up outside capture (lazy allocations, cudaFuncSetAttribute), on a side stream as torch requires
+            cap = torch.cuda.Stream(device=dev)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                snap = (eng.pflat.clone(), eng.adam_m.clone(), eng.adam_v.clone())
+                self._step_impl(*static)
+                eng.pflat.copy_(snap[0]); eng.adam_m.copy_(snap[1]); eng.adam_v.copy_(snap[2])
+                self.step_dev.copy_(saved)
+            torch.cuda.current_stream().wait_stream(cap)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                w = self._step_impl(*static)
+            self.step_dev.copy_(saved)   # capture does not execute, but keep the counters explicit
+            self._graphs[key] = (g, static, w)
+        g, static, w = self._graphs[key]
+        for dst, src in zip(static, (seq, dec, pos, neg)):
+            if isinstance(src, torch.Tensor):
+                dst.copy_(src, non_blocking=True)
+            else:
+                dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32)), non_blocking=True)
+        g.replay()
         self._w = w
         return w
 

@@ -79,7 +79,7 @@ typedef struct {
   const float* dx_extra;      /* extra grad wrt block input, e.g. the reconstruction-MSE grad (NULL = 0) */
   const float* drec;          /* external grad wrt rec (compat mode, NULL = none) */
   float nll_coef;             /* fused independence loss: lambda2 / (M_global*nh), 0 = off */
-  float* dq; float* dk; float* dv; float* dctx; float* dy;   /* scratch [M,H] each; dk, dv must be ZEROED by the caller */
+  float* dq; float* dk; float* dv; float* dctx; float* dy;   /* scratch [M,H] each */
   float* dx;                  /* out: grad wrt block input (overwritten) */
   float* g_ln1_w; float* g_ln1_b; adt_mha_g g_attn; float* g_ln2_w; float* g_ln2_b; adt_ffn_g g_ffn;
   float* g_sparse_w; float* g_sparse_b;
@@ -110,7 +110,7 @@ typedef struct {
   const float* out; const float* enc_in; float mse_coef;   /* fused MSE: lambda1*2/(M_global*H); enc_in NULL = off */
   const float* dout;                                       /* grad wrt block output (NULL = 0) */
   float* denc;                                             /* out: grad wrt enc_in (overwritten; may be NULL) */
-  float* dq; float* dk; float* dv; float* dctx; float* dd; float* dq2; float* dk2; float* dv2; float* dctx2; /* scratch; dk,dv,dk2,dv2 ZEROED by caller */
+  float* dq; float* dk; float* dv; float* dctx; float* dd; float* dq2; float* dk2; float* dv2; float* dctx2; /* scratch [M,H] each */
   float* dfeats;                                           /* accumulated (+=) */
   float* dx;                                               /* out: grad wrt decoder block input */
   float* g_ln_w; float* g_ln_b; adt_mha_g g_slf; adt_mha_g g_enc; adt_ffn_g g_ffn;

@@ -160,3 +160,26 @@ def test_full_c2_shape_properties():
         assert not set(ids[u].tolist()) & set(ix[ip[u]:ip[u + 1]].tolist())
     full = m.predict(None, seq, None, True).cpu().numpy()
     assert np.allclose(np.take_along_axis(full, ids.astype(np.int64), axis=1), s, rtol=1e-4, atol=1e-5)
+
+
+def test_cuda_graph_step_matches_eager():
+    """the captured-graph step (device-side dropout/Adam counters) must reproduce the eager step exactly up to the
+    fp32 atomics of the weight gradients."""
+    from adt_b200 import testing as T
+    from adt_b200.trainer import FusedTrainer
+    g = T.load_golden("c2mini_p5")
+    l1, l2, wd = [float(x) for x in g["lambdas1"]], [float(x) for x in g["lambdas2"]], float(g["wd"])
+    batch = (g["seq"], g["dec"], g["pos"], g["neg"])
+    res = []
+    for use_graph in (False, True):
+        m = T.model_from_golden(g).train()
+        tr = FusedTrainer(m, l1, l2, weight_decay=wd, seed=int(g["drop_seed"]), use_graph=use_graph)
+        tr.t = int(g["drop_step"])
+        losses = []
+        for _ in range(4):
+            tr.step(*batch)
+            losses.append(tr.loss())
+        res.append((losses, m.engine.pflat.detach().cpu().clone()))
+    assert abs(res[0][0][0] - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-5), (res[0][0], res[1][0])
+    assert torch.allclose(res[0][1], res[1][1], rtol=1e-3, atol=2e-4)
