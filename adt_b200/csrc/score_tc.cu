@@ -1,0 +1,401 @@
+// K7 on the 5th-generation tensor cores: bf16 catalog scoring as a TMA-fed tcgen05.mma GEMM with accumulators in
+// TMEM and a fused streaming top-K' epilogue; exact fp32 re-score + provable-exactness check behind it.
+//
+//   warp 0 (1 thread) : TMA producer   - user-feature tile A [128 x H] once, item tiles B [BN x H] in a 2-stage ring
+//   warp 1 (1 thread) : MMA issuer     - tcgen05.mma.kind::f16 M=128,N=BN,K=16 into one of two TMEM accumulators
+//   warps 2..5        : epilogue       - tcgen05.ld the 128 x BN scores (thread == user row), threshold filter,
+//                                        seen-item check, insert into the thread's private top-K' list in smem
+//
+// Only [splits][U][K'] (score,id) candidates ever reach HBM.  rescore_select_kernel then recomputes the candidates'
+// scores in fp32 (same arithmetic as the reference's fp32 matmul), picks the top-K, and flags a user when the bf16
+// rounding bound  eps = 2^-7 |f_u| max_i|e_i|  cannot exclude that a non-candidate belongs in the top-K (those users
+// are re-run on the exact fp32 kernel by the host, evaluate.py).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/adt_b200.h"
+#include "tc.cuh"
+
+using namespace adt;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int TC_THREADS = 192;
+
+struct TcArgs {
+  const int* seen_indptr; const int* seen_idx;
+  float* part_scores; int* part_ids; float* part_thr;
+  int U, n_items, item_offset, KC, n_splits, debug;
+};
+
+__device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int u, int item) {
+  if (!a.seen_indptr) return false;
+  int lo = a.seen_indptr[u], hi = a.seen_indptr[u + 1];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = a.seen_idx[mid];
+    if (v == item) return true;
+    if (v < item) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+template <int KB, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = KB * BM * 128;
+  constexpr int B_STAGE = KB * BN * 128;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + A_BYTES;
+  const int KCP = a.KC <= 32 ? 32 : 64;                       // list slots per user row (one or two per lane)
+  uint32_t* lk = reinterpret_cast<uint32_t*>(sB + 2 * B_STAGE);   // [128][KCP] order-preserving score keys
+  int* li = reinterpret_cast<int*>(lk + BM * KCP);                // [128][KCP] item ids
+  float* thr_s = reinterpret_cast<float*>(li + BM * KCP);         // [128] current K'-th best score per row
+  float* vsm = thr_s + BM;                                        // [4][32][32] chunk parking area of the epilogue warps
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vsm + 4 * 1024);
+  uint64_t* full = bars;          // [2] B stage filled (TMA tx)
+  uint64_t* empty = bars + 2;     // [2] B stage consumed (tcgen05.commit)
+  uint64_t* tfull = bars + 4;     // [2] accumulator ready (tcgen05.commit)
+  uint64_t* tempty = bars + 6;    // [2] accumulator drained (4 epilogue warps)
+  uint64_t* abar = bars + 8;      // A tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, u0 = blockIdx.y * BM;
+  int per = (a.n_items + a.n_splits - 1) / a.n_splits;
+  per = (per + 7) & ~7;
+  const int it0 = min(a.n_items, split * per), it1 = min(a.n_items, it0 + per);
+  const int ntiles = (it1 - it0 + BN - 1) / BN;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(full + i, 1);
+      tc::mbar_init(empty + i, 1);
+      tc::mbar_init(tfull + i, 1);
+      tc::mbar_init(tempty + i, 4);
+    }
+    tc::mbar_init(abar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<2 * BN>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(abar, A_BYTES);
+      for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sA + kb * BM * 128, &tmA, kb * 64, u0, abar);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t & 1;
+        tc::mbar_wait(empty + st, ((t >> 1) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(full + st, B_STAGE);
+        for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sB + st * B_STAGE + kb * BN * 128, &tmB, kb * 64, it0 + t * BN, full + st);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BN);
+      tc::mbar_wait(abar, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t & 1;
+        tc::mbar_wait(tempty + st, ((t >> 1) & 1) ^ 1);
+        tc::mbar_wait(full + st, (t >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + st * BN;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t ad = tc::smem_desc_k_sw128(tc::smem_u32(sA + kb * BM * 128));
+          const uint64_t bd = tc::smem_desc_k_sw128(tc::smem_u32(sB + st * B_STAGE + kb * BN * 128));
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)   // 4 x K=16 per 64-wide swizzle atom: +32 bytes on the start address
+            tc::mma_bf16_ss(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+        }
+        tc::mma_commit(empty + st);
+        tc::mma_commit(tfull + st);
+      }
+    }
+  } else {
+    // epilogue: thread == user row for the threshold filter; list maintenance is warp-cooperative
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const int u = u0 + row;
+    const int KC = a.KC;
+    for (int k = 0; k < KCP; ++k) {          // slots >= KC are permanently "infinitely good" so they are never the minimum
+      lk[row * KCP + k] = k < KC ? 0u : 0xffffffffu;
+      li[row * KCP + k] = -1;
+    }
+    thr_s[row] = u < a.U ? -INFINITY : INFINITY;
+    __syncwarp();
+    auto fkey = [](float f) -> uint32_t {
+      const uint32_t b = __float_as_uint(f);
+      return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    };
+    // warp-cooperative insert of (score sc, local item index itl) into the list of row rrow (slots spread over lanes)
+    auto insert = [&](int rrow, float sc, int itl) -> float {
+      float new_thr = __int_as_float(0x7fc00000);
+      uint32_t* Lk = lk + rrow * KCP;
+      uint32_t k0 = Lk[lane];
+      uint32_t k1 = KCP == 64 ? Lk[lane + 32] : 0xffffffffu;
+      uint32_t mk = min(k0, k1);
+      const uint32_t wm = __reduce_min_sync(0xffffffffu, mk);
+      const uint32_t key = fkey(sc);
+      if (key > wm) {
+        const int item = a.item_offset + itl;
+        if (!tc_is_seen(a, u0 + rrow, item)) {
+          const int who = __ffs(__ballot_sync(0xffffffffu, mk == wm)) - 1;
+          if (lane == who) {
+            if (k0 == wm) { Lk[lane] = key; li[rrow * KCP + lane] = item; k0 = key; }
+            else { Lk[lane + 32] = key; li[rrow * KCP + lane + 32] = item; k1 = key; }
+          }
+          mk = min(k0, k1);
+          const uint32_t nm = __reduce_min_sync(0xffffffffu, mk);
+          new_thr = nm == 0u ? -INFINITY : __uint_as_float((nm & 0x80000000u) ? (nm & 0x7fffffffu) : ~nm);
+          if (lane == 0) thr_s[rrow] = new_thr;
+          __syncwarp();
+        }
+      }
+      return new_thr;
+    };
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t & 1;
+      tc::mbar_wait(tfull + st, (t >> 1) & 1);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
+        if (c0 + 32 == BN) {               // accumulator fully read: hand it back to the MMA warp
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tempty + st);
+        }
+        const int ib = it0 + t * BN + c0;
+        const int nvalid = it1 - ib;
+        if (nvalid < 32) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c >= nvalid) v[c] = -INFINITY;
+        }
+        if (a.debug == 1) continue;      // pipeline-only timing experiment
+        const float thr = thr_s[row];
+        unsigned m = 0u;                    // bit c set <=> this row's score in column c beats the row threshold
+#pragma unroll
+        for (int c = 0; c < 32; ++c) m |= (v[c] > thr) ? (1u << c) : 0u;
+        unsigned bb = __ballot_sync(0xffffffffu, m != 0u);
+        if (bb == 0u || a.debug == 2) continue;   // common case once the lists are warm
+        // park the 32x32 chunk in smem; visit only the (row, column) pairs that fired, with ONE copy of the insert code
+        float* vs = vsm + q * 1024;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) vs[c * 32 + lane] = v[c];
+        __syncwarp();
+        while (bb) {
+          const int src = __ffs(bb) - 1;
+          bb &= bb - 1;
+          unsigned mm = __shfl_sync(0xffffffffu, m, src);
+          while (mm) {
+            const int c = __ffs(mm) - 1;
+            mm &= mm - 1;
+            insert(32 * q + src, vs[c * 32 + src], ib + c);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (u < a.U) {
+      const long long o = ((long long)split * a.U + u) * KC;
+      for (int k = 0; k < KC; ++k) {
+        const uint32_t key = lk[row * KCP + k];
+        const int id = li[row * KCP + k];
+        a.part_scores[o + k] = id >= 0 ? __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key) : -INFINITY;
+        a.part_ids[o + k] = id;
+      }
+      a.part_thr[(long long)split * a.U + u] = thr_s[row];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// fp32 -> bf16 rows (round to nearest even) + max squared row norm (atomicMax on the float bits; values >= 0)
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int H,
+                                                      float* __restrict__ max_normsq) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + w; r < rows; r += (long long)gridDim.x * 8) {
+    float ns = 0.f;
+    for (int c = 2 * l; c < H; c += 64) {
+      const float2 v = *reinterpret_cast<const float2*>(x + r * H + c);
+      ns = fmaf(v.x, v.x, fmaf(v.y, v.y, ns));
+      *reinterpret_cast<__nv_bfloat162*>(y + r * H + c) = __floats2bfloat162_rn(v.x, v.y);
+    }
+    if (max_normsq) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+      if (l == 0) atomicMax(reinterpret_cast<unsigned int*>(max_normsq), __float_as_uint(ns));
+    }
+  }
+}
+
+struct RescoreArgs {
+  const float* feats; const float* E; const float* part_scores; const int* part_ids; const float* part_thr; const float* max_normsq;
+  float* out_scores; int* out_ids; int* flags;
+  int U, H, item_offset, K, KC, n_splits;
+};
+
+constexpr int RS_MAXC = 2048;   // candidates per user (n_splits * KC)
+
+__global__ void __launch_bounds__(128) rescore_select_kernel(RescoreArgs a) {
+  extern __shared__ float rs_smem[];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int u = blockIdx.x * 4 + w;
+  if (u >= a.U) return;
+  float* cs = rs_smem + w * 2 * RS_MAXC;
+  int* ci = reinterpret_cast<int*>(cs + RS_MAXC);
+  const int n = a.n_splits * a.KC;
+  const float* f = a.feats + (long long)u * a.H;
+  float fn = 0.f;
+  for (int c = l; c < a.H; c += 32) fn = fmaf(f[c], f[c], fn);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fn += __shfl_xor_sync(0xffffffffu, fn, o);
+  float thr_max = -INFINITY;
+  for (int s = l; s < a.n_splits; s += 32) thr_max = fmaxf(thr_max, a.part_thr[(long long)s * a.U + u]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) thr_max = fmaxf(thr_max, __shfl_xor_sync(0xffffffffu, thr_max, o));
+  // exact fp32 re-score, lane per candidate
+  for (int c = l; c < n; c += 32) {
+    const int s = c / a.KC, k = c - s * a.KC;
+    const long long o = ((long long)s * a.U + u) * a.KC + k;
+    const int id = a.part_ids[o];
+    float sc = -INFINITY;
+    if (id >= 0) {
+      const float* e = a.E + (long long)(id - a.item_offset) * a.H;
+      float acc = 0.f;
+      for (int h = 0; h < a.H; h += 4) {
+        const float4 ev = *reinterpret_cast<const float4*>(e + h);
+        const float4 fv = *reinterpret_cast<const float4*>(f + h);
+        acc = fmaf(fv.x, ev.x, acc); acc = fmaf(fv.y, ev.y, acc); acc = fmaf(fv.z, ev.z, acc); acc = fmaf(fv.w, ev.w, acc);
+      }
+      sc = acc;
+    }
+    cs[c] = sc;
+    ci[c] = id;
+  }
+  __syncwarp();
+  float kth = -INFINITY;
+  for (int k = 0; k < a.K; ++k) {
+    float bs = -INFINITY;
+    int bi = 0x7fffffff, bp = -1;
+    for (int c = l; c < n; c += 32) {
+      const float s = cs[c];
+      const int id = ci[c];
+      if (id >= 0 && (s > bs || (s == bs && id < bi))) { bs = s; bi = id; bp = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (op >= 0 && (bp < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; bp = op; }
+    }
+    if (bp >= 0 && (bp & 31) == l) ci[bp] = -1;   // consumed (owner lane of slot bp is bp % 32)
+    __syncwarp();
+    if (l == 0) {
+      a.out_scores[(long long)u * a.K + k] = bp >= 0 ? bs : -INFINITY;
+      a.out_ids[(long long)u * a.K + k] = bp >= 0 ? bi : -1;
+    }
+    kth = bp >= 0 ? bs : -INFINITY;
+  }
+  if (l == 0) {
+    const float eps = 0.0078125f * sqrtf(fn) * sqrtf(*a.max_normsq);   // 2^-7 |f| max|e|
+    a.flags[u] = (thr_max > -INFINITY && !(kth > thr_max + eps)) ? 1 : 0;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows][H] tensor, box = [box_rows][64 cols], 128-byte swizzle
+int make_map(CUtensorMap* m, const void* base, long long rows, int H, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return ADT_E_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)H, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)H * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ADT_OK : ADT_E_CUDA;
+}
+
+template <int KB, int BN>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
+  const size_t smem = 1024 + (size_t)KB * BM * 128 + 2 * (size_t)KB * BN * 128 + (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 + BM * 4 + 4 * 1024 * 4 + 128;
+  if (smem > 227 * 1024) return ADT_E_SHAPE;
+  cudaFuncSetAttribute(score_tc_kernel<KB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  score_tc_kernel<KB, BN><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+}  // namespace
+
+extern "C" int adt_to_bf16(const float* x, void* y, int64_t rows, int32_t H, float* max_normsq, adt_stream_t s_) {
+  if (H & 1) return ADT_E_SHAPE;
+  const long long blocks = (rows + 7) / 8;
+  to_bf16_kernel<<<(int)(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16), 256, 0, (cudaStream_t)s_>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), (long long)rows, H, max_normsq);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (a->H % 64 || a->H > 256 || a->K <= 0 || a->K > a->KC || a->KC > 64 || a->n_splits <= 0 || a->n_splits * a->KC > RS_MAXC || a->U <= 0)
+    return ADT_E_SHAPE;
+  CUtensorMap tmA, tmB;
+  const int KB = a->H / 64;
+  const int BN = KB == 4 ? 64 : 128;
+  if (int e = make_map(&tmA, a->feats_bf16, a->U, a->H, BM)) return e;
+  if (int e = make_map(&tmB, a->item_emb_bf16, a->n_items, a->H, BN)) return e;
+  TcArgs k;
+  k.seen_indptr = a->seen_indptr; k.seen_idx = a->seen_idx; k.part_scores = a->part_scores; k.part_ids = a->part_ids; k.part_thr = a->part_thr;
+  k.U = a->U; k.n_items = a->n_items; k.item_offset = a->item_offset; k.KC = a->KC; k.n_splits = a->n_splits;
+  { const char* dbg = getenv("ADT_TC_DEBUG"); k.debug = dbg ? atoi(dbg) : 0; }
+  dim3 grid(a->n_splits, (a->U + BM - 1) / BM);
+  int rc;
+  if (KB == 1) rc = launch_tc<1, 128>(tmA, tmB, k, grid, s);
+  else if (KB == 2) rc = launch_tc<2, 128>(tmA, tmB, k, grid, s);
+  else if (KB == 4) rc = launch_tc<4, 64>(tmA, tmB, k, grid, s);
+  else return ADT_E_SHAPE;
+  if (rc) return rc;
+  RescoreArgs r;
+  r.feats = a->feats; r.E = a->item_emb; r.part_scores = a->part_scores; r.part_ids = a->part_ids; r.part_thr = a->part_thr;
+  r.max_normsq = a->max_normsq; r.out_scores = a->out_scores; r.out_ids = a->out_ids; r.flags = a->flags;
+  r.U = a->U; r.H = a->H; r.item_offset = a->item_offset; r.K = a->K; r.KC = a->KC; r.n_splits = a->n_splits;
+  const size_t rs = (size_t)4 * 2 * RS_MAXC * sizeof(float);
+  cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
+  rescore_select_kernel<<<(a->U + 3) / 4, 128, rs, s>>>(r);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}

@@ -39,8 +39,11 @@ def merge_topk(scores, ids, K):
 
 
 class CatalogScorer:
-    def __init__(self, model, K=10, n_splits=None, process_group=None):
+    def __init__(self, model, K=10, n_splits=None, process_group=None, use_tensor_cores=True):
         self.model, self.K = model, int(K)
+        self.use_tc = use_tensor_cores
+        self._tab = None           # (bf16 copy of this rank's catalog shard, max |e|^2 scalar)
+        self.fallback_users = 0    # users re-run on the exact fp32 kernel because the bf16 bound was inconclusive
         self.lib = L.lib()
         self.pg = process_group
         self.world, self.rank = 1, 0
@@ -67,6 +70,60 @@ class CatalogScorer:
         feats = m.final_feats(seq)
         return self.topk_from_feats(feats, seen_indptr, seen_idx)
 
+    def refresh_table(self):
+        """(re)build the bf16 copy of the catalog shard -- call after the item table changed (e.g. once per eval pass)."""
+        E = self.model.item_emb.weight
+        lo, hi = shard_bounds(E.shape[0], self.world, self.rank)
+        shard = E[lo:hi]
+        tab = torch.empty(shard.shape, dtype=torch.bfloat16, device=E.device)
+        mx = torch.zeros(1, dtype=torch.float32, device=E.device)
+        st = ctypes.c_void_p(torch.cuda.current_stream(E.device).cuda_stream)
+        L.check(self.lib.adt_to_bf16(L.ptr(shard), L.ptr(tab), ctypes.c_int64(shard.shape[0]), ctypes.c_int32(shard.shape[1]), L.ptr(mx), st),
+                "adt_to_bf16")
+        self._tab = (tab, mx)
+
+    @torch.no_grad()
+    def _topk_tc(self, feats, ip, ix, lo, hi):
+        """tensor-core path: tcgen05 candidate generation + exact fp32 re-score; exact-kernel fallback for flagged users."""
+        dev = feats.device
+        U, H = feats.shape
+        E = self.model.item_emb.weight
+        if self._tab is None:
+            self.refresh_table()
+        tab, mx = self._tab
+        n_items = hi - lo
+        K = self.K
+        KC = min(64, max(K + 8, 2 * K))
+        tiles = (U + 127) // 128
+        S = max(1, min(2048 // KC, max(1, 148 // tiles), (n_items + 127) // 128))
+        key = ("tc", U, S, KC)
+        if key not in self._buf:
+            self._buf[key] = (torch.empty(S, U, KC, device=dev), torch.empty(S, U, KC, dtype=torch.int32, device=dev),
+                              torch.empty(S, U, device=dev), torch.empty(U, K, device=dev), torch.empty(U, K, dtype=torch.int32, device=dev),
+                              torch.empty(U, dtype=torch.int32, device=dev), torch.empty(U, H, dtype=torch.bfloat16, device=dev))
+        ps, pi, pt, os_, oi, flags, fb = self._buf[key]
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        L.check(self.lib.adt_to_bf16(L.ptr(feats), L.ptr(fb), ctypes.c_int64(U), ctypes.c_int32(H), None, st), "adt_to_bf16")
+        a = L.fill(L.adt_score_topk_tc_args(), feats=feats, feats_bf16=fb, U=U, H=H, item_emb=E[lo:hi], item_emb_bf16=tab, n_items=n_items,
+                   item_offset=lo, max_normsq=mx, seen_indptr=ip, seen_idx=ix, K=K, KC=KC, n_splits=S, part_scores=ps, part_ids=pi,
+                   part_thr=pt, out_scores=os_, out_ids=oi, flags=flags)
+        L.check(self.lib.adt_score_topk_tc(ctypes.byref(a), st), "adt_score_topk_tc")
+        bad = torch.nonzero(flags, as_tuple=False).flatten()
+        if bad.numel():
+            self.fallback_users += int(bad.numel())
+            sub_ip = sub_ix = None
+            if ip is not None:
+                ipc, ixc = ip.cpu().numpy(), ix.cpu().numpy()
+                rows = bad.cpu().numpy()
+                lens = ipc[rows + 1] - ipc[rows]
+                sub_ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+                sub_ix = np.concatenate([ixc[ipc[r]:ipc[r + 1]] for r in rows]).astype(np.int32) if lens.sum() else np.zeros(0, np.int32)
+            es, ei = self._topk_exact(feats[bad].contiguous(), _as_ids(sub_ip, dev) if sub_ip is not None else None,
+                                      _as_ids(sub_ix, dev) if sub_ix is not None else None, lo, hi)
+            os_[bad] = es
+            oi[bad] = ei
+        return os_, oi
+
     @torch.no_grad()
     def topk_from_feats(self, feats, seen_indptr=None, seen_idx=None):
         m = self.model
@@ -74,22 +131,34 @@ class CatalogScorer:
         U, H = feats.shape
         E = m.item_emb.weight
         lo, hi = shard_bounds(E.shape[0], self.world, self.rank)
-        n_items = hi - lo
-        tiles = (U + 63) // 64
-        S = self.n_splits or max(1, min(256, (2 * 148 + tiles - 1) // tiles, (n_items + 255) // 256))
-        ps, pi, os_, oi = self._buffers(U, S, dev)
         ip = _as_ids(seen_indptr, dev) if seen_indptr is not None else None
         ix = _as_ids(seen_idx, dev) if seen_idx is not None else None
-        a = L.fill(L.adt_score_topk_args(), feats=feats, U=U, H=H, item_emb=E[lo:hi], n_items=n_items, item_offset=lo,
-                   seen_indptr=ip, seen_idx=ix, K=self.K, n_splits=S, part_scores=ps, part_ids=pi, out_scores=os_, out_ids=oi)
-        L.check(self.lib.adt_score_topk(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "adt_score_topk")
+        if self.use_tc and H % 64 == 0:
+            os_, oi = self._topk_tc(feats, ip, ix, lo, hi)
+        else:
+            os_, oi = self._topk_exact(feats, ip, ix, lo, hi)
         if self.world == 1:
             return os_, oi
         gs = torch.empty(self.world, U, self.K, device=dev)
         gi = torch.empty(self.world, U, self.K, dtype=torch.int32, device=dev)
-        torch.distributed.all_gather_into_tensor(gs, os_, group=self.pg)
-        torch.distributed.all_gather_into_tensor(gi, oi, group=self.pg)
+        torch.distributed.all_gather_into_tensor(gs, os_.contiguous(), group=self.pg)
+        torch.distributed.all_gather_into_tensor(gi, oi.contiguous(), group=self.pg)
         return merge_topk(gs, gi, self.K)
+
+    @torch.no_grad()
+    def _topk_exact(self, feats, ip, ix, lo, hi):
+        m = self.model
+        dev = feats.device
+        U, H = feats.shape
+        E = m.item_emb.weight
+        n_items = hi - lo
+        tiles = (U + 63) // 64
+        S = self.n_splits or max(1, min(256, (2 * 148 + tiles - 1) // tiles, (n_items + 255) // 256))
+        ps, pi, os_, oi = self._buffers(U, S, dev)
+        a = L.fill(L.adt_score_topk_args(), feats=feats, U=U, H=H, item_emb=E[lo:hi], n_items=n_items, item_offset=lo,
+                   seen_indptr=ip, seen_idx=ix, K=self.K, n_splits=S, part_scores=ps, part_ids=pi, out_scores=os_, out_ids=oi)
+        L.check(self.lib.adt_score_topk(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "adt_score_topk")
+        return os_, oi
 
 
 def hit_ndcg_mrr(answers, topk_ids, ks=(5, 10)):

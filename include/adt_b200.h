@@ -185,6 +185,23 @@ typedef struct {
 } adt_score_topk_args;
 int adt_score_topk(const adt_score_topk_args* a, adt_stream_t stream);
 
+/* K7 on the tensor cores (H % 64 == 0): bf16 TMA-fed tcgen05.mma GEMM (fp32 accumulators in TMEM) with a fused
+ * streaming top-KC epilogue per (catalog split, user), then an exact fp32 re-score of the <= n_splits*KC candidates
+ * per user and the final top-K.  flags[u] = 1 when the bf16 rounding bound cannot prove that the fp32 top-K is
+ * contained in the candidate set; the caller re-runs those users through adt_score_topk (exact).  n_splits*KC <= 2048. */
+int adt_to_bf16(const float* x, void* y_bf16, int64_t rows, int32_t H, float* max_normsq /* atomicMax'ed, may be NULL */,
+                adt_stream_t stream);
+typedef struct {
+  const float* feats; const void* feats_bf16; int32_t U, H;          /* [U,H] fp32 and its bf16 copy */
+  const float* item_emb; const void* item_emb_bf16; int32_t n_items; int32_t item_offset;
+  const float* max_normsq;                                           /* device scalar: max_i |item_emb[i]|^2 */
+  const int32_t* seen_indptr; const int32_t* seen_idx;
+  int32_t K, KC, n_splits;
+  float* part_scores; int32_t* part_ids; float* part_thr;            /* scratch [n_splits][U][KC], [n_splits][U] */
+  float* out_scores; int32_t* out_ids; int32_t* flags;               /* [U][K], [U][K], [U] */
+} adt_score_topk_tc_args;
+int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t stream);
+
 /* test helper: out[i] = keep-multiplier (0 or 1/(1-p)) of element base+i of a dropout site */
 int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t stream);
 

@@ -98,8 +98,9 @@ def test_sort_scatter_add_bit_exact(B, Lq, H, I, p):
     assert np.allclose(dP.cpu().numpy(), pref, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("U,H,I,K", [(70, 64, 3000, 10), (130, 256, 999, 40), (5, 16, 40, 10)])
-def test_catalog_topk_matches_oracle(U, H, I, K):
+@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("U,H,I,K", [(70, 64, 3000, 10), (130, 256, 999, 40), (5, 16, 40, 10), (300, 128, 20000, 10)])
+def test_catalog_topk_matches_oracle(U, H, I, K, use_tc):
     import types
     from adt_b200.evaluate import CatalogScorer
     from oracle import sasrec_oracle as O
@@ -111,7 +112,7 @@ def test_catalog_topk_matches_oracle(U, H, I, K):
     indptr[1:] = np.cumsum([len(s) for s in seen])
     idx = np.concatenate(seen).astype(np.int32) if indptr[-1] else np.zeros(0, np.int32)
     fake = types.SimpleNamespace(item_emb=types.SimpleNamespace(weight=E.cuda()))
-    sc = CatalogScorer(fake, K=K)
+    sc = CatalogScorer(fake, K=K, use_tensor_cores=use_tc)
     s, ids = sc.topk_from_feats(feats.cuda(), indptr, idx)
     ids = ids.cpu().numpy()
     scores = (feats @ E.t()).numpy()
@@ -183,3 +184,23 @@ def test_cuda_graph_step_matches_eager():
     assert abs(res[0][0][0] - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
     assert np.allclose(res[0][0], res[1][0], rtol=1e-5), (res[0][0], res[1][0])
     assert torch.allclose(res[0][1], res[1][1], rtol=1e-3, atol=2e-4)
+
+
+def test_catalog_topk_tc_near_ties_fall_back_to_exact():
+    """scores packed into a band far narrower than bf16 resolution: the tensor-core pass cannot prove exactness, must
+    flag the users and the exact fp32 kernel must still deliver the reference ranking."""
+    import types
+    from adt_b200.evaluate import CatalogScorer
+    rng = np.random.default_rng(3)
+    U, H, I, K = 64, 64, 4000, 10
+    base = rng.standard_normal(H).astype(np.float32)
+    E = torch.from_numpy((base[None, :] + 1e-4 * rng.standard_normal((I + 1, H))).astype(np.float32)).cuda()
+    feats = torch.from_numpy(rng.standard_normal((U, H)).astype(np.float32)).cuda()
+    fake = types.SimpleNamespace(item_emb=types.SimpleNamespace(weight=E))
+    ex = CatalogScorer(fake, K=K, use_tensor_cores=False)
+    tc = CatalogScorer(fake, K=K, use_tensor_cores=True)
+    s0, i0 = ex.topk_from_feats(feats)
+    s1, i1 = tc.topk_from_feats(feats)
+    assert tc.fallback_users > 0
+    assert torch.equal(i0, i1)
+    assert torch.equal(s0, s1)
