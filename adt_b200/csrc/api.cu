@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/adt_b200.h"
@@ -95,7 +96,9 @@ static const size_t SMEM_MAX = 227 * 1024 - 2048;   // leave room for the kernel
 
 // rows-per-CTA choice: 64 when the tile set fits, else 32
 static int pick_tm(size_t row_floats, size_t* bytes) {
-  for (int tm = 64; tm >= 32; tm >>= 1) {
+  static int pref = -1;
+  if (pref < 0) { const char* e = getenv("ADT_TM"); pref = e ? atoi(e) : 64; if (pref != 32) pref = 64; }
+  for (int tm = pref; tm >= 32; tm >>= 1) {
     const size_t b = ((size_t)tm * row_floats + WS_FLOATS) * sizeof(float);
     if (b <= SMEM_MAX) {
       *bytes = b;

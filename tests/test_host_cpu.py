@@ -1,0 +1,168 @@
+"""CPU tests: C-ABI library loads and exports every declared symbol, the host-side mirror of the reference interface
+(parameter names/shapes, error behaviour), metric/merge host logic, and the N>1 paths on gloo (world_size 2)."""
+import os
+import types
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_names, load_golden, sd_from
+
+
+def test_header_parses_and_library_exports_every_symbol():
+    import __graft_entry__ as g
+    from adt_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    lib = _lib.lib()
+    assert len(_lib.FUNCTIONS) >= 18
+    for f in _lib.FUNCTIONS:
+        assert hasattr(lib, f), f
+    assert lib.adt_version() >= 100
+    # struct layouts come from the header: spot-check one
+    d = _lib.adt_dropout()
+    assert [n for n, _ in d._fields_] == ["enabled", "p", "seed", "step", "site", "base", "step_dev"]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_state_dict_matches_reference_names_and_shapes(name):
+    """drop-in contract: reference checkpoints load into our module and vice versa."""
+    from adt_b200 import SASRecADT
+    g = load_golden(name)
+    d = g["dims"]
+    args = types.SimpleNamespace(device="cpu", num_heads=d["nh"], maxlen=d["L"], num_layers=d["nl"], hidden_units=d["H"], dropout=0.5)
+    m = SASRecADT(100, d["I"], args)
+    ref = sd_from(g)
+    ours = m.state_dict()
+    assert list(ours.keys()) == list(ref.keys())
+    for k in ref:
+        assert tuple(ours[k].shape) == tuple(ref[k].shape), k
+    m.load_state_dict(ref)  # strict
+    assert [n for n, _ in m.named_parameters()] == [k for k in ref.keys()]
+
+
+def test_no_cpu_fallback():
+    from adt_b200 import SASRecADT
+    from adt_b200._lib import AdtError
+    args = types.SimpleNamespace(device="cpu", num_heads=2, maxlen=8, num_layers=1, hidden_units=16, dropout=0.0)
+    m = SASRecADT(10, 20, args)
+    ids = np.ones((2, 8), np.int64)
+    with pytest.raises(AdtError):
+        m(None, ids, ids, ids, ids)
+    with pytest.raises(AdtError):
+        m.predict(None, ids, ids)
+
+
+def test_lambdas_tables_and_candidate_mapping():
+    from adt_b200.lambdas import get_lambdas, get_weight, candidate_to_lambdas
+    assert get_lambdas("ml-1m") == ([0.104292, 0.065892], [0.100833, 0.000607])   # sasrec/utils.py:856
+    assert get_lambdas("beauty") == ([0.0124, 0.122], [0.0001, 0.0])
+    assert get_lambdas("nope") is None
+    choice = [0, 0.0001, 0.0005, 0.001, 0.005, 0.01]
+    cand = [0.7053411308078107, 0.9542592593410837, 0.9296478828883573, 0.28425047269448145, 0.1600125621449342, 0.47495464861462977]
+    rec, ind = candidate_to_lambdas(cand, choice, choice)
+    txt = open(os.path.join(os.path.dirname(__file__), "golden", "candidates_to_lambdas.txt")).read().strip()
+    assert f"{rec} {ind}" == txt
+    assert get_weight(choice, 0.0) == 0
+
+
+def test_merge_topk_and_shards():
+    from adt_b200.evaluate import merge_topk, shard_bounds
+    rng = np.random.default_rng(0)
+    U, I, K, S = 7, 203, 5, 3
+    scores = torch.from_numpy(rng.standard_normal((U, I)).astype(np.float32))
+    scores[:, 17] = scores[:, 23]  # an exact tie: lower id first
+    bounds = [shard_bounds(I, S, r) for r in range(S)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == I and all(bounds[i][1] == bounds[i + 1][0] for i in range(S - 1))
+    ps, pi = [], []
+    for lo, hi in bounds:
+        s, i = torch.topk(scores[:, lo:hi], min(K, hi - lo), dim=1)
+        pad = K - s.shape[1]
+        ps.append(torch.cat([s, torch.full((U, pad), float("-inf"))], 1))
+        pi.append(torch.cat([(i + lo).int(), torch.full((U, pad), -1, dtype=torch.int32)], 1))
+    ms, mi = merge_topk(torch.stack(ps), torch.stack(pi), K)
+    order = np.lexsort((np.tile(np.arange(I), (U, 1)), -scores.numpy()), axis=1)[:, :K]
+    assert np.array_equal(mi.numpy(), order)
+
+
+def test_metrics_match_oracle():
+    from adt_b200.evaluate import hit_ndcg_mrr, sampled_metrics
+    from oracle import sasrec_oracle as O
+    rng = np.random.default_rng(1)
+    U, K = 50, 40
+    pred = np.stack([rng.permutation(200)[:K] for _ in range(U)])
+    answers = np.where(rng.random(U) < 0.6, pred[np.arange(U), rng.integers(0, K, U)], 999)
+    ours = hit_ndcg_mrr(answers, pred)
+    ref = O.full_sort_metrics(answers.reshape(-1, 1), pred)
+    for k in ref:
+        assert abs(ours[k] - ref[k]) < 1e-12, k
+    logits = rng.standard_normal((U, 101)).astype(np.float32)
+    (ndcg_r, hr_r), auc_r, rank_r = O.rank_metrics(-logits)
+    rank = (logits[:, 1:] > logits[:, :1]).sum(1)
+    assert np.array_equal(rank, rank_r)
+    (ndcg, hr), auc = sampled_metrics(rank, 101)
+    assert hr == hr_r and abs(auc - auc_r) < 1e-12 and all(abs(ndcg[k] - ndcg_r[k]) < 1e-6 for k in ndcg)
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adt_b200.evaluate import merge_topk, shard_bounds
+    from oracle import sasrec_oracle as O
+    from helpers import load_golden, sd_from, ids
+    # (1) item-sharded evaluation: local top-K on this rank's catalog slice, all_gather, merge == single-process top-K
+    g = torch.Generator().manual_seed(5)
+    U, I, H, K = 9, 101, 8, 4
+    feats, E = torch.randn(U, H, generator=g), torch.randn(I, H, generator=g)
+    lo, hi = shard_bounds(I, world, rank)
+    s, i = torch.topk(feats @ E[lo:hi].t(), K, dim=1)
+    gs = [torch.empty_like(s) for _ in range(world)]
+    gi = [torch.empty(U, K, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(gs, s.contiguous())
+    dist.all_gather(gi, (i + lo).int().contiguous())
+    ms, mi = merge_topk(torch.stack(gs), torch.stack(gi), K)
+    ref = torch.topk(feats @ E.t(), K, dim=1)[1]
+    ok1 = bool(torch.equal(mi.long(), ref))
+    # (2) data-parallel loss normalisation: BCE is a mean over the valid positions of the GLOBAL batch (main.py:151-153),
+    #     MSE/NLL means over global rows: all-reduced accumulators reproduce the single-process loss
+    gd = load_golden("tiny_p0")
+    d = gd["dims"]
+    cfg = O.Cfg(d["I"], d["L"], d["H"], d["nh"], d["nl"], 0.0)
+    sd = sd_from(gd)
+    seq, dec, pos, neg = ids(gd)
+    l1, l2, wd = list(gd["lambdas1"]), list(gd["lambdas2"]), float(gd["wd"])
+    B = seq.shape[0]
+    sl = slice(rank * B // world, (rank + 1) * B // world)
+    out = O.forward(sd, cfg, seq[sl], dec[sl], pos[sl], neg[sl])
+    valid = pos[sl] != 0
+    acc = torch.zeros(3 + 2 * d["nl"], dtype=torch.float64)
+    acc[0] = torch.nn.functional.softplus(-out["pos_logits"][valid]).double().sum()
+    acc[1] = torch.nn.functional.softplus(out["neg_logits"][valid]).double().sum()
+    acc[2] = valid.sum()
+    for j in range(d["nl"]):     # decoder layer j pairs with enc_inputs[nl-1-j]; dec_outputs is already reversed
+        i_enc = d["nl"] - 1 - j
+        acc[3 + j] = ((out["enc_inputs"][i_enc] - out["dec_outputs"][i_enc]) ** 2).double().sum()
+    for l in range(d["nl"]):
+        r = out["rec_true"][l]
+        acc[3 + d["nl"] + l] = -torch.diagonal(r, dim1=-2, dim2=-1).double().sum()
+    dist.all_reduce(acc)
+    Mg, Hh, nh, nl = B * d["L"], d["H"], d["nh"], d["nl"]
+    total = (acc[0] + acc[1]) / acc[2]
+    for j in range(nl):
+        total = total + l1[nl - 1 - j] * acc[3 + j] / (Mg * Hh)
+    for l in range(nl):
+        total = total + l2[nl - 1] * acc[3 + nl + l] / (Mg * nh)
+    total = total + wd * torch.norm(sd["item_emb.weight"]).double()
+    ok2 = abs(float(total) - float(gd["loss"])) / abs(float(gd["loss"])) < 1e-5
+    ret[rank] = (ok1, ok2)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_eval_and_dp_loss():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: (True, True), 1: (True, True)}
