@@ -15,7 +15,8 @@ namespace adt {
 constexpr int NT = 256;        // threads per CTA for all row-tile kernels
 constexpr int CH = 64;         // weight chunk edge (rows and cols)
 constexpr int CHP = CH + 4;    // padded chunk row stride in floats (272 B: 16B aligned, LDS.128 conflict free)
-constexpr int WS_FLOATS = 2 * CH * CHP;  // double-buffered staging area
+constexpr int WS_NST = 2;                // depth of the weight-chunk ring
+constexpr int WS_FLOATS = WS_NST * CH * CHP;  // staging area
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 dropout (must match oracle/philox.py bit for bit)
@@ -341,6 +342,85 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ A, int lda, 
     __syncthreads();
     const float* buf = Ws + (t & 1) * CH * CHP;
     // round the reduction length up to 4 (staged zeros make the tail harmless)
+    const int rlen = min(CH, Kred - rc * CH);
+    if (!NN) mma_nt<RM>(acc, A, lda, rc * CH, buf, rlen);
+    else mma_nn<RM>(acc, A, lda, rc * CH, buf, rlen);
+    if (rc == nrc - 1) {
+      const int col = oc * CH + 4 * tx;
+      if (col < Nout) {
+#pragma unroll
+        for (int i = 0; i < RM; ++i) epi(i, ty + 16 * i, col, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight stream: all GEMMs of a kernel are declared up-front; their [64x64] chunks flow through an NST-deep cp.async
+// ring that keeps prefetching ACROSS GEMM boundaries, so a GEMM phase never starts with an exposed global->smem
+// round trip (at H=64 every GEMM is a single chunk: without this each phase would wait for its own load).
+// One (possibly empty) cp.async group is committed per issue() so that wait_group<NST-1> is always the right count.
+// ---------------------------------------------------------------------------------------------
+struct GemmDesc {
+  const float* W; long long ldw; int Nout, Kred, nn;   // nn = 0: Y = A W^T (W [Nout][Kred]) ; nn = 1: Y = A W (W [Kred][Nout])
+};
+constexpr int WS_MAXG = 8;
+struct WStreamState {
+  GemmDesc g[WS_MAXG];
+  int ng;
+};
+
+template <int NST>
+struct WStream {
+  WStreamState* st;   // shared memory
+  float* bufs;        // NST * CH * CHP floats
+  int next_g, next_t, slot_issue, slot_cons, last_slot;
+
+  __device__ __forceinline__ void issue() {
+    if (next_g < st->ng) {
+      const GemmDesc d = st->g[next_g];
+      const int noc = (d.Nout + CH - 1) / CH, nrc = (d.Kred + CH - 1) / CH;
+      const int oc = next_t / nrc, rc = next_t - oc * nrc;
+      float* buf = bufs + slot_issue * CH * CHP;
+      if (!d.nn) stage_chunk<true>(buf, d.W, d.ldw, oc * CH, rc * CH, min(CH, d.Nout - oc * CH), min(CH, d.Kred - rc * CH));
+      else stage_chunk<false>(buf, d.W, d.ldw, rc * CH, oc * CH, min(CH, d.Kred - rc * CH), min(CH, d.Nout - oc * CH));
+      if (++next_t == noc * nrc) { next_t = 0; ++next_g; }
+    }
+    slot_issue = slot_issue + 1 == NST ? 0 : slot_issue + 1;
+    cp_async_commit();
+  }
+  // call once, by all threads, after the descriptors were written to *st and __syncthreads()
+  __device__ __forceinline__ void start(WStreamState* s, float* b) {
+    st = s; bufs = b; next_g = next_t = 0; slot_issue = slot_cons = 0; last_slot = NST - 1;
+#pragma unroll
+    for (int i = 0; i < NST - 1; ++i) issue();
+  }
+  // the most recently consumed ring slot: free to use as scratch until the next gemm_stream call
+  __device__ __forceinline__ float* scratch() const { return bufs + last_slot * CH * CHP; }
+};
+
+// GEMM number gi of the stream (must be consumed in declaration order).  Same contract as gemm_tile.
+template <int TM, bool NN, int NST, class Epi>
+__device__ __forceinline__ void gemm_stream(const float* __restrict__ A, int lda, WStream<NST>& ws, int gi, Epi epi) {
+  constexpr int RM = TM / 16;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int Nout = ws.st->g[gi].Nout, Kred = ws.st->g[gi].Kred;
+  const int noc = (Nout + CH - 1) / CH, nrc = (Kred + CH - 1) / CH;
+  const int total = noc * nrc;
+  float acc[RM][4];
+  for (int t = 0; t < total; ++t) {
+    const int oc = t / nrc, rc = t - oc * nrc;
+    if (rc == 0) {
+#pragma unroll
+      for (int i = 0; i < RM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    }
+    ws.issue();
+    cp_async_wait<NST - 1>();
+    __syncthreads();
+    const float* buf = ws.bufs + ws.slot_cons * CH * CHP;
+    ws.last_slot = ws.slot_cons;
+    ws.slot_cons = ws.slot_cons + 1 == NST ? 0 : ws.slot_cons + 1;
     const int rlen = min(CH, Kred - rc * CH);
     if (!NN) mma_nt<RM>(acc, A, lda, rc * CH, buf, rlen);
     else mma_nn<RM>(acc, A, lda, rc * CH, buf, rlen);

@@ -54,6 +54,16 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   float* Ws = Y + TM * ld;    // weight staging; reused as LN-bwd / sparse-head scratch
   const int row0 = blockIdx.x * TM;
   const int rows = min(TM, M - row0);
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{p.C2, H, H, H, 1};
+    wst.g[1] = GemmDesc{p.C1, H, H, H, 1};
+    wst.g[2] = GemmDesc{p.Wo, H, H, H, 1};
+    wst.ng = 3;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
 
   // 1./2. dO = (dout + mse_coef*(out-enc_in)) * keep ; y/c ; a = relu(h1*m1) ; dh2 = dO*m2
   tile_foreach4<TM>(H, [&](int r, int c) {
@@ -85,7 +95,7 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   wgrad_tile(Bt, ld, H, A, ld, H, rows, p.gC2, H);
   colsum_atomic(Bt, ld, H, rows, p.gc2);
   // 4. da = dh2 C2 ; dh1 = da * [a>0] * m1   (element-wise overwrite of A; A is not this GEMM's operand)
-  gemm_tile<TM, true>(Bt, ld, H, p.C2, H, H, Ws, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST>(Bt, ld, ws, 0, [&](int, int r, int col, float4 acc) {
     const float4 a = ld4(A + r * ld + col);
     float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
     if (p.drop1.enabled) m = drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)(row0 + r) * H + col) >> 2);
@@ -102,12 +112,12 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   wgrad_tile(A, ld, H, Z, ld, H, rows, p.gC1, H);
   colsum_atomic(A, ld, H, rows, p.gc1);
   // 6. dz (enc) / dc (dec) = dO + dh1 C1  -> Bt
-  gemm_tile<TM, true>(A, ld, H, p.C1, H, H, Ws, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST>(A, ld, ws, 1, [&](int, int r, int col, float4 acc) {
     st4(Bt + r * ld + col, f4_add(acc, ld4(G + r * ld + col)));
   });
   if (!IS_DEC) {
     // 7. dy = LN2^T(dz) -> G
-    ln_bwd_tile<TM, false>(Y, Bt, G, ld, H, p.ln2_g, 1e-8f, row0, M, p.gln2_g, p.gln2_b, Ws);
+    ln_bwd_tile<TM, false>(Y, Bt, G, ld, H, p.ln2_g, 1e-8f, row0, M, p.gln2_g, p.gln2_b, ws.scratch());
     // 8. dres = dy ; dWo += dy^T ctx
     store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
     load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
@@ -115,11 +125,11 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     wgrad_tile(G, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(G, ld, H, rows, p.gbo);
     // 9. dctx = dy Wo (+ independence-head adjoint) -> Bt -> global
-    gemm_tile<TM, true>(G, ld, H, p.Wo, H, H, Ws, [&](int, int r, int col, float4 acc) { st4(Bt + r * ld + col, acc); });
+    gemm_stream<TM, true, WS_NST>(G, ld, ws, 2, [&](int, int r, int col, float4 acc) { st4(Bt + r * ld + col, acc); });
     if (p.nll_coef != 0.f || p.drec) {
       const int nh = p.nh, hd = H / nh, n2 = nh * nh;
-      float* lgs = Ws;                 // [TM][nh*nh] logits -> dlogits
-      float* dbs = Ws + TM * n2;       // [nh] bias-grad partial
+      float* lgs = ws.scratch();       // [TM][nh*nh] logits -> dlogits
+      float* dbs = lgs + TM * n2;      // [nh] bias-grad partial
       for (int i = threadIdx.x; i < nh; i += NT) dbs[i] = 0.f;
       for (int i = threadIdx.x; i < TM * n2; i += NT) {
         const int r = i / n2, cj = i - r * n2, c = cj / nh, j = cj - c * nh;
@@ -184,7 +194,7 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     __syncthreads();
     wgrad_tile(Bt, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(Bt, ld, H, rows, p.gbo);
-    gemm_tile<TM, true>(Bt, ld, H, p.Wo, H, H, Ws, [&](int, int r, int col, float4 acc) {
+    gemm_stream<TM, true, WS_NST>(Bt, ld, ws, 2, [&](int, int r, int col, float4 acc) {
       if (row0 + r < M) st4(p.dctx + (long long)(row0 + r) * H + col, acc);
     });
   }
@@ -216,11 +226,21 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
   const int Lk4 = (Lk + 3) & ~3;
   const int rows = min(TM, L - i0);
 
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{k + seq_off, H, Lk, hd, 0};
+    wst.g[1] = GemmDesc{v + seq_off, H, Lk, hd, 0};
+    wst.g[2] = GemmDesc{k + seq_off, H, hd, Lk, 1};
+    wst.ng = 3;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
   load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
   load_tile<TM>(dCs, ldq, dctx + seq_off, H, 0, hd, i0, L);
   __syncthreads();
-  gemm_tile<TM, false>(Qs, ldq, hd, k + seq_off, H, Lk, Ws, [&](int, int r, int col, float4 a) { st4(Ps + r * lds + col, a); });
-  gemm_tile<TM, false>(dCs, ldq, hd, v + seq_off, H, Lk, Ws, [&](int, int r, int col, float4 a) { st4(dPs + r * lds + col, a); });
+  gemm_stream<TM, false, WS_NST>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) { st4(Ps + r * lds + col, a); });
+  gemm_stream<TM, false, WS_NST>(dCs, ldq, ws, 1, [&](int, int r, int col, float4 a) { st4(dPs + r * lds + col, a); });
 
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int r = w; r < TM; r += NT / 32) {
@@ -272,7 +292,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
   }
   __syncthreads();
   // dq = dS k
-  gemm_tile<TM, true>(dPs, lds, Lk, k + seq_off, H, hd, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, true, WS_NST>(dPs, lds, ws, 2, [&](int, int r, int col, float4 a) {
     if (i0 + r < L) st4(dq + seq_off + (long long)(i0 + r) * H + col, a);
   });
   // dk += dS^T q ; dv += Pd^T dctx   (plain stores when this CTA is the only query tile of the sequence)
@@ -310,6 +330,16 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   float* Ws = KV + TM * ld2;
   const int row0 = blockIdx.x * TM;
   const int rows = min(TM, M - row0);
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{p.Win2, H, H, H, 1};
+    wst.g[1] = GemmDesc{p.Win2 + (long long)H * H, H, H, 2 * H, 1};
+    wst.g[2] = GemmDesc{p.Wo1, H, H, H, 1};
+    wst.ng = 3;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
   tile_foreach4<TM>(H, [&](int r, int c) {
     float4 g = zero4(), a = zero4();
     if (row0 + r < M) {
@@ -323,14 +353,14 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   __syncthreads();
   wgrad_tile(T0, ld, H, T1, ld, H, rows, p.gWin2, H);
   colsum_atomic(T0, ld, H, rows, p.gbin2);
-  gemm_tile<TM, true>(T0, ld, H, p.Win2, H, H, Ws, [&](int, int r, int col, float4 acc) { st4(DA + r * ld + col, acc); });
+  gemm_stream<TM, true, WS_NST>(T0, ld, ws, 0, [&](int, int r, int col, float4 acc) { st4(DA + r * ld + col, acc); });
   load_tile<TM>(KV, ld2, p.dk2, H, 0, H, row0, M);
   load_tile<TM>(KV + H, ld2, p.dv2, H, 0, H, row0, M);
   load_tile<TM>(T1, ld, p.feats, H, 0, H, row0, M);
   __syncthreads();
   wgrad_tile(KV, ld2, 2 * H, T1, ld, H, rows, p.gWin2 + (long long)H * H, H);
   colsum_atomic(KV, ld2, 2 * H, rows, p.gbin2 + H);
-  gemm_tile<TM, true>(KV, ld2, 2 * H, p.Win2 + (long long)H * H, H, H, Ws, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST>(KV, ld2, ws, 1, [&](int, int r, int col, float4 acc) {
     if (row0 + r < M) {
       float* d = p.dfeats + (long long)(row0 + r) * H + col;
       st4(d, f4_add(ld4(d), acc));
@@ -340,7 +370,7 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   __syncthreads();
   wgrad_tile(DA, ld, H, T1, ld, H, rows, p.gWo1, H);
   colsum_atomic(DA, ld, H, rows, p.gbo1);
-  gemm_tile<TM, true>(DA, ld, H, p.Wo1, H, H, Ws, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST>(DA, ld, ws, 2, [&](int, int r, int col, float4 acc) {
     if (row0 + r < M) st4(p.dctx1 + (long long)(row0 + r) * H + col, acc);
   });
 }
@@ -372,6 +402,16 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   float* Ws = D + TM * ld;
   const int row0 = blockIdx.x * TM;
   const int rows = min(TM, M - row0);
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{p.Win, H, H, H, 1};
+    wst.g[1] = GemmDesc{p.Win + (long long)H * H, H, H, H, 1};
+    wst.g[2] = GemmDesc{p.Win + 2ll * H * H, H, H, H, 1};
+    wst.ng = 3;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
   tile_foreach4<TM>(H, [&](int r, int c) {
     float4 xv = zero4(), g = zero4();
     if (row0 + r < M) {
@@ -387,22 +427,22 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   __syncthreads();
   wgrad_tile(T, ld, H, N, ld, H, rows, p.gWin, H);
   colsum_atomic(T, ld, H, rows, p.gbin);
-  gemm_tile<TM, true>(T, ld, H, p.Win, H, H, Ws, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST>(T, ld, ws, 0, [&](int, int r, int col, float4 acc) {
     if (p.dnorm_extra && row0 + r < M) acc = f4_add(acc, ld4(p.dnorm_extra + (long long)(row0 + r) * H + col));
     st4(D + r * ld + col, acc);
   });
-  if (!p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, Ws);
+  if (!p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, ws.scratch());
   const float* Xkv = p.kv_from_norm ? N : X;
   for (int which = 0; which < 2; ++which) {
     load_tile<TM>(T, ld, which == 0 ? p.dk : p.dv, H, 0, H, row0, M);
     __syncthreads();
     wgrad_tile(T, ld, H, Xkv, ld, H, rows, p.gWin + (long long)(1 + which) * H * H, H);
     colsum_atomic(T, ld, H, rows, p.gbin + (1 + which) * H);
-    gemm_tile<TM, true>(T, ld, H, p.Win + (long long)(1 + which) * H * H, H, H, Ws, [&](int, int r, int col, float4 acc) {
+    gemm_stream<TM, true, WS_NST>(T, ld, ws, 1 + which, [&](int, int r, int col, float4 acc) {
       st4(D + r * ld + col, f4_add(acc, ld4(D + r * ld + col)));
     });
   }
-  if (p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, Ws);
+  if (p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, ws.scratch());
   tile_foreach4<TM>(H, [&](int r, int c) {
     if (row0 + r < M) {
       const long long gi = (long long)(row0 + r) * H + c;

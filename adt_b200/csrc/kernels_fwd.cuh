@@ -53,19 +53,28 @@ __global__ void __launch_bounds__(NT) pre_fwd_kernel(const float* __restrict__ x
   float* Ns = Xs + TM * ld;
   float* Ws = Ns + TM * ld;
   const int row0 = blockIdx.x * TM;
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{Win, H, H, H, 0};
+    wst.g[1] = GemmDesc{Win + (long long)H * H, H, 2 * H, H, 0};
+    wst.ng = 2;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
   load_tile<TM>(Xs, ld, x, H, 0, H, row0, M);
   __syncthreads();
   ln_tile<TM>(Xs, Ns, ld, H, ln_g, ln_b, 1e-8f, row0, M);
   __syncthreads();
   if (norm_out) store_tile<TM>(Ns, ld, norm_out, H, 0, H, row0, M);
-  gemm_tile<TM, false>(Ns, ld, H, Win, H, H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(Ns, ld, ws, 0, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
       const float4 b = *reinterpret_cast<const float4*>(bin + col);
       *reinterpret_cast<float4*>(q + (long long)(row0 + r) * H + col) = f4_scale(f4_add(a, b), qscale);
     }
   });
   const float* Akv = kv_from_norm ? Ns : Xs;
-  gemm_tile<TM, false>(Akv, ld, H, Win + (long long)H * H, H, 2 * H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(Akv, ld, ws, 1, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
       const float4 b = *reinterpret_cast<const float4*>(bin + H + col);
       float* dst = col < H ? (k + (long long)(row0 + r) * H + col) : (v + (long long)(row0 + r) * H + (col - H));
@@ -108,9 +117,18 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
   const long long seq_off = (long long)b * L * H + (long long)h * hd;
   const int Lk = mask_mode == 0 ? min(L, i0 + TM) : L;  // keys this tile can see
 
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{k + seq_off, H, Lk, hd, 0};
+    wst.g[1] = GemmDesc{v + seq_off, H, hd, Lk, 1};
+    wst.ng = 2;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
   load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
   __syncthreads();
-  gemm_tile<TM, false>(Qs, ldq, hd, k + seq_off, H, Lk, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) {
     *reinterpret_cast<float4*>(Ss + r * lds + col) = a;
   });
 
@@ -165,7 +183,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
-  gemm_tile<TM, true>(Ss, lds, Lk, v + seq_off, H, hd, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, true, WS_NST>(Ss, lds, ws, 1, [&](int, int r, int col, float4 a) {
     if (i0 + r < L) *reinterpret_cast<float4*>(ctx + seq_off + (long long)(i0 + r) * H + col) = a;
   });
 }
@@ -187,20 +205,30 @@ __global__ void __launch_bounds__(NT) mid_fwd_kernel(const float* __restrict__ c
   float* T2 = T1 + TM * ld;
   float* Ws = T2 + TM * ld;
   const int row0 = blockIdx.x * TM;
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{Wo1, H, H, H, 0};
+    wst.g[1] = GemmDesc{Win2, H, H, H, 0};
+    wst.g[2] = GemmDesc{Win2 + (long long)H * H, H, 2 * H, H, 0};
+    wst.ng = 3;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
   load_tile<TM>(T0, ld, ctx1, H, 0, H, row0, M);
   load_tile<TM>(T2, ld, feats, H, 0, H, row0, M);
   __syncthreads();
-  gemm_tile<TM, false>(T0, ld, H, Wo1, H, H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
     const float4 o = f4_add(a, *reinterpret_cast<const float4*>(bo1 + col));
     *reinterpret_cast<float4*>(T1 + r * ld + col) = o;
     if (a_out && row0 + r < M) *reinterpret_cast<float4*>(a_out + (long long)(row0 + r) * H + col) = o;
   });
-  gemm_tile<TM, false>(T1, ld, H, Win2, H, H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
     if (row0 + r < M)
       *reinterpret_cast<float4*>(q2 + (long long)(row0 + r) * H + col) =
           f4_scale(f4_add(a, *reinterpret_cast<const float4*>(bin2 + col)), qscale);
   });
-  gemm_tile<TM, false>(T2, ld, H, Win2 + (long long)H * H, H, 2 * H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
       const float4 o = f4_add(a, *reinterpret_cast<const float4*>(bin2 + H + col));
       float* dst = col < H ? (k2 + (long long)(row0 + r) * H + col) : (v2 + (long long)(row0 + r) * H + (col - H));
@@ -244,6 +272,16 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
   float* T2 = T1 + TM * ld;
   float* Ws = T2 + TM * ld;
   const int row0 = blockIdx.x * TM;
+  __shared__ WStreamState wst;
+  if (threadIdx.x == 0) {
+    wst.g[0] = GemmDesc{p.Wo, H, H, H, 0};
+    wst.g[1] = GemmDesc{p.C1, H, H, H, 0};
+    wst.g[2] = GemmDesc{p.C2, H, H, H, 0};
+    wst.ng = 3;
+  }
+  __syncthreads();
+  WStream<WS_NST> ws;
+  ws.start(&wst, Ws);
   load_tile<TM>(T0, ld, p.ctx, H, 0, H, row0, M);
   if (!IS_DEC) {
     load_tile<TM>(T2, ld, p.resid, H, 0, H, row0, M);
@@ -251,7 +289,7 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     ln_tile<TM>(T2, T1, ld, H, p.ln1_g, p.ln1_b, 1e-8f, row0, M);
   }
   __syncthreads();
-  gemm_tile<TM, false>(T0, ld, H, p.Wo, H, H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
     float4 o = f4_add(a, *reinterpret_cast<const float4*>(p.bo + col));
     if (!IS_DEC) o = f4_add(o, *reinterpret_cast<const float4*>(T1 + r * ld + col));
     *reinterpret_cast<float4*>(T1 + r * ld + col) = o;
@@ -262,7 +300,7 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     // hd, logits parked in the (idle) weight staging area, then one thread per (row, c) log-softmax.
     if (p.rec || p.acc) {
       const int nh = p.nh, hd = H / nh, n2 = nh * nh;
-      float* lgs = Ws;
+      float* lgs = ws.scratch();
       for (int i = threadIdx.x; i < TM * n2; i += NT) {
         const int r = i / n2, cj = i - r * n2, c = cj / nh, j = cj - c * nh;
         const float* xr = T0 + r * ld + c * hd;
@@ -296,14 +334,14 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     ln_tile<TM>(T1, T1, ld, H, p.ln2_g, p.ln2_b, 1e-8f, row0, M);
     __syncthreads();
   }
-  gemm_tile<TM, false>(T1, ld, H, p.C1, H, H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
     float4 h1 = f4_add(a, *reinterpret_cast<const float4*>(p.c1 + col));
     if (p.h1_save && row0 + r < M) *reinterpret_cast<float4*>(p.h1_save + (long long)(row0 + r) * H + col) = h1;
     if (p.drop1.enabled) h1 = f4_mul(h1, drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)(row0 + r) * H + col) >> 2));
     *reinterpret_cast<float4*>(T2 + r * ld + col) = make_float4(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), fmaxf(h1.z, 0.f), fmaxf(h1.w, 0.f));
   });
   double sq = 0.0;
-  gemm_tile<TM, false>(T2, ld, H, p.C2, H, H, Ws, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
     if (row0 + r >= M) return;
     float4 h2 = f4_add(a, *reinterpret_cast<const float4*>(p.c2 + col));
     if (p.drop2.enabled) h2 = f4_mul(h2, drop_mul4(p.drop2, (p.drop2.base + (unsigned long long)(row0 + r) * H + col) >> 2));

@@ -48,11 +48,11 @@ class FusedTrainer:
         return self.eng._stream()
 
     # ------------------------------------------------------------------------------------------
-    def _step_impl(self, seq, dec, pos, neg):
-        """the device work of one step on int32 device ids; every launch goes to the current stream (capturable)."""
-        eng, m = self.eng, self.model
+    # the step is three stream-ordered segments; with world > 1 the two NCCL all-reduces sit BETWEEN them (issued
+    # eagerly), so each segment can be captured into its own CUDA graph without capturing a collective
+    def _seg_forward(self, seq, dec, pos, neg):
+        eng = self.eng
         B, Lq = seq.shape
-        grads = {n: eng.grad_view(n) for n, _ in eng.order}
         self.step_dev.add_(1)
         eng.gflat.zero_()
         cur = torch.cuda.current_stream()
@@ -62,12 +62,16 @@ class FusedTrainer:
         with torch.cuda.stream(self.side):
             eng.sort_ids(seq, dec, pos, neg, w)
         w = eng.forward(seq, dec, pos, neg, training=True, fused_loss=True)
-        if self.world > 1:
-            torch.distributed.all_reduce(w["acc"], group=self.pg)
         cur.wait_stream(self.side)
+        return w
+
+    def _seg_backward(self, seq, dec, pos, neg, w):
+        eng = self.eng
+        grads = {n: eng.grad_view(n) for n, _ in eng.order}
         eng.backward(seq, dec, pos, neg, w, grads, lambdas1=self.l1, lambdas2=self.l2)
-        if self.world > 1:
-            torch.distributed.all_reduce(eng.gflat, group=self.pg)
+
+    def _seg_optimizer(self, w):
+        eng, m = self.eng, self.model
         nl = m.num_layers
         acc = w["acc"]
         s = self._stream()
@@ -75,7 +79,7 @@ class FusedTrainer:
         if self.use_norm_decay and self.wd != 0.0:
             normsq = acc[3 + 2 * nl:]
             L.check(self.lib.adt_sumsq(L.ptr(E), ctypes.c_int64(E.numel()), L.ptr(normsq), s), "adt_sumsq")
-            L.check(self.lib.adt_norm_decay_grad(L.ptr(grads["item_emb.weight"]), L.ptr(E), ctypes.c_int64(E.numel()),
+            L.check(self.lib.adt_norm_decay_grad(L.ptr(eng.grad_view("item_emb.weight")), L.ptr(E), ctypes.c_int64(E.numel()),
                                                  ctypes.c_float(self.wd), L.ptr(normsq), s), "adt_norm_decay_grad")
         gn = acc[4 + 2 * nl:]
         n = eng.gflat.numel()
@@ -84,6 +88,16 @@ class FusedTrainer:
                    beta2=self.betas[1], eps=self.eps, weight_decay=self.adam_wd, step=0, max_norm=self.clip, gnormsq=gn,
                    step_dev=self.step_dev[1:])
         L.check(self.lib.adt_adam(ctypes.byref(a), s), "adt_adam")
+
+    def _step_impl(self, seq, dec, pos, neg):
+        """eager step on int32 device ids; every launch goes to the current stream."""
+        w = self._seg_forward(seq, dec, pos, neg)
+        if self.world > 1:
+            torch.distributed.all_reduce(w["acc"], group=self.pg)
+        self._seg_backward(seq, dec, pos, neg, w)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
+        self._seg_optimizer(w)
         return w
 
     def _prepare(self, B, Lq):
@@ -131,18 +145,35 @@ class FusedTrainer:
                 eng.pflat.copy_(snap[0]); eng.adam_m.copy_(snap[1]); eng.adam_v.copy_(snap[2])
                 self.step_dev.copy_(saved)
             torch.cuda.current_stream().wait_stream(cap)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                w = self._step_impl(*static)
+            w = eng.workspace(B, Lq)
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_impl(*static)
+                graphs = [g]
+            else:
+                graphs = []
+                for seg in (lambda: self._seg_forward(*static), lambda: self._seg_backward(*static, w), lambda: self._seg_optimizer(w)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        seg()
+                    graphs.append(g)
             self.step_dev.copy_(saved)   # capture does not execute, but keep the counters explicit
-            self._graphs[key] = (g, static, w)
-        g, static, w = self._graphs[key]
+            self._graphs[key] = (graphs, static, w)
+        graphs, static, w = self._graphs[key]
         for dst, src in zip(static, (seq, dec, pos, neg)):
             if isinstance(src, torch.Tensor):
                 dst.copy_(src, non_blocking=True)
             else:
                 dst.copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32)), non_blocking=True)
-        g.replay()
+        if len(graphs) == 1:
+            graphs[0].replay()
+        else:
+            graphs[0].replay()
+            torch.distributed.all_reduce(w["acc"], group=self.pg)
+            graphs[1].replay()
+            torch.distributed.all_reduce(eng.gflat, group=self.pg)
+            graphs[2].replay()
         self._w = w
         return w
 
