@@ -146,6 +146,77 @@ def run(name, B, L, H, nh, nl, I, p, lambdas1, lambdas2, wd, seed=23, dtype=torc
     print(name, "loss", float(loss), "gnorm", float(gnorm), "sites", inj.k)
 
 
+def run_super(name, B, L, H, nh, nl, I, p, cand, wd, seed=23):
+    """SuperSASRecModel (sasrec/supersasrec.py) + the warm-up step of sasrec/evolution.py:282-316."""
+    sys.path.insert(0, REF)
+    import supersasrec as refsuper  # noqa
+    rec_choice = [0, 0.0001, 0.0005, 0.001, 0.005, 0.01]     # evolution.py:95-96
+    ind_choice = [0, 0.0001, 0.0005, 0.001, 0.0015, 0.002]
+    torch.manual_seed(seed)
+    args = types.SimpleNamespace(device="cpu", num_heads=nh, maxlen=L, num_layers=nl, hidden_units=H, dropout=p)
+    m = refsuper.SuperSASRecModel(100, I, rec_choice, ind_choice, args)
+    for _, prm in m.named_parameters():
+        try:
+            torch.nn.init.xavier_normal_(prm.data)
+        except Exception:
+            pass
+    g = torch.Generator().manual_seed(seed + 1)
+    for _, prm in m.named_parameters():
+        if prm.dim() == 1:
+            prm.data.add_(0.1 * torch.randn(prm.shape, generator=g))
+    rng = np.random.default_rng(seed)
+    seq, dec, pos, neg = synth_batch(rng, B, L, I)
+    cand = np.array(cand)
+    m.set_choice(cand)
+    rec_w, ind_w = [cand[2 * i] for i in range(nl)], [cand[2 * i + 1] for i in range(nl)]
+    sd0 = {k: v.detach().clone().numpy() for k, v in m.state_dict().items()}
+    kinds = ["blh"] + ["attn", "bhl", "bhl"] * (4 * nl) + ["blh"] + ["attn", "attn", "lhb", "lhb"] * (4 * nl)
+    inj = DropInjector(B, L, H, nh, nl, p, seed=1234, step=7)
+    inj.kinds = kinds
+    orig = F.dropout
+    F.dropout = inj
+    try:
+        m.train()
+        pl, nlg, enc_in, dec_out, rec = m(None, seq, dec, pos, neg)
+    finally:
+        F.dropout = orig
+    bce = torch.nn.BCEWithLogitsLoss()
+    idx = np.where(pos != 0)
+    loss = bce(pl[idx], torch.ones_like(pl)[idx]) + bce(nlg[idx], torch.zeros_like(nlg)[idx])
+    for i in range(len(enc_in)):
+        loss = loss + rec_w[i] * F.mse_loss(enc_in[i], dec_out[i])
+    label = torch.tile(torch.arange(nh), [B * L, 1])
+    for l in range(len(rec)):
+        loss = loss + ind_w[i] * F.nll_loss(rec[l].view(B * L, nh, nh), label)   # stale i (evolution.py:313)
+    opt = torch.optim.Adam(m.parameters(), lr=0.001, betas=(0.9, 0.999), weight_decay=wd)
+    opt.zero_grad()
+    loss.backward()
+    gnorm = torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+    grads = {k: prm.grad.detach().clone().numpy() for k, prm in m.named_parameters() if prm.grad is not None}
+    opt.step()
+    m.eval()
+    with torch.no_grad():
+        cnd = rng.integers(1, I + 1, size=(B, 11))
+        pred_c = m.predict(None, seq, cnd).numpy()
+    out = {"seq": seq, "dec": dec, "pos": pos, "neg": neg, "cand_items": cnd, "cfg": np.array([B, L, H, nh, nl, I]), "p": np.array(p),
+           "drop_seed": np.array(1234), "drop_step": np.array(7), "choice": cand, "wd": np.array(wd),
+           "shared_idx": np.array(m.encoder.shared_idx), "shared_weights": np.array(m.encoder.shared_weights),
+           "pos_logits": pl.detach().numpy(), "neg_logits": nlg.detach().numpy(), "loss": loss.detach().numpy(), "gnorm": gnorm.numpy(),
+           "pred_cand": pred_c, "n_grads": np.array(len(grads))}
+    for i in range(nl):
+        out[f"enc_in{i}"] = enc_in[i].detach().numpy()
+        out[f"dec_out{i}"] = dec_out[i].detach().numpy()
+        out[f"rec_ind{i}"] = rec[i].detach().numpy()
+    for k, v in sd0.items():
+        out["sd0/" + k] = v.astype(np.float16) if k not in grads and v.ndim > 1 else v   # inactive blocks: names/shapes only matter
+    for k, v in grads.items():
+        out["grad/" + k] = v
+        out["sd1/" + k] = m.state_dict()[k].detach().numpy()
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, f"super_{name}.npz"), **out)
+    print("super", name, "loss", float(loss), "gnorm", float(gnorm), "sites", inj.k, "grads", len(grads), "idx", m.encoder.shared_idx)
+
+
 def lambdas_known_answer():
     """candidates_to_lambdas.py:11-24 run as __main__ -> its printed output is the only
     golden vector the reference itself carries for this path (pins _get_weight)."""
@@ -161,4 +232,5 @@ if __name__ == "__main__":
     run("tiny_p5", B=4, L=8, H=16, nh=2, nl=2, I=30, p=0.5, lambdas1=[0.0124, 0.122], lambdas2=[0.0001, 0.05], wd=1e-4)
     run("c2mini_p5", B=6, L=50, H=64, nh=2, nl=2, I=200, p=0.5, lambdas1=[0.0124, 0.122], lambdas2=[0.0001, 0.0], wd=1e-4)
     run("h128_p2", B=3, L=20, H=128, nh=4, nl=1, I=60, p=0.2, lambdas1=[0.104292], lambdas2=[0.100833], wd=1e-3)
+    run_super("tiny_p5", B=4, L=8, H=16, nh=2, nl=2, I=30, p=0.5, cand=[3e-4, 1.2e-3, 2e-3, 5e-5], wd=1e-4)
     lambdas_known_answer()

@@ -155,7 +155,13 @@ def _gloo_worker(rank, world, port, ret):
         total = total + l2[nl - 1] * acc[3 + nl + l] / (Mg * nh)
     total = total + wd * torch.norm(sd["item_emb.weight"]).double()
     ok2 = abs(float(total) - float(gd["loss"])) / abs(float(gd["loss"])) < 1e-5
-    ret[rank] = (ok1, ok2)
+    # (3) evolution: one candidate per rank, gathered fitness identical on every rank and equal to the serial result
+    from adt_b200.evolution import evaluate_population
+    cands = [np.array([0.1 * c, 0.05 * c + 0.2]) for c in range(5)]
+    fit = lambda c: (float(c.sum()), float(c[0] * 2), float(c[1] - 1))
+    res = evaluate_population(cands, fit)
+    ok3 = bool(np.allclose(res, np.array([fit(c) for c in cands])))
+    ret[rank] = (ok1, ok2, ok3)
     dist.destroy_process_group()
 
 
@@ -165,4 +171,4 @@ def test_world_size_2_gloo_sharded_eval_and_dp_loss():
     ret = mgr.dict()
     port = 29500 + os.getpid() % 2000
     mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
-    assert dict(ret) == {0: (True, True), 1: (True, True)}
+    assert dict(ret) == {0: (True, True, True), 1: (True, True, True)}

@@ -1,0 +1,92 @@
+"""Supernet: block selection (CPU) and forward/backward parity against a fixture produced by
+the unmodified reference SuperSASRecModel + the evolution.py warm-up step (GPU)."""
+import os
+import types
+import numpy as np
+import pytest
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "super_tiny_p5.npz")
+REC = [0, 0.0001, 0.0005, 0.001, 0.005, 0.01]
+IND = [0, 0.0001, 0.0005, 0.001, 0.0015, 0.002]
+
+
+def _load():
+    z = np.load(GOLDEN)
+    return {k: z[k] for k in z.files}
+
+
+def test_set_choice_matches_reference_selection():
+    from adt_b200.supernet import get_shared, get_position
+    g = _load()
+    idx, w = get_shared(g["choice"], REC, IND)
+    assert np.array_equal(np.array(idx), g["shared_idx"])
+    assert np.allclose(np.array(w), g["shared_weights"], rtol=0, atol=1e-15)
+    assert idx == [(9, 15, 10, 16), (18, 24, 19, 25)]            # SURVEY section 4 probe
+    with pytest.raises(IndexError):                               # quirk B9: lambda >= max(choice) raises
+        get_position(0.01, REC)
+
+
+def test_supernet_state_dict_names():
+    from adt_b200.supernet import SuperSASRecModel
+    g = _load()
+    B, L, H, nh, nl, I = [int(v) for v in g["cfg"]]
+    args = types.SimpleNamespace(device="cpu", num_heads=nh, maxlen=L, num_layers=nl, hidden_units=H, dropout=0.5)
+    m = SuperSASRecModel(100, I, REC, IND, args)
+    ref_keys = [k[4:] for k in g if k.startswith("sd0/")]
+    assert list(m.state_dict().keys()) == ref_keys
+    assert all(tuple(m.state_dict()[k].shape) == g["sd0/" + k].shape for k in ref_keys)
+
+
+@pytest.mark.gpu
+def test_supernet_forward_backward_parity():
+    import torch.nn.functional as F
+    from adt_b200.supernet import SuperSASRecModel
+    from adt_b200.testing import rel_err
+    g = _load()
+    B, L, H, nh, nl, I = [int(v) for v in g["cfg"]]
+    args = types.SimpleNamespace(device="cuda", num_heads=nh, maxlen=L, num_layers=nl, hidden_units=H, dropout=float(g["p"]))
+    m = SuperSASRecModel(100, I, REC, IND, args)
+    m.load_state_dict({k[4:]: torch.from_numpy(np.array(v)).float() for k, v in g.items() if k.startswith("sd0/")})
+    m = m.cuda().train()
+    m.drop_seed, m.drop_step = int(g["drop_seed"]), int(g["drop_step"])
+    m.set_choice(g["choice"])
+    pos = g["pos"]
+    pl, nlg, enc_in, dec_out, rec = m(None, g["seq"], g["dec"], pos, g["neg"])
+    assert rel_err(pl, g["pos_logits"]) < 5e-5 and rel_err(nlg, g["neg_logits"]) < 5e-5
+    for i in range(nl):
+        assert rel_err(enc_in[i], g[f"enc_in{i}"]) < 5e-5
+        assert rel_err(dec_out[i], g[f"dec_out{i}"]) < 5e-5
+        assert rel_err(rec[i], g[f"rec_ind{i}"]) < 5e-5
+    # the warm-up loss lines of sasrec/evolution.py:296-316 on our outputs
+    cand = g["choice"]
+    rec_w, ind_w = [cand[2 * i] for i in range(nl)], [cand[2 * i + 1] for i in range(nl)]
+    bce = torch.nn.BCEWithLogitsLoss()
+    idx = np.where(pos != 0)
+    loss = bce(pl[idx], torch.ones_like(pl)[idx]) + bce(nlg[idx], torch.zeros_like(nlg)[idx])
+    for i in range(nl):
+        loss = loss + rec_w[i] * F.mse_loss(enc_in[i], dec_out[i])
+    label = torch.tile(torch.arange(nh), [B * L, 1]).cuda()
+    for l in range(nl):
+        loss = loss + ind_w[i] * F.nll_loss(rec[l].view(B * L, nh, nh), label)
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    opt = torch.optim.Adam(m.parameters(), lr=0.001, betas=(0.9, 0.999), weight_decay=float(g["wd"]))
+    opt.zero_grad()
+    loss.backward()
+    gn = torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+    assert abs(float(gn) - float(g["gnorm"])) / float(g["gnorm"]) < 1e-4
+    n_grads = 0
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            assert "grad/" + k not in g, k          # inactive candidate blocks get no gradient (Adam skips them)
+        else:
+            n_grads += 1
+            assert rel_err(p.grad, g["grad/" + k]) < 1e-3, k
+    assert n_grads == int(g["n_grads"])
+    opt.step()
+    for k, p in m.named_parameters():
+        if "sd1/" + k in g:
+            big = np.abs(g["grad/" + k]) > 1e-5
+            assert np.abs(p.detach().cpu().numpy() - g["sd1/" + k])[big].max(initial=0.0) < 5e-6, k
+    m.eval()
+    assert rel_err(m.predict(None, g["seq"], g["cand_items"]), g["pred_cand"]) < 5e-5
