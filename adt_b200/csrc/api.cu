@@ -119,26 +119,23 @@ static int check_dims(int B, int L, int H, int nh) {
   return ADT_OK;
 }
 
-#define LAUNCH_TM(tm, KERN, grid, smem, stream, ...)                                   \
-  do {                                                                                 \
-    if ((tm) == 64) {                                                                  \
-      set_smem(KERN<64>, smem);                                                        \
-      KERN<64><<<grid, NT, smem, stream>>>(__VA_ARGS__);                               \
-    } else {                                                                           \
-      set_smem(KERN<32>, smem);                                                        \
-      KERN<32><<<grid, NT, smem, stream>>>(__VA_ARGS__);                               \
-    }                                                                                  \
+#define LAUNCH_ONE(K, grid, smem, stream, ...) \
+  do { set_smem(K, smem); K<<<grid, NT, smem, stream>>>(__VA_ARGS__); } while (0)
+
+#define LAUNCH_TM(tm, mma, KERN, grid, smem, stream, ...)                                        \
+  do {                                                                                           \
+    if ((tm) == 64 && !(mma)) LAUNCH_ONE((KERN<64, false>), grid, smem, stream, __VA_ARGS__);     \
+    else if ((tm) == 64) LAUNCH_ONE((KERN<64, true>), grid, smem, stream, __VA_ARGS__);           \
+    else if (!(mma)) LAUNCH_ONE((KERN<32, false>), grid, smem, stream, __VA_ARGS__);              \
+    else LAUNCH_ONE((KERN<32, true>), grid, smem, stream, __VA_ARGS__);                           \
   } while (0)
 
-#define LAUNCH_TM2(tm, KERN, FLAG, grid, smem, stream, ...)                            \
-  do {                                                                                 \
-    if ((tm) == 64) {                                                                  \
-      set_smem(KERN<64, FLAG>, smem);                                                  \
-      KERN<64, FLAG><<<grid, NT, smem, stream>>>(__VA_ARGS__);                         \
-    } else {                                                                           \
-      set_smem(KERN<32, FLAG>, smem);                                                  \
-      KERN<32, FLAG><<<grid, NT, smem, stream>>>(__VA_ARGS__);                         \
-    }                                                                                  \
+#define LAUNCH_TM2(tm, mma, KERN, FLAG, grid, smem, stream, ...)                                 \
+  do {                                                                                           \
+    if ((tm) == 64 && !(mma)) LAUNCH_ONE((KERN<64, FLAG, false>), grid, smem, stream, __VA_ARGS__); \
+    else if ((tm) == 64) LAUNCH_ONE((KERN<64, FLAG, true>), grid, smem, stream, __VA_ARGS__);     \
+    else if (!(mma)) LAUNCH_ONE((KERN<32, FLAG, false>), grid, smem, stream, __VA_ARGS__);        \
+    else LAUNCH_ONE((KERN<32, FLAG, true>), grid, smem, stream, __VA_ARGS__);                     \
   } while (0)
 
 extern "C" int adt_version(void) { return 100; }
@@ -158,21 +155,23 @@ extern "C" int adt_embed_fwd(const adt_embed_fwd_args* a, adt_stream_t s_) {
 
 // shared launch helpers -------------------------------------------------------------------------------------
 static int launch_pre_fwd(const float* x, const float* ln_w, const float* ln_b, const adt_mha_w& w, float* q, float* k, float* v,
-                          float* norm_out, int M, int H, int nh, int kv_from_norm, cudaStream_t s) {
+                          float* norm_out, int M, int H, int nh, int kv_from_norm, int mma, cudaStream_t s) {
   size_t smem;
-  const int tm = pick_tm(2 * (size_t)(H + 4), &smem);
+  const int pad = mma ? 8 : 4;
+  const int tm = pick_tm(2 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "pre_fwd: tile does not fit shared memory");
   const float qscale = 1.0f / sqrtf((float)(H / nh));
   const int grid = (M + tm - 1) / tm;
   TIMED("pre_fwd", s);
-  LAUNCH_TM(tm, pre_fwd_kernel, grid, smem, s, x, ln_w, ln_b, w.in_w, w.in_b, q, k, v, norm_out, M, H, qscale, kv_from_norm);
+  LAUNCH_TM(tm, mma, pre_fwd_kernel, grid, smem, s, x, ln_w, ln_b, w.in_w, w.in_b, q, k, v, norm_out, M, H, qscale, kv_from_norm);
   return check_launch("pre_fwd");
 }
 
 static int launch_attn_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, const int* key_ids, int B, int L,
-                           int H, int nh, int mask_mode, const adt_dropout& d, int training, cudaStream_t s) {
+                           int H, int nh, int mask_mode, const adt_dropout& d, int training, int mma, cudaStream_t s) {
   const int hd = H / nh;
-  const size_t rowf = (size_t)(hd + 4) + (size_t)(((L + 3) & ~3) + 4);
+  const int pad = mma ? 8 : 4;
+  const size_t rowf = (size_t)(hd + pad) + (size_t)(((L + 3) & ~3) + pad);
   size_t smem;
   int tm = pick_tm(rowf, &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_fwd: tile does not fit shared memory");
@@ -181,15 +180,16 @@ static int launch_attn_fwd(const float* q, const float* k, const float* v, float
   if (!training) dd.enabled = 0;
   dim3 grid((L + tm - 1) / tm, nh, B);
   TIMED("attn_fwd", s);
-  LAUNCH_TM(tm, attn_fwd_kernel, grid, smem, s, q, k, v, ctx, lse, key_ids, L, H, nh, mask_mode, mk_drop(dd));
+  LAUNCH_TM(tm, mma, attn_fwd_kernel, grid, smem, s, q, k, v, ctx, lse, key_ids, L, H, nh, mask_mode, mk_drop(dd));
   return check_launch("attn_fwd");
 }
 
 static int launch_attn_bwd(const float* q, const float* k, const float* v, const float* dctx, const float* lse, const int* key_ids,
                            float* dq, float* dk, float* dv, int B, int L, int H, int nh, int mask_mode, const adt_dropout& d,
-                           cudaStream_t s) {
+                           int mma, cudaStream_t s) {
   const int hd = H / nh;
-  const size_t rowf = 2 * (size_t)(hd + 4) + 2 * (size_t)(((L + 3) & ~3) + 4);
+  const int pad = mma ? 8 : 4;
+  const size_t rowf = 2 * (size_t)(hd + pad) + 2 * (size_t)(((L + 3) & ~3) + pad);
   size_t smem;
   int tm = pick_tm(rowf, &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_bwd: tile does not fit shared memory");
@@ -200,7 +200,7 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
     cudaMemsetAsync(dv, 0, (size_t)B * L * H * sizeof(float), s);
   }
   TIMED("attn_bwd", s);
-  LAUNCH_TM(tm, attn_bwd_kernel, grid, smem, s, q, k, v, dctx, lse, key_ids, dq, dk, dv, L, H, nh, mask_mode, mk_drop(d));
+  LAUNCH_TM(tm, mma, attn_bwd_kernel, grid, smem, s, q, k, v, dctx, lse, key_ids, dq, dk, dv, L, H, nh, mask_mode, mk_drop(d));
   return check_launch("attn_bwd");
 }
 
@@ -215,8 +215,9 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   cudaStream_t s = (cudaStream_t)s_;
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
-  if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, s)) return e;
-  if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, s))
+  const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
+  if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, a->precision, s)) return e;
+  if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))
     return e;
   PostFwdArgs p;
   memset(&p, 0, sizeof(p));
@@ -229,9 +230,9 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training));
   p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
   size_t smem;
-  const int tm = pick_tm(3 * (size_t)(H + 4), &smem);
+  const int tm = pick_tm(3 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_fwd: tile does not fit shared memory");
-  { TIMED("enc_post_fwd", s); LAUNCH_TM2(tm, post_fwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
+  { TIMED("enc_post_fwd", s); LAUNCH_TM2(tm, mma, post_fwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
   return check_launch("enc post_fwd");
 }
 
@@ -239,6 +240,7 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   cudaStream_t s = (cudaStream_t)s_;
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
+  const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   PostBwdArgs p;
   memset(&p, 0, sizeof(p));
   p.dout = a->dout; p.ids = a->ids; p.ctx = a->ctx; p.u = a->y; p.h1 = a->h1;
@@ -251,12 +253,12 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
   size_t smem;
-  int tm = pick_tm(4 * (size_t)(H + 4), &smem);
+  int tm = pick_tm(4 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
-  { TIMED("enc_post_bwd", s); LAUNCH_TM2(tm, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
+  { TIMED("enc_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
   if (int e = check_launch("enc post_bwd")) return e;
   if (int e = launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
-                              a->drop_attn, s))
+                              a->drop_attn, a->precision, s))
     return e;
   PreBwdArgs r;
   memset(&r, 0, sizeof(r));
@@ -264,8 +266,8 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   r.ln_g = a->ln1_w; r.ln_b = a->ln1_b; r.Win = a->attn.in_w; r.dx = a->dx;
   r.gWin = a->g_attn.in_w; r.gbin = a->g_attn.in_b; r.gln_g = a->g_ln1_w; r.gln_b = a->g_ln1_b;
   r.M = M; r.H = H; r.qscale = 1.0f / sqrtf((float)(H / a->nh)); r.kv_from_norm = 0;
-  tm = pick_tm(4 * (size_t)(H + 4), &smem);
-  { TIMED("pre_bwd", s); LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
+  tm = pick_tm(4 * (size_t)(H + pad), &smem);
+  { TIMED("pre_bwd", s); LAUNCH_TM(tm, mma, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
   return check_launch("enc pre_bwd");
 }
 
@@ -274,18 +276,19 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   cudaStream_t s = (cudaStream_t)s_;
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
-  if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, s)) return e;
-  if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, s))
+  const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
+  if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, a->precision, s)) return e;
+  if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
     return e;
   size_t smem;
-  int tm = pick_tm(3 * (size_t)(H + 4), &smem);
+  int tm = pick_tm(3 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_fwd: tile does not fit shared memory");
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
   { TIMED("mid_fwd", s);
-  LAUNCH_TM(tm, mid_fwd_kernel, (M + tm - 1) / tm, smem, s, a->ctx1, a->feats, a->slf.out_w, a->slf.out_b, a->enc.in_w, a->enc.in_b, a->a,
+  LAUNCH_TM(tm, mma, mid_fwd_kernel, (M + tm - 1) / tm, smem, s, a->ctx1, a->feats, a->slf.out_w, a->slf.out_b, a->enc.in_w, a->enc.in_b, a->a,
             a->q2, a->k2, a->v2, M, H, qscale); }
   if (int e = check_launch("mid_fwd")) return e;
-  if (int e = launch_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, s))
+  if (int e = launch_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, a->precision, s))
     return e;
   PostFwdArgs p;
   memset(&p, 0, sizeof(p));
@@ -295,7 +298,7 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training));
   p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
-  { TIMED("dec_post_fwd", s); LAUNCH_TM2(tm, post_fwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
+  { TIMED("dec_post_fwd", s); LAUNCH_TM2(tm, mma, post_fwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
   return check_launch("dec post_fwd");
 }
 
@@ -303,6 +306,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   cudaStream_t s = (cudaStream_t)s_;
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
+  const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
   PostBwdArgs p;
   memset(&p, 0, sizeof(p));
@@ -313,13 +317,13 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
   size_t smem;
-  int tm = pick_tm(4 * (size_t)(H + 4), &smem);
+  int tm = pick_tm(4 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
-  { TIMED("dec_post_bwd", s); LAUNCH_TM2(tm, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
+  { TIMED("dec_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
   if (int e = check_launch("dec post_bwd")) return e;
   // cross attention (keys/values from the encoder features)
   if (int e = launch_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,
-                              a->drop_enc, s))
+                              a->drop_enc, a->precision, s))
     return e;
   MidBwdArgs m;
   memset(&m, 0, sizeof(m));
@@ -327,12 +331,12 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   m.Wo1 = a->slf.out_w; m.Win2 = a->enc.in_w; m.dfeats = a->dfeats; m.dctx1 = a->dctx;
   m.gWo1 = a->g_slf.out_w; m.gbo1 = a->g_slf.out_b; m.gWin2 = a->g_enc.in_w; m.gbin2 = a->g_enc.in_b;
   m.M = M; m.H = H; m.qscale = qscale;
-  tm = pick_tm(3 * (size_t)(H + 4) + (size_t)(2 * H + 4), &smem);
+  tm = pick_tm(3 * (size_t)(H + pad) + (size_t)(2 * H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_bwd: tile does not fit shared memory");
-  { TIMED("mid_bwd", s); LAUNCH_TM(tm, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m); }
+  { TIMED("mid_bwd", s); LAUNCH_TM(tm, mma, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m); }
   if (int e = check_launch("mid_bwd")) return e;
   if (int e = launch_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
-                              a->drop_slf, s))
+                              a->drop_slf, a->precision, s))
     return e;
   PreBwdArgs r;
   memset(&r, 0, sizeof(r));
@@ -340,8 +344,8 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   r.ln_g = a->ln_w; r.ln_b = a->ln_b; r.Win = a->slf.in_w; r.dx = a->dx;
   r.gWin = a->g_slf.in_w; r.gbin = a->g_slf.in_b; r.gln_g = a->g_ln_w; r.gln_b = a->g_ln_b;
   r.M = M; r.H = H; r.qscale = qscale; r.kv_from_norm = 1;
-  tm = pick_tm(4 * (size_t)(H + 4), &smem);
-  { TIMED("pre_bwd", s); LAUNCH_TM(tm, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
+  tm = pick_tm(4 * (size_t)(H + pad), &smem);
+  { TIMED("pre_bwd", s); LAUNCH_TM(tm, mma, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
   return check_launch("dec pre_bwd");
 }
 

@@ -7,6 +7,7 @@
 // double-buffered cp.async staging area.  All arithmetic is fp32 (the reference
 // is fp32 end to end) with fp32 FFMA register tiles.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,8 +16,10 @@ namespace adt {
 constexpr int NT = 256;        // threads per CTA for all row-tile kernels
 constexpr int CH = 64;         // weight chunk edge (rows and cols)
 constexpr int CHP = CH + 4;    // padded chunk row stride in floats (272 B: 16B aligned, LDS.128 conflict free)
+constexpr int CHPB = CH + 8;   // chunk row stride of K-major chunks in bf16-MMA mode (288 B: LDS.64 fragment loads conflict free)
 constexpr int WS_NST = 2;                // depth of the weight-chunk ring
-constexpr int WS_FLOATS = WS_NST * CH * CHP;  // staging area
+constexpr int WS_SLOT = CH * CHPB;       // floats per ring slot (large enough for both strides)
+constexpr int WS_FLOATS = WS_NST * WS_SLOT;  // staging area
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 dropout (must match oracle/philox.py bit for bit)
@@ -234,7 +237,7 @@ __device__ __forceinline__ void ln_bwd_tile(const float* __restrict__ X, const f
 // PERM: store global chunk row n at smem row (n>>2) + 16*(n&3) so that the NT micro-kernel's thread tx
 //       reads rows tx+16j (conflict free) while owning the 4 CONTIGUOUS output columns 4tx..4tx+3.
 // ---------------------------------------------------------------------------------------------
-template <bool PERM>
+template <bool PERM, int STRIDE = CHP>
 __device__ __forceinline__ void stage_chunk(float* __restrict__ buf, const float* __restrict__ G, long long ldg, int r0, int c0,
                                             int nr, int nc) {
 #pragma unroll
@@ -244,7 +247,7 @@ __device__ __forceinline__ void stage_chunk(float* __restrict__ buf, const float
     const bool ok = (r < nr) && (4 * c4 < nc);
     const int rs = PERM ? ((r >> 2) + 16 * (r & 3)) : r;
     const float* src = ok ? (G + (long long)(r0 + r) * ldg + c0 + 4 * c4) : G;
-    cp_async16(buf + rs * CHP + 4 * c4, src, ok);
+    cp_async16(buf + rs * STRIDE + 4 * c4, src, ok);
   }
 }
 
@@ -371,7 +374,7 @@ struct WStreamState {
   int ng;
 };
 
-template <int NST>
+template <int NST, bool MMA = false>
 struct WStream {
   WStreamState* st;   // shared memory
   float* bufs;        // NST * CH * CHP floats
@@ -382,9 +385,13 @@ struct WStream {
       const GemmDesc d = st->g[next_g];
       const int noc = (d.Nout + CH - 1) / CH, nrc = (d.Kred + CH - 1) / CH;
       const int oc = next_t / nrc, rc = next_t - oc * nrc;
-      float* buf = bufs + slot_issue * CH * CHP;
-      if (!d.nn) stage_chunk<true>(buf, d.W, d.ldw, oc * CH, rc * CH, min(CH, d.Nout - oc * CH), min(CH, d.Kred - rc * CH));
-      else stage_chunk<false>(buf, d.W, d.ldw, rc * CH, oc * CH, min(CH, d.Kred - rc * CH), min(CH, d.Nout - oc * CH));
+      float* buf = bufs + slot_issue * WS_SLOT;
+      if (!d.nn) {
+        if (MMA) stage_chunk<false, CHPB>(buf, d.W, d.ldw, oc * CH, rc * CH, min(CH, d.Nout - oc * CH), min(CH, d.Kred - rc * CH));
+        else stage_chunk<true, CHP>(buf, d.W, d.ldw, oc * CH, rc * CH, min(CH, d.Nout - oc * CH), min(CH, d.Kred - rc * CH));
+      } else {
+        stage_chunk<false, CHP>(buf, d.W, d.ldw, rc * CH, oc * CH, min(CH, d.Kred - rc * CH), min(CH, d.Nout - oc * CH));
+      }
       if (++next_t == noc * nrc) { next_t = 0; ++next_g; }
     }
     slot_issue = slot_issue + 1 == NST ? 0 : slot_issue + 1;
@@ -397,38 +404,144 @@ struct WStream {
     for (int i = 0; i < NST - 1; ++i) issue();
   }
   // the most recently consumed ring slot: free to use as scratch until the next gemm_stream call
-  __device__ __forceinline__ float* scratch() const { return bufs + last_slot * CH * CHP; }
+  __device__ __forceinline__ float* scratch() const { return bufs + last_slot * WS_SLOT; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// bf16 tensor-core GEMM cores (mma.sync.m16n8k16, fp32 accumulate).  Operands stay fp32 in shared memory and are
+// rounded to bf16 when the fragments are packed, so the fp32 and bf16 modes share every tile, epilogue and kernel.
+// Warp layout over the [TM x 64] output chunk: WR = TM/16 warps along rows, WC = 8/WR along columns; each warp owns
+// 16 rows x (64/WC) columns = NB n-blocks of 8.  Fragment lane mapping: g = lane>>2, t = lane&3.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragment of rows [r0, r0+16) x k [kb, kb+16) of a row-major fp32 tile; k >= klim reads as 0
+__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const float* __restrict__ A, int lda, int r0, int kb, int klim) {
+  const int g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
+  const float* p0 = A + (r0 + g) * lda + kb + 2 * t;
+  const float* p1 = p0 + 8 * lda;
+  const bool lo = kb + 2 * t < klim, hi = kb + 2 * t + 8 < klim;
+  const float2 z = make_float2(0.f, 0.f);
+  const float2 v0 = lo ? *reinterpret_cast<const float2*>(p0) : z;
+  const float2 v1 = lo ? *reinterpret_cast<const float2*>(p1) : z;
+  const float2 v2 = hi ? *reinterpret_cast<const float2*>(p0 + 8) : z;
+  const float2 v3 = hi ? *reinterpret_cast<const float2*>(p1 + 8) : z;
+  a[0] = pack_bf16(v0.x, v0.y); a[1] = pack_bf16(v1.x, v1.y); a[2] = pack_bf16(v2.x, v2.y); a[3] = pack_bf16(v3.x, v3.y);
+}
+
+template <int TM>
+struct MmaShape {
+  static constexpr int WR = TM / 16, WC = 8 / WR, NB = 8 / WC;   // NB n-blocks of 8 columns per warp
+};
+
+// acc += A[rows][k0..k0+klen) * Wc^T, Wc = chunk [n][k] (stride CHPB, not permuted)
+template <int TM>
+__device__ __forceinline__ void mma_nt_bf16(float (&acc)[MmaShape<TM>::NB][4], const float* __restrict__ A, int lda, int k0,
+                                            const float* __restrict__ Wc, int klen) {
+  using S = MmaShape<TM>;
+  const int warp = threadIdx.x >> 5, g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
+  const int r0 = 16 * (warp % S::WR), c0 = (64 / S::WC) * (warp / S::WR);
+  for (int kk = 0; kk < klen; kk += 16) {
+    uint32_t a[4];
+    load_a_frag(a, A, lda, r0, k0 + kk, k0 + klen);
+    const bool lo = kk + 2 * t < klen, hi = kk + 2 * t + 8 < klen;
+#pragma unroll
+    for (int j = 0; j < S::NB; ++j) {
+      const float* wp = Wc + (c0 + 8 * j + g) * CHPB + kk + 2 * t;
+      const float2 z = make_float2(0.f, 0.f);
+      const float2 w0 = lo ? *reinterpret_cast<const float2*>(wp) : z;
+      const float2 w1 = hi ? *reinterpret_cast<const float2*>(wp + 8) : z;
+      mma16816(acc[j], a, pack_bf16(w0.x, w0.y), pack_bf16(w1.x, w1.y));
+    }
+  }
+}
+// acc += A[rows][n0..n0+nlen) * Wc, Wc = chunk [k][n] (stride CHP)
+template <int TM>
+__device__ __forceinline__ void mma_nn_bf16(float (&acc)[MmaShape<TM>::NB][4], const float* __restrict__ A, int lda, int n0,
+                                            const float* __restrict__ Wc, int nlen) {
+  using S = MmaShape<TM>;
+  const int warp = threadIdx.x >> 5, g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
+  const int r0 = 16 * (warp % S::WR), c0 = (64 / S::WC) * (warp / S::WR);
+  for (int kk = 0; kk < nlen; kk += 16) {
+    uint32_t a[4];
+    load_a_frag(a, A, lda, r0, n0 + kk, n0 + nlen);
+    const bool lo = kk + 2 * t < nlen, hi = kk + 2 * t + 8 < nlen;
+#pragma unroll
+    for (int j = 0; j < S::NB; ++j) {
+      const float* wp = Wc + (kk + 2 * t) * CHP + c0 + 8 * j + g;
+      const float w00 = lo ? wp[0] : 0.f, w01 = lo ? wp[CHP] : 0.f;
+      const float w10 = hi ? wp[8 * CHP] : 0.f, w11 = hi ? wp[9 * CHP] : 0.f;
+      mma16816(acc[j], a, pack_bf16(w00, w01), pack_bf16(w10, w11));
+    }
+  }
+}
+// After the MMAs a thread holds, per n-block j, (row g: cols 2t,2t+1) and (row g+8: cols 2t,2t+1).  One exchange with the
+// lane of the neighbouring t turns that into ONE float4 of 4 contiguous columns: even t keeps row g, odd t row g+8.
+// -> row_local (within the CTA tile), column offset (within the 64 chunk) and the float4 for n-block j.
+template <int TM>
+__device__ __forceinline__ float4 mma_out4(const float (&c)[4], int j, int& row_local, int& col_in_chunk) {
+  using S = MmaShape<TM>;
+  const int warp = threadIdx.x >> 5, g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
+  const bool odd = t & 1;
+  // send what the partner needs: even lanes give away their row g+8 pair, odd lanes their row g pair
+  const float sx = odd ? c[0] : c[2], sy = odd ? c[1] : c[3];
+  const float rx = __shfl_xor_sync(0xffffffffu, sx, 1), ry = __shfl_xor_sync(0xffffffffu, sy, 1);
+  row_local = 16 * (warp % S::WR) + (odd ? g + 8 : g);
+  col_in_chunk = (64 / S::WC) * (warp / S::WR) + 8 * j + 4 * (t >> 1);
+  return odd ? make_float4(rx, ry, c[2], c[3]) : make_float4(c[0], c[1], rx, ry);
+}
+
 // GEMM number gi of the stream (must be consumed in declaration order).  Same contract as gemm_tile.
-template <int TM, bool NN, int NST, class Epi>
-__device__ __forceinline__ void gemm_stream(const float* __restrict__ A, int lda, WStream<NST>& ws, int gi, Epi epi) {
+template <int TM, bool NN, int NST, bool MMA, class Epi>
+__device__ __forceinline__ void gemm_stream(const float* __restrict__ A, int lda, WStream<NST, MMA>& ws, int gi, Epi epi) {
   constexpr int RM = TM / 16;
+  constexpr int NB = MmaShape<TM>::NB;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int Nout = ws.st->g[gi].Nout, Kred = ws.st->g[gi].Kred;
   const int noc = (Nout + CH - 1) / CH, nrc = (Kred + CH - 1) / CH;
   const int total = noc * nrc;
-  float acc[RM][4];
+  float acc[MMA ? NB : RM][4];
   for (int t = 0; t < total; ++t) {
     const int oc = t / nrc, rc = t - oc * nrc;
     if (rc == 0) {
 #pragma unroll
-      for (int i = 0; i < RM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      for (int i = 0; i < (MMA ? NB : RM); ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     }
     ws.issue();
     cp_async_wait<NST - 1>();
     __syncthreads();
-    const float* buf = ws.bufs + ws.slot_cons * CH * CHP;
+    const float* buf = ws.bufs + ws.slot_cons * WS_SLOT;
     ws.last_slot = ws.slot_cons;
     ws.slot_cons = ws.slot_cons + 1 == NST ? 0 : ws.slot_cons + 1;
     const int rlen = min(CH, Kred - rc * CH);
-    if (!NN) mma_nt<RM>(acc, A, lda, rc * CH, buf, rlen);
-    else mma_nn<RM>(acc, A, lda, rc * CH, buf, rlen);
+    if constexpr (MMA) {
+      if (!NN) mma_nt_bf16<TM>(reinterpret_cast<float(&)[NB][4]>(acc), A, lda, rc * CH, buf, rlen);
+      else mma_nn_bf16<TM>(reinterpret_cast<float(&)[NB][4]>(acc), A, lda, rc * CH, buf, rlen);
+    } else {
+      if (!NN) mma_nt<RM>(reinterpret_cast<float(&)[RM][4]>(acc), A, lda, rc * CH, buf, rlen);
+      else mma_nn<RM>(reinterpret_cast<float(&)[RM][4]>(acc), A, lda, rc * CH, buf, rlen);
+    }
     if (rc == nrc - 1) {
-      const int col = oc * CH + 4 * tx;
-      if (col < Nout) {
+      if constexpr (MMA) {
 #pragma unroll
-        for (int i = 0; i < RM; ++i) epi(i, ty + 16 * i, col, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        for (int j = 0; j < NB; ++j) {
+          int rl, cc;
+          const float4 v = mma_out4<TM>(reinterpret_cast<float(&)[NB][4]>(acc)[j], j, rl, cc);
+          if (oc * CH + cc < Nout) epi(j, rl, oc * CH + cc, v);
+        }
+      } else {
+        const int col = oc * CH + 4 * tx;
+        if (col < Nout) {
+#pragma unroll
+          for (int i = 0; i < RM; ++i) epi(i, ty + 16 * i, col, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        }
       }
     }
     __syncthreads();
@@ -469,6 +582,55 @@ __device__ __forceinline__ void wgrad_tile(const float* __restrict__ dY, int ldy
     }
 }
 
+// bf16 tensor-core weight gradient: dW[n][k] (+)= sum_{r<rows} dY[r][n] * X[r][k].  M = n, N = k, K = rows of the tile.
+// TMR = allocated tile rows (multiple of 16); rows >= `rows` are masked to zero.
+template <bool ATOMIC, int TMR>
+__device__ __forceinline__ void wgrad_tile_bf16(const float* __restrict__ dY, int ldy, int N, const float* __restrict__ X, int ldx, int K,
+                                                int rows, float* __restrict__ dW, long long ldw) {
+  const int warp = threadIdx.x >> 5, g = (threadIdx.x & 31) >> 2, t = threadIdx.x & 3;
+  const int wn = 16 * (warp & 3), wk = 32 * (warp >> 2);     // warp tile: 16 n x 32 k of the 64x64 output chunk
+  for (int n0 = 0; n0 < N; n0 += CH)
+    for (int k0 = 0; k0 < K; k0 += CH) {
+      if (n0 + wn >= N || k0 + wk >= K) continue;
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      const int n = n0 + wn + g;
+#pragma unroll 2
+      for (int r0 = 0; r0 < TMR && r0 < rows; r0 += 16) {
+        const int ra = r0 + 2 * t, rb = ra + 8;
+        const bool va = ra < rows, va1 = ra + 1 < rows, vb = rb < rows, vb1 = rb + 1 < rows;
+        const bool n_ok = n < N, n8_ok = n + 8 < N;
+        uint32_t a[4];
+        a[0] = pack_bf16(va && n_ok ? dY[ra * ldy + n] : 0.f, va1 && n_ok ? dY[(ra + 1) * ldy + n] : 0.f);
+        a[1] = pack_bf16(va && n8_ok ? dY[ra * ldy + n + 8] : 0.f, va1 && n8_ok ? dY[(ra + 1) * ldy + n + 8] : 0.f);
+        a[2] = pack_bf16(vb && n_ok ? dY[rb * ldy + n] : 0.f, vb1 && n_ok ? dY[(rb + 1) * ldy + n] : 0.f);
+        a[3] = pack_bf16(vb && n8_ok ? dY[rb * ldy + n + 8] : 0.f, vb1 && n8_ok ? dY[(rb + 1) * ldy + n + 8] : 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + wk + 8 * j + g;
+          const bool k_ok = k < K;
+          const uint32_t b0 = pack_bf16(va && k_ok ? X[ra * ldx + k] : 0.f, va1 && k_ok ? X[(ra + 1) * ldx + k] : 0.f);
+          const uint32_t b1 = pack_bf16(vb && k_ok ? X[rb * ldx + k] : 0.f, vb1 && k_ok ? X[(rb + 1) * ldx + k] : 0.f);
+          mma16816(acc[j], a, b0, b1);
+        }
+      }
+      // acc[j]: (row n0+wn+g | +8, cols k0+wk+8j+2t,+1) -> float4 per thread after the pair exchange
+      const bool odd = t & 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sx = odd ? acc[j][0] : acc[j][2], sy = odd ? acc[j][1] : acc[j][3];
+        const float rx = __shfl_xor_sync(0xffffffffu, sx, 1), ry = __shfl_xor_sync(0xffffffffu, sy, 1);
+        const int nr = n0 + wn + (odd ? g + 8 : g), kc = k0 + wk + 8 * j + 4 * (t >> 1);
+        const float4 val = odd ? make_float4(rx, ry, acc[j][2], acc[j][3]) : make_float4(acc[j][0], acc[j][1], rx, ry);
+        if (nr < N && kc < K) {
+          float4* dst = reinterpret_cast<float4*>(dW + (long long)nr * ldw + kc);
+          if (ATOMIC) atomicAdd(dst, val); else *dst = val;
+        }
+      }
+    }
+}
+
 // db[n] += sum_{r<rows} dY[r][n]
 __device__ __forceinline__ void colsum_atomic(const float* __restrict__ dY, int ldy, int N, int rows, float* __restrict__ db) {
   for (int n = threadIdx.x; n < N; n += NT) {
@@ -477,6 +639,16 @@ __device__ __forceinline__ void colsum_atomic(const float* __restrict__ dY, int 
     atomicAdd(db + n, s);
   }
 }
+
+// dispatch helper: fp32 FFMA or bf16 tensor-core weight gradient
+template <bool MMA, bool ATOMIC, int TMR>
+__device__ __forceinline__ void wgrad_any(const float* __restrict__ dY, int ldy, int N, const float* __restrict__ X, int ldx, int K,
+                                          int rows, float* __restrict__ dW, long long ldw) {
+  if constexpr (MMA) wgrad_tile_bf16<ATOMIC, TMR>(dY, ldy, N, X, ldx, K, rows, dW, ldw);
+  else wgrad_tile<ATOMIC>(dY, ldy, N, X, ldx, K, rows, dW, ldw);
+}
+template <bool MMA>
+__host__ __device__ constexpr int tile_pad() { return MMA ? 8 : 4; }
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }

@@ -42,11 +42,11 @@ struct PostBwdArgs {
   DropDesc drop1, drop2;
 };
 
-template <int TM, bool IS_DEC>
+template <int TM, bool IS_DEC, bool MMA>
 __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int H = p.H, M = p.M;
-  const int ld = H + 4;
+  const int ld = H + tile_pad<MMA>();
   float* G = smem;            // dO -> (enc) dy
   float* A = G + TM * ld;     // a = relu(h1*m1) -> dh1 -> ctx
   float* Bt = A + TM * ld;    // dh2 -> z -> dz/dc -> dctx
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     wst.ng = 3;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
 
   // 1./2. dO = (dout + mse_coef*(out-enc_in)) * keep ; y/c ; a = relu(h1*m1) ; dh2 = dO*m2
@@ -92,10 +92,10 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   });
   __syncthreads();
   // 3. dC2 += dh2^T a ; dc2 += colsum(dh2)
-  wgrad_tile(Bt, ld, H, A, ld, H, rows, p.gC2, H);
+  wgrad_any<MMA, true, TM>(Bt, ld, H, A, ld, H, rows, p.gC2, H);
   colsum_atomic(Bt, ld, H, rows, p.gc2);
   // 4. da = dh2 C2 ; dh1 = da * [a>0] * m1   (element-wise overwrite of A; A is not this GEMM's operand)
-  gemm_stream<TM, true, WS_NST>(Bt, ld, ws, 0, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST, MMA>(Bt, ld, ws, 0, [&](int, int r, int col, float4 acc) {
     const float4 a = ld4(A + r * ld + col);
     float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
     if (p.drop1.enabled) m = drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)(row0 + r) * H + col) >> 2);
@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     __syncthreads();
     Z = Bt;
   }
-  wgrad_tile(A, ld, H, Z, ld, H, rows, p.gC1, H);
+  wgrad_any<MMA, true, TM>(A, ld, H, Z, ld, H, rows, p.gC1, H);
   colsum_atomic(A, ld, H, rows, p.gc1);
   // 6. dz (enc) / dc (dec) = dO + dh1 C1  -> Bt
-  gemm_stream<TM, true, WS_NST>(A, ld, ws, 1, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST, MMA>(A, ld, ws, 1, [&](int, int r, int col, float4 acc) {
     st4(Bt + r * ld + col, f4_add(acc, ld4(G + r * ld + col)));
   });
   if (!IS_DEC) {
@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
     load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
     __syncthreads();
-    wgrad_tile(G, ld, H, A, ld, H, rows, p.gWo, H);
+    wgrad_any<MMA, true, TM>(G, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(G, ld, H, rows, p.gbo);
     // 9. dctx = dy Wo (+ independence-head adjoint) -> Bt -> global
-    gemm_stream<TM, true, WS_NST>(G, ld, ws, 2, [&](int, int r, int col, float4 acc) { st4(Bt + r * ld + col, acc); });
+    gemm_stream<TM, true, WS_NST, MMA>(G, ld, ws, 2, [&](int, int r, int col, float4 acc) { st4(Bt + r * ld + col, acc); });
     if (p.nll_coef != 0.f || p.drec) {
       const int nh = p.nh, hd = H / nh, n2 = nh * nh;
       float* lgs = ws.scratch();       // [TM][nh*nh] logits -> dlogits
@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
     load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
     __syncthreads();
-    wgrad_tile(Bt, ld, H, A, ld, H, rows, p.gWo, H);
+    wgrad_any<MMA, true, TM>(Bt, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(Bt, ld, H, rows, p.gbo);
-    gemm_stream<TM, true, WS_NST>(Bt, ld, ws, 2, [&](int, int r, int col, float4 acc) {
+    gemm_stream<TM, true, WS_NST, MMA>(Bt, ld, ws, 2, [&](int, int r, int col, float4 acc) {
       if (row0 + r < M) st4(p.dctx + (long long)(row0 + r) * H + col, acc);
     });
   }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
 // log-sum-exp; dq is owned by the CTA (plain stores), dk/dv are accumulated with vector atomics because
 // several query tiles of a sequence contribute to the same keys.
 // -------------------------------------------------------------------------------------------------
-template <int TM>
+template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                       const float* __restrict__ v, const float* __restrict__ dctx,
                                                       const float* __restrict__ lse, const int* __restrict__ key_ids,
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
                                                       int H, int nh, int mask_mode, DropDesc drop) {
   extern __shared__ __align__(16) float smem[];
   const int hd = H / nh;
-  const int ldq = hd + 4;
-  const int lds = ((L + 3) & ~3) + 4;
+  const int ldq = hd + tile_pad<MMA>();
+  const int lds = ((L + 3) & ~3) + tile_pad<MMA>();
   float* Qs = smem;
   float* dCs = Qs + TM * ldq;
   float* Ps = dCs + TM * ldq;
@@ -234,13 +234,13 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
     wst.ng = 3;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
   load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
   load_tile<TM>(dCs, ldq, dctx + seq_off, H, 0, hd, i0, L);
   __syncthreads();
-  gemm_stream<TM, false, WS_NST>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) { st4(Ps + r * lds + col, a); });
-  gemm_stream<TM, false, WS_NST>(dCs, ldq, ws, 1, [&](int, int r, int col, float4 a) { st4(dPs + r * lds + col, a); });
+  gemm_stream<TM, false, WS_NST, MMA>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) { st4(Ps + r * lds + col, a); });
+  gemm_stream<TM, false, WS_NST, MMA>(dCs, ldq, ws, 1, [&](int, int r, int col, float4 a) { st4(dPs + r * lds + col, a); });
 
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int r = w; r < TM; r += NT / 32) {
@@ -292,16 +292,16 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
   }
   __syncthreads();
   // dq = dS k
-  gemm_stream<TM, true, WS_NST>(dPs, lds, ws, 2, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, true, WS_NST, MMA>(dPs, lds, ws, 2, [&](int, int r, int col, float4 a) {
     if (i0 + r < L) st4(dq + seq_off + (long long)(i0 + r) * H + col, a);
   });
   // dk += dS^T q ; dv += Pd^T dctx   (plain stores when this CTA is the only query tile of the sequence)
   if (gridDim.x == 1) {
-    wgrad_tile<false>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
-    wgrad_tile<false>(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
+    wgrad_any<MMA, false, TM>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
+    wgrad_any<MMA, false, TM>(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
   } else {
-    wgrad_tile<true>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
-    wgrad_tile<true>(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
+    wgrad_any<MMA, true, TM>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
+    wgrad_any<MMA, true, TM>(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
   }
 }
 
@@ -318,11 +318,11 @@ struct MidBwdArgs {
   int M, H; float qscale;
 };
 
-template <int TM>
+template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int H = p.H, M = p.M;
-  const int ld = H + 4, ld2 = 2 * H + 4;
+  const int ld = H + tile_pad<MMA>(), ld2 = 2 * H + tile_pad<MMA>();
   float* T0 = smem;              // dq2*scale
   float* T1 = T0 + TM * ld;      // a -> feats -> ctx1
   float* DA = T1 + TM * ld;      // grad wrt a
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
     wst.ng = 3;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
   tile_foreach4<TM>(H, [&](int r, int c) {
     float4 g = zero4(), a = zero4();
@@ -351,16 +351,16 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
     st4(T1 + r * ld + c, a);
   });
   __syncthreads();
-  wgrad_tile(T0, ld, H, T1, ld, H, rows, p.gWin2, H);
+  wgrad_any<MMA, true, TM>(T0, ld, H, T1, ld, H, rows, p.gWin2, H);
   colsum_atomic(T0, ld, H, rows, p.gbin2);
-  gemm_stream<TM, true, WS_NST>(T0, ld, ws, 0, [&](int, int r, int col, float4 acc) { st4(DA + r * ld + col, acc); });
+  gemm_stream<TM, true, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 acc) { st4(DA + r * ld + col, acc); });
   load_tile<TM>(KV, ld2, p.dk2, H, 0, H, row0, M);
   load_tile<TM>(KV + H, ld2, p.dv2, H, 0, H, row0, M);
   load_tile<TM>(T1, ld, p.feats, H, 0, H, row0, M);
   __syncthreads();
-  wgrad_tile(KV, ld2, 2 * H, T1, ld, H, rows, p.gWin2 + (long long)H * H, H);
+  wgrad_any<MMA, true, TM>(KV, ld2, 2 * H, T1, ld, H, rows, p.gWin2 + (long long)H * H, H);
   colsum_atomic(KV, ld2, 2 * H, rows, p.gbin2 + H);
-  gemm_stream<TM, true, WS_NST>(KV, ld2, ws, 1, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST, MMA>(KV, ld2, ws, 1, [&](int, int r, int col, float4 acc) {
     if (row0 + r < M) {
       float* d = p.dfeats + (long long)(row0 + r) * H + col;
       st4(d, f4_add(ld4(d), acc));
@@ -368,9 +368,9 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   });
   load_tile<TM>(T1, ld, p.ctx1, H, 0, H, row0, M);
   __syncthreads();
-  wgrad_tile(DA, ld, H, T1, ld, H, rows, p.gWo1, H);
+  wgrad_any<MMA, true, TM>(DA, ld, H, T1, ld, H, rows, p.gWo1, H);
   colsum_atomic(DA, ld, H, rows, p.gbo1);
-  gemm_stream<TM, true, WS_NST>(DA, ld, ws, 2, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST, MMA>(DA, ld, ws, 2, [&](int, int r, int col, float4 acc) {
     if (row0 + r < M) st4(p.dctx1 + (long long)(row0 + r) * H + col, acc);
   });
 }
@@ -390,11 +390,11 @@ struct PreBwdArgs {
   int M, H; float qscale; int kv_from_norm;
 };
 
-template <int TM>
+template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   const int H = p.H, M = p.M;
-  const int ld = H + 4;
+  const int ld = H + tile_pad<MMA>();
   float* X = smem;
   float* N = X + TM * ld;
   float* T = N + TM * ld;
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
     wst.ng = 3;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
   tile_foreach4<TM>(H, [&](int r, int c) {
     float4 xv = zero4(), g = zero4();
@@ -425,9 +425,9 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   __syncthreads();
   ln_tile<TM>(X, N, ld, H, p.ln_g, p.ln_b, 1e-8f, row0, M);
   __syncthreads();
-  wgrad_tile(T, ld, H, N, ld, H, rows, p.gWin, H);
+  wgrad_any<MMA, true, TM>(T, ld, H, N, ld, H, rows, p.gWin, H);
   colsum_atomic(T, ld, H, rows, p.gbin);
-  gemm_stream<TM, true, WS_NST>(T, ld, ws, 0, [&](int, int r, int col, float4 acc) {
+  gemm_stream<TM, true, WS_NST, MMA>(T, ld, ws, 0, [&](int, int r, int col, float4 acc) {
     if (p.dnorm_extra && row0 + r < M) acc = f4_add(acc, ld4(p.dnorm_extra + (long long)(row0 + r) * H + col));
     st4(D + r * ld + col, acc);
   });
@@ -436,9 +436,9 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   for (int which = 0; which < 2; ++which) {
     load_tile<TM>(T, ld, which == 0 ? p.dk : p.dv, H, 0, H, row0, M);
     __syncthreads();
-    wgrad_tile(T, ld, H, Xkv, ld, H, rows, p.gWin + (long long)(1 + which) * H * H, H);
+    wgrad_any<MMA, true, TM>(T, ld, H, Xkv, ld, H, rows, p.gWin + (long long)(1 + which) * H * H, H);
     colsum_atomic(T, ld, H, rows, p.gbin + (1 + which) * H);
-    gemm_stream<TM, true, WS_NST>(T, ld, ws, 1 + which, [&](int, int r, int col, float4 acc) {
+    gemm_stream<TM, true, WS_NST, MMA>(T, ld, ws, 1 + which, [&](int, int r, int col, float4 acc) {
       st4(D + r * ld + col, f4_add(acc, ld4(D + r * ld + col)));
     });
   }

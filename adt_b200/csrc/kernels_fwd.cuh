@@ -41,14 +41,14 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
 //   encoder (kv_from_norm=0, modules.py:646-647,124-130): Qn=LN(x); q=(Qn Wq^T+bq)*qscale; k,v = x Wkv^T + bkv
 //   decoder (kv_from_norm=1, modules.py:668-670)        : d =LN(x); q,k,v all from d; d is written to norm_out
 // -------------------------------------------------------------------------------------------------
-template <int TM>
+template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) pre_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ln_g,
                                                      const float* __restrict__ ln_b, const float* __restrict__ Win,
                                                      const float* __restrict__ bin, float* __restrict__ q, float* __restrict__ k,
                                                      float* __restrict__ v, float* __restrict__ norm_out, int M, int H, float qscale,
                                                      int kv_from_norm) {
   extern __shared__ __align__(16) float smem[];
-  const int ld = H + 4;
+  const int ld = H + tile_pad<MMA>();
   float* Xs = smem;
   float* Ns = Xs + TM * ld;
   float* Ws = Ns + TM * ld;
@@ -60,21 +60,21 @@ __global__ void __launch_bounds__(NT) pre_fwd_kernel(const float* __restrict__ x
     wst.ng = 2;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
   load_tile<TM>(Xs, ld, x, H, 0, H, row0, M);
   __syncthreads();
   ln_tile<TM>(Xs, Ns, ld, H, ln_g, ln_b, 1e-8f, row0, M);
   __syncthreads();
   if (norm_out) store_tile<TM>(Ns, ld, norm_out, H, 0, H, row0, M);
-  gemm_stream<TM, false, WS_NST>(Ns, ld, ws, 0, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(Ns, ld, ws, 0, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
       const float4 b = *reinterpret_cast<const float4*>(bin + col);
       *reinterpret_cast<float4*>(q + (long long)(row0 + r) * H + col) = f4_scale(f4_add(a, b), qscale);
     }
   });
   const float* Akv = kv_from_norm ? Ns : Xs;
-  gemm_stream<TM, false, WS_NST>(Akv, ld, ws, 1, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(Akv, ld, ws, 1, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
       const float4 b = *reinterpret_cast<const float4*>(bin + H + col);
       float* dst = col < H ? (k + (long long)(row0 + r) * H + col) : (v + (long long)(row0 + r) * H + (col - H));
@@ -101,15 +101,15 @@ __device__ __forceinline__ float4 drop_mul4_unaligned(const DropDesc& d, unsigne
 //   mask_mode 1: key padding only (kid[b][j] != 0), bidirectional   Bert4Rec (bert4rec/model/modules.py:88-91)
 // lse (optional) = rowmax + log(rowsum) is saved for the backward pass.
 // -------------------------------------------------------------------------------------------------
-template <int TM>
+template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                       const float* __restrict__ v, float* __restrict__ ctx, float* __restrict__ lse,
                                                       const int* __restrict__ key_ids, int L, int H, int nh, int mask_mode,
                                                       DropDesc drop) {
   extern __shared__ __align__(16) float smem[];
   const int hd = H / nh;
-  const int ldq = hd + 4;
-  const int lds = ((L + 3) & ~3) + 4;
+  const int ldq = hd + tile_pad<MMA>();
+  const int lds = ((L + 3) & ~3) + tile_pad<MMA>();
   float* Qs = smem;
   float* Ss = Qs + TM * ldq;
   float* Ws = Ss + TM * lds;
@@ -124,11 +124,11 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
     wst.ng = 2;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
   load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
   __syncthreads();
-  gemm_stream<TM, false, WS_NST>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) {
     *reinterpret_cast<float4*>(Ss + r * lds + col) = a;
   });
 
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
-  gemm_stream<TM, true, WS_NST>(Ss, lds, ws, 1, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, true, WS_NST, MMA>(Ss, lds, ws, 1, [&](int, int r, int col, float4 a) {
     if (i0 + r < L) *reinterpret_cast<float4*>(ctx + seq_off + (long long)(i0 + r) * H + col) = a;
   });
 }
@@ -192,14 +192,14 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
 // mid_fwd (decoder): a = ctx1 Wo1^T + bo1 ; q2 = (a Wq2^T + bq2)*qscale ; k2,v2 = feats Wkv2^T + bkv2
 // (modules.py:669-672: self-attention out-projection followed by the cross-attention in-projection)
 // -------------------------------------------------------------------------------------------------
-template <int TM>
+template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) mid_fwd_kernel(const float* __restrict__ ctx1, const float* __restrict__ feats,
                                                      const float* __restrict__ Wo1, const float* __restrict__ bo1,
                                                      const float* __restrict__ Win2, const float* __restrict__ bin2,
                                                      float* __restrict__ a_out, float* __restrict__ q2, float* __restrict__ k2,
                                                      float* __restrict__ v2, int M, int H, float qscale) {
   extern __shared__ __align__(16) float smem[];
-  const int ld = H + 4;
+  const int ld = H + tile_pad<MMA>();
   float* T0 = smem;
   float* T1 = T0 + TM * ld;
   float* T2 = T1 + TM * ld;
@@ -213,22 +213,22 @@ __global__ void __launch_bounds__(NT) mid_fwd_kernel(const float* __restrict__ c
     wst.ng = 3;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
   load_tile<TM>(T0, ld, ctx1, H, 0, H, row0, M);
   load_tile<TM>(T2, ld, feats, H, 0, H, row0, M);
   __syncthreads();
-  gemm_stream<TM, false, WS_NST>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
     const float4 o = f4_add(a, *reinterpret_cast<const float4*>(bo1 + col));
     *reinterpret_cast<float4*>(T1 + r * ld + col) = o;
     if (a_out && row0 + r < M) *reinterpret_cast<float4*>(a_out + (long long)(row0 + r) * H + col) = o;
   });
-  gemm_stream<TM, false, WS_NST>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
     if (row0 + r < M)
       *reinterpret_cast<float4*>(q2 + (long long)(row0 + r) * H + col) =
           f4_scale(f4_add(a, *reinterpret_cast<const float4*>(bin2 + col)), qscale);
   });
-  gemm_stream<TM, false, WS_NST>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
       const float4 o = f4_add(a, *reinterpret_cast<const float4*>(bin2 + H + col));
       float* dst = col < H ? (k2 + (long long)(row0 + r) * H + col) : (v2 + (long long)(row0 + r) * H + (col - H));
@@ -261,12 +261,12 @@ struct PostFwdArgs {
   DropDesc drop1, drop2;
 };
 
-template <int TM, bool IS_DEC>
+template <int TM, bool IS_DEC, bool MMA>
 __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ double red[NT / 32];
   const int H = p.H, M = p.M;
-  const int ld = H + 4;
+  const int ld = H + tile_pad<MMA>();
   float* T0 = smem;
   float* T1 = T0 + TM * ld;
   float* T2 = T1 + TM * ld;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     wst.ng = 3;
   }
   __syncthreads();
-  WStream<WS_NST> ws;
+  WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
   load_tile<TM>(T0, ld, p.ctx, H, 0, H, row0, M);
   if (!IS_DEC) {
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     ln_tile<TM>(T2, T1, ld, H, p.ln1_g, p.ln1_b, 1e-8f, row0, M);
   }
   __syncthreads();
-  gemm_stream<TM, false, WS_NST>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
     float4 o = f4_add(a, *reinterpret_cast<const float4*>(p.bo + col));
     if (!IS_DEC) o = f4_add(o, *reinterpret_cast<const float4*>(T1 + r * ld + col));
     *reinterpret_cast<float4*>(T1 + r * ld + col) = o;
@@ -334,14 +334,14 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     ln_tile<TM>(T1, T1, ld, H, p.ln2_g, p.ln2_b, 1e-8f, row0, M);
     __syncthreads();
   }
-  gemm_stream<TM, false, WS_NST>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
     float4 h1 = f4_add(a, *reinterpret_cast<const float4*>(p.c1 + col));
     if (p.h1_save && row0 + r < M) *reinterpret_cast<float4*>(p.h1_save + (long long)(row0 + r) * H + col) = h1;
     if (p.drop1.enabled) h1 = f4_mul(h1, drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)(row0 + r) * H + col) >> 2));
     *reinterpret_cast<float4*>(T2 + r * ld + col) = make_float4(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), fmaxf(h1.z, 0.f), fmaxf(h1.w, 0.f));
   });
   double sq = 0.0;
-  gemm_stream<TM, false, WS_NST>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
+  gemm_stream<TM, false, WS_NST, MMA>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
     if (row0 + r >= M) return;
     float4 h2 = f4_add(a, *reinterpret_cast<const float4*>(p.c2 + col));
     if (p.drop2.enabled) h2 = f4_mul(h2, drop_mul4(p.drop2, (p.drop2.base + (unsigned long long)(row0 + r) * H + col) >> 2));

@@ -66,18 +66,18 @@ __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    stage_chunk<true>(Ws, a.E, H, c0, 0, ncols, min(CH, H));
+    stage_chunk<true, CHP>(Ws, a.E, H, c0, 0, ncols, min(CH, H));
     cp_async_commit();
     for (int rc = 0; rc < nrc; ++rc) {
       if (rc + 1 < nrc) {
-        stage_chunk<true>(Ws + ((rc + 1) & 1) * CH * CHP, a.E, H, c0, (rc + 1) * CH, ncols, min(CH, H - (rc + 1) * CH));
+        stage_chunk<true, CHP>(Ws + ((rc + 1) & 1) * WS_SLOT, a.E, H, c0, (rc + 1) * CH, ncols, min(CH, H - (rc + 1) * CH));
         cp_async_commit();
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
       __syncthreads();
-      mma_nt<4>(acc, Fs, ld, rc * CH, Ws + (rc & 1) * CH * CHP, min(CH, H - rc * CH));
+      mma_nt<4>(acc, Fs, ld, rc * CH, Ws + (rc & 1) * WS_SLOT, min(CH, H - rc * CH));
       __syncthreads();
     }
 #pragma unroll

@@ -39,9 +39,10 @@ def merge_topk(scores, ids, K):
 
 
 class CatalogScorer:
-    def __init__(self, model, K=10, n_splits=None, process_group=None, use_tensor_cores=True):
+    def __init__(self, model, K=10, n_splits=None, process_group=None, use_tensor_cores=True, tc_min_items=32768):
         self.model, self.K = model, int(K)
         self.use_tc = use_tensor_cores
+        self.tc_min_items = tc_min_items   # below this catalog size the exact fp32 kernel is already latency bound and cheaper
         self._tab = None           # (bf16 copy of this rank's catalog shard, max |e|^2 scalar)
         self.fallback_users = 0    # users re-run on the exact fp32 kernel because the bf16 bound was inconclusive
         self.lib = L.lib()
@@ -133,7 +134,7 @@ class CatalogScorer:
         lo, hi = shard_bounds(E.shape[0], self.world, self.rank)
         ip = _as_ids(seen_indptr, dev) if seen_indptr is not None else None
         ix = _as_ids(seen_idx, dev) if seen_idx is not None else None
-        if self.use_tc and H % 64 == 0:
+        if self.use_tc and H % 64 == 0 and (hi - lo) >= self.tc_min_items:
             os_, oi = self._topk_tc(feats, ip, ix, lo, hi)
         else:
             os_, oi = self._topk_exact(feats, ip, ix, lo, hi)

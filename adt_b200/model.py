@@ -102,6 +102,7 @@ class Engine:
         self.global_rows = None    # M of the global batch (None -> local)
         self.gflat = None
         self.step_dev = None       # optional int32 device tensor: [0] is added to the dropout step at run time
+        self.precision = 0         # 0: fp32 FFMA GEMM cores (reference precision) ; 1: bf16 tensor-core cores, fp32 accumulate
 
     # ------------------------------------------------------------------ parameters / flat buffers
     def dev(self):
@@ -224,7 +225,7 @@ class Engine:
                        q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"],
                        out=w["x"][l + 1], rec=sv["rec"],
                        nll_acc=(w["acc"][3 + m.num_layers + l:] if (nll and m.num_heads > 1) else None),
-                       B=B, L=Lq, H=m.hidden, nh=m.num_heads, training=int(training), mask_mode=0,
+                       B=B, L=Lq, H=m.hidden, nh=m.num_heads, training=int(training), mask_mode=0, precision=self.precision,
                        drop_attn=self._drop(sa, "attn", training, B, Lq), drop_ffn1=self._drop(s1, "row", training, B, Lq),
                        drop_ffn2=self._drop(s2, "row", training, B, Lq))
             L.check(self.lib.adt_enc_block_fwd(L.ctypes.byref(a), self._stream()), "adt_enc_block_fwd")
@@ -249,7 +250,7 @@ class Engine:
                        ln_w=layer.layer_norm.weight, ln_b=layer.layer_norm.bias, slf=_mha_w(layer.slf_attn), enc=_mha_w(layer.enc_attn),
                        ffn=_ffn_w(layer.pos_ffn), enc_in=w["x"][nl - 1 - j] if fused_mse else None,
                        out=w["xd"][j + 1], mse_acc=(w["acc"][3 + j:] if fused_mse else None),
-                       B=B, L=Lq, H=m.hidden, nh=m.num_heads, training=int(training), mask_mode=0,
+                       B=B, L=Lq, H=m.hidden, nh=m.num_heads, training=int(training), mask_mode=0, precision=self.precision,
                        drop_slf=self._drop(ss, "attn", training, B, Lq), drop_enc=self._drop(se, "attn", training, B, Lq),
                        drop_ffn1=self._drop(s1, "row", training, B, Lq), drop_ffn2=self._drop(s2, "row", training, B, Lq),
                        **{k: sv[k] for k in ("d", "q1", "k1", "v1", "ctx1", "lse1", "a", "q2", "k2", "v2", "ctx2", "lse2", "c", "h1")})
@@ -311,7 +312,7 @@ class Engine:
                        dq=w["dq"], dk=z4[0], dv=z4[1], dctx=w["dctx"], dd=w["dres"], dq2=w["dq2"], dk2=z4[2], dv2=z4[3], dctx2=w["dctx2"],
                        dfeats=w["dfeats"], dx=out_dx, g_ln_w=g[pre + "layer_norm.weight"], g_ln_b=g[pre + "layer_norm.bias"],
                        g_slf=mg(pre + "slf_attn."), g_enc=mg(pre + "enc_attn."), g_ffn=fg(pre + "pos_ffn."),
-                       B=B, L=Lq, H=H, nh=nh, mask_mode=0,
+                       B=B, L=Lq, H=H, nh=nh, mask_mode=0, precision=self.precision,
                        drop_slf=self._drop(ss, "attn", True, B, Lq), drop_enc=self._drop(se, "attn", True, B, Lq),
                        drop_ffn1=self._drop(s1, "row", True, B, Lq), drop_ffn2=self._drop(s2, "row", True, B, Lq),
                        **{k: sv[k] for k in ("d", "q1", "k1", "v1", "ctx1", "lse1", "a", "q2", "k2", "v2", "ctx2", "lse2", "c", "h1")})
@@ -350,7 +351,7 @@ class Engine:
                        g_attn=mg(pre + "attention_layer."), g_ln2_w=g[pre + "forward_layernorm.weight"],
                        g_ln2_b=g[pre + "forward_layernorm.bias"], g_ffn=fg(pre + "forward_layer."),
                        g_sparse_w=g[pre + "sparse.weight"], g_sparse_b=g[pre + "sparse.bias"],
-                       B=B, L=Lq, H=H, nh=nh, mask_mode=0,
+                       B=B, L=Lq, H=H, nh=nh, mask_mode=0, precision=self.precision,
                        drop_attn=self._drop(sa, "attn", True, B, Lq), drop_ffn1=self._drop(s1, "row", True, B, Lq),
                        drop_ffn2=self._drop(s2, "row", True, B, Lq))
             L.check(self.lib.adt_enc_block_bwd(L.ctypes.byref(a), self._stream()), "adt_enc_block_bwd")

@@ -64,7 +64,7 @@ def compat_loss(model, outs, pos, l1, l2, wd):
     return loss
 
 
-def check_golden(name, verbose=False):
+def check_golden(name, verbose=False, precision="fp32"):
     """Run compat forward/backward and the fused step on fixture `name`; return {quantity: relative error}."""
     from .trainer import FusedTrainer
     g = load_golden(name)
@@ -76,6 +76,7 @@ def check_golden(name, verbose=False):
     m = model_from_golden(g)
     m.train()
     m.engine.drop_seed, m.engine.drop_step = int(g["drop_seed"]), int(g["drop_step"])
+    m.engine.precision = {"fp32": 0, "bf16": 1}[precision]
     outs = m(None, seq, dec, pos, neg)
     errs["pos_logits"] = rel_err(outs[0], g["pos_logits"])
     errs["neg_logits"] = rel_err(outs[1], g["neg_logits"])
@@ -95,7 +96,7 @@ def check_golden(name, verbose=False):
     # ---- fused path
     m2 = model_from_golden(g)
     m2.train()
-    tr = FusedTrainer(m2, l1, l2, weight_decay=wd, lr=1e-3, betas=(0.9, 0.98), clip=5.0, seed=int(g["drop_seed"]))
+    tr = FusedTrainer(m2, l1, l2, weight_decay=wd, lr=1e-3, betas=(0.9, 0.98), clip=5.0, seed=int(g["drop_seed"]), precision=precision)
     tr.t = int(g["drop_step"])
     tr.step(seq, dec, pos, neg)
     errs["fused_loss"] = abs(tr.loss() - float(g["loss"])) / abs(float(g["loss"]))
@@ -115,6 +116,7 @@ def check_golden(name, verbose=False):
     # ---- predict
     m3 = model_from_golden(g, prefix="sd1/")
     m3.eval()
+    m3.engine.precision = {"fp32": 0, "bf16": 1}[precision]
     errs["pred_cand"] = rel_err(m3.predict(None, seq, g["cand"]), g["pred_cand"])
     errs["pred_full"] = rel_err(m3.predict(None, seq, None, True), g["pred_full"])
     if verbose:

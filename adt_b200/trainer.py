@@ -21,7 +21,7 @@ from .model import _as_ids
 
 class FusedTrainer:
     def __init__(self, model, lambdas1, lambdas2, weight_decay=0.0, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, clip=5.0,
-                 adam_weight_decay=0.0, seed=0, process_group=None, use_norm_decay=True, use_graph=False):
+                 adam_weight_decay=0.0, seed=0, process_group=None, use_norm_decay=True, use_graph=False, precision="fp32"):
         self.model = model
         self.eng = model.engine
         self.l1, self.l2 = [float(x) for x in lambdas1], [float(x) for x in lambdas2]
@@ -36,6 +36,7 @@ class FusedTrainer:
             self.world = torch.distributed.get_world_size(process_group)
             self.rank = torch.distributed.get_rank(process_group)
         self.eng.drop_seed = int(seed)
+        self.eng.precision = {"fp32": 0, "bf16": 1}[precision]
         self.t = 0
         self._w = None
         self.use_graph = use_graph

@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="GEMM cores of the block kernels: fp32 FFMA (reference precision) or bf16 tensor cores with fp32 accumulate")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     return ap.parse_args()
@@ -185,7 +187,7 @@ def main():
     model.load_state_dict(init_state_dict(cfg))
     model = model.to(dev).train()
     l1, l2 = get_lambdas(cfg["dataset"])
-    tr = FusedTrainer(model, l1, l2, weight_decay=cfg["wd"], lr=1e-3, betas=(0.9, 0.98), clip=5.0, seed=23, use_graph=True)
+    tr = FusedTrainer(model, l1, l2, weight_decay=cfg["wd"], lr=1e-3, betas=(0.9, 0.98), clip=5.0, seed=23, use_graph=True, precision=args.precision)
     B, Lq, H = cfg["B"], cfg["L"], cfg["H"]
 
     rng = np.random.default_rng(23 + rank)
@@ -243,6 +245,29 @@ def main():
     e2e_value = world * B * K / (e2e_ms / 1e3)
 
     trace("per-kernel timing")
+    # ---- the other precision mode of the block GEMM cores, for the record (short device-resident run)
+    other = "fp32" if args.precision == "bf16" else "bf16"
+    tr2 = FusedTrainer(model, l1, l2, weight_decay=cfg["wd"], lr=1e-3, betas=(0.9, 0.98), clip=5.0, seed=23, use_graph=True,
+                       precision=other)
+    tr2.t, tr2._counter_t = tr.t, None
+    for i in range(3):
+        tr2.step(*resident[i % POOL])
+    barrier()
+    K2 = min(K, 20)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K2)]
+    for k in range(K2):
+        flush.zero_()
+        ev2[k][0].record()
+        tr2.step(*resident[k % POOL])
+        ev2[k][1].record()
+    barrier()
+    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+    other_mode = {"dtype": other, "value": world * B * K2 / (t2.item() / 1e3), "ms_per_step": t2.item() / K2, "steps": K2}
+    tr.eng.precision = {"fp32": 0, "bf16": 1}[args.precision]
+    tr.t, tr._counter_t = tr2.t, None
+
     # ---- per-kernel live timing (separate pass, events inside the library) for the roofline object
     names_buf = ctypes.create_string_buffer(4096)
     tot = (ctypes.c_float * 64)()
@@ -282,7 +307,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                 "traffic": None, "peak_source": peak_src, "avg_us": kern[top]["avg_us"],
                 "share_of_step": kern[top]["ms_total"] / max(sum(v["ms_total"] for v in kern.values()), 1e-9),
-                "note": "fp32 FFMA row-tile kernels are compute (CUDA-core) bound at this shape; HBM fraction reported as asked"}
+                "note": "at B=256 x L=50 x H=64 one launch is 0.45 waves of row-tile CTAs: latency/issue bound, not HBM bound (DESIGN.md section 4)"}
 
     trace("eval")
     # ---- full-catalog evaluation users/sec (encoder forward + K7 scoring + fused top-10), 512 users per batch
@@ -324,7 +349,7 @@ def main():
         launches_per_step += (3 * passes - 1) + 3
         line = {
             "metric": "train_seqs_per_sec", "value": value, "unit": "seqs/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
             "config": {"workload": f"SASRec-ADT {args.config}: train step + full-catalog eval (items={cfg['items']}, maxlen={Lq}, "
                                    f"hidden={H}, heads={nh}, blocks={nl}, batch={B}/GPU, dropout={cfg['p']})",
@@ -334,7 +359,7 @@ def main():
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": int(round(launches_per_step * K)),
             "eval_users_per_sec": eval_users, "eval": {"users_per_batch": U, "K": 10, "items": cfg["items"] + 1, **metrics},
-            "loss": last_loss,
+            "loss": last_loss, "other_precision": other_mode,
             "roofline": roofline, "kernels_us": {k_: round(v["avg_us"], 2) for k_, v in sorted(kern.items())},
             "kernel_ms_per_step": step_kernel_ms,
             "cpu_baseline": cpu, "clocks": clocks,

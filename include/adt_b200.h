@@ -67,6 +67,7 @@ typedef struct {
   double* nll_acc;                                         /* += -sum_{r,c} rec[r][c][c]   (may be NULL) */
   int32_t B, L, H, nh, training, mask_mode;                /* mask_mode 0 causal, 1 key-padding (bidirectional) */
   adt_dropout drop_attn, drop_ffn1, drop_ffn2;
+  int32_t precision;                                       /* 0: fp32 FFMA GEMM cores; 1: bf16 tensor-core cores (fp32 accumulate) */
 } adt_enc_block_fwd_args;
 int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t stream);
 
@@ -85,6 +86,7 @@ typedef struct {
   float* g_sparse_w; float* g_sparse_b;
   int32_t B, L, H, nh, mask_mode;
   adt_dropout drop_attn, drop_ffn1, drop_ffn2;
+  int32_t precision;
 } adt_enc_block_bwd_args;
 int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t stream);
 
@@ -99,6 +101,7 @@ typedef struct {
   double* mse_acc;                                         /* += sum (enc_in - out)^2   (may be NULL) */
   int32_t B, L, H, nh, training, mask_mode;
   adt_dropout drop_slf, drop_enc, drop_ffn1, drop_ffn2;
+  int32_t precision;
 } adt_dec_block_fwd_args;
 int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t stream);
 
@@ -116,6 +119,7 @@ typedef struct {
   float* g_ln_w; float* g_ln_b; adt_mha_g g_slf; adt_mha_g g_enc; adt_ffn_g g_ffn;
   int32_t B, L, H, nh, mask_mode;
   adt_dropout drop_slf, drop_enc, drop_ffn1, drop_ffn2;
+  int32_t precision;
 } adt_dec_block_bwd_args;
 int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t stream);
 

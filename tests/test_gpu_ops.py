@@ -112,7 +112,7 @@ def test_catalog_topk_matches_oracle(U, H, I, K, use_tc):
     indptr[1:] = np.cumsum([len(s) for s in seen])
     idx = np.concatenate(seen).astype(np.int32) if indptr[-1] else np.zeros(0, np.int32)
     fake = types.SimpleNamespace(item_emb=types.SimpleNamespace(weight=E.cuda()))
-    sc = CatalogScorer(fake, K=K, use_tensor_cores=use_tc)
+    sc = CatalogScorer(fake, K=K, use_tensor_cores=use_tc, tc_min_items=0)
     s, ids = sc.topk_from_feats(feats.cuda(), indptr, idx)
     ids = ids.cpu().numpy()
     scores = (feats @ E.t()).numpy()
@@ -198,7 +198,7 @@ def test_catalog_topk_tc_near_ties_fall_back_to_exact():
     feats = torch.from_numpy(rng.standard_normal((U, H)).astype(np.float32)).cuda()
     fake = types.SimpleNamespace(item_emb=types.SimpleNamespace(weight=E))
     ex = CatalogScorer(fake, K=K, use_tensor_cores=False)
-    tc = CatalogScorer(fake, K=K, use_tensor_cores=True)
+    tc = CatalogScorer(fake, K=K, use_tensor_cores=True, tc_min_items=0)
     s0, i0 = ex.topk_from_feats(feats)
     s1, i1 = tc.topk_from_feats(feats)
     assert tc.fallback_users > 0

@@ -41,7 +41,7 @@ def _worker(rank, world, port, ret):
     same = bool(torch.equal(flat, other))
     # item-sharded eval == unsharded exact eval
     m.eval()
-    sc = CatalogScorer(m, K=5, use_tensor_cores=True)
+    sc = CatalogScorer(m, K=5, use_tensor_cores=True, tc_min_items=0)
     s, i = sc.topk(seq)
     ref = m.predict(None, seq, None, True)
     rs, ri = torch.topk(ref, 5, dim=1)

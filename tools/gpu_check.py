@@ -21,10 +21,11 @@ def p(*a):
 
 
 p(torch.cuda.get_device_name(0), torch.version.cuda)
-names = sys.argv[1:] or testing.golden_names()
+prec = "bf16" if "--bf16" in sys.argv else "fp32"
+names = [a for a in sys.argv[1:] if not a.startswith("--")] or testing.golden_names()
 for name in names:
     try:
-        errs = testing.check_golden(name)
+        errs = testing.check_golden(name, precision=prec)
         torch.cuda.synchronize()
         for k, v in errs.items():
             flag = "" if v <= testing.tolerance(k) else "   <-- FAIL"

@@ -16,7 +16,7 @@ def run(U, H, I, K, seen=True, seed=0):
         ip = np.zeros(U + 1, np.int32); ip[1:] = np.cumsum([len(x) for x in s]); ix = np.concatenate(s).astype(np.int32)
     fake = types.SimpleNamespace(item_emb=types.SimpleNamespace(weight=E))
     ex = CatalogScorer(fake, K=K, use_tensor_cores=False)
-    tc = CatalogScorer(fake, K=K, use_tensor_cores=True)
+    tc = CatalogScorer(fake, K=K, use_tensor_cores=True, tc_min_items=0)
     s0, i0 = ex.topk_from_feats(feats, ip, ix)
     s1, i1 = tc.topk_from_feats(feats, ip, ix)
     torch.cuda.synchronize()
