@@ -76,7 +76,7 @@ class EmbedFn(torch.autograd.Function):
 
 
 def _scatter(dev, M, B, Lq, H, max_id, seq=None, pos=None, neg=None, dx_enc=None, feats=None, cpos=None, cneg=None, drop_enc=None,
-             dE=None, dP=None):
+             dE=None, dP=None, emb_scale=0.0):
     """sorted segmented scatter-add for a subset of the four lookup sources (missing sources are all-padding)."""
     lib = L.lib()
     zeros = torch.zeros(B, Lq, dtype=torch.int32, device=dev)
@@ -90,7 +90,7 @@ def _scatter(dev, M, B, Lq, H, max_id, seq=None, pos=None, neg=None, dx_enc=None
     nodrop = L.adt_dropout()
     b = L.fill(L.adt_embed_bwd_args(), keys=keys, vals=vals, seq=seq if seq is not None else zeros, dec=zeros, B=B, L=Lq, H=H,
                dx_enc=dx_enc, dx_dec=None, feats=feats, cpos=cpos, cneg=cneg, drop_enc=drop_enc if drop_enc is not None else nodrop,
-               drop_dec=nodrop, d_item_emb=dE, d_pos_emb=dP, head=_f(dE, nb, H), tail=_f(dE, nb, H), has_tail=i32(nb))
+               drop_dec=nodrop, d_item_emb=dE, d_pos_emb=dP, head=_f(dE, nb, H), tail=_f(dE, nb, H), has_tail=i32(nb), emb_scale=emb_scale)
     L.check(lib.adt_embed_bwd(ctypes.byref(b), _stream(dev)), "adt_embed_bwd")
 
 

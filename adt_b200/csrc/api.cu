@@ -9,6 +9,7 @@
 #include "kernels_bwd.cuh"
 #include "kernels_embed_opt.cuh"
 #include "kernels_fwd.cuh"
+#include "kernels_generic.cuh"
 
 using namespace adt;
 
@@ -424,7 +425,7 @@ extern "C" int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t s_) {
   memset(&sa, 0, sizeof(sa));
   sa.keys = a->keys; sa.vals = a->vals; sa.N = 4 * M; sa.M = M; sa.H = a->H;
   sa.dx_enc = a->dx_enc; sa.dx_dec = a->dx_dec; sa.feats = a->feats; sa.cpos = a->cpos; sa.cneg = a->cneg;
-  sa.scale = (float)sqrt((double)a->H);
+  sa.scale = a->emb_scale != 0.f ? a->emb_scale : (float)sqrt((double)a->H);
   sa.drop_enc = mk_drop(a->drop_enc); sa.drop_dec = mk_drop(a->drop_dec);
   sa.dE = a->d_item_emb; sa.head = a->head; sa.tail = a->tail; sa.has_tail = a->has_tail;
   const int nb = (sa.N + 31) / 32;
@@ -464,4 +465,100 @@ extern "C" int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_
   const long long blocks = (n + 255) / 256;
   philox_mask_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(out, (long long)n, mk_drop(*d));
   return check_launch("adt_philox_mask");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic ops
+extern "C" int adt_linear_fwd(const adt_linear_fwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (a->M <= 0 || (a->K & 3) || a->N <= 0 || a->K > 2048) return fail(ADT_E_SHAPE, "%s", "linear_fwd: K must be a multiple of 4, K <= 2048");
+  const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
+  size_t smem;
+  const int tm = pick_tm((size_t)(a->K + pad), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "linear_fwd: tile does not fit shared memory");
+  LinearFwdArgs p;
+  p.x = a->x; p.W = a->w; p.b = a->b; p.y = a->y; p.pre = a->pre; p.M = a->M; p.K = a->K; p.N = a->N; p.act = a->act;
+  p.scale = a->scale == 0.f ? 1.f : a->scale;
+  p.ldy = a->ldy ? a->ldy : a->N;
+  TIMED("linear_fwd", s);
+  LAUNCH_TM(tm, mma, linear_fwd_kernel, (a->M + tm - 1) / tm, smem, s, p);
+  return check_launch("linear_fwd");
+}
+
+extern "C" int adt_linear_bwd(const adt_linear_bwd_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (a->M <= 0 || (a->K & 3) || a->N <= 0) return fail(ADT_E_SHAPE, "%s", "linear_bwd: K must be a multiple of 4");
+  const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
+  size_t smem;
+  const int tm = pick_tm((size_t)(a->K + pad) + (size_t)(((a->N + 3) & ~3) + pad), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "linear_bwd: tile does not fit shared memory");
+  LinearBwdArgs p;
+  p.x = a->x; p.W = a->w; p.dy = a->dy; p.dx = a->dx; p.gW = a->g_w; p.gb = a->g_b; p.M = a->M; p.K = a->K; p.N = a->N;
+  p.accumulate_dx = a->accumulate_dx; p.scale = a->scale == 0.f ? 1.f : a->scale;
+  p.lddy = a->lddy ? a->lddy : a->N;
+  TIMED("linear_bwd", s);
+  LAUNCH_TM(tm, mma, linear_bwd_kernel, (a->M + tm - 1) / tm, smem, s, p);
+  return check_launch("linear_bwd");
+}
+
+extern "C" int adt_act_bwd(const float* dy, const float* pre, float* dpre, int64_t n, int32_t act, adt_stream_t s_) {
+  if (n & 3) return fail(ADT_E_SHAPE, "%s", "act_bwd: n must be a multiple of 4");
+  const long long n4 = n / 4, blocks = (n4 + 255) / 256;
+  act_bwd_kernel<<<(int)(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16), 256, 0, (cudaStream_t)s_>>>(dy, pre, dpre, n4, act);
+  return check_launch("act_bwd");
+}
+
+static DrlArgs mk_drl(const adt_drl_args* a) {
+  DrlArgs p;
+  p.a = a->a; p.r = a->r; p.gamma = a->gamma; p.beta = a->beta; p.y = a->y; p.dy = a->dy; p.da = a->da; p.dr = a->dr;
+  p.ggamma = a->g_gamma; p.gbeta = a->g_beta; p.M = a->M; p.H = a->H; p.mode = a->mode; p.eps = a->eps; p.drop = mk_drop(a->drop);
+  return p;
+}
+extern "C" int adt_drop_res_ln_fwd(const adt_drl_args* a, adt_stream_t s_) {
+  if (a->H > 256 || a->H <= 0) return fail(ADT_E_SHAPE, "%s", "drop_res_ln: H <= 256");
+  const int grid = min((a->M + 7) / 8, 148 * 8);
+  drl_fwd_kernel<<<grid, NT, 0, (cudaStream_t)s_>>>(mk_drl(a));
+  return check_launch("drop_res_ln_fwd");
+}
+extern "C" int adt_drop_res_ln_bwd(const adt_drl_args* a, adt_stream_t s_) {
+  if (a->H > 256 || a->H <= 0) return fail(ADT_E_SHAPE, "%s", "drop_res_ln: H <= 256");
+  const int grid = min((a->M + 7) / 8, 148 * 4);
+  drl_bwd_kernel<<<grid, NT, 0, (cudaStream_t)s_>>>(mk_drl(a));
+  return check_launch("drop_res_ln_bwd");
+}
+
+extern "C" int adt_gather3(const int32_t* ia, const float* A, const int32_t* ib, const float* B, const int32_t* ic, const float* C, float* sdst,
+                           int32_t M, int32_t H, adt_stream_t s_) {
+  if (H & 3) return fail(ADT_E_SHAPE, "%s", "gather3: H % 4");
+  const long long n = (long long)M * (H / 4), blocks = (n + 255) / 256;
+  gather3_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)s_>>>(ia, A, ib, B, ic, C, sdst, M, H);
+  return check_launch("gather3");
+}
+extern "C" int adt_small_table_grad(const int32_t* ids, const float* dx, float* g, int32_t M, int32_t H, int32_t padding_idx,
+                                    adt_stream_t s_) {
+  if (H & 3) return fail(ADT_E_SHAPE, "%s", "small_table_grad: H % 4");
+  const long long n = (long long)M * (H / 4), blocks = (n + 255) / 256;
+  small_table_grad_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)s_>>>(ids, dx, g, M, H, padding_idx);
+  return check_launch("small_table_grad");
+}
+
+extern "C" int adt_attention_fwd(const adt_attention_args* a, adt_stream_t s_) {
+  if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
+  return launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->key_ids, a->B, a->L, a->H, a->nh, a->mask_mode, a->drop, a->training,
+                         a->precision ? 1 : 0, (cudaStream_t)s_);
+}
+extern "C" int adt_attention_bwd(const adt_attention_args* a, adt_stream_t s_) {
+  if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
+  return launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->key_ids, a->dq, a->dk, a->dv, a->B, a->L, a->H, a->nh, a->mask_mode, a->drop,
+                         a->precision ? 1 : 0, (cudaStream_t)s_);
+}
+
+extern "C" int adt_softmax_ce_fwd(const float* logits, const int32_t* labels, float* lse, double* loss_acc, int32_t R, int32_t V,
+                                  adt_stream_t s_) {
+  softmax_ce_kernel<<<min(R, 148 * 8), NT, 0, (cudaStream_t)s_>>>(const_cast<float*>(logits), labels, lse, loss_acc, R, V, 0, 0.f);
+  return check_launch("softmax_ce_fwd");
+}
+extern "C" int adt_softmax_ce_bwd(float* logits, const int32_t* labels, const float* lse, float coef, int32_t R, int32_t V, adt_stream_t s_) {
+  softmax_ce_kernel<<<min(R, 148 * 8), NT, 0, (cudaStream_t)s_>>>(logits, labels, const_cast<float*>(lse), nullptr, R, V, 1, coef);
+  return check_launch("softmax_ce_bwd");
 }

@@ -160,6 +160,7 @@ typedef struct {
   adt_dropout drop_enc, drop_dec;
   float* d_item_emb; float* d_pos_emb;      /* d_pos_emb accumulated */
   float* head; float* tail; int32_t* has_tail;   /* scratch: ceil(4*M/32) x H floats (x2), ceil(4*M/32) ints */
+  float emb_scale;                               /* factor on the dx_enc/dx_dec rows; 0 -> sqrt(H) (SASRec, model.py:35) */
 } adt_embed_bwd_args;
 int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t stream);
 
@@ -208,6 +209,50 @@ int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t stream);
 
 /* test helper: out[i] = keep-multiplier (0 or 1/(1-p)) of element base+i of a dropout site */
 int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t stream);
+
+/* ---- generic ops for the post-LN backbones (Bert4Rec-ADT: /root/reference/bert4rec/model/modules.py) ---------------- */
+/* y = act((x W^T + b) * scale), act 0 none / 1 relu / 2 gelu(erf); pre (optional) receives the pre-activation.
+ * Replaces nn.Linear (+ nn.GELU): modules.py:57-72 (q/k/v/out transfer), :128-139 (FFN), bert.py:80-90 (head). */
+typedef struct {
+  const float* x; const float* w; const float* b; float* y; float* pre;
+  int32_t M, K, N, act; float scale; int32_t precision;
+  int32_t ldy;                                 /* row stride of y/pre in floats (0 -> N): lets a wide output be produced in column blocks */
+} adt_linear_fwd_args;
+int adt_linear_fwd(const adt_linear_fwd_args* a, adt_stream_t stream);
+/* dx = scale * dy W (dx NULL: skipped; accumulate_dx: +=) ; g_w += scale * dy^T x ; g_b += scale * colsum(dy) */
+typedef struct {
+  const float* x; const float* w; const float* dy; float* dx; float* g_w; float* g_b;
+  int32_t M, K, N, accumulate_dx; float scale; int32_t precision;
+  int32_t lddy;                                /* row stride of dy in floats (0 -> N) */
+} adt_linear_bwd_args;
+int adt_linear_bwd(const adt_linear_bwd_args* a, adt_stream_t stream);
+int adt_act_bwd(const float* dy, const float* pre, float* dpre, int64_t n, int32_t act, adt_stream_t stream);
+/* mode 0: y = LN(dropout(a) + r)  (DropResidualNormalizeLayer, modules.py:104-117)
+ * mode 1: y = dropout(LN(a + r))  (BertEmbedding, modules.py:42-48).   r may be NULL. */
+typedef struct {
+  const float* a; const float* r; const float* gamma; const float* beta; float* y;
+  const float* dy; float* da; float* dr; float* g_gamma; float* g_beta;     /* backward only */
+  int32_t M, H, mode; float eps; adt_dropout drop;
+} adt_drl_args;
+int adt_drop_res_ln_fwd(const adt_drl_args* a, adt_stream_t stream);
+int adt_drop_res_ln_bwd(const adt_drl_args* a, adt_stream_t stream);
+/* s[row] = A[ia[row]] + B[ib[row]] + C[ic[row]] (B, C may be NULL) ; g[ids[row]] += dx[row] for ids != padding_idx */
+int adt_gather3(const int32_t* ia, const float* A, const int32_t* ib, const float* B, const int32_t* ic, const float* C, float* s,
+                int32_t M, int32_t H, adt_stream_t stream);
+int adt_small_table_grad(const int32_t* ids, const float* dx, float* g, int32_t M, int32_t H, int32_t padding_idx, adt_stream_t stream);
+/* multi-head attention core on projected q (pre-scaled), k, v [B*L, H]: softmax(q k^T + mask) -> dropout -> . v
+ * mask_mode 0 causal, 1 key padding (key_ids[b][j] == 0 -> -1e9, modules.py:88-91).  lse [B,nh,L] saved for backward. */
+typedef struct {
+  const float* q; const float* k; const float* v; float* ctx; float* lse; const int32_t* key_ids;
+  const float* dctx; float* dq; float* dk; float* dv;                       /* backward only */
+  int32_t B, L, H, nh, mask_mode, training; adt_dropout drop; int32_t precision;
+} adt_attention_args;
+int adt_attention_fwd(const adt_attention_args* a, adt_stream_t stream);
+int adt_attention_bwd(const adt_attention_args* a, adt_stream_t stream);
+/* softmax cross-entropy over logits rows [R,V] (nn.CrossEntropyLoss on the rows that carry a label, trainer.py:113-115).
+ * fwd: lse[r], *loss_acc += sum_r (lse[r] - logits[r][labels[r]]).  bwd: logits <- (softmax - onehot) * coef, in place. */
+int adt_softmax_ce_fwd(const float* logits, const int32_t* labels, float* lse, double* loss_acc, int32_t R, int32_t V, adt_stream_t stream);
+int adt_softmax_ce_bwd(float* logits, const int32_t* labels, const float* lse, float coef, int32_t R, int32_t V, adt_stream_t stream);
 
 /* optional per-kernel CUDA-event timing (used by bench.py for the live roofline number; off by default) */
 int adt_timing_enable(int on);

@@ -1,0 +1,99 @@
+"""GPU parity of Bert4Rec-ADT against fixtures of the UNMODIFIED reference BertModel +
+trainer.py:100-132 step: compat forward (full logits), caller-side loss, backward, clip, Adam; fused masked-CE loss;
+predict."""
+import glob
+import os
+import types
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def grad_close(a, b):
+    """|a-b| <= 1e-3 * max|b| + 1e-7: the key-bias gradients are identically zero in exact arithmetic (softmax is invariant
+    to a constant added to every key score), so both sides only hold ~1e-9 rounding noise there."""
+    a = a.detach().cpu().numpy().astype(np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() <= 1e-3 * np.abs(b).max() + 1e-7
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN, "bert_*.npz")))
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN, f"bert_{name}.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _model(g, prefix="sd0/"):
+    from adt_b200.bert4rec import BertModel
+    B, L, H, nh, nl, I, inner = [int(v) for v in g["cfg"]]
+    args = types.SimpleNamespace(device="cuda", num_heads=nh, maxlen=L, num_layers=nl, hidden_units=H, dropout=float(g["p"]),
+                                 attention_dropout=float(g["pa"]), inner_units=inner, type_vocab_size=2)
+    m = BertModel(100, I, args)
+    sd = {k[len(prefix):]: torch.from_numpy(np.array(v)) for k, v in g.items() if k.startswith(prefix)}
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.drop_seed, m.drop_step = int(g["drop_seed"]), int(g["drop_step"])
+    return m
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_bert_compat_step(name):
+    import torch.nn.functional as F
+    from adt_b200.testing import rel_err
+    g = _load(name)
+    B, L, H, nh, nl, I, inner = [int(v) for v in g["cfg"]]
+    m = _model(g).train()
+    pos_ids = torch.arange(L).repeat(B, 1)
+    sent = torch.zeros(B, L, dtype=torch.long)
+    logits, enc_in, dec_out, ind = m(torch.from_numpy(g["seq"]), torch.from_numpy(g["dec"]), pos_ids, sent, pos_ids, sent)
+    assert rel_err(logits, g["logits"]) < 5e-5
+    for i in range(nl):
+        assert rel_err(enc_in[i], g[f"enc_in{i}"]) < 5e-5
+        assert rel_err(dec_out[i], g[f"dec_out{i}"]) < 5e-5
+        assert rel_err(ind[i], g[f"ind{i}"]) < 5e-5
+    lab = torch.from_numpy(g["labels"]).cuda()
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0)(logits.view(-1, logits.size(-1)), lab.view(-1))   # trainer.py:113-115
+    l1, l2 = list(g["lambda1"]), list(g["lambda2"])
+    for i in range(nl):
+        if l1[i] != 0:
+            loss = loss + l1[i] * F.mse_loss(enc_in[i], dec_out[i])
+    label = torch.tile(torch.arange(nh), [B * L, 1]).cuda()
+    for l in range(nl):
+        if l2[l] != 0:
+            loss = loss + l2[l] * F.nll_loss(ind[l].view(B * L, nh, nh), label)
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    opt = torch.optim.Adam(m.parameters(), lr=0.001, betas=(0.9, 0.999), weight_decay=float(g["wd"]))
+    opt.zero_grad()
+    loss.backward()
+    gn = torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+    assert abs(float(gn) - float(g["gnorm"])) / float(g["gnorm"]) < 1e-4
+    for k, p in m.named_parameters():
+        assert grad_close(p.grad, g["grad/" + k]), k
+    opt.step()
+    for k, p in m.named_parameters():
+        big = np.abs(g["grad/" + k]) > 1e-5
+        assert np.abs(p.detach().cpu().numpy() - g["sd1/" + k])[big].max(initial=0.0) < 5e-6, k
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_bert_fused_masked_loss_and_predict(name):
+    from adt_b200.testing import rel_err
+    g = _load(name)
+    m = _model(g).train()
+    loss = m.fused_loss(g["seq"], g["dec"], g["labels"], list(g["lambda1"]), list(g["lambda2"]))
+    assert abs(float(loss) - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    loss.backward()
+    gn = torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+    assert abs(float(gn) - float(g["gnorm"])) / float(g["gnorm"]) < 1e-4
+    for k, p in m.named_parameters():
+        assert grad_close(p.grad, g["grad/" + k]), k
+    B, L = g["seq"].shape
+    m2 = _model(g, prefix="sd1/").eval()
+    pos_ids = torch.arange(L).repeat(B, 1)
+    sent = torch.zeros(B, L, dtype=torch.long)
+    pred = m2.predict(None, torch.from_numpy(g["seq"]), pos_ids, sent, torch.from_numpy(g["cand"]))
+    assert rel_err(pred, g["pred"]) < 5e-5
