@@ -97,3 +97,40 @@ def test_bert_fused_masked_loss_and_predict(name):
     sent = torch.zeros(B, L, dtype=torch.long)
     pred = m2.predict(None, torch.from_numpy(g["seq"]), pos_ids, sent, torch.from_numpy(g["cand"]))
     assert rel_err(pred, g["pred"]) < 5e-5
+
+
+def test_bert_ml20m_like_shape_vs_oracle():
+    """template shape of bert4rec/templates/ml-1m.json (maxlen 200, hidden 256, 4 heads, inner 1024) with a vocabulary wide
+    enough (V = 1600) to need two column blocks of the tied head; fused masked-CE loss and all gradients vs the oracle."""
+    from adt_b200.bert4rec import BertModel
+    from oracle import bert_oracle as BO
+    from oracle.sasrec_oracle import Drop
+    B, L, H, nh, nl, I, inner, p, pa = 2, 200, 256, 4, 1, 1500, 1024, 0.5, 0.5
+    torch.manual_seed(0)
+    args = types.SimpleNamespace(device="cuda", num_heads=nh, maxlen=L, num_layers=nl, hidden_units=H, dropout=p, attention_dropout=pa,
+                                 inner_units=inner, type_vocab_size=2)
+    m = BertModel(10, I, args)
+    for prm in m.parameters():
+        prm.data.normal_(0.01, 0.05) if prm.dim() >= 2 else prm.data.add_(0.1 * torch.randn(prm.shape))
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    rng = np.random.default_rng(4)
+    seq = np.zeros((B, L), np.int64); dec = seq.copy(); lab = seq.copy()
+    for b, n in enumerate([200, 61]):
+        items = rng.integers(1, I + 1, size=n)
+        msk = rng.random(n) < 0.2
+        msk[-1] = True
+        dec[b, L - n:] = items
+        seq[b, L - n:] = np.where(msk, I + 1, items)
+        lab[b, L - n:] = np.where(msk, items, 0)
+    cfg = BO.BCfg(I, L, H, nh, nl, inner, p, pa)
+    out = BO.forward(sd, cfg, torch.from_numpy(seq), torch.from_numpy(dec), Drop(0.5, 77, 5, train=True))
+    l1, l2 = [0.005], [0.0019]
+    ref = BO.loss(cfg, out, torch.from_numpy(lab), l1, l2)
+    ref.backward()
+    m = m.cuda().train()
+    m.drop_seed, m.drop_step = 77, 5
+    loss = m.fused_loss(seq, dec, lab, l1, l2)
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < 1e-5
+    loss.backward()
+    for k, prm in m.named_parameters():
+        assert grad_close(prm.grad, sd[k].grad.numpy()), k
