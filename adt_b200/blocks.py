@@ -40,7 +40,7 @@ class DropCfg:
         d = L.adt_dropout()
         d.enabled = 1 if (self.training and self.p > 0.0) else 0
         d.p, d.seed, d.step, d.site = self.p, self.seed, self.step, self.site
-        d.base = self.b0 * (nh * Lq * Lq if kind == "attn" else Lq * H)
+        d.base = self.b0 * (nh * Lq if kind == "attn" else Lq * H)   # attention sites: ROW offset ; row sites: element offset
         d.step_dev = None
         if self.training and self.p > 0.0:
             self.site += 1

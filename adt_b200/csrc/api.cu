@@ -83,6 +83,8 @@ static DropDesc mk_drop(const adt_dropout& d) {
   if (t < 0) t = 0;
   if (t > 4294967295.0) t = 4294967295.0;
   r.thr = (uint32_t)t;
+  double t16 = floor((double)d.p * 65536.0 + 0.5);
+  r.thr16 = (uint32_t)(t16 < 0 ? 0 : (t16 > 65535.0 ? 65535.0 : t16));
   r.scale = 1.0f / (1.0f - d.p);
   r.seed_lo = (uint32_t)(d.seed & 0xffffffffull);
   r.seed_hi = (uint32_t)(d.seed >> 32);
@@ -561,4 +563,9 @@ extern "C" int adt_softmax_ce_fwd(const float* logits, const int32_t* labels, fl
 extern "C" int adt_softmax_ce_bwd(float* logits, const int32_t* labels, const float* lse, float coef, int32_t R, int32_t V, adt_stream_t s_) {
   softmax_ce_kernel<<<min(R, 148 * 8), NT, 0, (cudaStream_t)s_>>>(logits, labels, const_cast<float*>(lse), nullptr, R, V, 1, coef);
   return check_launch("softmax_ce_bwd");
+}
+
+extern "C" int adt_debug_read(long long* out, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_dbg_clock, sizeof(long long) * (n < 64 ? n : 64)) == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }

@@ -13,6 +13,10 @@
 
 namespace adt {
 
+// phase timestamps of CTA (0,0,0) for latency debugging (read back with adt_debug_read)
+__device__ long long g_dbg_clock[64];
+#define ADT_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
+
 constexpr int NT = 256;        // threads per CTA for all row-tile kernels
 constexpr int CH = 64;         // weight chunk edge (rows and cols)
 constexpr int CHP = CH + 4;    // padded chunk row stride in floats (272 B: 16B aligned, LDS.128 conflict free)
@@ -27,6 +31,7 @@ constexpr int WS_FLOATS = WS_NST * WS_SLOT;  // staging area
 struct DropDesc {
   uint32_t enabled;   // 0: identity
   uint32_t thr;       // keep iff rnd >= thr
+  uint32_t thr16;     // 16-bit threshold of the attention-probability sites
   float scale;        // 1/(1-p)
   uint32_t seed_lo, seed_hi, step, site;
   unsigned long long base;  // element offset added to every index (batch offset b0 * per-sample elements)
@@ -60,6 +65,16 @@ __device__ __forceinline__ float drop_mul1(const DropDesc& d, unsigned long long
   const uint32_t lane = (uint32_t)idx & 3u;
   const uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
   return v >= d.thr ? d.scale : 0.f;
+}
+
+// attention-probability sites: multipliers for keys 8*c8 .. 8*c8+7 of row r (padded row stride lp8 = ceil8(L)/8 calls):
+// 16-bit lane k of philox(ctr = r*lp8 + c8); d.base holds the ROW offset of this rank.
+__device__ __forceinline__ void drop_mul8_attn(const DropDesc& d, unsigned long long r, int lp8, int c8, float (&m)[8]) {
+  const unsigned long long c = r * (unsigned long long)lp8 + (unsigned long long)c8;
+  const uint4 x = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), d.site, drop_step(d), d.seed_lo, d.seed_hi);
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = ((w[k >> 1] >> (16 * (k & 1))) & 0xffffu) >= d.thr16 ? d.scale : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -128,106 +143,138 @@ __device__ __forceinline__ void store_tile(const float* __restrict__ T, int ld, 
   }
 }
 
-// LayerNorm of every row of a tile (warp per row), biased variance, eps inside the sqrt
-// (torch.nn.LayerNorm; reference uses eps=1e-8, sasrec/modules.py:638,640,660 and model.py:29).
-// dst may alias src.  Rows with row0+r >= M are written as zeros.
+// LayerNorm of every row of a tile, biased variance, eps inside the sqrt (torch.nn.LayerNorm; reference eps=1e-8,
+// sasrec/modules.py:638,640,660 and model.py:29).  FOUR lanes per row (64 rows in flight per pass, two shuffle steps
+// per reduction) instead of a warp per row: the per-row dependent chain (sum -> mean -> var -> rsqrt) is latency
+// bound, so rows must run side by side.  dst may alias src.  Rows with row0+r >= M are written as zeros.
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
 template <int TM>
 __device__ __forceinline__ void ln_tile(const float* __restrict__ S, float* __restrict__ D, int ld, int C,
-                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int row0, int M) {
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int r = w; r < TM; r += NT / 32) {
-    const float* s = S + r * ld;
-    float* d = D + r * ld;
-    if (row0 + r >= M) {
-      for (int c = l; c < C; c += 32) d[c] = 0.f;
-      continue;
-    }
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int row0, int M,
+                                        float* __restrict__ stats = nullptr) {
+  const int q = threadIdx.x & 3, n4 = C >> 2;
+  for (int r = threadIdx.x >> 2; r < ((TM + 63) & ~63); r += NT / 4) {
+    const bool in_tile = r < TM;
+    const bool valid = in_tile && (row0 + r < M);
+    const float* s = S + (in_tile ? r : 0) * ld;
     float sum = 0.f;
-    for (int c = l; c < C; c += 32) sum += s[c];
-    const float mean = warp_sum(sum) / (float)C;
+    if (valid)
+      for (int g = q; g < n4; g += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(s + 4 * g);
+        sum += (v.x + v.y) + (v.z + v.w);
+      }
+    const float mean = quad_sum(sum) / (float)C;
     float var = 0.f;
-    for (int c = l; c < C; c += 32) {
-      const float t = s[c] - mean;
-      var += t * t;
+    if (valid)
+      for (int g = q; g < n4; g += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(s + 4 * g);
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        var += (a * a + b * b) + (c * c + d * d);
+      }
+    const float rstd = 1.0f / sqrtf(quad_sum(var) / (float)C + eps);
+    if (stats && in_tile && q == 0) { stats[2 * r] = valid ? mean : 0.f; stats[2 * r + 1] = valid ? rstd : 0.f; }
+    if (!in_tile) continue;
+    float* d = D + r * ld;
+    for (int g = q; g < n4; g += 4) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        const float4 v = *reinterpret_cast<const float4*>(s + 4 * g);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + g), be = __ldg(reinterpret_cast<const float4*>(beta) + g);
+        o = make_float4((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y, (v.z - mean) * rstd * ga.z + be.z,
+                        (v.w - mean) * rstd * ga.w + be.w);
+      }
+      *reinterpret_cast<float4*>(d + 4 * g) = o;
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(var) / (float)C + eps);
-    for (int c = l; c < C; c += 32) d[c] = (s[c] - mean) * rstd * gamma[c] + beta[c];
   }
 }
 
 // LayerNorm backward on a tile. X: LN input rows, G: upstream grad rows (dL/d out). Writes dX into DX (may alias G,
-// must not alias X) -- if ACCUM, adds to DX instead.  dgamma/dbeta are accumulated with atomics (one per column per CTA).
-// red: smem scratch of 2*(NT/32)*C floats.
+// must not alias X) -- if ACCUM, adds to DX instead.  Four lanes per row for the row statistics; dgamma/dbeta are
+// column sums over the tile done by (column, row-group) threads and added with atomics.
+// red: smem scratch of >= 4*TM floats (mean, rstd per row).
 template <int TM, bool ACCUM>
 __device__ __forceinline__ void ln_bwd_tile(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ DX, int ld,
                                             int C, const float* __restrict__ gamma, float eps, int row0, int M,
                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ red) {
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  constexpr int NW = NT / 32;
-  float dg[8], db[8];  // C <= 256 -> at most 8 columns per lane
-#pragma unroll
-  for (int u = 0; u < 8; ++u) dg[u] = db[u] = 0.f;
-  for (int r = w; r < TM; r += NW) {
-    if (row0 + r >= M) {
-      if (!ACCUM)
-        for (int c = l; c < C; c += 32) DX[r * ld + c] = 0.f;
-      continue;
-    }
-    const float* x = X + r * ld;
-    const float* g = G + r * ld;
+  const int q = threadIdx.x & 3, n4 = C >> 2;
+  // column sums first (they need the un-overwritten G when DX aliases G): dgamma[c] = sum_r g*xhat, dbeta[c] = sum_r g
+  for (int r = threadIdx.x >> 2; r < ((TM + 63) & ~63); r += NT / 4) {
+    const bool in_tile = r < TM;
+    const bool valid = in_tile && (row0 + r < M);
+    const float* x = X + (in_tile ? r : 0) * ld;
     float sum = 0.f;
-    for (int c = l; c < C; c += 32) sum += x[c];
-    const float mean = warp_sum(sum) / (float)C;
+    if (valid)
+      for (int g = q; g < n4; g += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + 4 * g);
+        sum += (v.x + v.y) + (v.z + v.w);
+      }
+    const float mean = quad_sum(sum) / (float)C;
     float var = 0.f;
-    for (int c = l; c < C; c += 32) {
-      const float t = x[c] - mean;
-      var += t * t;
+    if (valid)
+      for (int g = q; g < n4; g += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + 4 * g);
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        var += (a * a + b * b) + (c * c + d * d);
+      }
+    const float rstd = 1.0f / sqrtf(quad_sum(var) / (float)C + eps);
+    if (in_tile && q == 0) { red[2 * r] = mean; red[2 * r + 1] = valid ? rstd : 0.f; }
+  }
+  __syncthreads();
+  {
+    const int groups = NT / C > 0 ? NT / C : 1;
+    const int col = threadIdx.x % C, grp = threadIdx.x / C;
+    if (grp < groups) {
+      for (int c = col; c < C; c += NT) {   // (only iterates once unless C > NT)
+        float dg = 0.f, db = 0.f;
+        for (int r = grp; r < TM; r += groups) {
+          const float rs = red[2 * r + 1];
+          if (rs != 0.f) {
+            const float g = G[r * ld + c];
+            dg = fmaf(g, (X[r * ld + c] - red[2 * r]) * rs, dg);
+            db += g;
+          }
+        }
+        atomicAdd(dgamma + c, dg);
+        atomicAdd(dbeta + c, db);
+      }
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(var) / (float)C + eps);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x >> 2; r < ((TM + 63) & ~63); r += NT / 4) {
+    const bool in_tile = r < TM;
+    const float mean = in_tile ? red[2 * r] : 0.f, rstd = in_tile ? red[2 * r + 1] : 0.f;
+    const bool valid = in_tile && rstd != 0.f;
+    const float* x = X + (in_tile ? r : 0) * ld;
+    const float* gr = G + (in_tile ? r : 0) * ld;
     float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = l + 32 * u;
-      if (c < C) {
-        const float xh = (x[c] - mean) * rstd;
-        const float gg = g[c] * gamma[c];
-        s1 += gg;
-        s2 += gg * xh;
-        dg[u] += g[c] * xh;
-        db[u] += g[c];
+    if (valid)
+      for (int g = q; g < n4; g += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + 4 * g), gv = *reinterpret_cast<const float4*>(gr + 4 * g);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + g);
+        const float g0 = gv.x * ga.x, g1 = gv.y * ga.y, g2 = gv.z * ga.z, g3 = gv.w * ga.w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * (xv.x - mean) + g1 * (xv.y - mean)) * rstd + (g2 * (xv.z - mean) + g3 * (xv.w - mean)) * rstd;
       }
-    }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = l + 32 * u;
-      if (c < C) {
-        const float xh = (x[c] - mean) * rstd;
-        const float v = rstd * (g[c] * gamma[c] - s1 - xh * s2);
-        if (ACCUM) DX[r * ld + c] += v; else DX[r * ld + c] = v;
+    s1 = quad_sum(s1) / (float)C;
+    s2 = quad_sum(s2) / (float)C;
+    if (!in_tile) continue;
+    float* dx = DX + r * ld;
+    for (int g = q; g < n4; g += 4) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + 4 * g), gv = *reinterpret_cast<const float4*>(gr + 4 * g);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + g);
+        o = make_float4(rstd * (gv.x * ga.x - s1 - (xv.x - mean) * rstd * s2), rstd * (gv.y * ga.y - s1 - (xv.y - mean) * rstd * s2),
+                        rstd * (gv.z * ga.z - s1 - (xv.z - mean) * rstd * s2), rstd * (gv.w * ga.w - s1 - (xv.w - mean) * rstd * s2));
       }
+      float4* dst = reinterpret_cast<float4*>(dx + 4 * g);
+      if (ACCUM) { const float4 old = *dst; o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w); }
+      *dst = o;
     }
-  }
-  // cross-warp reduction of dgamma/dbeta
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int c = l + 32 * u;
-    if (c < C) {
-      red[w * C + c] = dg[u];
-      red[(NW + w) * C + c] = db[u];
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += NT) {
-    float a = 0.f, b = 0.f;
-    for (int i = 0; i < NW; ++i) {
-      a += red[i * C + c];
-      b += red[(NW + i) * C + c];
-    }
-    atomicAdd(dgamma + c, a);
-    atomicAdd(dbeta + c, b);
   }
   __syncthreads();
 }
@@ -377,14 +424,22 @@ struct WStreamState {
 template <int NST, bool MMA = false>
 struct WStream {
   WStreamState* st;   // shared memory
-  float* bufs;        // NST * CH * CHP floats
-  int next_g, next_t, slot_issue, slot_cons, last_slot;
+  float* bufs;        // NST * WS_SLOT floats
+  int next_g, slot_issue, slot_cons, last_slot;
+  // iteration state of the GEMM being issued (kept in registers: no divisions, no descriptor reloads per chunk)
+  GemmDesc d;
+  int oc, rc, noc, nrc;
 
+  __device__ __forceinline__ void load_desc() {
+    if (next_g < st->ng) {
+      d = st->g[next_g];
+      noc = (d.Nout + CH - 1) / CH;
+      nrc = (d.Kred + CH - 1) / CH;
+    }
+    oc = rc = 0;
+  }
   __device__ __forceinline__ void issue() {
     if (next_g < st->ng) {
-      const GemmDesc d = st->g[next_g];
-      const int noc = (d.Nout + CH - 1) / CH, nrc = (d.Kred + CH - 1) / CH;
-      const int oc = next_t / nrc, rc = next_t - oc * nrc;
       float* buf = bufs + slot_issue * WS_SLOT;
       if (!d.nn) {
         if (MMA) stage_chunk<false, CHPB>(buf, d.W, d.ldw, oc * CH, rc * CH, min(CH, d.Nout - oc * CH), min(CH, d.Kred - rc * CH));
@@ -392,20 +447,30 @@ struct WStream {
       } else {
         stage_chunk<false, CHP>(buf, d.W, d.ldw, rc * CH, oc * CH, min(CH, d.Kred - rc * CH), min(CH, d.Nout - oc * CH));
       }
-      if (++next_t == noc * nrc) { next_t = 0; ++next_g; }
+      if (++rc == nrc) {
+        rc = 0;
+        if (++oc == noc) { ++next_g; load_desc(); }
+      }
     }
     slot_issue = slot_issue + 1 == NST ? 0 : slot_issue + 1;
     cp_async_commit();
   }
   // call once, by all threads, after the descriptors were written to *st and __syncthreads()
   __device__ __forceinline__ void start(WStreamState* s, float* b) {
-    st = s; bufs = b; next_g = next_t = 0; slot_issue = slot_cons = 0; last_slot = NST - 1;
+    st = s; bufs = b; next_g = 0; slot_issue = slot_cons = 0; last_slot = NST - 1;
+    load_desc();
 #pragma unroll
     for (int i = 0; i < NST - 1; ++i) issue();
   }
   // the most recently consumed ring slot: free to use as scratch until the next gemm_stream call
   __device__ __forceinline__ float* scratch() const { return bufs + last_slot * WS_SLOT; }
 };
+
+// warm the L1 with a small read-only vector (biases, LayerNorm affine) so that the first epilogue / LN touch hits
+__device__ __forceinline__ void prefetch_vec(const float* p, int n) {
+  if (p)
+    for (int i = threadIdx.x * 32; i < n; i += NT * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
+}
 
 // ---------------------------------------------------------------------------------------------
 // bf16 tensor-core GEMM cores (mma.sync.m16n8k16, fp32 accumulate).  Operands stay fp32 in shared memory and are
@@ -508,15 +573,18 @@ __device__ __forceinline__ void gemm_stream(const float* __restrict__ A, int lda
   const int noc = (Nout + CH - 1) / CH, nrc = (Kred + CH - 1) / CH;
   const int total = noc * nrc;
   float acc[MMA ? NB : RM][4];
+  int oc = 0, rc = 0;
   for (int t = 0; t < total; ++t) {
-    const int oc = t / nrc, rc = t - oc * nrc;
     if (rc == 0) {
 #pragma unroll
       for (int i = 0; i < (MMA ? NB : RM); ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     }
+    if (gi == 0 && t == 0) ADT_STAMP(16);
     ws.issue();
+    if (gi == 0 && t == 0) ADT_STAMP(17);
     cp_async_wait<NST - 1>();
     __syncthreads();
+    if (gi == 0 && t == 0) ADT_STAMP(18);
     const float* buf = ws.bufs + ws.slot_cons * WS_SLOT;
     ws.last_slot = ws.slot_cons;
     ws.slot_cons = ws.slot_cons + 1 == NST ? 0 : ws.slot_cons + 1;
@@ -528,14 +596,17 @@ __device__ __forceinline__ void gemm_stream(const float* __restrict__ A, int lda
       if (!NN) mma_nt<RM>(reinterpret_cast<float(&)[RM][4]>(acc), A, lda, rc * CH, buf, rlen);
       else mma_nn<RM>(reinterpret_cast<float(&)[RM][4]>(acc), A, lda, rc * CH, buf, rlen);
     }
+    if (gi == 0 && t == 0) ADT_STAMP(19);
     if (rc == nrc - 1) {
       if constexpr (MMA) {
 #pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          int rl, cc;
-          const float4 v = mma_out4<TM>(reinterpret_cast<float(&)[NB][4]>(acc)[j], j, rl, cc);
-          if (oc * CH + cc < Nout) epi(j, rl, oc * CH + cc, v);
-        }
+        float4 v[NB];
+        int rl = 0, cc[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) v[j] = mma_out4<TM>(reinterpret_cast<float(&)[NB][4]>(acc)[j], j, rl, cc[j]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (oc * CH + cc[j] < Nout) epi(j, rl, oc * CH + cc[j], v[j]);
       } else {
         const int col = oc * CH + 4 * tx;
         if (col < Nout) {
@@ -544,7 +615,10 @@ __device__ __forceinline__ void gemm_stream(const float* __restrict__ A, int lda
         }
       }
     }
+    if (gi == 0 && t == 0) ADT_STAMP(20);
     __syncthreads();
+    if (gi == 0 && t == 0) ADT_STAMP(21);
+    if (++rc == nrc) { rc = 0; ++oc; }
   }
 }
 
@@ -631,12 +705,16 @@ __device__ __forceinline__ void wgrad_tile_bf16(const float* __restrict__ dY, in
     }
 }
 
-// db[n] += sum_{r<rows} dY[r][n]
+// db[n] += sum_{r<rows} dY[r][n]  (thread per column, 4 independent partial sums; one atomic per column per CTA)
 __device__ __forceinline__ void colsum_atomic(const float* __restrict__ dY, int ldy, int N, int rows, float* __restrict__ db) {
   for (int n = threadIdx.x; n < N; n += NT) {
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s += dY[r * ldy + n];
-    atomicAdd(db + n, s);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 3 < rows; r += 4) {
+      s0 += dY[r * ldy + n]; s1 += dY[(r + 1) * ldy + n]; s2 += dY[(r + 2) * ldy + n]; s3 += dY[(r + 3) * ldy + n];
+    }
+    for (; r < rows; ++r) s0 += dY[r * ldy + n];
+    atomicAdd(db + n, (s0 + s1) + (s2 + s3));
   }
 }
 

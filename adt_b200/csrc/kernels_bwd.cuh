@@ -242,52 +242,51 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
   gemm_stream<TM, false, WS_NST, MMA>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) { st4(Ps + r * lds + col, a); });
   gemm_stream<TM, false, WS_NST, MMA>(dCs, ldq, ws, 1, [&](int, int r, int col, float4 a) { st4(dPs + r * lds + col, a); });
 
+  // per-row part, LPR lanes per row / 32/LPR rows side by side per warp (see attn_fwd)
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int r = w; r < TM; r += NT / 32) {
+  const int lpr = Lk4 <= 64 ? 8 : 32;
+  const int rpw = 32 / lpr;
+  const int sub = l % lpr;
+  for (int r = w * rpw + l / lpr; r < TM; r += (NT / 32) * rpw) {
     const int i = i0 + r;
     float* prow = Ps + r * lds;
     float* drow = dPs + r * lds;
-    if (i >= L) {
-      for (int j = l; j < Lk4; j += 32) prow[j] = drow[j] = 0.f;
-      continue;
+    const bool valid = i < L;
+    const int nj = !valid ? 0 : (mask_mode == 0 ? i + 1 : L);
+    const float ls = valid ? lse[((long long)b * nh + h) * L + i] : 0.f;
+    const int j0 = 8 * sub;
+    float sv[8], dv8[8], mv[8];
+    {
+      float4 s0 = zero4(), s1 = zero4(), d0 = zero4(), d1 = zero4();
+      if (j0 < nj) { s0 = ld4(prow + j0); d0 = ld4(drow + j0); }
+      if (j0 + 4 < nj) { s1 = ld4(prow + j0 + 4); d1 = ld4(drow + j0 + 4); }
+      sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+      dv8[0] = d0.x; dv8[1] = d0.y; dv8[2] = d0.z; dv8[3] = d0.w; dv8[4] = d1.x; dv8[5] = d1.y; dv8[6] = d1.z; dv8[7] = d1.w;
     }
-    const int nj = mask_mode == 0 ? i + 1 : L;
-    const float ls = lse[((long long)b * nh + h) * L + i];
-    const unsigned long long rbase = drop.base + (((unsigned long long)b * nh + h) * L + i) * (unsigned long long)L;
-    float pv[8], dpv[8], mv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mv[c] = 1.f;
+    if (drop.enabled && j0 < nj) drop_mul8_attn(drop, drop.base + ((unsigned long long)b * nh + h) * L + i, ((L + 7) & ~7) >> 3, sub, mv);
     float delta = 0.f;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j0 = 4 * l + 128 * u;
-      float4 s4 = zero4(), d4 = zero4(), m4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (j0 < nj) {
-        s4 = ld4(prow + j0);
-        d4 = ld4(drow + j0);
-        if (drop.enabled) m4 = drop_mul4_unaligned(drop, rbase + j0);
+    for (int c = 0; c < 8; ++c) {
+      float pj = 0.f, dp = 0.f;
+      if (j0 + c < nj) {
+        float sc = sv[c];
+        if (mask_mode == 1 && key_ids[b * L + j0 + c] == 0) sc = -1e9f;
+        pj = expf(sc - ls);
+        dp = dv8[c] * mv[c];
+        delta = fmaf(dp, pj, delta);
       }
-      const float st[4] = {s4.x, s4.y, s4.z, s4.w}, dt[4] = {d4.x, d4.y, d4.z, d4.w}, mt[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float pj = 0.f, dp = 0.f;
-        if (j0 + c < nj) {
-          float sc = st[c];
-          if (mask_mode == 1 && key_ids[b * L + j0 + c] == 0) sc = -1e9f;
-          pj = expf(sc - ls);
-          dp = dt[c] * mt[c];
-          delta = fmaf(dp, pj, delta);
-        }
-        pv[4 * u + c] = pj; dpv[4 * u + c] = dp; mv[4 * u + c] = mt[c];
-      }
+      sv[c] = pj; dv8[c] = dp;
     }
-    delta = warp_sum(delta);
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j0 = 4 * l + 128 * u;
-      if (j0 < Lk4) {
-        st4(prow + j0, make_float4(pv[4 * u] * mv[4 * u], pv[4 * u + 1] * mv[4 * u + 1], pv[4 * u + 2] * mv[4 * u + 2], pv[4 * u + 3] * mv[4 * u + 3]));
-        st4(drow + j0, make_float4(pv[4 * u] * (dpv[4 * u] - delta), pv[4 * u + 1] * (dpv[4 * u + 1] - delta),
-                                   pv[4 * u + 2] * (dpv[4 * u + 2] - delta), pv[4 * u + 3] * (dpv[4 * u + 3] - delta)));
-      }
+    for (int o = lpr >> 1; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+    if (j0 < Lk4) {
+      st4(prow + j0, make_float4(sv[0] * mv[0], sv[1] * mv[1], sv[2] * mv[2], sv[3] * mv[3]));
+      st4(drow + j0, make_float4(sv[0] * (dv8[0] - delta), sv[1] * (dv8[1] - delta), sv[2] * (dv8[2] - delta), sv[3] * (dv8[3] - delta)));
+    }
+    if (j0 + 4 < Lk4) {
+      st4(prow + j0 + 4, make_float4(sv[4] * mv[4], sv[5] * mv[5], sv[6] * mv[6], sv[7] * mv[7]));
+      st4(drow + j0 + 4, make_float4(sv[4] * (dv8[4] - delta), sv[5] * (dv8[5] - delta), sv[6] * (dv8[6] - delta), sv[7] * (dv8[7] - delta)));
     }
   }
   __syncthreads();

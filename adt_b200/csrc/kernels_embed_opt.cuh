@@ -261,12 +261,18 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     const float tn = (float)sqrt(*a.gnormsq);
     coef = fminf(a.max_norm / (tn + 1e-6f), 1.0f);
   }
-  float bc1 = a.bc1, bc2 = a.bc2;
-  if (a.step_dev) {
-    const double t = (double)*a.step_dev;
-    bc1 = (float)(1.0 - pow((double)a.beta1, t));
-    bc2 = (float)(1.0 - pow((double)a.beta2, t));
+  __shared__ float bc_s[2];
+  if (threadIdx.x == 0) {       // one thread evaluates the double-precision bias corrections for the CTA
+    float b1 = a.bc1, b2 = a.bc2;
+    if (a.step_dev) {
+      const double t = (double)*a.step_dev;
+      b1 = (float)(1.0 - pow((double)a.beta1, t));
+      b2 = (float)(1.0 - pow((double)a.beta2, t));
+    }
+    bc_s[0] = b1; bc_s[1] = b2;
   }
+  __syncthreads();
+  const float bc1 = bc_s[0], bc2 = bc_s[1];
   const float step = a.lr / bc1;
   const float isb2 = 1.0f / sqrtf(bc2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {

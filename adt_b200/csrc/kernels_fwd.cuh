@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(NT) pre_fwd_kernel(const float* __restrict__ x
   float* Ns = Xs + TM * ld;
   float* Ws = Ns + TM * ld;
   const int row0 = blockIdx.x * TM;
+  ADT_STAMP(0);
+  prefetch_vec(ln_g, H); prefetch_vec(ln_b, H); prefetch_vec(bin, 3 * H);
   __shared__ WStreamState wst;
   if (threadIdx.x == 0) {
     wst.g[0] = GemmDesc{Win, H, H, H, 0};
@@ -62,25 +64,30 @@ __global__ void __launch_bounds__(NT) pre_fwd_kernel(const float* __restrict__ x
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
+  ADT_STAMP(1);
   load_tile<TM>(Xs, ld, x, H, 0, H, row0, M);
   __syncthreads();
+  ADT_STAMP(2);
   ln_tile<TM>(Xs, Ns, ld, H, ln_g, ln_b, 1e-8f, row0, M);
   __syncthreads();
+  ADT_STAMP(3);
   if (norm_out) store_tile<TM>(Ns, ld, norm_out, H, 0, H, row0, M);
   gemm_stream<TM, false, WS_NST, MMA>(Ns, ld, ws, 0, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
-      const float4 b = *reinterpret_cast<const float4*>(bin + col);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bin + col));
       *reinterpret_cast<float4*>(q + (long long)(row0 + r) * H + col) = f4_scale(f4_add(a, b), qscale);
     }
   });
+  ADT_STAMP(4);
   const float* Akv = kv_from_norm ? Ns : Xs;
   gemm_stream<TM, false, WS_NST, MMA>(Akv, ld, ws, 1, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
-      const float4 b = *reinterpret_cast<const float4*>(bin + H + col);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bin + H + col));
       float* dst = col < H ? (k + (long long)(row0 + r) * H + col) : (v + (long long)(row0 + r) * H + (col - H));
       *reinterpret_cast<float4*>(dst) = f4_add(a, b);
     }
   });
+  ADT_STAMP(5);
 }
 
 // multipliers for 4 consecutive elements starting at an arbitrary (not 4-aligned) linear index
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
   const int i0 = blockIdx.x * TM, h = blockIdx.y, b = blockIdx.z;
   const long long seq_off = (long long)b * L * H + (long long)h * hd;
   const int Lk = mask_mode == 0 ? min(L, i0 + TM) : L;  // keys this tile can see
-
+  ADT_STAMP(8);
   __shared__ WStreamState wst;
   if (threadIdx.x == 0) {
     wst.g[0] = GemmDesc{k + seq_off, H, Lk, hd, 0};
@@ -126,66 +133,70 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
+  ADT_STAMP(9);
   load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
   __syncthreads();
+  ADT_STAMP(10);
   gemm_stream<TM, false, WS_NST, MMA>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) {
     *reinterpret_cast<float4*>(Ss + r * lds + col) = a;
   });
+  ADT_STAMP(11);
 
-  // softmax + dropout, warp per row
+  // softmax + dropout.  A lane owns 8 consecutive keys (one aligned Philox call); a row is handled by LPR lanes
+  // (8 when all visible keys fit 64, else 32) so that 32/LPR rows run side by side in every warp -- the per-row chain
+  // (max -> exp -> sum -> 1/sum) is latency bound.
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int Lk4 = (Lk + 3) & ~3;
-  for (int r = w; r < TM; r += NT / 32) {
+  const int lpr = Lk4 <= 64 ? 8 : 32;
+  const int rpw = 32 / lpr;                 // rows per warp per pass
+  const int sub = l % lpr;
+  for (int r = w * rpw + l / lpr; r < TM; r += (NT / 32) * rpw) {
     const int i = i0 + r;
     float* srow = Ss + r * lds;
-    if (i >= L) {
-      for (int j = l; j < Lk4; j += 32) srow[j] = 0.f;
-      continue;
+    const bool valid = i < L;
+    const int nj = !valid ? 0 : (mask_mode == 0 ? i + 1 : L);
+    const int j0 = 8 * sub;
+    float sv[8];
+    {
+      float4 s0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s1 = s0;
+      if (j0 < nj) s0 = *reinterpret_cast<const float4*>(srow + j0);
+      if (j0 + 4 < nj) s1 = *reinterpret_cast<const float4*>(srow + j0 + 4);
+      sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
     }
-    const int nj = mask_mode == 0 ? i + 1 : L;
-    float sv[8];      // lane owns keys 4l..4l+3 and 128+4l..128+4l+3
     float mx = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j0 = 4 * l + 128 * u;
-      float4 s4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      if (j0 < nj) s4 = *reinterpret_cast<const float4*>(srow + j0);
-      float t[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float sc = (j0 + c < nj) ? t[c] : -INFINITY;
-        if (mask_mode == 1 && j0 + c < nj && key_ids[b * L + j0 + c] == 0) sc = -1e9f;
-        sv[4 * u + c] = sc;
-        mx = fmaxf(mx, sc);
-      }
+    for (int c = 0; c < 8; ++c) {
+      float sc = (j0 + c < nj) ? sv[c] : -INFINITY;
+      if (mask_mode == 1 && j0 + c < nj && key_ids[b * L + j0 + c] == 0) sc = -1e9f;
+      sv[c] = sc;
+      mx = fmaxf(mx, sc);
     }
-    mx = warp_max(mx);
+    for (int o = lpr >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float e = sv[u] == -INFINITY ? 0.f : expf(sv[u] - mx);
-      sv[u] = e;
+    for (int c = 0; c < 8; ++c) {
+      const float e = sv[c] == -INFINITY ? 0.f : expf(sv[c] - mx);
+      sv[c] = e;
       sum += e;
     }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    if (lse && l == 0) lse[((long long)b * nh + h) * L + i] = mx + logf(sum);
-    const unsigned long long rbase = drop.base + (((unsigned long long)b * nh + h) * L + i) * (unsigned long long)L;
+    for (int o = lpr >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = valid ? 1.0f / sum : 0.f;
+    if (lse && valid && sub == 0) lse[((long long)b * nh + h) * L + i] = mx + logf(sum);
+    if (drop.enabled && j0 < nj) {
+      float m[8];
+      drop_mul8_attn(drop, drop.base + ((unsigned long long)b * nh + h) * L + i, ((L + 7) & ~7) >> 3, sub, m);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j0 = 4 * l + 128 * u;
-      if (j0 < Lk4) {
-        float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (drop.enabled && j0 < nj) m = drop_mul4_unaligned(drop, rbase + j0);
-        *reinterpret_cast<float4*>(srow + j0) =
-            make_float4(sv[4 * u] * inv * m.x, sv[4 * u + 1] * inv * m.y, sv[4 * u + 2] * inv * m.z, sv[4 * u + 3] * inv * m.w);
-      }
+      for (int c = 0; c < 8; ++c) sv[c] *= m[c];
     }
+    if (j0 < Lk4) *reinterpret_cast<float4*>(srow + j0) = make_float4(sv[0] * inv, sv[1] * inv, sv[2] * inv, sv[3] * inv);
+    if (j0 + 4 < Lk4) *reinterpret_cast<float4*>(srow + j0 + 4) = make_float4(sv[4] * inv, sv[5] * inv, sv[6] * inv, sv[7] * inv);
   }
   __syncthreads();
+  ADT_STAMP(12);
   gemm_stream<TM, true, WS_NST, MMA>(Ss, lds, ws, 1, [&](int, int r, int col, float4 a) {
     if (i0 + r < L) *reinterpret_cast<float4*>(ctx + seq_off + (long long)(i0 + r) * H + col) = a;
   });
+  ADT_STAMP(13);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -205,6 +216,7 @@ __global__ void __launch_bounds__(NT) mid_fwd_kernel(const float* __restrict__ c
   float* T2 = T1 + TM * ld;
   float* Ws = T2 + TM * ld;
   const int row0 = blockIdx.x * TM;
+  prefetch_vec(bo1, H); prefetch_vec(bin2, 3 * H);
   __shared__ WStreamState wst;
   if (threadIdx.x == 0) {
     wst.g[0] = GemmDesc{Wo1, H, H, H, 0};
@@ -219,18 +231,18 @@ __global__ void __launch_bounds__(NT) mid_fwd_kernel(const float* __restrict__ c
   load_tile<TM>(T2, ld, feats, H, 0, H, row0, M);
   __syncthreads();
   gemm_stream<TM, false, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
-    const float4 o = f4_add(a, *reinterpret_cast<const float4*>(bo1 + col));
+    const float4 o = f4_add(a, __ldg(reinterpret_cast<const float4*>(bo1 + col)));
     *reinterpret_cast<float4*>(T1 + r * ld + col) = o;
     if (a_out && row0 + r < M) *reinterpret_cast<float4*>(a_out + (long long)(row0 + r) * H + col) = o;
   });
   gemm_stream<TM, false, WS_NST, MMA>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
     if (row0 + r < M)
       *reinterpret_cast<float4*>(q2 + (long long)(row0 + r) * H + col) =
-          f4_scale(f4_add(a, *reinterpret_cast<const float4*>(bin2 + col)), qscale);
+          f4_scale(f4_add(a, __ldg(reinterpret_cast<const float4*>(bin2 + col))), qscale);
   });
   gemm_stream<TM, false, WS_NST, MMA>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
     if (row0 + r < M) {
-      const float4 o = f4_add(a, *reinterpret_cast<const float4*>(bin2 + H + col));
+      const float4 o = f4_add(a, __ldg(reinterpret_cast<const float4*>(bin2 + H + col)));
       float* dst = col < H ? (k2 + (long long)(row0 + r) * H + col) : (v2 + (long long)(row0 + r) * H + (col - H));
       *reinterpret_cast<float4*>(dst) = o;
     }
@@ -272,6 +284,8 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
   float* T2 = T1 + TM * ld;
   float* Ws = T2 + TM * ld;
   const int row0 = blockIdx.x * TM;
+  prefetch_vec(p.bo, H); prefetch_vec(p.c1, H); prefetch_vec(p.c2, H);
+  if (!IS_DEC) { prefetch_vec(p.ln1_g, H); prefetch_vec(p.ln1_b, H); prefetch_vec(p.ln2_g, H); prefetch_vec(p.ln2_b, H); }
   __shared__ WStreamState wst;
   if (threadIdx.x == 0) {
     wst.g[0] = GemmDesc{p.Wo, H, H, H, 0};
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
   }
   __syncthreads();
   gemm_stream<TM, false, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
-    float4 o = f4_add(a, *reinterpret_cast<const float4*>(p.bo + col));
+    float4 o = f4_add(a, __ldg(reinterpret_cast<const float4*>(p.bo + col)));
     if (!IS_DEC) o = f4_add(o, *reinterpret_cast<const float4*>(T1 + r * ld + col));
     *reinterpret_cast<float4*>(T1 + r * ld + col) = o;
     if (p.u_save && row0 + r < M) *reinterpret_cast<float4*>(p.u_save + (long long)(row0 + r) * H + col) = o;
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
     __syncthreads();
   }
   gemm_stream<TM, false, WS_NST, MMA>(T1, ld, ws, 1, [&](int, int r, int col, float4 a) {
-    float4 h1 = f4_add(a, *reinterpret_cast<const float4*>(p.c1 + col));
+    float4 h1 = f4_add(a, __ldg(reinterpret_cast<const float4*>(p.c1 + col)));
     if (p.h1_save && row0 + r < M) *reinterpret_cast<float4*>(p.h1_save + (long long)(row0 + r) * H + col) = h1;
     if (p.drop1.enabled) h1 = f4_mul(h1, drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)(row0 + r) * H + col) >> 2));
     *reinterpret_cast<float4*>(T2 + r * ld + col) = make_float4(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), fmaxf(h1.z, 0.f), fmaxf(h1.w, 0.f));
@@ -343,7 +357,7 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
   double sq = 0.0;
   gemm_stream<TM, false, WS_NST, MMA>(T2, ld, ws, 2, [&](int, int r, int col, float4 a) {
     if (row0 + r >= M) return;
-    float4 h2 = f4_add(a, *reinterpret_cast<const float4*>(p.c2 + col));
+    float4 h2 = f4_add(a, __ldg(reinterpret_cast<const float4*>(p.c2 + col)));
     if (p.drop2.enabled) h2 = f4_mul(h2, drop_mul4(p.drop2, (p.drop2.base + (unsigned long long)(row0 + r) * H + col) >> 2));
     float4 o = f4_add(h2, *reinterpret_cast<const float4*>(T1 + r * ld + col));
     const long long g = (long long)(row0 + r) * H + col;

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(NT) linear_fwd_kernel(LinearFwdArgs p) {
     if (row0 + r >= p.M) return;
     const long long o = (long long)(row0 + r) * p.ldy + col;
     if (vec) {
-      if (p.b) a = f4_add(a, ld4(p.b + col));
+      if (p.b) a = f4_add(a, __ldg(reinterpret_cast<const float4*>(p.b + col)));
       a = f4_scale(a, p.scale);
       if (p.pre) st4(p.pre + o, a);
       st4(p.y + o, make_float4(act_f(a.x, p.act), act_f(a.y, p.act), act_f(a.z, p.act), act_f(a.w, p.act)));

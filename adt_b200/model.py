@@ -186,7 +186,7 @@ class Engine:
         d.step = int(self.drop_step)
         d.step_dev = self.step_dev.data_ptr() if self.step_dev is not None else None
         d.site = int(site)
-        per = m.num_heads * Lq * Lq if kind == "attn" else Lq * m.hidden
+        per = m.num_heads * Lq if kind == "attn" else Lq * m.hidden   # attention sites: ROW offset ; row sites: element offset
         d.base = int(self.batch_offset) * per
         return d
 

@@ -256,6 +256,7 @@ int adt_softmax_ce_bwd(float* logits, const int32_t* labels, const float* lse, f
 
 /* optional per-kernel CUDA-event timing (used by bench.py for the live roofline number; off by default) */
 int adt_timing_enable(int on);
+int adt_debug_read(long long* out, int n);   /* clock64() phase stamps of CTA 0 of the instrumented kernels (debug) */
 int adt_timing_collect(char* names_buf, int buf_len, float* total_ms, int* counts, int max_names);
 
 #ifdef __cplusplus

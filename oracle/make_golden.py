@@ -41,7 +41,10 @@ class DropInjector:
         self.k += 1
         B, L, H, nh = self.B, self.L, self.H, self.nh
         nat = (B, nh, L, L) if kind == "attn" else (B, L, H)
-        keep = philox.keep_mask(int(np.prod(nat)), p, self.seed, self.step, site).reshape(nat)
+        if kind == "attn":
+            keep = philox.keep_mask_attn(B * nh * L, L, p, self.seed, self.step, site).reshape(nat)
+        else:
+            keep = philox.keep_mask(int(np.prod(nat)), p, self.seed, self.step, site).reshape(nat)
         m = torch.from_numpy(keep).to(x.dtype)
         if kind == "attn":
             m = m.reshape(B * nh, L, L)

@@ -26,7 +26,11 @@ class Inj:
             return x
         site = self.k
         self.k += 1
-        keep = philox.keep_mask(x.numel(), p, self.seed, self.step, site).reshape(tuple(x.shape))
+        if x.dim() == 4:     # attention weights [B,nh,L,L]
+            B, nh, Lq, Lk = x.shape
+            keep = philox.keep_mask_attn(B * nh * Lq, Lk, p, self.seed, self.step, site).reshape(tuple(x.shape))
+        else:
+            keep = philox.keep_mask(x.numel(), p, self.seed, self.step, site).reshape(tuple(x.shape))
         return x * torch.from_numpy(keep).to(x.dtype) * torch.tensor(1.0 / (1.0 - p), dtype=torch.float32).to(x.dtype)
 
 

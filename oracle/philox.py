@@ -12,8 +12,10 @@ mask from Philox4x32-10 keyed by (seed, step) with counter (element>>2, site):
     thr = round(p * 2**32)          (so P[keep] = 1-p)
 
 `idx` is the element's linear index in OUR natural layout
-  * [B,L,H] sites        : ((b0+b)*L + t)*H + c
-  * attention-prob sites : (((b0+b)*nh + h)*L + i)*L + j
+  * [B,L,H] sites        : ((b0+b)*L + t)*H + c          (32-bit lanes, formula above)
+  * attention-prob sites : row r = ((b0+b)*nh + h)*L + i, key j, padded row stride Lp = ceil8(L):
+        e = r*Lp + j ; 16-bit lane (e & 7) of philox(ctr=(e>>3, site, step)) ; keep iff rnd16 >= round(p*2**16)
+    (one Philox call per 8 probabilities, always aligned -> cheap inside the softmax loop)
 The oracle permutes the mask into whatever layout the reference has at that
 call site.
 """
@@ -67,6 +69,22 @@ def keep_mask(n, p, seed, step, site, offset=0):
     r = np.stack(r, axis=-1)
     rnd = np.take_along_axis(r, lane[:, None], axis=1)[:, 0]
     return rnd >= np.uint32(threshold(p))
+
+
+def keep_mask_attn(rows, L, p, seed, step, site, row_offset=0):
+    """Boolean keep-mask [rows, L] of an attention-probability site (16-bit lanes, padded row stride)."""
+    Lp = (L + 7) & ~7
+    r = np.arange(row_offset, row_offset + rows, dtype=np.uint64)[:, None]
+    e = r * np.uint64(Lp) + np.arange(L, dtype=np.uint64)[None, :]
+    q = e >> np.uint64(3)
+    lane = (e & np.uint64(7)).astype(np.int64)
+    out = philox4x32_10((q & _MASK32).astype(np.uint32), (q >> np.uint64(32)).astype(np.uint32), np.uint32(site), np.uint32(step),
+                        np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
+    words = np.stack(out, axis=-1)                                    # [rows, L, 4]
+    w = np.take_along_axis(words, (lane >> 1)[..., None], axis=-1)[..., 0]
+    rnd16 = (w >> ((lane & 1) * 16).astype(np.uint32)) & np.uint32(0xFFFF)
+    thr = min(max(int(round(float(p) * 65536.0)), 0), 0xFFFF)
+    return rnd16 >= np.uint32(thr)
 
 
 if __name__ == "__main__":

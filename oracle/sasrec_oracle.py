@@ -50,10 +50,14 @@ class Drop:
         return self.train and self.p > 0.0
 
     def mask(self, site, shape, dtype):
-        """keep-mask * 1/(1-p) in natural layout `shape` ([B,L,H] or [B,nh,L,L])."""
+        """keep-mask * 1/(1-p) in natural layout `shape` ([B,L,H] row sites or [B,nh,L,L] attention-probability sites)."""
         n = int(np.prod(shape))
-        per_b = n // shape[0]
-        keep = philox.keep_mask(n, self.p, self.seed, self.step, site, offset=self.b0 * per_b)
+        if len(shape) == 4:
+            B, nh, Lq, Lk = shape
+            keep = philox.keep_mask_attn(B * nh * Lq, Lk, self.p, self.seed, self.step, site, row_offset=self.b0 * nh * Lq)
+        else:
+            per_b = n // shape[0]
+            keep = philox.keep_mask(n, self.p, self.seed, self.step, site, offset=self.b0 * per_b)
         m = torch.from_numpy(keep.reshape(shape)).to(dtype)
         return m * torch.tensor(1.0 / (1.0 - self.p), dtype=torch.float32).to(dtype)
 
