@@ -76,20 +76,21 @@ class EmbedFn(torch.autograd.Function):
 
 
 def _scatter(dev, M, B, Lq, H, max_id, seq=None, pos=None, neg=None, dx_enc=None, feats=None, cpos=None, cneg=None, drop_enc=None,
-             dE=None, dP=None, emb_scale=0.0):
+             dE=None, dP=None, emb_scale=0.0, dec=None, dx_dec=None):
     """sorted segmented scatter-add for a subset of the four lookup sources (missing sources are all-padding)."""
     lib = L.lib()
     zeros = torch.zeros(B, Lq, dtype=torch.int32, device=dev)
     i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
     N = 4 * M
     keys, vals, kt, vt, hist = i32(N), i32(N), i32(N), i32(N), i32(256 * ((N + 255) // 256))
-    a = L.fill(L.adt_embed_sort_args(), seq=seq if seq is not None else zeros, dec=zeros, pos=pos if pos is not None else zeros,
+    a = L.fill(L.adt_embed_sort_args(), seq=seq if seq is not None else zeros, dec=dec if dec is not None else zeros,
+               pos=pos if pos is not None else zeros,
                neg=neg if neg is not None else zeros, M=M, max_id=max_id, keys=keys, vals=vals, keys_tmp=kt, vals_tmp=vt, hist=hist)
     L.check(lib.adt_embed_sort(ctypes.byref(a), _stream(dev)), "adt_embed_sort")
     nb = (N + 31) // 32
     nodrop = L.adt_dropout()
-    b = L.fill(L.adt_embed_bwd_args(), keys=keys, vals=vals, seq=seq if seq is not None else zeros, dec=zeros, B=B, L=Lq, H=H,
-               dx_enc=dx_enc, dx_dec=None, feats=feats, cpos=cpos, cneg=cneg, drop_enc=drop_enc if drop_enc is not None else nodrop,
+    b = L.fill(L.adt_embed_bwd_args(), keys=keys, vals=vals, seq=seq if seq is not None else zeros, dec=dec if dec is not None else zeros,
+               B=B, L=Lq, H=H, dx_enc=dx_enc, dx_dec=dx_dec, feats=feats, cpos=cpos, cneg=cneg, drop_enc=drop_enc if drop_enc is not None else nodrop,
                drop_dec=nodrop, d_item_emb=dE, d_pos_emb=dP, head=_f(dE, nb, H), tail=_f(dE, nb, H), has_tail=i32(nb), emb_scale=emb_scale)
     L.check(lib.adt_embed_bwd(ctypes.byref(b), _stream(dev)), "adt_embed_bwd")
 

@@ -10,6 +10,7 @@
 #include "kernels_embed_opt.cuh"
 #include "kernels_fwd.cuh"
 #include "kernels_generic.cuh"
+#include "kernels_stosa.cuh"
 
 using namespace adt;
 
@@ -563,6 +564,71 @@ extern "C" int adt_softmax_ce_fwd(const float* logits, const int32_t* labels, fl
 extern "C" int adt_softmax_ce_bwd(float* logits, const int32_t* labels, const float* lse, float coef, int32_t R, int32_t V, adt_stream_t s_) {
   softmax_ce_kernel<<<min(R, 148 * 8), NT, 0, (cudaStream_t)s_>>>(logits, labels, const_cast<float*>(lse), nullptr, R, V, 1, coef);
   return check_launch("softmax_ce_bwd");
+}
+
+// ---- STOSA-ADT -------------------------------------------------------------------------------------------------
+extern "C" int adt_act_fwd(const float* x, float* y, int64_t n, int32_t act, adt_stream_t s_) {
+  if (n & 3) return fail(ADT_E_SHAPE, "%s", "act_fwd: n must be a multiple of 4");
+  const long long n4 = n / 4, blocks = (n4 + 255) / 256;
+  act_fwd_kernel<<<(int)(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16), 256, 0, (cudaStream_t)s_>>>(x, y, n4, act);
+  return check_launch("act_fwd");
+}
+static int launch_wattn(const adt_wattention_args* a, bool bwd, cudaStream_t s) {
+  if (a->B <= 0 || a->L <= 0 || a->nh <= 0 || a->H % a->nh || ((a->H / a->nh) & 3)) return fail(ADT_E_SHAPE, "%s", "wattention: dims");
+  const int hd = a->H / a->nh;
+  const size_t smem = wattn_smem_floats(a->L, hd, bwd) * sizeof(float);
+  if (smem > 220 * 1024) return fail(ADT_E_SHAPE, "%s", "wattention: (L, H/nh) tile does not fit shared memory");
+  WAttnArgs p;
+  p.mq = a->mq; p.cq = a->cq; p.mk = a->mk; p.ck = a->ck; p.mv = a->mv; p.cv = a->cv; p.mctx = a->mctx; p.cctx = a->cctx; p.lse = a->lse;
+  p.key_ids = a->key_ids; p.dmctx = a->dmctx; p.dcctx = a->dcctx; p.dmq = a->dmq; p.dcq = a->dcq; p.dmk = a->dmk; p.dck = a->dck;
+  p.dmv = a->dmv; p.dcv = a->dcv; p.B = a->B; p.L = a->L; p.H = a->H; p.nh = a->nh; p.inv_sqrt_hd = 1.0f / sqrtf((float)hd);
+  p.drop = mk_drop(a->drop);
+  const int grid = min(a->B * a->nh, 148 * 8);
+  if (bwd) {
+    cudaFuncSetAttribute(wattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wattn_bwd_kernel<<<grid, NT, smem, s>>>(p);
+  } else {
+    cudaFuncSetAttribute(wattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wattn_fwd_kernel<<<grid, NT, smem, s>>>(p);
+  }
+  return check_launch(bwd ? "wattention_bwd" : "wattention_fwd");
+}
+extern "C" int adt_wattention_fwd(const adt_wattention_args* a, adt_stream_t s_) { return launch_wattn(a, false, (cudaStream_t)s_); }
+extern "C" int adt_wattention_bwd(const adt_wattention_args* a, adt_stream_t s_) { return launch_wattn(a, true, (cudaStream_t)s_); }
+
+static WBprArgs mk_wbpr(const adt_wbpr_args* a) {
+  WBprArgs p;
+  p.sm = a->seq_mean; p.sc = a->seq_cov; p.Em = a->item_mean; p.Ec = a->item_cov; p.pos = a->pos; p.neg = a->neg; p.acc = a->acc;
+  p.gcoef = a->gcoef; p.dsm = a->d_seq_mean; p.dsc = a->d_seq_cov; p.gpm = a->g_pos_mean; p.gpc = a->g_pos_cov; p.gnm = a->g_neg_mean;
+  p.gnc = a->g_neg_cov; p.M = a->M; p.H = a->H;
+  return p;
+}
+extern "C" int adt_wbpr_fwd(const adt_wbpr_args* a, adt_stream_t s_) {
+  if (a->M <= 0 || a->H <= 0) return fail(ADT_E_SHAPE, "%s", "wbpr: dims");
+  wbpr_fwd_kernel<<<min((a->M + 7) / 8, 148 * 8), NT, 0, (cudaStream_t)s_>>>(mk_wbpr(a));
+  return check_launch("wbpr_fwd");
+}
+extern "C" int adt_wbpr_bwd(const adt_wbpr_args* a, adt_stream_t s_) {
+  if (a->M <= 0 || a->H <= 0) return fail(ADT_E_SHAPE, "%s", "wbpr: dims");
+  wbpr_bwd_kernel<<<min((a->M + 7) / 8, 148 * 8), NT, 0, (cudaStream_t)s_>>>(mk_wbpr(a));
+  return check_launch("wbpr_bwd");
+}
+extern "C" int adt_sqdiff_fwd(const float* a, const float* b, int64_t n, double* acc, adt_stream_t s_) {
+  if (n & 3) return fail(ADT_E_SHAPE, "%s", "sqdiff: n must be a multiple of 4");
+  const long long n4 = n / 4, blocks = (n4 + 255) / 256;
+  sqdiff_fwd_kernel<<<(int)(blocks < 148 * 8 ? (blocks > 0 ? blocks : 1) : 148 * 8), 256, 0, (cudaStream_t)s_>>>(a, b, n4, acc);
+  return check_launch("sqdiff_fwd");
+}
+extern "C" int adt_sqdiff_bwd(const float* a, const float* b, const float* g, float scale, float* da, float* db, int64_t n, adt_stream_t s_) {
+  if (n & 3) return fail(ADT_E_SHAPE, "%s", "sqdiff: n must be a multiple of 4");
+  const long long n4 = n / 4, blocks = (n4 + 255) / 256;
+  sqdiff_bwd_kernel<<<(int)(blocks < 148 * 8 ? (blocks > 0 ? blocks : 1) : 148 * 8), 256, 0, (cudaStream_t)s_>>>(a, b, g, scale, da, db, n4);
+  return check_launch("sqdiff_bwd");
+}
+extern "C" int adt_wcatalog_rows(const float* mean, const float* cov, float* out, int32_t n, int32_t H, int32_t is_user, adt_stream_t s_) {
+  if (n <= 0 || H <= 0) return fail(ADT_E_SHAPE, "%s", "wcatalog_rows: dims");
+  wcatalog_kernel<<<min((n + 7) / 8, 148 * 8), NT, 0, (cudaStream_t)s_>>>(mean, cov, out, n, H, is_user);
+  return check_launch("wcatalog_rows");
 }
 
 extern "C" int adt_debug_read(long long* out, int n) {

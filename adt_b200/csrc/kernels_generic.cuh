@@ -11,8 +11,13 @@ __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff
 __device__ __forceinline__ float gelu_grad(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
 }
-__device__ __forceinline__ float act_f(float x, int act) { return act == 1 ? fmaxf(x, 0.f) : act == 2 ? gelu_f(x) : x; }
-__device__ __forceinline__ float act_g(float x, int act) { return act == 1 ? (x > 0.f ? 1.f : 0.f) : act == 2 ? gelu_grad(x) : 1.f; }
+// act codes: 0 none, 1 relu, 2 gelu (erf), 3 elu, 4 elu + 1 (the covariance stream of STOSA, stosa/modules.py:232-234)
+__device__ __forceinline__ float act_f(float x, int act) {
+  return act == 1 ? fmaxf(x, 0.f) : act == 2 ? gelu_f(x) : act == 3 ? (x > 0.f ? x : expm1f(x)) : act == 4 ? (x > 0.f ? x : expm1f(x)) + 1.f : x;
+}
+__device__ __forceinline__ float act_g(float x, int act) {
+  return act == 1 ? (x > 0.f ? 1.f : 0.f) : act == 2 ? gelu_grad(x) : act >= 3 ? (x > 0.f ? 1.f : expf(x)) : 1.f;
+}
 
 // y = act((x W^T + b) * scale) ; optional pre-activation copy.  x [M,K] row-major, W [N,K] (nn.Linear), y [M,N].
 struct LinearFwdArgs {
@@ -105,6 +110,13 @@ __global__ void __launch_bounds__(NT) linear_bwd_kernel(LinearBwdArgs p) {
     });
 }
 
+// y = act(x), elementwise
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(act_f(v.x, act), act_f(v.y, act), act_f(v.z, act), act_f(v.w, act));
+  }
+}
 // dpre = dy * act'(pre)
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, float* __restrict__ dpre,
                                                       long long n4, int act) {

@@ -211,7 +211,7 @@ int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t stream);
 int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t stream);
 
 /* ---- generic ops for the post-LN backbones (Bert4Rec-ADT: /root/reference/bert4rec/model/modules.py) ---------------- */
-/* y = act((x W^T + b) * scale), act 0 none / 1 relu / 2 gelu(erf); pre (optional) receives the pre-activation.
+/* y = act((x W^T + b) * scale), act 0 none / 1 relu / 2 gelu(erf) / 3 elu / 4 elu+1; pre (optional) receives the pre-activation.
  * Replaces nn.Linear (+ nn.GELU): modules.py:57-72 (q/k/v/out transfer), :128-139 (FFN), bert.py:80-90 (head). */
 typedef struct {
   const float* x; const float* w; const float* b; float* y; float* pre;
@@ -253,6 +253,51 @@ int adt_attention_bwd(const adt_attention_args* a, adt_stream_t stream);
  * fwd: lse[r], *loss_acc += sum_r (lse[r] - logits[r][labels[r]]).  bwd: logits <- (softmax - onehot) * coef, in place. */
 int adt_softmax_ce_fwd(const float* logits, const int32_t* labels, float* lse, double* loss_acc, int32_t R, int32_t V, adt_stream_t stream);
 int adt_softmax_ce_bwd(float* logits, const int32_t* labels, const float* lse, float coef, int32_t R, int32_t V, adt_stream_t stream);
+
+/* ---- STOSA-ADT -------------------------------------------------------------------------------
+ * elementwise activation y = act(x) (act codes of adt_linear_fwd); n % 4 == 0. */
+int adt_act_fwd(const float* x, float* y, int64_t n, int32_t act, adt_stream_t stream);
+/* Wasserstein attention core on projected streams [B*L, H] (cov streams already ELU+1) -- replaces the score / softmax /
+ * dropout / context lines of DistAttention.forward and DistEDAttention.forward (stosa/modules.py:240-254, :330-344):
+ *   S_ij = -( |mq_i - mk_j|^2 in matmul form + sum cq_i + sum ck_j - 2 sqrt(cq_i).sqrt(ck_j) ) / sqrt(hd) + mask_ij,
+ *   mask_ij = 0 if key_ids[b][j] > 0 and j <= i else float(-2^32+1) (additive, models.py:229-233), P = dropout(softmax(S)),
+ *   mctx = P mv, cctx = P^2 cv.  bwd returns the gradients of all six streams.  Needs (8 L + 64)(hd + 4) + 96 L floats of
+ *   shared memory in bwd (L=100, hd=16 -> 108 KB); larger shapes return ADT_E_SHAPE. */
+typedef struct {
+  const float* mq; const float* cq; const float* mk; const float* ck; const float* mv; const float* cv;
+  float* mctx; float* cctx; float* lse;            /* softmax row statistics (max, 1/sum) [B, nh, L, 2]: written by fwd, read by bwd */
+  const int32_t* key_ids;                          /* [B, L] ids of the KEY sequence */
+  const float* dmctx; const float* dcctx;          /* bwd only */
+  float* dmq; float* dcq; float* dmk; float* dck; float* dmv; float* dcv;
+  int32_t B, L, H, nh; adt_dropout drop;           /* attention-probability site (base = row offset) */
+} adt_wattention_args;
+int adt_wattention_fwd(const adt_wattention_args* a, adt_stream_t stream);
+int adt_wattention_bwd(const adt_wattention_args* a, adt_stream_t stream);
+/* BPR + positive-vs-negative loss on elementwise Wasserstein distances (stosa/trainer.py:358-391).
+ * fwd: acc[0] += sum_t softplus(-(d_neg - d_pos + 1e-24)), acc[1] += sum_t max(d_pos - d_pn, 0), acc[2] += sum_t (sign(d_neg-d_pos)+1)/2,
+ *      acc[3] += #targets (pos id > 0).  bwd: gcoef[0] = dLoss/d(acc[0]), gcoef[1] = dLoss/d(acc[1]) (device scalars) ->
+ *      gradients of the sequence streams and per-row gradients of the looked-up table rows (cov rows through ELU+1),
+ *      to be scatter-added by adt_embed_sort + adt_embed_bwd. */
+typedef struct {
+  const float* seq_mean; const float* seq_cov;     /* [M, H] */
+  const float* item_mean; const float* item_cov;   /* tables [I+1, H]; cov raw (ELU+1 applied inside) */
+  const int32_t* pos; const int32_t* neg;          /* [M] */
+  double* acc;                                     /* [4] */
+  const float* gcoef;                              /* [2], bwd only */
+  float* d_seq_mean; float* d_seq_cov; float* g_pos_mean; float* g_pos_cov; float* g_neg_mean; float* g_neg_cov;   /* [M, H], bwd only */
+  int32_t M, H;
+} adt_wbpr_args;
+int adt_wbpr_fwd(const adt_wbpr_args* a, adt_stream_t stream);
+int adt_wbpr_bwd(const adt_wbpr_args* a, adt_stream_t stream);
+/* reconstruction term (F.mse_loss of sasrec/main.py:158, bert4rec/trainer.py:121, stosa/trainer.py:519-520):
+ * fwd: *acc += sum (a-b)^2 ; bwd: da = 2 (a-b) * g[0] * scale, db = -da (g: device scalar, scale = lambda / n). n % 4 == 0. */
+int adt_sqdiff_fwd(const float* a, const float* b, int64_t n, double* acc, adt_stream_t stream);
+int adt_sqdiff_bwd(const float* a, const float* b, const float* g, float scale, float* da, float* db, int64_t n, adt_stream_t stream);
+/* rows for full-sort evaluation through adt_score_topk (stosa/trainer.py:464-479, modules.py:30-43), width 2H+4:
+ *   is_user = 0: [ mean_i | sqrt(elu(cov_i)+1) | -(|mean_i|^2 + sum(elu(cov_i)+1)) | 0 0 0 ]   (catalog rows, cov raw)
+ *   is_user = 1: [ 2 mean_u | 2 sqrt(cov_u) | 1 | 0 0 0 ]                                        (user rows, cov already ELU+1)
+ * so that <user row, catalog row> = -distance(u, i) + const(u): the largest dot product is the smallest distance. */
+int adt_wcatalog_rows(const float* mean, const float* cov, float* out, int32_t n, int32_t H, int32_t is_user, adt_stream_t stream);
 
 /* optional per-kernel CUDA-event timing (used by bench.py for the live roofline number; off by default) */
 int adt_timing_enable(int on);

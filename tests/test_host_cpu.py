@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import golden_names, load_golden, sd_from
+from helpers import golden_names, load_golden, sd_from, GOLDEN
 
 
 def test_header_parses_and_library_exports_every_symbol():
@@ -172,3 +172,21 @@ def test_world_size_2_gloo_sharded_eval_and_dp_loss():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
     assert dict(ret) == {0: (True, True, True), 1: (True, True, True)}
+
+
+def test_stosa_surface_on_cpu():
+    """reference parameter names/shapes (fixtures hold the reference's own state_dict) and the loud no-CPU-fallback error."""
+    from adt_b200.stosa import DisenDistSAModel
+    from adt_b200._lib import AdtError
+    z = np.load(os.path.join(GOLDEN, "stosa_beauty_p3.npz"))
+    B, L, H, nh, nl, I = [int(v) for v in z["cfg"]]
+    args = types.SimpleNamespace(item_size=I + 2, num_users=B, maxlen=L, hidden_units=H, num_heads=nh, num_layers=nl, dropout=0.3,
+                                 attention_dropout=0.3, initializer_range=0.02, pvn_weight=0.005)
+    m = DisenDistSAModel(args)
+    ref = {k[4:]: z[k].shape for k in z.files if k.startswith("sd0/")}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == ref
+    assert list(m.state_dict().keys()) == list(ref.keys())
+    with pytest.raises(AdtError):
+        m.finetune(z["seq"], z["dec"], np.arange(B))
+    with pytest.raises(ValueError):      # stosa/modules.py:191-194
+        DisenDistSAModel(types.SimpleNamespace(**{**vars(args), "num_heads": 5}))
