@@ -304,8 +304,13 @@ def main():
     }
     peak, peak_src = peaks()
     ach = alg_bytes.get(top, 0) / (kern[top]["avg_us"] * 1e-6) / 1e9 if top in alg_bytes else None
+    traffic = None      # measured DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (C2 shape only)
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")
+    if args.config == "C2" and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["bytes_per_launch"].get(top)
     roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                "traffic": None, "peak_source": peak_src, "avg_us": kern[top]["avg_us"],
+                "traffic": traffic, "alg_bytes": alg_bytes.get(top), "peak_source": peak_src, "avg_us": kern[top]["avg_us"],
                 "share_of_step": kern[top]["ms_total"] / max(sum(v["ms_total"] for v in kern.values()), 1e-9),
                 "note": "at B=256 x L=50 x H=64 one launch is 0.45 waves of row-tile CTAs: latency/issue bound, not HBM bound (DESIGN.md section 4)"}
 
