@@ -123,8 +123,27 @@ static int check_dims(int B, int L, int H, int nh) {
   return ADT_OK;
 }
 
+// Row-tile kernels are launched with programmatic stream serialization (opt-in with ADT_PDL=1: measured neutral at the C2 shape): each of them calls
+// griddepcontrol.launch_dependents on entry and griddepcontrol.wait before it touches activations, so the next kernel's
+// prologue (shared-memory carve-up, weight-ring prefetch) overlaps the tail of the current one.
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_PDL"); v = e ? (atoi(e) != 0) : 0; }
+  return v != 0;
+}
+template <class... Exp, class... Act>
+static void launch_pdl(void (*kern)(Exp...), dim3 grid, size_t smem, cudaStream_t stream, Act&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<Exp>(args)...);
+}
 #define LAUNCH_ONE(K, grid, smem, stream, ...) \
-  do { set_smem(K, smem); K<<<grid, NT, smem, stream>>>(__VA_ARGS__); } while (0)
+  do { set_smem(K, smem); launch_pdl(K, dim3(grid), smem, stream, __VA_ARGS__); } while (0)
 
 #define LAUNCH_TM(tm, mma, KERN, grid, smem, stream, ...)                                        \
   do {                                                                                           \
@@ -281,9 +300,12 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
-  if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, a->precision, s)) return e;
-  if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
-    return e;
+  if (a->phase != 2) {
+    if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, a->precision, s)) return e;
+    if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
+      return e;
+    if (a->phase == 1) return ADT_OK;
+  }
   size_t smem;
   int tm = pick_tm(3 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_fwd: tile does not fit shared memory");
@@ -312,6 +334,10 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  size_t smem;
+  int tm = pick_tm(4 * (size_t)(H + pad), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
+  if (a->phase != 1) {
   PostBwdArgs p;
   memset(&p, 0, sizeof(p));
   p.dout = a->dout; p.out = a->out; p.enc_in = a->enc_in; p.mse_coef = a->mse_coef; p.denc = a->denc; p.ids = a->ids;
@@ -320,9 +346,6 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   p.gWo = a->g_enc.out_w; p.gbo = a->g_enc.out_b; p.gC1 = a->g_ffn.w1; p.gc1 = a->g_ffn.b1; p.gC2 = a->g_ffn.w2; p.gc2 = a->g_ffn.b2;
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
-  size_t smem;
-  int tm = pick_tm(4 * (size_t)(H + pad), &smem);
-  if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
   { TIMED("dec_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
   if (int e = check_launch("dec post_bwd")) return e;
   // cross attention (keys/values from the encoder features)
@@ -339,6 +362,8 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_bwd: tile does not fit shared memory");
   { TIMED("mid_bwd", s); LAUNCH_TM(tm, mma, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m); }
   if (int e = check_launch("mid_bwd")) return e;
+  if (a->phase == 2) return ADT_OK;
+  }
   if (int e = launch_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
                               a->drop_slf, a->precision, s))
     return e;

@@ -17,6 +17,11 @@ namespace adt {
 __device__ long long g_dbg_clock[64];
 #define ADT_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_dbg_clock[i] = clock64(); } while (0)
 
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute): the next kernel of the stream may be
+// scheduled while this one still runs; it must not touch anything a predecessor produces before pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int NT = 256;        // threads per CTA for all row-tile kernels
 constexpr int CH = 64;         // weight chunk edge (rows and cols)
 constexpr int CHP = CH + 4;    // padded chunk row stride in floats (272 B: 16B aligned, LDS.128 conflict free)
@@ -121,16 +126,22 @@ __device__ __forceinline__ void cta_accumulate(double v, double* dst, double* sc
 // Activation tiles: smem [TM][ld] fp32, ld = C + 4 (C multiple of 4).
 // ---------------------------------------------------------------------------------------------
 // Load rows row0..row0+TM-1 (rows >= M are zero filled) of a row-major [M, ldg] matrix, columns c0..c0+C-1.
+// ASYNCHRONOUS: the rows are fetched with cp.async (all 16-byte pieces of the tile in flight at once instead of one dependent
+// round trip per loop iteration); the tile is only valid after tile_sync().
 template <int TM>
 __device__ __forceinline__ void load_tile(float* __restrict__ T, int ld, const float* __restrict__ G, long long ldg, int c0,
                                           int C, int row0, int M) {
   const int c4n = C >> 2;
   for (int s = threadIdx.x; s < TM * c4n; s += NT) {
     const int r = s / c4n, c4 = s - r * c4n;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < M) v = *reinterpret_cast<const float4*>(G + (long long)(row0 + r) * ldg + c0 + 4 * c4);
-    *reinterpret_cast<float4*>(T + r * ld + 4 * c4) = v;
+    const bool ok = row0 + r < M;
+    cp_async16(T + r * ld + 4 * c4, G + (ok ? (long long)(row0 + r) * ldg + c0 + 4 * c4 : 0ll), ok);
   }
+}
+// completes every outstanding cp.async of this thread (tile loads and weight-ring chunks alike), then the CTA barrier
+__device__ __forceinline__ void tile_sync() {
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncthreads();
 }
 template <int TM>
 __device__ __forceinline__ void store_tile(const float* __restrict__ T, int ld, float* __restrict__ G, long long ldg, int c0,

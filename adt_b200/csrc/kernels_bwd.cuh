@@ -17,6 +17,26 @@ __device__ __forceinline__ void tile_foreach4(int C, F f) {
   }
 }
 
+// like tile_foreach4, but the global loads of up to UNR elements (LOAD fills a V) are issued before the first USE consumes
+// them: one memory round trip per batch instead of one per element
+template <int TM, int UNR, class V, class LD, class USE>
+__device__ __forceinline__ void tile_foreach4_ld(int C, LD ldf, USE usef) {
+  const int c4n = C >> 2, n = TM * c4n;
+  for (int s0 = threadIdx.x; s0 < n; s0 += UNR * NT) {
+    V v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int s = s0 + u * NT;
+      if (s < n) { const int r = s / c4n; ldf(r, 4 * (s - r * c4n), v[u]); }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int s = s0 + u * NT;
+      if (s < n) { const int r = s / c4n; usef(r, 4 * (s - r * c4n), v[u]); }
+    }
+  }
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -45,6 +65,7 @@ struct PostBwdArgs {
 template <int TM, bool IS_DEC, bool MMA>
 __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   const int H = p.H, M = p.M;
   const int ld = H + tile_pad<MMA>();
   float* G = smem;            // dO -> (enc) dy
@@ -64,22 +85,34 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
+  pdl_wait();   // weights may be prefetched early; activations only after the predecessors completed
 
   // 1./2. dO = (dout + mse_coef*(out-enc_in)) * keep ; y/c ; a = relu(h1*m1) ; dh2 = dO*m2
-  tile_foreach4<TM>(H, [&](int r, int c) {
-    float4 g = zero4(), a = zero4(), y = zero4(), d2 = zero4();
+  struct PostLd { float4 g, o, e, y, h; int id; };
+  tile_foreach4_ld<TM, 2, PostLd>(H, [&](int r, int c, PostLd& v) {
+    v.g = v.o = v.e = v.y = v.h = zero4();
+    v.id = 0;
     if (row0 + r < M) {
       const long long gi = (long long)(row0 + r) * H + c;
-      if (p.dout) g = ld4(p.dout + gi);
+      if (p.dout) v.g = ld4(p.dout + gi);
+      if (IS_DEC && p.enc_in) { v.o = ld4(p.out + gi); v.e = ld4(p.enc_in + gi); }
+      v.id = p.ids[row0 + r];
+      v.y = ld4(p.u + gi);
+      v.h = ld4(p.h1 + gi);
+    }
+  }, [&](int r, int c, const PostLd& v) {
+    float4 g = zero4(), a = zero4(), d2 = zero4();
+    if (row0 + r < M) {
+      const long long gi = (long long)(row0 + r) * H + c;
+      g = v.g;
       if (IS_DEC && p.enc_in) {
-        const float4 o = ld4(p.out + gi), e = ld4(p.enc_in + gi);
-        const float4 d = make_float4(p.mse_coef * (o.x - e.x), p.mse_coef * (o.y - e.y), p.mse_coef * (o.z - e.z), p.mse_coef * (o.w - e.w));
+        const float4 d = make_float4(p.mse_coef * (v.o.x - v.e.x), p.mse_coef * (v.o.y - v.e.y), p.mse_coef * (v.o.z - v.e.z),
+                                     p.mse_coef * (v.o.w - v.e.w));
         g = f4_add(g, d);
         if (p.denc) st4(p.denc + gi, make_float4(-d.x, -d.y, -d.z, -d.w));
       }
-      if (p.ids[row0 + r] == 0) g = zero4();
-      y = ld4(p.u + gi);
-      float4 h = ld4(p.h1 + gi);
+      if (v.id == 0) g = zero4();
+      float4 h = v.h;
       if (p.drop1.enabled) h = f4_mul(h, drop_mul4(p.drop1, (p.drop1.base + (unsigned long long)gi) >> 2));
       a = make_float4(fmaxf(h.x, 0.f), fmaxf(h.y, 0.f), fmaxf(h.z, 0.f), fmaxf(h.w, 0.f));
       d2 = g;
@@ -87,7 +120,7 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     }
     st4(G + r * ld + c, g);
     st4(A + r * ld + c, a);
-    st4(Y + r * ld + c, y);
+    st4(Y + r * ld + c, v.y);
     st4(Bt + r * ld + c, d2);
   });
   __syncthreads();
@@ -121,7 +154,7 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     // 8. dres = dy ; dWo += dy^T ctx
     store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
     load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
-    __syncthreads();
+    tile_sync();
     wgrad_any<MMA, true, TM>(G, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(G, ld, H, rows, p.gbo);
     // 9. dctx = dy Wo (+ independence-head adjoint) -> Bt -> global
@@ -191,7 +224,7 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     // 7. dres = dd = dO ; dWo += dc^T ctx ; dctx = dc Wo
     store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
     load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
-    __syncthreads();
+    tile_sync();
     wgrad_any<MMA, true, TM>(Bt, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(Bt, ld, H, rows, p.gbo);
     gemm_stream<TM, true, WS_NST, MMA>(Bt, ld, ws, 2, [&](int, int r, int col, float4 acc) {
@@ -212,6 +245,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
                                                       float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int L,
                                                       int H, int nh, int mask_mode, DropDesc drop) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   const int hd = H / nh;
   const int ldq = hd + tile_pad<MMA>();
   const int lds = ((L + 3) & ~3) + tile_pad<MMA>();
@@ -235,12 +269,17 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
   }
   __syncthreads();
   WStream<WS_NST, MMA> ws;
+  pdl_wait();   // q/k/v come from the preceding kernel
+  ADT_STAMP(36);
   ws.start(&wst, Ws);
   load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
   load_tile<TM>(dCs, ldq, dctx + seq_off, H, 0, hd, i0, L);
-  __syncthreads();
+  tile_sync();
+  ADT_STAMP(37);
   gemm_stream<TM, false, WS_NST, MMA>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) { st4(Ps + r * lds + col, a); });
+  ADT_STAMP(38);
   gemm_stream<TM, false, WS_NST, MMA>(dCs, ldq, ws, 1, [&](int, int r, int col, float4 a) { st4(dPs + r * lds + col, a); });
+  ADT_STAMP(39);
 
   // per-row part, LPR lanes per row / 32/LPR rows side by side per warp (see attn_fwd)
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -290,10 +329,12 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
     }
   }
   __syncthreads();
+  ADT_STAMP(40);
   // dq = dS k
   gemm_stream<TM, true, WS_NST, MMA>(dPs, lds, ws, 2, [&](int, int r, int col, float4 a) {
     if (i0 + r < L) st4(dq + seq_off + (long long)(i0 + r) * H + col, a);
   });
+  ADT_STAMP(41);
   // dk += dS^T q ; dv += Pd^T dctx   (plain stores when this CTA is the only query tile of the sequence)
   if (gridDim.x == 1) {
     wgrad_any<MMA, false, TM>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
@@ -302,6 +343,7 @@ __global__ void __launch_bounds__(NT) attn_bwd_kernel(const float* __restrict__ 
     wgrad_any<MMA, true, TM>(dPs, lds, Lk, Qs, ldq, hd, rows, dk + seq_off, H);
     wgrad_any<MMA, true, TM>(Ps, lds, Lk, dCs, ldq, hd, rows, dv + seq_off, H);
   }
+  ADT_STAMP(42);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -320,6 +362,7 @@ struct MidBwdArgs {
 template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   const int H = p.H, M = p.M;
   const int ld = H + tile_pad<MMA>(), ld2 = 2 * H + tile_pad<MMA>();
   float* T0 = smem;              // dq2*scale
@@ -339,15 +382,18 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
-  tile_foreach4<TM>(H, [&](int r, int c) {
-    float4 g = zero4(), a = zero4();
+  pdl_wait();   // weights may be prefetched early; activations only after the predecessors completed
+  struct Ld2 { float4 a, b; };
+  tile_foreach4_ld<TM, 4, Ld2>(H, [&](int r, int c, Ld2& v) {
+    v.a = v.b = zero4();
     if (row0 + r < M) {
       const long long gi = (long long)(row0 + r) * H + c;
-      g = f4_scale(ld4(p.dq2 + gi), p.qscale);
-      a = ld4(p.a + gi);
+      v.a = ld4(p.dq2 + gi);
+      v.b = ld4(p.a + gi);
     }
-    st4(T0 + r * ld + c, g);
-    st4(T1 + r * ld + c, a);
+  }, [&](int r, int c, const Ld2& v) {
+    st4(T0 + r * ld + c, f4_scale(v.a, p.qscale));
+    st4(T1 + r * ld + c, v.b);
   });
   __syncthreads();
   wgrad_any<MMA, true, TM>(T0, ld, H, T1, ld, H, rows, p.gWin2, H);
@@ -356,7 +402,7 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   load_tile<TM>(KV, ld2, p.dk2, H, 0, H, row0, M);
   load_tile<TM>(KV + H, ld2, p.dv2, H, 0, H, row0, M);
   load_tile<TM>(T1, ld, p.feats, H, 0, H, row0, M);
-  __syncthreads();
+  tile_sync();
   wgrad_any<MMA, true, TM>(KV, ld2, 2 * H, T1, ld, H, rows, p.gWin2 + (long long)H * H, H);
   colsum_atomic(KV, ld2, 2 * H, rows, p.gbin2 + H);
   gemm_stream<TM, true, WS_NST, MMA>(KV, ld2, ws, 1, [&](int, int r, int col, float4 acc) {
@@ -366,7 +412,7 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
     }
   });
   load_tile<TM>(T1, ld, p.ctx1, H, 0, H, row0, M);
-  __syncthreads();
+  tile_sync();
   wgrad_any<MMA, true, TM>(DA, ld, H, T1, ld, H, rows, p.gWo1, H);
   colsum_atomic(DA, ld, H, rows, p.gbo1);
   gemm_stream<TM, true, WS_NST, MMA>(DA, ld, ws, 2, [&](int, int r, int col, float4 acc) {
@@ -392,6 +438,7 @@ struct PreBwdArgs {
 template <int TM, bool MMA>
 __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   const int H = p.H, M = p.M;
   const int ld = H + tile_pad<MMA>();
   float* X = smem;
@@ -411,45 +458,57 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
-  tile_foreach4<TM>(H, [&](int r, int c) {
-    float4 xv = zero4(), g = zero4();
+  pdl_wait();   // weights may be prefetched early; activations only after the predecessors completed
+  ADT_STAMP(24);
+  struct Ld2 { float4 a, b; };
+  tile_foreach4_ld<TM, 4, Ld2>(H, [&](int r, int c, Ld2& v) {
+    v.a = v.b = zero4();
     if (row0 + r < M) {
       const long long gi = (long long)(row0 + r) * H + c;
-      xv = ld4(p.x + gi);
-      g = f4_scale(ld4(p.dq + gi), p.qscale);
+      v.a = ld4(p.x + gi);
+      v.b = ld4(p.dq + gi);
     }
-    st4(X + r * ld + c, xv);
-    st4(T + r * ld + c, g);
+  }, [&](int r, int c, const Ld2& v) {
+    st4(X + r * ld + c, v.a);
+    st4(T + r * ld + c, f4_scale(v.b, p.qscale));
   });
   __syncthreads();
+  ADT_STAMP(25);
   ln_tile<TM>(X, N, ld, H, p.ln_g, p.ln_b, 1e-8f, row0, M);
   __syncthreads();
+  ADT_STAMP(26);
   wgrad_any<MMA, true, TM>(T, ld, H, N, ld, H, rows, p.gWin, H);
+  ADT_STAMP(27);
   colsum_atomic(T, ld, H, rows, p.gbin);
+  ADT_STAMP(28);
   gemm_stream<TM, true, WS_NST, MMA>(T, ld, ws, 0, [&](int, int r, int col, float4 acc) {
     if (p.dnorm_extra && row0 + r < M) acc = f4_add(acc, ld4(p.dnorm_extra + (long long)(row0 + r) * H + col));
     st4(D + r * ld + col, acc);
   });
+  ADT_STAMP(29);
   if (!p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, ws.scratch());
+  ADT_STAMP(30);
   const float* Xkv = p.kv_from_norm ? N : X;
   for (int which = 0; which < 2; ++which) {
     load_tile<TM>(T, ld, which == 0 ? p.dk : p.dv, H, 0, H, row0, M);
-    __syncthreads();
+    tile_sync();
     wgrad_any<MMA, true, TM>(T, ld, H, Xkv, ld, H, rows, p.gWin + (long long)(1 + which) * H * H, H);
     colsum_atomic(T, ld, H, rows, p.gbin + (1 + which) * H);
     gemm_stream<TM, true, WS_NST, MMA>(T, ld, ws, 1 + which, [&](int, int r, int col, float4 acc) {
       st4(D + r * ld + col, f4_add(acc, ld4(D + r * ld + col)));
     });
   }
+  ADT_STAMP(31);
   if (p.kv_from_norm) ln_bwd_tile<TM, false>(X, D, D, ld, H, p.ln_g, 1e-8f, row0, M, p.gln_g, p.gln_b, ws.scratch());
-  tile_foreach4<TM>(H, [&](int r, int c) {
-    if (row0 + r < M) {
-      const long long gi = (long long)(row0 + r) * H + c;
-      float4 d = ld4(D + r * ld + c);
-      if (p.dx_extra) d = f4_add(d, ld4(p.dx_extra + gi));
-      st4(p.dx + gi, d);
-    }
+  ADT_STAMP(32);
+  struct Ld1 { float4 a; };
+  tile_foreach4_ld<TM, 4, Ld1>(H, [&](int r, int c, Ld1& v) {
+    v.a = zero4();
+    if (p.dx_extra && row0 + r < M) v.a = ld4(p.dx_extra + (long long)(row0 + r) * H + c);
+  }, [&](int r, int c, const Ld1& v) {
+    if (row0 + r < M) st4(p.dx + (long long)(row0 + r) * H + c, f4_add(ld4(D + r * ld + c), v.a));
   });
+  ADT_STAMP(33);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(NT) pre_fwd_kernel(const float* __restrict__ x
                                                      float* __restrict__ v, float* __restrict__ norm_out, int M, int H, float qscale,
                                                      int kv_from_norm) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   const int ld = H + tile_pad<MMA>();
   float* Xs = smem;
   float* Ns = Xs + TM * ld;
@@ -64,9 +65,10 @@ __global__ void __launch_bounds__(NT) pre_fwd_kernel(const float* __restrict__ x
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
+  pdl_wait();   // weights may be prefetched early; activations only after the predecessors completed
   ADT_STAMP(1);
   load_tile<TM>(Xs, ld, x, H, 0, H, row0, M);
-  __syncthreads();
+  tile_sync();
   ADT_STAMP(2);
   ln_tile<TM>(Xs, Ns, ld, H, ln_g, ln_b, 1e-8f, row0, M);
   __syncthreads();
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
                                                       const int* __restrict__ key_ids, int L, int H, int nh, int mask_mode,
                                                       DropDesc drop) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   const int hd = H / nh;
   const int ldq = hd + tile_pad<MMA>();
   const int lds = ((L + 3) & ~3) + tile_pad<MMA>();
@@ -132,10 +135,11 @@ __global__ void __launch_bounds__(NT) attn_fwd_kernel(const float* __restrict__ 
   }
   __syncthreads();
   WStream<WS_NST, MMA> ws;
+  pdl_wait();   // q/k/v come from the preceding kernel
   ws.start(&wst, Ws);
   ADT_STAMP(9);
   load_tile<TM>(Qs, ldq, q + seq_off, H, 0, hd, i0, L);
-  __syncthreads();
+  tile_sync();
   ADT_STAMP(10);
   gemm_stream<TM, false, WS_NST, MMA>(Qs, ldq, ws, 0, [&](int, int r, int col, float4 a) {
     *reinterpret_cast<float4*>(Ss + r * lds + col) = a;
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(NT) mid_fwd_kernel(const float* __restrict__ c
                                                      float* __restrict__ a_out, float* __restrict__ q2, float* __restrict__ k2,
                                                      float* __restrict__ v2, int M, int H, float qscale) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   const int ld = H + tile_pad<MMA>();
   float* T0 = smem;
   float* T1 = T0 + TM * ld;
@@ -227,9 +232,10 @@ __global__ void __launch_bounds__(NT) mid_fwd_kernel(const float* __restrict__ c
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
+  pdl_wait();   // weights may be prefetched early; activations only after the predecessors completed
   load_tile<TM>(T0, ld, ctx1, H, 0, H, row0, M);
   load_tile<TM>(T2, ld, feats, H, 0, H, row0, M);
-  __syncthreads();
+  tile_sync();
   gemm_stream<TM, false, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
     const float4 o = f4_add(a, __ldg(reinterpret_cast<const float4*>(bo1 + col)));
     *reinterpret_cast<float4*>(T1 + r * ld + col) = o;
@@ -276,6 +282,7 @@ struct PostFwdArgs {
 template <int TM, bool IS_DEC, bool MMA>
 __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
   extern __shared__ __align__(16) float smem[];
+  pdl_trigger();
   __shared__ double red[NT / 32];
   const int H = p.H, M = p.M;
   const int ld = H + tile_pad<MMA>();
@@ -296,13 +303,14 @@ __global__ void __launch_bounds__(NT) post_fwd_kernel(PostFwdArgs p) {
   __syncthreads();
   WStream<WS_NST, MMA> ws;
   ws.start(&wst, Ws);
+  pdl_wait();   // weights may be prefetched early; activations only after the predecessors completed
   load_tile<TM>(T0, ld, p.ctx, H, 0, H, row0, M);
   if (!IS_DEC) {
     load_tile<TM>(T2, ld, p.resid, H, 0, H, row0, M);
-    __syncthreads();
+    tile_sync();
     ln_tile<TM>(T2, T1, ld, H, p.ln1_g, p.ln1_b, 1e-8f, row0, M);
   }
-  __syncthreads();
+  tile_sync();
   gemm_stream<TM, false, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 a) {
     float4 o = f4_add(a, __ldg(reinterpret_cast<const float4*>(p.bo + col)));
     if (!IS_DEC) o = f4_add(o, *reinterpret_cast<const float4*>(T1 + r * ld + col));

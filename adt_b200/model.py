@@ -101,6 +101,7 @@ class Engine:
         self.batch_offset = 0      # first global sample index of this rank (data parallel)
         self.global_rows = None    # M of the global batch (None -> local)
         self.gflat = None
+        self.side_stream = None    # optional second stream: decoder work that is independent of the encoder runs beside it
         self.step_dev = None       # optional int32 device tensor: [0] is added to the dropout step at run time
         self.precision = 0         # 0: fp32 FFMA GEMM cores (reference precision) ; 1: bf16 tensor-core cores, fp32 accumulate
 
@@ -166,6 +167,7 @@ class Engine:
         for k in ("dq", "dctx", "dres", "dq2", "dctx2", "dfeats", "dxa", "dxb", "dxd_a", "dxd_b"):
             w[k] = f(M, H)
         w["denc"] = [f(M, H) for _ in range(nl)]
+        w["side"] = {k: f(M, H) for k in ("dq", "dk", "dv", "dctx", "dres")}   # decoder block 0 backward, run beside the encoder backward
         w["cpos"], w["cneg"] = f(M), f(M)
         N = 4 * M
         i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
@@ -238,12 +240,17 @@ class Engine:
                    pos_logits=w["pos_logits"], neg_logits=w["neg_logits"], acc=w["acc"] if with_loss else None, M=w["M"], H=m.hidden)
         L.check(self.lib.adt_final_logits_loss_fwd(L.ctypes.byref(a), self._stream()), "adt_final_logits_loss_fwd")
 
-    def decode(self, dec, training, w, fused_mse):
+    def decode(self, dec, training, w, fused_mse, phases=(0,)):
+        """phases=(0,): embedding + all decoder blocks.  phases=(1,): embedding + LN/self-attention of block 0 only (needs
+        nothing from the encoder); phases=(2,): the rest.  (1,) then (2,) equals (0,)."""
         m = self.m
         B, Lq, nl = w["B"], w["L"], m.num_layers
         sites = self._sites()
-        self.embed(dec, w["xd"][0], sites["dec_emb"], training, B, Lq)
+        if phases[0] != 2:
+            self.embed(dec, w["xd"][0], sites["dec_emb"], training, B, Lq)
         for j, layer in enumerate(m.decoder.decoder_layers):
+            if phases[0] == 1 and j > 0:
+                break
             sv = w["dec"][j]
             ss, se, s1, s2 = sites[("dec", j)]
             a = L.fill(L.adt_dec_block_fwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec,
@@ -253,6 +260,7 @@ class Engine:
                        B=B, L=Lq, H=m.hidden, nh=m.num_heads, training=int(training), mask_mode=0, precision=self.precision,
                        drop_slf=self._drop(ss, "attn", training, B, Lq), drop_enc=self._drop(se, "attn", training, B, Lq),
                        drop_ffn1=self._drop(s1, "row", training, B, Lq), drop_ffn2=self._drop(s2, "row", training, B, Lq),
+                       phase=(phases[0] if j == 0 else 0),
                        **{k: sv[k] for k in ("d", "q1", "k1", "v1", "ctx1", "lse1", "a", "q2", "k2", "v2", "ctx2", "lse2", "c", "h1")})
             L.check(self.lib.adt_dec_block_fwd(L.ctypes.byref(a), self._stream()), "adt_dec_block_fwd")
 
@@ -262,9 +270,21 @@ class Engine:
         w = self.workspace(B, Lq)
         if fused_loss:
             w["acc"].zero_()
+        side = self.side_stream
+        if side is None:
+            self.encode(seq, training, w, nll=fused_loss)
+            self.final(w, pos, neg, with_loss=fused_loss)
+            self.decode(dec, training, w, fused_mse=fused_loss)
+            return w
+        # the decoder's embedding + first self-attention do not depend on the encoder: run them beside it
+        cur = torch.cuda.current_stream(self.dev())
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.decode(dec, training, w, fused_mse=fused_loss, phases=(1,))
         self.encode(seq, training, w, nll=fused_loss)
-        self.final(w, pos, neg, with_loss=fused_loss)
-        self.decode(dec, training, w, fused_mse=fused_loss)
+        self.final(w, pos, neg, with_loss=fused_loss)       # writes the encoder features the cross-attention reads
+        cur.wait_stream(side)
+        self.decode(dec, training, w, fused_mse=fused_loss, phases=(2,))
         return w
 
     # ------------------------------------------------------------------ backward
@@ -291,6 +311,7 @@ class Engine:
         fg = lambda pre: L.fill(L.adt_ffn_g(), w1=g[pre + "conv1.weight"], b1=g[pre + "conv1.bias"], w2=g[pre + "conv2.weight"],
                                 b2=g[pre + "conv2.bias"])
         z4 = w["zero4"]
+        side = self.side_stream
         w["dfeats"].zero_()
         # ---- decoder blocks, last to first
         dxd, bufs = None, [w["dxd_a"], w["dxd_b"]]
@@ -304,12 +325,16 @@ class Engine:
                 dout = eo[j] if dout is None else dout + eo[j]
             i_enc = nl - 1 - j
             out_dx = bufs[j % 2]
+            split = side is not None and j == 0
+            sb = w["side"] if split else None
             a = L.fill(L.adt_dec_block_bwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec,
                        ln_w=layer.layer_norm.weight, ln_b=layer.layer_norm.bias, slf=_mha_w(layer.slf_attn), enc=_mha_w(layer.enc_attn),
                        ffn=_ffn_w(layer.pos_ffn), out=w["xd"][j + 1], enc_in=w["x"][i_enc] if fused else None,
                        mse_coef=(float(lambdas1[i_enc]) * 2.0 / (Mg * H)) if fused else 0.0,
                        dout=dout, denc=w["denc"][i_enc] if fused else None,
-                       dq=w["dq"], dk=z4[0], dv=z4[1], dctx=w["dctx"], dd=w["dres"], dq2=w["dq2"], dk2=z4[2], dv2=z4[3], dctx2=w["dctx2"],
+                       dq=sb["dq"] if split else w["dq"], dk=sb["dk"] if split else z4[0], dv=sb["dv"] if split else z4[1],
+                       dctx=sb["dctx"] if split else w["dctx"], dd=sb["dres"] if split else w["dres"],
+                       dq2=w["dq2"], dk2=z4[2], dv2=z4[3], dctx2=w["dctx2"], phase=2 if split else 0,
                        dfeats=w["dfeats"], dx=out_dx, g_ln_w=g[pre + "layer_norm.weight"], g_ln_b=g[pre + "layer_norm.bias"],
                        g_slf=mg(pre + "slf_attn."), g_enc=mg(pre + "enc_attn."), g_ffn=fg(pre + "pos_ffn."),
                        B=B, L=Lq, H=H, nh=nh, mask_mode=0, precision=self.precision,
@@ -317,6 +342,12 @@ class Engine:
                        drop_ffn1=self._drop(s1, "row", True, B, Lq), drop_ffn2=self._drop(s2, "row", True, B, Lq),
                        **{k: sv[k] for k in ("d", "q1", "k1", "v1", "ctx1", "lse1", "a", "q2", "k2", "v2", "ctx2", "lse2", "c", "h1")})
             L.check(self.lib.adt_dec_block_bwd(L.ctypes.byref(a), self._stream()), "adt_dec_block_bwd")
+            if split:   # self-attention + LN adjoints of block 0 feed only the decoder embedding: beside the encoder backward
+                cur = torch.cuda.current_stream(self.dev())
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    a.phase = 1
+                    L.check(self.lib.adt_dec_block_bwd(L.ctypes.byref(a), self._stream()), "adt_dec_block_bwd")
             dxd = out_dx
         dx_dec_emb = dxd
         # ---- last LayerNorm + logits + BCE
@@ -357,6 +388,8 @@ class Engine:
             L.check(self.lib.adt_enc_block_bwd(L.ctypes.byref(a), self._stream()), "adt_enc_block_bwd")
             dx, other = other, dx
         # ---- embeddings: sorted segmented scatter-add into the table, batch reduction into pos_emb
+        if side is not None:
+            torch.cuda.current_stream(self.dev()).wait_stream(side)
         a = L.fill(L.adt_embed_bwd_args(), keys=w["keys"], vals=w["vals"], seq=seq, dec=dec, B=B, L=Lq, H=H,
                    dx_enc=dx, dx_dec=dx_dec_emb, feats=w["feats"], cpos=w["cpos"], cneg=w["cneg"],
                    drop_enc=self._drop(sites["enc_emb"], "row", True, B, Lq), drop_dec=self._drop(sites["dec_emb"], "row", True, B, Lq),

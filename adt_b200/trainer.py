@@ -21,7 +21,8 @@ from .model import _as_ids
 
 class FusedTrainer:
     def __init__(self, model, lambdas1, lambdas2, weight_decay=0.0, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, clip=5.0,
-                 adam_weight_decay=0.0, seed=0, process_group=None, use_norm_decay=True, use_graph=False, precision="fp32"):
+                 adam_weight_decay=0.0, seed=0, process_group=None, use_norm_decay=True, use_graph=False, precision="fp32",
+                 overlap=True):
         self.model = model
         self.eng = model.engine
         self.l1, self.l2 = [float(x) for x in lambdas1], [float(x) for x in lambdas2]
@@ -40,6 +41,7 @@ class FusedTrainer:
         self.t = 0
         self._w = None
         self.use_graph = use_graph
+        self.overlap = overlap        # run the encoder-independent decoder kernels on a second stream (fork/join inside the step)
         self._graphs = {}
         self.step_dev = None
         self._counter_t = None
@@ -109,6 +111,8 @@ class FusedTrainer:
             # [0] dropout stream counter (step index of the NEXT step minus one), [1] Adam step count
             self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
             self.side = torch.cuda.Stream(device=dev)
+            if self.overlap:
+                eng.side_stream = torch.cuda.Stream(device=dev)
         eng.batch_offset = self.rank * B
         eng.global_rows = self.world * B * Lq
         eng.drop_step = 0

@@ -102,6 +102,8 @@ typedef struct {
   int32_t B, L, H, nh, training, mask_mode;
   adt_dropout drop_slf, drop_enc, drop_ffn1, drop_ffn2;
   int32_t precision;
+  int32_t phase;   /* 0: whole block; 1: only LN + self-attention (independent of the encoder -> may run beside it on another
+                    * stream); 2: the rest (cross-attention on `feats`, FFN) */
 } adt_dec_block_fwd_args;
 int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t stream);
 
@@ -120,6 +122,8 @@ typedef struct {
   int32_t B, L, H, nh, mask_mode;
   adt_dropout drop_slf, drop_enc, drop_ffn1, drop_ffn2;
   int32_t precision;
+  int32_t phase;   /* 0: whole block; 2: FFN + cross-attention adjoints (produce dfeats, dctx, dd); 1: self-attention + LN adjoints
+                    * (produce dx; nothing the encoder backward needs -> may run beside it on another stream) */
 } adt_dec_block_bwd_args;
 int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t stream);
 
