@@ -170,7 +170,9 @@ extern "C" int adt_embed_fwd(const adt_embed_fwd_args* a, adt_stream_t s_) {
   if (int e = check_dims(a->B, a->L, a->H, 1)) return e;
   const int M = a->B * a->L;
   const long long n = (long long)M * (a->H / 4);
-  const int grid = (int)((n + 255) / 256);
+  if (n >= (1ll << 31)) return fail(ADT_E_SHAPE, "%s", "embed_fwd: B*L*H/4 must be < 2^31");
+  const long long blocks = (n + 255) / 256;
+  const int grid = (int)(blocks < 148 * 32 ? blocks : 148 * 32);
   TIMED("embed_fwd", s);
   embed_fwd_kernel<<<grid, 256, 0, s>>>(a->ids, a->item_emb, a->pos_emb, a->x, M, a->L, a->H, (float)sqrt((double)a->H), mk_drop(a->drop));
   return check_launch("adt_embed_fwd");
@@ -421,17 +423,24 @@ extern "C" int adt_embed_sort(const adt_embed_sort_args* a, adt_stream_t s_) {
   const int* kin = nullptr;
   const int* vin = nullptr;
   TIMED("embed_sort", s);
+  // offsets: exclusive scan of the 256*nW digit counters.  Small inputs: one CTA.  Large inputs: per-tile scans + a scan of
+  // the tile totals kept in the unused upper part of `hist` (its size is 256*ceil(N/256) >= 256*nW + tiles there).
+  const int nh = 256 * nW, tiles = (nh + 4095) / 4096;
+  const long long room = 256ll * ((N + 255) / 256) - nh;
+  const bool tiled = tiles > 2 && room >= tiles;
+  int* tsum = tiled ? a->hist + nh : nullptr;
   for (int p = 0; p < passes; ++p) {
     const int shift = 8 * p;
-    if (p == 0) {
-      radix_hist_kernel<true><<<grid, 256, 0, s>>>(src, nullptr, N, shift, a->hist, nW);
-      exclusive_scan_kernel<<<1, 1024, 0, s>>>(a->hist, 256 * nW);
-      radix_scatter_kernel<true><<<grid, 256, 0, s>>>(src, nullptr, nullptr, N, shift, a->hist, nW, kbuf[cur], vbuf[cur]);
+    if (p == 0) radix_hist_kernel<true><<<grid, 256, 0, s>>>(src, nullptr, N, shift, a->hist, nW);
+    else radix_hist_kernel<false><<<grid, 256, 0, s>>>(src, kin, N, shift, a->hist, nW);
+    if (tiled) {
+      scan_tiles_kernel<<<tiles, 1024, 0, s>>>(a->hist, nh, tsum);
+      exclusive_scan_kernel<<<1, 1024, 0, s>>>(tsum, tiles);
     } else {
-      radix_hist_kernel<false><<<grid, 256, 0, s>>>(src, kin, N, shift, a->hist, nW);
-      exclusive_scan_kernel<<<1, 1024, 0, s>>>(a->hist, 256 * nW);
-      radix_scatter_kernel<false><<<grid, 256, 0, s>>>(src, kin, vin, N, shift, a->hist, nW, kbuf[cur], vbuf[cur]);
+      exclusive_scan_kernel<<<1, 1024, 0, s>>>(a->hist, nh);
     }
+    if (p == 0) radix_scatter_kernel<true><<<grid, 256, 0, s>>>(src, nullptr, nullptr, N, shift, a->hist, nW, kbuf[cur], vbuf[cur], tsum);
+    else radix_scatter_kernel<false><<<grid, 256, 0, s>>>(src, kin, vin, N, shift, a->hist, nW, kbuf[cur], vbuf[cur], tsum);
     kin = kbuf[cur];
     vin = vbuf[cur];
     cur ^= 1;
@@ -446,8 +455,9 @@ extern "C" int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t s_) {
   if (NT / (a->H / 4) < 1) return fail(ADT_E_SHAPE, "%s", "embed_bwd: H");
   TIMED("embed_bwd", s);
   if (a->d_pos_emb) {
-    if (a->dx_enc) posgrad_kernel<<<a->L, NT, 0, s>>>(a->dx_enc, a->seq, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_enc));
-    if (a->dx_dec) posgrad_kernel<<<a->L, NT, 0, s>>>(a->dx_dec, a->dec, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_dec));
+    const int BS = (a->B + 148 * 4 - 1) / (148 * 4), pg = (a->B + BS - 1) / BS;   // sequences per CTA / CTAs
+    if (a->dx_enc) posgrad_kernel<<<pg, NT, 0, s>>>(a->dx_enc, a->seq, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_enc), BS);
+    if (a->dx_dec) posgrad_kernel<<<pg, NT, 0, s>>>(a->dx_dec, a->dec, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_dec), BS);
   }
   ScatterArgs sa;
   memset(&sa, 0, sizeof(sa));
@@ -457,7 +467,8 @@ extern "C" int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t s_) {
   sa.drop_enc = mk_drop(a->drop_enc); sa.drop_dec = mk_drop(a->drop_dec);
   sa.dE = a->d_item_emb; sa.head = a->head; sa.tail = a->tail; sa.has_tail = a->has_tail;
   const int nb = (sa.N + 31) / 32;
-  scatter_phase1_kernel<<<(nb + 7) / 8, 256, 0, s>>>(sa);
+  if (a->H <= 128) scatter_phase1_kernel<1><<<(nb + 7) / 8, 256, 0, s>>>(sa);
+  else scatter_phase1_kernel<2><<<(nb + 7) / 8, 256, 0, s>>>(sa);
   scatter_phase2_kernel<<<(nb + 7) / 8, 256, 0, s>>>(sa);
   return check_launch("adt_embed_bwd");
 }
@@ -483,7 +494,9 @@ extern "C" int adt_adam(const adt_adam_args* a, adt_stream_t s_) {
   k.bc1 = (float)(1.0 - pow((double)a->beta1, (double)a->step));
   k.bc2 = (float)(1.0 - pow((double)a->beta2, (double)a->step));
   k.max_norm = a->max_norm; k.gnormsq = a->gnormsq; k.step_dev = a->step_dev;
-  const long long blocks = (a->n + 255) / 256;
+  if ((((uintptr_t)a->p | (uintptr_t)a->g | (uintptr_t)a->m | (uintptr_t)a->v) & 15) != 0)
+    return fail(ADT_E_ALIGN, "%s", "adam: buffers must be 16-byte aligned");
+  const long long blocks = (a->n / 4 + 255) / 256 + 1;
   TIMED("adam", (cudaStream_t)s_);
   adam_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(k);
   return check_launch("adt_adam");

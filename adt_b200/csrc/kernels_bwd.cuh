@@ -617,31 +617,25 @@ __global__ void __launch_bounds__(NT) final_bwd_kernel(FinalBwdArgs p) {
 
 // -------------------------------------------------------------------------------------------------
 // pos_emb gradient: dP[t][c] += sum_b dx[b][t][c] * m(b,t,c) * [id != 0]    (adjoint of K1 wrt pos_emb)
-// grid = L CTAs; thread (c4, bs) strides over the batch; plain block reduction, one atomic per element.
+// One CTA per group of BS sequences: every thread walks the contiguous [L, H] slab of a sequence (fully coalesced 128-bit
+// reads), sums its (t, c4) position over the group in registers, then one vector atomic per position.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) posgrad_kernel(const float* __restrict__ dx, const int* __restrict__ ids, float* __restrict__ gP,
-                                                     int B, int L, int H, DropDesc drop) {
-  __shared__ float4 red[NT];
-  const int t = blockIdx.x;
-  const int h4 = H >> 2;
-  const int c4 = threadIdx.x % h4, bs = threadIdx.x / h4, nbs = NT / h4;
-  float4 acc = zero4();
-  if (bs < nbs) {
-    for (int b = bs; b < B; b += nbs) {
+                                                     int B, int L, int H, DropDesc drop, int BS) {
+  const int h4 = H >> 2, n = L * h4;
+  const int b0 = blockIdx.x * BS, b1 = min(B, b0 + BS);
+  for (int s = threadIdx.x; s < n; s += NT) {
+    const int t = s / h4, c4 = s - t * h4;
+    float4 acc = zero4();
+    for (int b = b0; b < b1; ++b) {
       const int row = b * L + t;
-      if (ids[row] == 0) continue;
+      if (__ldg(ids + row) == 0) continue;
       const long long gi = (long long)row * H + 4 * c4;
       float4 g = ld4(dx + gi);
       if (drop.enabled) g = f4_mul(g, drop_mul4(drop, (drop.base + (unsigned long long)gi) >> 2));
       acc = f4_add(acc, g);
     }
-  }
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.x < h4) {
-    float4 s = zero4();
-    for (int i = 0; i < nbs; ++i) s = f4_add(s, red[i * h4 + threadIdx.x]);
-    atomicAdd(reinterpret_cast<float4*>(gP + (long long)t * H) + threadIdx.x, s);
+    atomicAdd(reinterpret_cast<float4*>(gP + (long long)t * H) + c4, acc);
   }
 }
 

@@ -85,15 +85,56 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(int* __restrict__ 
   }
 }
 
+// large inputs: one 4096-element tile per CTA, local exclusive scan in place + the tile total into tsum[tile]; tsum is then
+// scanned by exclusive_scan_kernel (one CTA) and added back by the scatter kernel when it reads its offsets
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(int* __restrict__ data, int n, int* __restrict__ tsum) {
+  __shared__ int wsum[32];
+  const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 4096 + 4 * threadIdx.x;
+  int v[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) v[c] = (i0 + c < n) ? data[i0 + c] : 0;
+  const int s = v[0] + v[1] + v[2] + v[3];
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (l >= o) incl += t;
+  }
+  if (l == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int x = wsum[l];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, x, o);
+      if (l >= o) x += t;
+    }
+    wsum[l] = x;
+  }
+  __syncthreads();
+  int run = incl - s + (w > 0 ? wsum[w - 1] : 0);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (i0 + c < n) data[i0 + c] = run;
+    run += v[c];
+  }
+  if (threadIdx.x == 1023) tsum[blockIdx.x] = wsum[31];
+}
+
 template <bool FIRST>
 __global__ void __launch_bounds__(256) radix_scatter_kernel(SortSrc s, const int* __restrict__ keys_in, const int* __restrict__ vals_in,
                                                             int N, int shift, const int* __restrict__ hist, int nW,
-                                                            int* __restrict__ keys_out, int* __restrict__ vals_out) {
+                                                            int* __restrict__ keys_out, int* __restrict__ vals_out,
+                                                            const int* __restrict__ tsum) {
   __shared__ int off[8][256];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int gw = blockIdx.x * 8 + w;
   if (gw >= nW) return;
-  for (int d = l; d < 256; d += 32) off[w][d] = hist[d * nW + gw];
+  for (int d = l; d < 256; d += 32) {
+    const int idx = d * nW + gw;
+    off[w][d] = hist[idx] + (tsum ? tsum[idx >> 12] : 0);
+  }
   __syncwarp();
   const int end = min(N, (gw + 1) * SORT_WCH);
   for (int base = gw * SORT_WCH; base < end; base += 32) {
@@ -146,6 +187,8 @@ __device__ __forceinline__ float4 scatter_row4(const ScatterArgs& a, int e, int 
   return f4_scale(ld4(a.feats + gi), cf);
 }
 
+// NS = float4 per lane: 1 for H <= 128, 2 for H <= 256
+template <int NS>
 __global__ void __launch_bounds__(256) scatter_phase1_kernel(ScatterArgs a) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int g = blockIdx.x * 8 + w;
@@ -157,36 +200,77 @@ __global__ void __launch_bounds__(256) scatter_phase1_kernel(ScatterArgs a) {
   const int prev_key = base > 0 ? a.keys[base - 1] : -1;
   const int next_key = base + 32 < a.N ? a.keys[base + 32] : -2;
   const int h4 = a.H >> 2;
-  float4 acc[2] = {zero4(), zero4()};   // H <= 256 -> at most 2 float4 per lane
+  float4 acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s] = zero4();
   int run_start = 0;
   bool tail_written = false;
-  for (int j = 0; j < cnt; ++j) {
-    const int key = __shfl_sync(0xffffffffu, key_l, j);
-    const int e = __shfl_sync(0xffffffffu, val_l, j);
-    const int key_next = j + 1 < cnt ? __shfl_sync(0xffffffffu, key_l, j + 1) : -3;
-    if (key == 0) { run_start = j + 1; continue; }   // padding_idx rows get no gradient
-    const bool fresh = (j == run_start);
+  // entries are consumed strictly in sorted order (deterministic sums), but the row loads of four consecutive entries are
+  // issued together so that a warp keeps several independent HBM requests in flight
+  for (int j0 = 0; j0 < cnt; j0 += 4) {
+    float4 v[4][NS];
+    float cf[4];
+    // 1. raw loads only (addresses depend on nothing but the shuffled element index): four rows in flight per warp
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int c4 = l + 32 * s;
-      if (c4 < h4) {
-        const float4 v = scatter_row4(a, e, 4 * c4);
-        acc[s] = fresh ? v : f4_add(acc[s], v);
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      const int key = __shfl_sync(0xffffffffu, key_l, j & 31);
+      const int e = __shfl_sync(0xffffffffu, val_l, j & 31);
+      #pragma unroll
+      for (int s = 0; s < NS; ++s) v[u][s] = zero4();
+      cf[u] = 0.f;
+      if (j < cnt && key != 0) {
+        const int src = e / a.M, row = e - src * a.M;
+        const float* base = src == 0 ? a.dx_enc : src == 1 ? a.dx_dec : a.feats;
+        cf[u] = src < 2 ? a.scale : __ldg((src == 2 ? a.cpos : a.cneg) + row);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const int c4 = l + 32 * s;
+          if (c4 < h4) v[u][s] = ld4(base + (long long)row * a.H + 4 * c4);
+        }
       }
     }
-    if (j == cnt - 1 || key_next != key) {
-      const bool from_before = (run_start == 0) && (key == prev_key);
-      const bool goes_after = (j == cnt - 1) && (key == next_key);
-      float* dst;
-      if (from_before) dst = a.head + (long long)g * a.H;
-      else if (goes_after) { dst = a.tail + (long long)g * a.H; tail_written = true; }
-      else dst = a.dE + (long long)key * a.H;
+    // 2. dropout mask / coefficient (same operation order as scatter_row4)
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      const int e = __shfl_sync(0xffffffffu, val_l, j & 31);
+      const int src = e / a.M, row = e - src * a.M;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
         const int c4 = l + 32 * s;
-        if (c4 < h4) st4(dst + 4 * c4, acc[s]);
+        if (src < 2) {
+          const DropDesc& d = src == 0 ? a.drop_enc : a.drop_dec;
+          if (d.enabled && c4 < h4 && cf[u] != 0.f)
+            v[u][s] = f4_mul(v[u][s], drop_mul4(d, (d.base + (unsigned long long)((long long)row * a.H + 4 * c4)) >> 2));
+        }
+        v[u][s] = f4_scale(v[u][s], cf[u]);
       }
-      run_start = j + 1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      if (j >= cnt) break;
+      const int key = __shfl_sync(0xffffffffu, key_l, j);
+      const int key_next = j + 1 < cnt ? __shfl_sync(0xffffffffu, key_l, j + 1) : -3;
+      if (key == 0) { run_start = j + 1; continue; }   // padding_idx rows get no gradient
+      const bool fresh = (j == run_start);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] = fresh ? v[u][s] : f4_add(acc[s], v[u][s]);
+      if (j == cnt - 1 || key_next != key) {
+        const bool from_before = (run_start == 0) && (key == prev_key);
+        const bool goes_after = (j == cnt - 1) && (key == next_key);
+        float* dst;
+        if (from_before) dst = a.head + (long long)g * a.H;
+        else if (goes_after) { dst = a.tail + (long long)g * a.H; tail_written = true; }
+        else dst = a.dE + (long long)key * a.H;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const int c4 = l + 32 * s;
+          if (c4 < h4) st4(dst + 4 * c4, acc[s]);
+        }
+        run_start = j + 1;
+      }
     }
   }
   if (l == 0) a.has_tail[g] = tail_written ? 1 : 0;
@@ -275,16 +359,30 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   const float bc1 = bc_s[0], bc2 = bc_s[1];
   const float step = a.lr / bc1;
   const float isb2 = 1.0f / sqrtf(bc2);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-    float g = a.g[i] * coef;
-    a.g[i] = g;
-    const float p = a.p[i];
-    if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
-    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
-    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
-    a.m[i] = m;
-    a.v[i] = v;
-    a.p[i] = p - step * (m / (sqrtf(v) * isb2 + a.eps));
+  const float ob1 = 1.f - a.beta1, ob2 = 1.f - a.beta2;
+  auto upd = [&](float& g, float& p, float& m, float& v) {
+    g *= coef;
+    float ge = g;
+    if (a.weight_decay != 0.f) ge = fmaf(a.weight_decay, p, ge);
+    m = a.beta1 * m + ob1 * ge;
+    v = a.beta2 * v + ob2 * ge * ge;
+    p = p - step * (m / (sqrtf(v) * isb2 + a.eps));
+  };
+  // 128-bit streaming body (the four arrays are 16-byte aligned segments of the flat buffers), scalar tail
+  const long long n4 = a.n >> 2;
+  float4* g4 = reinterpret_cast<float4*>(a.g);
+  float4* p4 = reinterpret_cast<float4*>(a.p);
+  float4* m4 = reinterpret_cast<float4*>(a.m);
+  float4* v4 = reinterpret_cast<float4*>(a.v);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 g = g4[i], p = p4[i], m = m4[i], v = v4[i];
+    upd(g.x, p.x, m.x, v.x); upd(g.y, p.y, m.y, v.y); upd(g.z, p.z, m.z, v.z); upd(g.w, p.w, m.w, v.w);
+    g4[i] = g; m4[i] = m; v4[i] = v; p4[i] = p;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    float g = a.g[i], p = a.p[i], m = a.m[i], v = a.v[i];
+    upd(g, p, m, v);
+    a.g[i] = g; a.m[i] = m; a.v[i] = v; a.p[i] = p;
   }
 }
 

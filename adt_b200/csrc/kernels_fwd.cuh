@@ -13,14 +13,15 @@ namespace adt {
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ ids, const float* __restrict__ E,
                                                         const float* __restrict__ P, float* __restrict__ x, int M, int L, int H,
                                                         float scale, DropDesc drop) {
-  const int h4 = H >> 2;
-  const long long n = (long long)M * h4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(i / h4), c4 = (int)(i - (long long)row * h4);
-    const int id = ids[row];
-    const int t = row % L;
+  // 32-bit index math (M*H/4 < 2^31, checked by the launcher): the kernel is HBM bound only if the per-element integer work stays small
+  const unsigned h4 = (unsigned)H >> 2;
+  const unsigned n = (unsigned)M * h4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned row = i / h4, c4 = i - row * h4;
+    const int id = __ldg(ids + row);
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (id != 0) {
+      const unsigned t = row % (unsigned)L;
       const float4 e = __ldg(reinterpret_cast<const float4*>(E + (long long)id * H) + c4);
       const float4 p = __ldg(reinterpret_cast<const float4*>(P + (long long)t * H) + c4);
       o.x = __fadd_rn(__fmul_rn(e.x, scale), p.x);
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int* __restrict__ 
         o = f4_mul(o, m);
       }
     }
-    reinterpret_cast<float4*>(x)[i] = o;
+    __stcs(reinterpret_cast<float4*>(x) + i, o);
   }
 }
 
