@@ -134,3 +134,20 @@ def test_bert_ml20m_like_shape_vs_oracle():
     loss.backward()
     for k, prm in m.named_parameters():
         assert grad_close(prm.grad, sd[k].grad.numpy()), k
+
+
+@pytest.mark.parametrize("name", NAMES[:2])
+def test_bert_flat_optimizer_step(name):
+    """fused masked loss + FlatOptimizer (clip 5.0 + Adam in libadt_b200.so) reproduces the reference's optimiser step."""
+    from adt_b200.dp import FlatOptimizer
+    g = _load(name)
+    m = _model(g).train()
+    opt = FlatOptimizer(m, lr=0.001, betas=(0.9, 0.999), weight_decay=float(g["wd"]), clip=5.0)
+    opt.zero_grad()
+    loss = m.fused_loss(g["seq"], g["dec"], g["labels"], list(g["lambda1"]), list(g["lambda2"]))
+    loss.backward()
+    opt.step()
+    assert abs(opt.grad_norm() - float(g["gnorm"])) / float(g["gnorm"]) < 1e-4
+    for k, p in m.named_parameters():
+        big = np.abs(g["grad/" + k]) > 1e-5
+        assert np.abs(p.detach().cpu().numpy() - g["sd1/" + k])[big].max(initial=0.0) < 5e-6, k

@@ -140,3 +140,21 @@ def test_stosa_beauty_shape_properties():
         assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, k
     ids = m.full_sort_topk(seq, K=40).cpu().numpy()
     assert ids.shape == (B, 40) and (ids >= 0).all() and all(len(set(r)) == 40 for r in ids)
+
+
+def test_stosa_flat_optimizer_step():
+    """FlatOptimizer (Adam in libadt_b200.so, no clipping: stosa/trainer.py:535-537) reproduces the reference's step."""
+    from adt_b200.dp import FlatOptimizer
+    g = _load("beauty_p3")
+    m = _model(g).train()
+    opt = FlatOptimizer(m, lr=0.001, betas=(0.9, 0.999), weight_decay=float(g["wd"]))
+    opt.zero_grad()
+    loss, _, _, _ = m.fused_loss(g["seq"], g["dec"], g["pos"], g["neg"], list(g["lambda1"]), list(g["lambda2"]))
+    loss.backward()
+    opt.step()
+    for k, p in m.named_parameters():
+        if "grad/" + k not in g:
+            assert np.abs(p.detach().cpu().numpy() - g["sd0/" + k]).max() == 0.0, k     # untouched parameters stay put
+            continue
+        big = np.abs(g["grad/" + k]) > 1e-5
+        assert np.abs(p.detach().cpu().numpy() - g["sd1/" + k])[big].max(initial=0.0) < 5e-6, k
