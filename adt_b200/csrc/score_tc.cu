@@ -31,6 +31,7 @@ constexpr int TC_THREADS = 192;
 struct TcArgs {
   const int* seen_indptr; const int* seen_idx;
   float* part_scores; int* part_ids; float* part_thr;
+  unsigned int* gthr;   // [U] best K'-th-best key published by any catalog split of this launch (order-preserving keys, 0 = none)
   int U, n_items, item_offset, KC, n_splits, debug;
 };
 
@@ -46,7 +47,8 @@ __device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int u, int item) {
   return false;
 }
 
-template <int KB, int BN>
+// NS = depth of the TMA ring of catalog tiles (B operand); accumulators are double buffered in TMEM
+template <int KB, int BN, int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -55,18 +57,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   constexpr int B_STAGE = KB * BN * 128;
   uint8_t* sA = smem;
   uint8_t* sB = sA + A_BYTES;
-  const int KCP = a.KC <= 32 ? 32 : 64;                       // list slots per user row (one or two per lane)
-  uint32_t* lk = reinterpret_cast<uint32_t*>(sB + 2 * B_STAGE);   // [128][KCP] order-preserving score keys
-  int* li = reinterpret_cast<int*>(lk + BM * KCP);                // [128][KCP] item ids
-  float* thr_s = reinterpret_cast<float*>(li + BM * KCP);         // [128] current K'-th best score per row
+  const int KCP = a.KC <= 32 ? 32 : 64;                       // list slots reserved per user row
+  uint32_t* lk = reinterpret_cast<uint32_t*>(sB + NS * B_STAGE);  // [KCP][128] order-preserving score keys, slot-major: the
+  int* li = reinterpret_cast<int*>(lk + BM * KCP);                // [KCP][128] item ids      thread that owns a row scans it conflict-free
+  float* thr_s = reinterpret_cast<float*>(li + BM * KCP);         // [128] (unused scratch)
   float* vsm = thr_s + BM;                                        // [4][32][32] chunk parking area of the epilogue warps
   uint64_t* bars = reinterpret_cast<uint64_t*>(vsm + 4 * 1024);
-  uint64_t* full = bars;          // [2] B stage filled (TMA tx)
-  uint64_t* empty = bars + 2;     // [2] B stage consumed (tcgen05.commit)
-  uint64_t* tfull = bars + 4;     // [2] accumulator ready (tcgen05.commit)
-  uint64_t* tempty = bars + 6;    // [2] accumulator drained (4 epilogue warps)
-  uint64_t* abar = bars + 8;      // A tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* full = bars;               // [NS] B stage filled (TMA tx)
+  uint64_t* empty = bars + NS;         // [NS] B stage consumed (tcgen05.commit)
+  uint64_t* tfull = bars + 2 * NS;     // [2] accumulator ready (tcgen05.commit)
+  uint64_t* tempty = bars + 2 * NS + 2;  // [2] accumulator drained (4 epilogue warps)
+  uint64_t* abar = bars + 2 * NS + 4;  // A tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, u0 = blockIdx.y * BM;
@@ -78,9 +80,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NS; ++i) {
       tc::mbar_init(full + i, 1);
       tc::mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       tc::mbar_init(tfull + i, 1);
       tc::mbar_init(tempty + i, 4);
     }
@@ -98,8 +102,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       tc::mbar_arrive_expect_tx(abar, A_BYTES);
       for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sA + kb * BM * 128, &tmA, kb * 64, u0, abar);
       for (int t = 0; t < ntiles; ++t) {
-        const int st = t & 1;
-        tc::mbar_wait(empty + st, ((t >> 1) & 1) ^ 1);
+        const int st = t % NS;
+        tc::mbar_wait(empty + st, ((t / NS) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(full + st, B_STAGE);
         for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sB + st * B_STAGE + kb * BN * 128, &tmB, kb * 64, it0 + t * BN, full + st);
       }
@@ -109,11 +113,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BN);
       tc::mbar_wait(abar, 0);
       for (int t = 0; t < ntiles; ++t) {
-        const int st = t & 1;
-        tc::mbar_wait(tempty + st, ((t >> 1) & 1) ^ 1);
-        tc::mbar_wait(full + st, (t >> 1) & 1);
+        const int st = t % NS, acc = t & 1;
+        tc::mbar_wait(tempty + acc, ((t >> 1) & 1) ^ 1);
+        tc::mbar_wait(full + st, (t / NS) & 1);
         tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + st * BN;
+        const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
           const uint64_t ad = tc::smem_desc_k_sw128(tc::smem_u32(sA + kb * BM * 128));
@@ -123,53 +127,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             tc::mma_bf16_ss(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
         }
         tc::mma_commit(empty + st);
-        tc::mma_commit(tfull + st);
+        tc::mma_commit(tfull + acc);
       }
     }
   } else {
-    // epilogue: thread == user row for the threshold filter; list maintenance is warp-cooperative
+    // epilogue: thread == user row, for the threshold filter AND for the maintenance of that row's candidate list: every lane
+    // inserts its own candidates into its own slot-major list (no cross-lane traffic, all 32 rows of a warp progress in parallel)
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const int u = u0 + row;
     const int KC = a.KC;
-    for (int k = 0; k < KCP; ++k) {          // slots >= KC are permanently "infinitely good" so they are never the minimum
-      lk[row * KCP + k] = k < KC ? 0u : 0xffffffffu;
-      li[row * KCP + k] = -1;
+    for (int k = 0; k < KC; ++k) {
+      lk[k * BM + row] = 0u;                 // key 0 = "worse than anything"
+      li[k * BM + row] = -1;
     }
-    thr_s[row] = u < a.U ? -INFINITY : INFINITY;
-    __syncwarp();
+    uint32_t mink = 0u;                      // smallest key in the list and its slot
+    int minpos = 0;
+    // rej: keys <= rej cannot be among the K' best of the WHOLE catalog: max of this split's K'-th best (mink) and the best
+    // K'-th best any other split has published so far (K' items of one split beat it, so the global K'-th best does too)
+    uint32_t rej = 0u, published = 0u;
+    float thr = u < a.U ? -INFINITY : INFINITY;   // rej as a float (-inf while nothing is known)
+    auto unkey = [](uint32_t k) -> float { return k == 0u ? -INFINITY : __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); };
     auto fkey = [](float f) -> uint32_t {
       const uint32_t b = __float_as_uint(f);
       return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
     };
-    // warp-cooperative insert of (score sc, local item index itl) into the list of row rrow (slots spread over lanes)
-    auto insert = [&](int rrow, float sc, int itl) -> float {
-      float new_thr = __int_as_float(0x7fc00000);
-      uint32_t* Lk = lk + rrow * KCP;
-      uint32_t k0 = Lk[lane];
-      uint32_t k1 = KCP == 64 ? Lk[lane + 32] : 0xffffffffu;
-      uint32_t mk = min(k0, k1);
-      const uint32_t wm = __reduce_min_sync(0xffffffffu, mk);
+    auto insert = [&](float sc, int itl) {
       const uint32_t key = fkey(sc);
-      if (key > wm) {
-        const int item = a.item_offset + itl;
-        if (!tc_is_seen(a, u0 + rrow, item)) {
-          const int who = __ffs(__ballot_sync(0xffffffffu, mk == wm)) - 1;
-          if (lane == who) {
-            if (k0 == wm) { Lk[lane] = key; li[rrow * KCP + lane] = item; k0 = key; }
-            else { Lk[lane + 32] = key; li[rrow * KCP + lane + 32] = item; k1 = key; }
-          }
-          mk = min(k0, k1);
-          const uint32_t nm = __reduce_min_sync(0xffffffffu, mk);
-          new_thr = nm == 0u ? -INFINITY : __uint_as_float((nm & 0x80000000u) ? (nm & 0x7fffffffu) : ~nm);
-          if (lane == 0) thr_s[rrow] = new_thr;
-          __syncwarp();
-        }
+      if (key <= rej) return;
+      const int item = a.item_offset + itl;
+      if (tc_is_seen(a, u, item)) return;
+      lk[minpos * BM + row] = key;
+      li[minpos * BM + row] = item;
+      uint32_t nm = 0xffffffffu;
+      int np = 0;
+      for (int k = 0; k < KC; ++k) {
+        const uint32_t x = lk[k * BM + row];
+        if (x < nm) { nm = x; np = k; }
       }
-      return new_thr;
+      mink = nm; minpos = np;
+      if (nm > rej) { rej = nm; thr = unkey(nm); }
     };
     for (int t = 0; t < ntiles; ++t) {
       const int st = t & 1;
+      // thresholds of the other splits: issue the (L2) load now, consume it after this tile
+      const uint32_t gnext = (a.gthr && u < a.U) ? __ldcg(a.gthr + u) : 0u;
       tc::mbar_wait(tfull + st, (t >> 1) & 1);
       tc::tc_fence_after();
 #pragma unroll 1
@@ -189,39 +191,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
             if (c >= nvalid) v[c] = -INFINITY;
         }
         if (a.debug == 1) continue;      // pipeline-only timing experiment
-        const float thr = thr_s[row];
         unsigned m = 0u;                    // bit c set <=> this row's score in column c beats the row threshold
 #pragma unroll
         for (int c = 0; c < 32; ++c) m |= (v[c] > thr) ? (1u << c) : 0u;
         unsigned bb = __ballot_sync(0xffffffffu, m != 0u);
         if (bb == 0u || a.debug == 2) continue;   // common case once the lists are warm
-        // park the 32x32 chunk in smem; visit only the (row, column) pairs that fired, with ONE copy of the insert code
+        // park the 32x32 chunk in smem (lane-contiguous, conflict free); every lane then walks ITS OWN fired columns with one
+        // copy of the insert code
         float* vs = vsm + q * 1024;
 #pragma unroll
         for (int c = 0; c < 32; ++c) vs[c * 32 + lane] = v[c];
         __syncwarp();
-        while (bb) {
-          const int src = __ffs(bb) - 1;
-          bb &= bb - 1;
-          unsigned mm = __shfl_sync(0xffffffffu, m, src);
-          while (mm) {
-            const int c = __ffs(mm) - 1;
-            mm &= mm - 1;
-            insert(32 * q + src, vs[c * 32 + src], ib + c);
-          }
+        while (m) {
+          const int c = __ffs(m) - 1;
+          m &= m - 1;
+          insert(vs[c * 32 + lane], ib + c);
         }
         __syncwarp();
+      }
+      if (a.gthr && u < a.U) {
+        if (mink > published) { atomicMax(a.gthr + u, mink); published = mink; }   // rare once the list is warm
+        if (gnext > rej) { rej = gnext; thr = unkey(gnext); }
       }
     }
     if (u < a.U) {
       const long long o = ((long long)split * a.U + u) * KC;
       for (int k = 0; k < KC; ++k) {
-        const uint32_t key = lk[row * KCP + k];
-        const int id = li[row * KCP + k];
+        const uint32_t key = lk[k * BM + row];
+        const int id = li[k * BM + row];
         a.part_scores[o + k] = id >= 0 ? __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key) : -INFINITY;
         a.part_ids[o + k] = id;
       }
-      a.part_thr[(long long)split * a.U + u] = thr_s[row];
+      a.part_thr[(long long)split * a.U + u] = thr;
     }
   }
   tc::tc_fence_before();
@@ -351,13 +352,21 @@ int make_map(CUtensorMap* m, const void* base, long long rows, int H, int box_ro
   return r == CUDA_SUCCESS ? ADT_OK : ADT_E_CUDA;
 }
 
+template <int KB, int BN, int NS>
+int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s, size_t smem) {
+  cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  score_tc_kernel<KB, BN, NS><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+// deepest catalog-tile ring (2..4 stages) that fits the 227 KB of shared memory next to the user tile and the top-K lists
 template <int KB, int BN>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
-  const size_t smem = 1024 + (size_t)KB * BM * 128 + 2 * (size_t)KB * BN * 128 + (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 + BM * 4 + 4 * 1024 * 4 + 128;
-  if (smem > 227 * 1024) return ADT_E_SHAPE;
-  cudaFuncSetAttribute(score_tc_kernel<KB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  score_tc_kernel<KB, BN><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
-  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+  const size_t fixed = 1024 + (size_t)KB * BM * 128 + (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 + BM * 4 + 4 * 1024 * 4 + 256;
+  const size_t stage = (size_t)KB * BN * 128, cap = 227 * 1024;
+  if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4>(tmA, tmB, k, grid, s, fixed + 4 * stage);
+  if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3>(tmA, tmB, k, grid, s, fixed + 3 * stage);
+  if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2>(tmA, tmB, k, grid, s, fixed + 2 * stage);
+  return ADT_E_SHAPE;
 }
 
 }  // namespace
@@ -382,6 +391,11 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   TcArgs k;
   k.seen_indptr = a->seen_indptr; k.seen_idx = a->seen_idx; k.part_scores = a->part_scores; k.part_ids = a->part_ids; k.part_thr = a->part_thr;
   k.U = a->U; k.n_items = a->n_items; k.item_offset = a->item_offset; k.KC = a->KC; k.n_splits = a->n_splits;
+  k.gthr = nullptr;
+  if (a->n_splits > 1 && a->flags) {     // `flags` doubles as the threshold exchange buffer until the re-score kernel overwrites it
+    k.gthr = reinterpret_cast<unsigned int*>(a->flags);
+    cudaMemsetAsync(a->flags, 0, sizeof(int) * (size_t)a->U, s);
+  }
   { const char* dbg = getenv("ADT_TC_DEBUG"); k.debug = dbg ? atoi(dbg) : 0; }
   dim3 grid(a->n_splits, (a->U + BM - 1) / BM);
   int rc;

@@ -29,6 +29,8 @@ def peaks():
 
 
 def timeit(fn, iters=10, warm=3):
+    if os.environ.get("MICRO_ONCE"):     # profiling runs (ncu): one launch of everything
+        iters, warm = 1, 0
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
     for _ in range(warm):
         fn()
