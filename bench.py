@@ -146,6 +146,12 @@ def time_cpu_reference(cfg, budget_s, steps=None, warmup=1):
     return cfg["B"] / (ms / 1e3), ms, len(ts), cores
 
 
+def workload_name(args, cfg):
+    """the SAME workload string for both arms (the driver compares the arms on it)"""
+    return (f"SASRec-ADT {args.config}: train step (items={cfg['items']}, maxlen={cfg['L']}, hidden={cfg['H']}, heads={cfg['nh']}, "
+            f"blocks={cfg['nl']}, batch={cfg['B']}/GPU, dropout={cfg['p']})")
+
+
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
@@ -153,7 +159,8 @@ def run_reference(args, cfg, rank, world):
     line = {"metric": "train_seqs_per_sec", "value": v, "unit": "seqs/s", "n_gpus": args.gpus, "steps": n, "warmup": 1,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": f"SASRec-ADT {args.config} train step (B={cfg['B']}, L={cfg['L']}, H={cfg['H']}, items={cfg['items']})"},
+            "config": {"workload": workload_name(args, cfg), "parallelism": "host cores of rank 0 (all torch threads)",
+                       "global_batch": cfg["B"]},
             "cpu_baseline": {"value": v, "unit": "seqs/s", "cores": cores, "kind": "port",
                              "sample": f"{n} full optimisation steps of one {cfg['B']}-sequence batch (median)"},
             "e2e": {"value": v, "unit": "seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -356,8 +363,7 @@ def main():
             "metric": "train_seqs_per_sec", "value": value, "unit": "seqs/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
-            "config": {"workload": f"SASRec-ADT {args.config}: train step + full-catalog eval (items={cfg['items']}, maxlen={Lq}, "
-                                   f"hidden={H}, heads={nh}, blocks={nl}, batch={B}/GPU, dropout={cfg['p']})",
+            "config": {"workload": workload_name(args, cfg),
                        "parallelism": f"dp{world}", "global_batch": world * B, "l2": "flushed between timed steps (256 MB write)",
                        "timing": "per-step CUDA events on the launch stream, max over ranks", "launch": "whole step replayed as one CUDA graph"},
             "e2e": {"value": e2e_value, "unit": "seqs/s", "h2d_bytes_per_step": 4 * B * Lq * 4, "d2h_bytes_per_step": 8 * (8 + 2 * nl),
