@@ -98,11 +98,14 @@ static DropDesc mk_drop(const adt_dropout& d) {
 
 static const size_t SMEM_MAX = 227 * 1024 - 2048;   // leave room for the kernels' small static arrays
 
-// rows-per-CTA choice: 64 when the tile set fits, else 32
-static int pick_tm(size_t row_floats, size_t* bytes) {
+// rows-per-CTA choice: the preferred tile height (ADT_TM = 32 / 64 / 128, default 64) when the tile set fits, else the next smaller
+// `tuned`: per-kernel measured preference used when ADT_TM is not set (C2 shape: mid_bwd is 20 % faster with 128-row tiles -- half
+// the weight-gradient atomics -- every other kernel is fastest at 64)
+static int pick_tm(size_t row_floats, size_t* bytes, int max_tm = 128, int tuned = 0) {
   static int pref = -1;
-  if (pref < 0) { const char* e = getenv("ADT_TM"); pref = e ? atoi(e) : 64; if (pref != 32) pref = 64; }
-  for (int tm = pref; tm >= 32; tm >>= 1) {
+  if (pref < 0) { const char* e = getenv("ADT_TM"); pref = e ? atoi(e) : 0; if (pref != 32 && pref != 64 && pref != 128) pref = 0; }
+  const int want = pref ? pref : (tuned ? tuned : 64);
+  for (int tm = want < max_tm ? want : max_tm; tm >= 32; tm >>= 1) {
     const size_t b = ((size_t)tm * row_floats + WS_FLOATS) * sizeof(float);
     if (b <= SMEM_MAX) {
       *bytes = b;
@@ -147,7 +150,9 @@ static void launch_pdl(void (*kern)(Exp...), dim3 grid, size_t smem, cudaStream_
 
 #define LAUNCH_TM(tm, mma, KERN, grid, smem, stream, ...)                                        \
   do {                                                                                           \
-    if ((tm) == 64 && !(mma)) LAUNCH_ONE((KERN<64, false>), grid, smem, stream, __VA_ARGS__);     \
+    if ((tm) == 128 && !(mma)) LAUNCH_ONE((KERN<128, false>), grid, smem, stream, __VA_ARGS__);   \
+    else if ((tm) == 128) LAUNCH_ONE((KERN<128, true>), grid, smem, stream, __VA_ARGS__);         \
+    else if ((tm) == 64 && !(mma)) LAUNCH_ONE((KERN<64, false>), grid, smem, stream, __VA_ARGS__); \
     else if ((tm) == 64) LAUNCH_ONE((KERN<64, true>), grid, smem, stream, __VA_ARGS__);           \
     else if (!(mma)) LAUNCH_ONE((KERN<32, false>), grid, smem, stream, __VA_ARGS__);              \
     else LAUNCH_ONE((KERN<32, true>), grid, smem, stream, __VA_ARGS__);                           \
@@ -155,7 +160,9 @@ static void launch_pdl(void (*kern)(Exp...), dim3 grid, size_t smem, cudaStream_
 
 #define LAUNCH_TM2(tm, mma, KERN, FLAG, grid, smem, stream, ...)                                 \
   do {                                                                                           \
-    if ((tm) == 64 && !(mma)) LAUNCH_ONE((KERN<64, FLAG, false>), grid, smem, stream, __VA_ARGS__); \
+    if ((tm) == 128 && !(mma)) LAUNCH_ONE((KERN<128, FLAG, false>), grid, smem, stream, __VA_ARGS__); \
+    else if ((tm) == 128) LAUNCH_ONE((KERN<128, FLAG, true>), grid, smem, stream, __VA_ARGS__);   \
+    else if ((tm) == 64 && !(mma)) LAUNCH_ONE((KERN<64, FLAG, false>), grid, smem, stream, __VA_ARGS__); \
     else if ((tm) == 64) LAUNCH_ONE((KERN<64, FLAG, true>), grid, smem, stream, __VA_ARGS__);     \
     else if (!(mma)) LAUNCH_ONE((KERN<32, FLAG, false>), grid, smem, stream, __VA_ARGS__);        \
     else LAUNCH_ONE((KERN<32, FLAG, true>), grid, smem, stream, __VA_ARGS__);                     \
@@ -198,7 +205,7 @@ static int launch_attn_fwd(const float* q, const float* k, const float* v, float
   const int pad = mma ? 8 : 4;
   const size_t rowf = (size_t)(hd + pad) + (size_t)(((L + 3) & ~3) + pad);
   size_t smem;
-  int tm = pick_tm(rowf, &smem);
+  int tm = pick_tm(rowf, &smem, 64);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_fwd: tile does not fit shared memory");
   if (L <= 32 && tm == 64) { tm = 32; smem = ((size_t)tm * rowf + WS_FLOATS) * sizeof(float); }
   adt_dropout dd = d;
@@ -216,7 +223,7 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
   const int pad = mma ? 8 : 4;
   const size_t rowf = 2 * (size_t)(hd + pad) + 2 * (size_t)(((L + 3) & ~3) + pad);
   size_t smem;
-  int tm = pick_tm(rowf, &smem);
+  int tm = pick_tm(rowf, &smem, 64);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "attn_bwd: tile does not fit shared memory");
   if (L <= 32 && tm == 64) { tm = 32; smem = ((size_t)tm * rowf + WS_FLOATS) * sizeof(float); }
   dim3 grid((L + tm - 1) / tm, nh, B);
@@ -360,7 +367,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   m.Wo1 = a->slf.out_w; m.Win2 = a->enc.in_w; m.dfeats = a->dfeats; m.dctx1 = a->dctx;
   m.gWo1 = a->g_slf.out_w; m.gbo1 = a->g_slf.out_b; m.gWin2 = a->g_enc.in_w; m.gbin2 = a->g_enc.in_b;
   m.M = M; m.H = H; m.qscale = qscale;
-  tm = pick_tm(3 * (size_t)(H + pad) + (size_t)(2 * H + pad), &smem);
+  tm = pick_tm(3 * (size_t)(H + pad) + (size_t)(2 * H + pad), &smem, 128, M >= 148 * 64 ? 128 : 64);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_bwd: tile does not fit shared memory");
   { TIMED("mid_bwd", s); LAUNCH_TM(tm, mma, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m); }
   if (int e = check_launch("mid_bwd")) return e;
