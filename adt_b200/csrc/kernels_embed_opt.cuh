@@ -289,12 +289,35 @@ __global__ void __launch_bounds__(256) scatter_phase2_kernel(ScatterArgs a) {
     const int c4 = l + 32 * s;
     acc[s] = c4 < h4 ? ld4(a.tail + (long long)g * a.H + 4 * c4) : zero4();
   }
-  for (int g2 = g + 1; g2 < nb && a.keys[g2 * 32] == key; ++g2) {
+  // the run continues through every following block that starts with the same key: find its length 32 blocks at a time (one
+  // key probe per lane), then add the heads strictly in block order with the loads of eight blocks in flight (popular items
+  // span hundreds of blocks; a dependent load per block was the whole cost of this kernel)
+  int g2 = g + 1;
+  while (g2 < nb) {
+    const int probe = g2 + l;
+    const bool same = probe < nb && a.keys[probe * 32] == key;
+    const unsigned ok = __ballot_sync(0xffffffffu, same);
+    const int len = ok == 0xffffffffu ? 32 : __ffs(~ok) - 1;     // leading blocks that belong to the run
+    for (int b0 = 0; b0 < len; b0 += 8) {
+      float4 hv[8][2];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int c4 = l + 32 * s;
-      if (c4 < h4) acc[s] = f4_add(acc[s], ld4(a.head + (long long)g2 * a.H + 4 * c4));
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int c4 = l + 32 * s;
+          hv[u][s] = (b0 + u < len && c4 < h4) ? ld4(a.head + (long long)(g2 + b0 + u) * a.H + 4 * c4) : zero4();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (b0 + u < len) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) acc[s] = f4_add(acc[s], hv[u][s]);
+        }
+      }
     }
+    if (len < 32) break;
+    g2 += 32;
   }
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
