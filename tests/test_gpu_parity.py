@@ -65,3 +65,35 @@ def test_bf16_tensor_core_mode_within_baseline_tolerance(T, name):
             if np.linalg.norm(b) > 1e-7:
                 cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
                 assert cos > 0.995, (k, cos)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_three_training_steps_track_the_oracle(T, use_graph):
+    """three consecutive optimisation steps (dropout step index, Adam moments and bias corrections advancing; in graph mode
+    through the device-side counters) against the oracle's train_step run three times with the same Philox streams."""
+    from adt_b200.trainer import FusedTrainer
+    from oracle import sasrec_oracle as O
+    g = T.load_golden("tiny_p5")
+    d = g["dims"]
+    l1, l2, wd = [float(x) for x in g["lambdas1"]], [float(x) for x in g["lambdas2"]], float(g["wd"])
+    cfg = O.Cfg(d["I"], d["L"], d["H"], d["nh"], d["nl"], float(g["p"]))
+    sd = {k[4:]: torch.from_numpy(np.array(v)).requires_grad_(True) for k, v in g.items() if k.startswith("sd0/")}
+    batch = tuple(torch.from_numpy(g[k]).long() for k in ("seq", "dec", "pos", "neg"))
+    seed, step0, p = int(g["drop_seed"]), int(g["drop_step"]), float(g["p"])
+    m = T.model_from_golden(g).train()
+    tr = FusedTrainer(m, l1, l2, weight_decay=wd, seed=seed, use_graph=use_graph)
+    tr.t = step0
+    opt = None
+    for k in range(3):
+        loss_ref, _, gn_ref, opt, _ = O.train_step(sd, cfg, batch, l1, l2, wd, drop=O.Drop(p, seed, step0 + k), adam_state=opt)
+        tr.step(g["seq"], g["dec"], g["pos"], g["neg"])
+        assert abs(tr.loss() - float(loss_ref)) / abs(float(loss_ref)) < 2e-5, k
+        assert abs(tr.grad_norm() - float(gn_ref)) / float(gn_ref) < 1e-4, k
+    for name, prm in m.named_parameters():
+        if sd[name].grad is None:
+            continue
+        ref = sd[name].detach().numpy()
+        got = prm.detach().cpu().numpy()
+        # Adam's first steps move every weight by ~lr * g/|g| : compare where the gradient is well above eps
+        big = np.abs(sd[name].grad.numpy()) > 1e-5
+        assert np.abs(got - ref)[big].max(initial=0.0) < 2e-5, name
