@@ -396,10 +396,11 @@ class Engine:
                    d_item_emb=g["item_emb.weight"], d_pos_emb=g["pos_emb.weight"], head=w["head"], tail=w["tail"], has_tail=w["has_tail"])
         L.check(self.lib.adt_embed_bwd(L.ctypes.byref(a), self._stream()), "adt_embed_bwd")
 
-    def loss_from_acc(self, w, lambdas1, lambdas2, weight_decay, emb_norm):
+    def loss_from_acc(self, w, lambdas1, lambdas2, weight_decay, emb_norm, acc=None):
         """Assemble main.py:152-170's scalar from the accumulators (host side, float64)."""
         m = self.m
-        acc = w["acc"].tolist()
+        if acc is None:
+            acc = w["acc"].tolist()
         Mg = self.global_rows or w["M"]
         nl, H, nh = m.num_layers, m.hidden, m.num_heads
         n = max(acc[2], 1.0)

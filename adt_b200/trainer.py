@@ -105,6 +105,14 @@ class FusedTrainer:
 
     def _prepare(self, B, Lq):
         eng = self.eng
+        # fast path of the replay loop: the flat buffers were validated when the graph for this shape was captured (the graph
+        # replays baked pointers anyway); only probe that the first / last parameters are still views of the flat buffer
+        if self.use_graph and (B, Lq) in self._graphs and eng.pflat is not None:
+            (n0, p0), (n1, p1) = eng.order[0], eng.order[-1]
+            base = eng.pflat.data_ptr()
+            if p0.data_ptr() == base + 4 * eng.offs[n0] and p1.data_ptr() == base + 4 * eng.offs[n1]:
+                return
+            self._graphs.clear()        # parameters were re-homed (e.g. .to() / re-init): rebuild buffers and re-capture
         dev = eng.dev()
         eng.ensure_flat()
         if self.step_dev is None or self.step_dev.device != dev:
@@ -185,9 +193,19 @@ class FusedTrainer:
     def loss(self):
         """Loss of the last step as main.py:174 would print it (synchronises)."""
         w, nl = self._w, self.model.num_layers
-        acc = w["acc"].tolist()
+        acc = self._read_acc(w)
         emb_norm = float(np.sqrt(acc[3 + 2 * nl])) if (self.use_norm_decay and self.wd != 0.0) else 0.0
-        return self.eng.loss_from_acc(w, self.l1, self.l2, self.wd if self.use_norm_decay else 0.0, emb_norm)
+        return self.eng.loss_from_acc(w, self.l1, self.l2, self.wd if self.use_norm_decay else 0.0, emb_norm, acc=acc)
+
+    def _read_acc(self, w):
+        """device accumulators -> host list through a persistent pinned buffer (one async copy + one stream sync)."""
+        a = w["acc"]
+        h = getattr(self, "_acc_host", None)
+        if h is None or h.numel() != a.numel():
+            h = self._acc_host = torch.empty(a.numel(), dtype=a.dtype).pin_memory()
+        h.copy_(a, non_blocking=True)
+        torch.cuda.current_stream(a.device).synchronize()
+        return h.tolist()
 
     def grad_norm(self):
-        return float(np.sqrt(self._w["acc"][4 + 2 * self.model.num_layers].item()))
+        return float(np.sqrt(self._read_acc(self._w)[4 + 2 * self.model.num_layers]))
