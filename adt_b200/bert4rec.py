@@ -105,6 +105,7 @@ class BertModel(nn.Module):
         self.mask_bias = nn.Parameter(torch.zeros(itemnum + 100))
         self.mask_layer_norm = nn.LayerNorm(H, eps=1e-5)
         self.drop_seed, self.drop_step, self.precision = 0, 0, 0
+        self.step_dev = None      # optional device-side dropout step counter (adt_b200.dp.GraphedStep)
         L.lib()
 
     # ------------------------------------------------------------------------------------------
@@ -187,7 +188,7 @@ class BertModel(nn.Module):
         dev = self.mask_bias.device
         src, dec = _ids(src_ids, dev), _ids(dec_ids, dev)
         sp, ss, dp, ds = (_ids(a, dev) for a in (seq_pos_ids, seq_sent_ids, deq_pos_ids, deq_sent_ids))
-        dc = DropCfg(self.dropout, self.drop_seed, self.drop_step, self.training)
+        dc = DropCfg(self.dropout, self.drop_seed, self.drop_step, self.training, step_dev=self.step_dev)
         feats, enc_inputs, inds = self._encode(src, sp, ss, dc)
         dec_outs = self._decode(dec, dp, ds, feats, src, dc)
         if self.training:

@@ -32,8 +32,9 @@ class DropCfg:
     """dropout context of one forward: p, seed, step, training, batch offset, and the running site counter that follows
     the reference's F.dropout call order."""
 
-    def __init__(self, p, seed, step, training, b0=0):
+    def __init__(self, p, seed, step, training, b0=0, step_dev=None):
         self.p, self.seed, self.step, self.training, self.b0 = float(p), int(seed), int(step), bool(training), int(b0)
+        self.step_dev = step_dev      # optional int32 device tensor added to `step` at run time (CUDA-graph replay)
         self.site = 0
 
     def next(self, kind, nh, Lq, H):
@@ -41,7 +42,7 @@ class DropCfg:
         d.enabled = 1 if (self.training and self.p > 0.0) else 0
         d.p, d.seed, d.step, d.site = self.p, self.seed, self.step, self.site
         d.base = self.b0 * (nh * Lq if kind == "attn" else Lq * H)   # attention sites: ROW offset ; row sites: element offset
-        d.step_dev = None
+        d.step_dev = self.step_dev.data_ptr() if self.step_dev is not None else None
         if self.training and self.p > 0.0:
             self.site += 1
         return d

@@ -238,6 +238,7 @@ class DisenDistSAModel(nn.Module):
         self.dropout_p, self.attention_dropout_p = float(args.dropout), float(args.attention_dropout)
         self.pvn_weight = float(getattr(args, "pvn_weight", 0.005))
         self.drop_seed, self.drop_step, self.precision = 0, 0, 0
+        self.step_dev = None      # optional device-side dropout step counter (adt_b200.dp.GraphedStep)
         self.apply(self.init_weights)
         L.lib()
 
@@ -301,7 +302,7 @@ class DisenDistSAModel(nn.Module):
         B, Lq = ids.shape
         nh, H = self.num_heads, self.hidden_units
         pos_ids = torch.arange(Lq, dtype=torch.int32, device=dev).repeat(B, 1)
-        dc = DropCfg(self.dropout_p, self.drop_seed, self.drop_step, self.training)
+        dc = DropCfg(self.dropout_p, self.drop_seed, self.drop_step, self.training, step_dev=self.step_dev)
         (m, c), (dm, dcv) = self._embed(ids, dec, pos_ids, dc, Lq)
         enc_inputs, rec_logits = [], []
         for layer in self.item_encoder.layer:

@@ -158,3 +158,29 @@ def test_stosa_flat_optimizer_step():
             continue
         big = np.abs(g["grad/" + k]) > 1e-5
         assert np.abs(p.detach().cpu().numpy() - g["sd1/" + k])[big].max(initial=0.0) < 5e-6, k
+
+
+def test_stosa_graphed_step_matches_eager():
+    """GraphedStep (whole step = one CUDA graph, device-side dropout/Adam counters) reproduces the eager loop step by step."""
+    from adt_b200.dp import FlatOptimizer, GraphedStep
+    g = _load("beauty_p3")
+    l1, l2 = list(g["lambda1"]), list(g["lambda2"])
+    batch = (g["seq"], g["dec"], g["pos"], g["neg"])
+    # eager reference loop
+    m0 = _model(g).train()
+    o0 = FlatOptimizer(m0, lr=0.001)
+    losses0 = []
+    for _ in range(3):
+        o0.zero_grad()
+        loss = m0.fused_loss(*batch, l1, l2)[0]
+        loss.backward()
+        o0.step()
+        losses0.append(float(loss))
+    # graphed loop
+    m1 = _model(g).train()
+    o1 = FlatOptimizer(m1, lr=0.001)
+    gs = GraphedStep(m1, o1, lambda s, d, p, n: m1.fused_loss(s, d, p, n, l1, l2)[0])
+    losses1 = [float(gs.step(*batch)) for _ in range(3)]
+    assert abs(losses0[0] - float(g["loss"])) / abs(float(g["loss"])) < 1e-5
+    assert np.allclose(losses0, losses1, rtol=2e-5), (losses0, losses1)
+    assert torch.allclose(o0.pflat, o1.pflat, rtol=1e-3, atol=2e-5)

@@ -75,11 +75,24 @@ def stosa():
         opt.step()
         out["loss"] = loss
     ms = timed(step)
+    from adt_b200.dp import GraphedStep
+    # fresh parameters: autograd binds a leaf's gradient accumulator to the stream of its FIRST forward, and the eager loop above
+    # ran on the default stream, which cannot be captured (see GraphedStep's docstring)
+    torch.manual_seed(0)
+    m = DisenDistSAModel(args).cuda().train()
+    opt = FlatOptimizer(m, lr=1e-3)
+    gs = GraphedStep(m, opt, lambda s, d, p, n: m.fused_loss(s, d, p, n, [0.0021], [0.0009])[0])
+    dev_batch = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda() for a in (seq, dec, pos, neg)]
+    ms_graph = timed(lambda: gs.step(*dev_batch))
     ev = timed(lambda: m.full_sort_topk(seq, K=40), warm=2, iters=5)
     print(json.dumps({"model": "STOSA-ADT C4 (B=256, L=100, H=64, nh=4, nl=1, items=12101)", "ms_per_step": ms, "seqs_per_sec": B / ms * 1e3,
+                      "ms_per_step_graphed": ms_graph, "seqs_per_sec_graphed": B / ms_graph * 1e3,
                       "loss": float(out["loss"]), "full_sort_users_per_sec": B / ev * 1e3}), flush=True)
 
 
 if __name__ == "__main__":
-    bert()
-    stosa()
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "bert"):
+        bert()
+    if which in ("all", "stosa"):
+        stosa()
