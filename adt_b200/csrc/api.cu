@@ -11,6 +11,7 @@
 #include "kernels_fwd.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_stosa.cuh"
+#include "kernels_attn_small.cuh"
 
 using namespace adt;
 
@@ -199,9 +200,26 @@ static int launch_pre_fwd(const float* x, const float* ln_w, const float* ln_b, 
   return check_launch("pre_fwd");
 }
 
+// short sequences in the bf16 tensor-core mode: one small CTA per (sequence, head) (kernels_attn_small.cuh); ADT_ATTN_SMALL=0 disables
+static bool use_attn_small(int L, int hd, int mma) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_ATTN_SMALL"); v = e ? (atoi(e) != 0) : 1; }
+  return v && mma && L <= 64 && (hd == 16 || hd == 32 || hd == 64);
+}
+
 static int launch_attn_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, const int* key_ids, int B, int L,
                            int H, int nh, int mask_mode, const adt_dropout& d, int training, int mma, cudaStream_t s) {
   const int hd = H / nh;
+  if (use_attn_small(L, hd, mma)) {
+    adt_dropout dd = d;
+    if (!training) dd.enabled = 0;
+    const DropDesc dr = mk_drop(dd);
+    TIMED("attn_fwd", s);
+    if (hd == 16) attn_small_fwd_kernel<16><<<B * nh, AS_NT, 0, s>>>(q, k, v, ctx, lse, key_ids, L, H, nh, mask_mode, dr);
+    else if (hd == 32) attn_small_fwd_kernel<32><<<B * nh, AS_NT, 0, s>>>(q, k, v, ctx, lse, key_ids, L, H, nh, mask_mode, dr);
+    else attn_small_fwd_kernel<64><<<B * nh, AS_NT, 0, s>>>(q, k, v, ctx, lse, key_ids, L, H, nh, mask_mode, dr);
+    return check_launch("attn_small_fwd");
+  }
   const int pad = mma ? 8 : 4;
   const size_t rowf = (size_t)(hd + pad) + (size_t)(((L + 3) & ~3) + pad);
   size_t smem;
@@ -220,6 +238,21 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
                            float* dq, float* dk, float* dv, int B, int L, int H, int nh, int mask_mode, const adt_dropout& d,
                            int mma, cudaStream_t s) {
   const int hd = H / nh;
+  if (use_attn_small(L, hd, mma)) {
+    const DropDesc dr = mk_drop(d);
+    TIMED("attn_bwd", s);
+#define ADT_AS_BWD(HD)                                                                                                   \
+    do {                                                                                                                 \
+      const size_t sm = (size_t)AsBwdSmem<HD>::TOTAL * 2;                                                                \
+      cudaFuncSetAttribute(attn_small_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);             \
+      attn_small_bwd_kernel<HD><<<B * nh, AS_NT, sm, s>>>(q, k, v, dctx, lse, key_ids, dq, dk, dv, L, H, nh, mask_mode, dr); \
+    } while (0)
+    if (hd == 16) ADT_AS_BWD(16);
+    else if (hd == 32) ADT_AS_BWD(32);
+    else ADT_AS_BWD(64);
+#undef ADT_AS_BWD
+    return check_launch("attn_small_bwd");
+  }
   const int pad = mma ? 8 : 4;
   const size_t rowf = 2 * (size_t)(hd + pad) + 2 * (size_t)(((L + 3) & ~3) + pad);
   size_t smem;

@@ -204,3 +204,36 @@ def test_catalog_topk_tc_near_ties_fall_back_to_exact():
     assert tc.fallback_users > 0
     assert torch.equal(i0, i1)
     assert torch.equal(s0, s1)
+
+
+@pytest.mark.parametrize("B,L,H,nh,mask_mode,p", [(5, 50, 64, 2, 0, 0.5), (3, 64, 64, 4, 0, 0.0), (4, 37, 128, 2, 1, 0.3), (2, 9, 32, 2, 0, 0.5),
+                                                  (3, 50, 64, 1, 1, 0.0)])
+def test_short_sequence_attention_kernels_match_generic_fp32(B, L, H, nh, mask_mode, p):
+    """the one-CTA-per-(sequence, head) bf16 attention kernels (L <= 64) against the generic fp32 row-tile kernels through the
+    same C-ABI entry: same masks, same Philox dropout stream (a misaligned mask would show up as O(1) errors)."""
+    import ctypes
+    from adt_b200 import _lib as L_
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(L * 131 + H)
+    M = B * L
+    q = (torch.randn(M, H, generator=g) * 0.5).to(dev)
+    k, v, dctx = (torch.randn(M, H, generator=g).to(dev) for _ in range(3))
+    ids = torch.randint(1, 100, (B, L), generator=g).int()
+    ids[:, : L // 3] = 0                                    # left padding
+    ids = ids.to(dev)
+    d = L_.adt_dropout()
+    d.enabled, d.p, d.seed, d.step, d.site, d.base, d.step_dev = (1 if p > 0 else 0), p, 99, 3, 5, 7 * nh * L, None
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    res = []
+    for prec in (0, 1):
+        ctx, lse = torch.zeros(M, H, device=dev), torch.zeros(B, nh, L, device=dev)
+        dq, dk, dv = (torch.zeros(M, H, device=dev) for _ in range(3))
+        a = L_.fill(L_.adt_attention_args(), q=q, k=k, v=v, ctx=ctx, lse=lse, key_ids=ids, dctx=dctx, dq=dq, dk=dk, dv=dv, B=B, L=L, H=H,
+                    nh=nh, mask_mode=mask_mode, training=1, drop=d, precision=prec)
+        L_.check(L_.lib().adt_attention_fwd(ctypes.byref(a), st), "adt_attention_fwd")
+        L_.check(L_.lib().adt_attention_bwd(ctypes.byref(a), st), "adt_attention_bwd")
+        torch.cuda.synchronize()
+        res.append([t.cpu().numpy() for t in (ctx, lse, dq, dk, dv)])
+    for name, a0, a1 in zip(("ctx", "lse", "dq", "dk", "dv"), res[0], res[1]):
+        err = np.abs(a0 - a1).max() / max(np.abs(a0).max(), 1e-6)
+        assert np.isfinite(a1).all() and err < 3e-2, (name, err)
