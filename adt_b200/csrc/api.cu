@@ -12,6 +12,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_stosa.cuh"
 #include "kernels_attn_small.cuh"
+#include "kernels_rowtile_small.cuh"
 
 using namespace adt;
 
@@ -269,6 +270,25 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
   return check_launch("attn_bwd");
 }
 
+// pre_bwd: narrow models (H == 64) in the bf16 mode take the weights-resident 128-thread kernel (ADT_ROW_SMALL=0 disables)
+static int launch_pre_bwd(const PreBwdArgs& r, int mma, cudaStream_t s) {
+  static int small = -1;
+  if (small < 0) { const char* e = getenv("ADT_ROW_SMALL"); small = e ? (atoi(e) != 0) : 1; }
+  TIMED("pre_bwd", s);
+  if (small && mma && r.H == RS_H) {
+    const size_t sm = PreBwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(pre_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    pre_bwd_small_kernel<<<(r.M + 63) / 64, AS_NT, sm, s>>>(r);
+    return check_launch("pre_bwd_small");
+  }
+  const int pad = mma ? 8 : 4;
+  size_t smem;
+  const int tm = pick_tm(4 * (size_t)(r.H + pad), &smem);
+  if (!tm) return fail(ADT_E_SHAPE, "%s", "pre_bwd: tile does not fit shared memory");
+  LAUNCH_TM(tm, mma, pre_bwd_kernel, (r.M + tm - 1) / tm, smem, s, r);
+  return check_launch("pre_bwd");
+}
+
 static adt_dropout row_drop(const adt_dropout& d, int training) {
   adt_dropout r = d;
   if (!training) r.enabled = 0;
@@ -331,9 +351,7 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   r.ln_g = a->ln1_w; r.ln_b = a->ln1_b; r.Win = a->attn.in_w; r.dx = a->dx;
   r.gWin = a->g_attn.in_w; r.gbin = a->g_attn.in_b; r.gln_g = a->g_ln1_w; r.gln_b = a->g_ln1_b;
   r.M = M; r.H = H; r.qscale = 1.0f / sqrtf((float)(H / a->nh)); r.kv_from_norm = 0;
-  tm = pick_tm(4 * (size_t)(H + pad), &smem);
-  { TIMED("pre_bwd", s); LAUNCH_TM(tm, mma, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
-  return check_launch("enc pre_bwd");
+  return launch_pre_bwd(r, mma, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -415,9 +433,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   r.ln_g = a->ln_w; r.ln_b = a->ln_b; r.Win = a->slf.in_w; r.dx = a->dx;
   r.gWin = a->g_slf.in_w; r.gbin = a->g_slf.in_b; r.gln_g = a->g_ln_w; r.gln_b = a->g_ln_b;
   r.M = M; r.H = H; r.qscale = qscale; r.kv_from_norm = 1;
-  tm = pick_tm(4 * (size_t)(H + pad), &smem);
-  { TIMED("pre_bwd", s); LAUNCH_TM(tm, mma, pre_bwd_kernel, (M + tm - 1) / tm, smem, s, r); }
-  return check_launch("dec pre_bwd");
+  return launch_pre_bwd(r, mma, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------

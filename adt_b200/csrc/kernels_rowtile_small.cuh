@@ -1,0 +1,300 @@
+// Narrow-model (H == 64) row-tile kernels for the bf16 tensor-core mode, built like kernels_attn_small.cuh: 128-thread CTAs,
+// every weight matrix of the kernel resident in shared memory as bf16 (no chunk ring, no per-chunk barriers), operands of all
+// products staged once as bf16 tiles (row-major and transposed), accumulators and LayerNorm adjoints kept in MMA fragments.
+//   pre_bwd_small_kernel == pre_bwd_kernel (kernels_bwd.cuh): adjoint of LayerNorm + packed QKV in-projection
+//   (sasrec/modules.py:646-647 / :668-670 with torch's packed in_proj, modules.py:124-130).
+#pragma once
+#include "common.cuh"
+#include "kernels_bwd.cuh"
+#include "kernels_attn_small.cuh"
+
+namespace adt {
+
+constexpr int RS_H = 64;                 // model width handled by these kernels
+constexpr int RS_LD = RS_H + 8;          // halfword stride of every bf16 tile (row-major and transposed): conflict-free fragments
+constexpr int RS_TILE = 64 * RS_LD;      // halfwords per [64][72] tile
+constexpr int RS_LF = RS_H + 4;          // float stride of the fp32 input tile (consecutive rows land on different banks)
+
+// 64 rows x 64 columns of a row-major fp32 matrix (row stride ld; rows >= nrows read as zero), scaled, into any of: a row-major
+// bf16 tile, a transposed bf16 tile, an fp32 tile [64][64].  N tensors at once: every global load is issued before the first store.
+template <int N>
+__device__ __forceinline__ void rs_load(const float* const (&src)[N], const long long (&ld)[N], const int (&nrows)[N], const float (&scale)[N],
+                                        __nv_bfloat16* const (&dst)[N], __nv_bfloat16* const (&dstT)[N], float* const (&dstF)[N]) {
+  constexpr int NIT = 64 * 16 / AS_NT;   // 8 float4 per thread per tensor
+  float4 v[N][NIT];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = threadIdx.x + it * AS_NT;
+      const int r = idx >> 4, c = (idx & 15) * 4;
+      v[n][it] = r < nrows[n] ? __ldg(reinterpret_cast<const float4*>(src[n] + (long long)r * ld[n] + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int idx = threadIdx.x + it * AS_NT;
+      const int r = idx >> 4, c = (idx & 15) * 4;
+      const float4 x = make_float4(v[n][it].x * scale[n], v[n][it].y * scale[n], v[n][it].z * scale[n], v[n][it].w * scale[n]);
+      if (dstF[n]) *reinterpret_cast<float4*>(dstF[n] + r * RS_LF + c) = x;
+      if (dst[n]) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst[n] + r * RS_LD + c);
+        d[0] = pack_bf16(x.x, x.y);
+        d[1] = pack_bf16(x.z, x.w);
+      }
+      if (dstT[n]) {
+        dstT[n][(c + 0) * RS_LD + r] = __float2bfloat16_rn(x.x);
+        dstT[n][(c + 1) * RS_LD + r] = __float2bfloat16_rn(x.y);
+        dstT[n][(c + 2) * RS_LD + r] = __float2bfloat16_rn(x.z);
+        dstT[n][(c + 3) * RS_LD + r] = __float2bfloat16_rn(x.w);
+      }
+    }
+  }
+}
+
+// acc[nb] (rows 16w+g, +8 ; columns 8nb+2t, +1) += A[16w.., k] * B[8nb.., k]^T over k = 0..63, both tiles [64][72] bf16 with k fast
+__device__ __forceinline__ void rs_mma(float (&acc)[8][4], const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int r0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    a[0] = ld_u32(A + (r0 + g) * RS_LD + 16 * ks + 2 * t);
+    a[1] = ld_u32(A + (r0 + g + 8) * RS_LD + 16 * ks + 2 * t);
+    a[2] = ld_u32(A + (r0 + g) * RS_LD + 16 * ks + 2 * t + 8);
+    a[3] = ld_u32(A + (r0 + g + 8) * RS_LD + 16 * ks + 2 * t + 8);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const __nv_bfloat16* bp = B + (8 * nb + g) * RS_LD + 16 * ks + 2 * t;
+      mma16816(acc[nb], a, ld_u32(bp), ld_u32(bp + 8));
+    }
+  }
+}
+
+// weight gradient of one projection: gW[j][c] += sum_r Tt[j][r] * Xt[c][r], gb[j] += sum_r Tt[j][r]   (warp w owns rows j = 16w..16w+15)
+__device__ __forceinline__ void rs_wgrad(const __nv_bfloat16* __restrict__ Tt, const __nv_bfloat16* __restrict__ Xt, float* __restrict__ gW,
+                                         float* __restrict__ gb) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[8][4], ones[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    a[0] = ld_u32(Tt + (16 * w + g) * RS_LD + 16 * ks + 2 * t);
+    a[1] = ld_u32(Tt + (16 * w + g + 8) * RS_LD + 16 * ks + 2 * t);
+    a[2] = ld_u32(Tt + (16 * w + g) * RS_LD + 16 * ks + 2 * t + 8);
+    a[3] = ld_u32(Tt + (16 * w + g + 8) * RS_LD + 16 * ks + 2 * t + 8);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const __nv_bfloat16* bp = Xt + (8 * nb + g) * RS_LD + 16 * ks + 2 * t;
+      mma16816(acc[nb], a, ld_u32(bp), ld_u32(bp + 8));
+    }
+    mma16816(ones, a, 0x3f803f80u, 0x3f803f80u);     // B = all ones (bf16 1.0): every column of `ones` is the row sum of Tt
+  }
+  const int j0 = 16 * w + g, j1 = j0 + 8;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    // lanes t and t^1 hold adjacent column pairs: even t gathers four contiguous columns -> one 128-bit reduction per row
+    const float x0 = __shfl_xor_sync(0xffffffffu, acc[nb][0], 1), x1 = __shfl_xor_sync(0xffffffffu, acc[nb][1], 1);
+    const float y0 = __shfl_xor_sync(0xffffffffu, acc[nb][2], 1), y1 = __shfl_xor_sync(0xffffffffu, acc[nb][3], 1);
+    if ((t & 1) == 0) {
+      atomicAdd(reinterpret_cast<float4*>(gW + (long long)j0 * RS_H + 8 * nb + 2 * t), make_float4(acc[nb][0], acc[nb][1], x0, x1));
+      atomicAdd(reinterpret_cast<float4*>(gW + (long long)j1 * RS_H + 8 * nb + 2 * t), make_float4(acc[nb][2], acc[nb][3], y0, y1));
+    }
+  }
+  if (t == 0) {
+    atomicAdd(gb + j0, ones[0]);
+    atomicAdd(gb + j1, ones[2]);
+  }
+}
+
+// LayerNorm adjoint on accumulator fragments: D (grad wrt LN output) -> grad wrt LN input, plus dgamma / dbeta column sums
+__device__ __forceinline__ void rs_ln_bwd(float (&D)[8][4], const float* __restrict__ Xf, const float* __restrict__ stats,
+                                          const float* __restrict__ gamma, float* __restrict__ ggamma, float* __restrict__ gbeta,
+                                          int rows_valid) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  const float mean0 = stats[2 * i0], rstd0 = stats[2 * i0 + 1], mean1 = stats[2 * i1], rstd1 = stats[2 * i1 + 1];
+  float s10 = 0.f, s20 = 0.f, s11 = 0.f, s21 = 0.f;
+  float xh[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c));
+    const float2 x0 = *reinterpret_cast<const float2*>(Xf + i0 * RS_LF + c), x1 = *reinterpret_cast<const float2*>(Xf + i1 * RS_LF + c);
+    xh[nb][0] = (x0.x - mean0) * rstd0; xh[nb][1] = (x0.y - mean0) * rstd0;
+    xh[nb][2] = (x1.x - mean1) * rstd1; xh[nb][3] = (x1.y - mean1) * rstd1;
+    // dgamma / dbeta partials of this thread's two rows, reduced over the 8 row groups of the warp below
+    float dg0 = D[nb][0] * xh[nb][0] + D[nb][2] * xh[nb][2], dg1 = D[nb][1] * xh[nb][1] + D[nb][3] * xh[nb][3];
+    float db0 = D[nb][0] + D[nb][2], db1 = D[nb][1] + D[nb][3];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      dg0 += __shfl_xor_sync(0xffffffffu, dg0, o); dg1 += __shfl_xor_sync(0xffffffffu, dg1, o);
+      db0 += __shfl_xor_sync(0xffffffffu, db0, o); db1 += __shfl_xor_sync(0xffffffffu, db1, o);
+    }
+    if (g == 0) {
+      atomicAdd(ggamma + c, dg0); atomicAdd(ggamma + c + 1, dg1);
+      atomicAdd(gbeta + c, db0); atomicAdd(gbeta + c + 1, db1);
+    }
+    D[nb][0] *= ga.x; D[nb][1] *= ga.y; D[nb][2] *= ga.x; D[nb][3] *= ga.y;
+    s10 += D[nb][0] + D[nb][1]; s20 += D[nb][0] * xh[nb][0] + D[nb][1] * xh[nb][1];
+    s11 += D[nb][2] + D[nb][3]; s21 += D[nb][2] * xh[nb][2] + D[nb][3] * xh[nb][3];
+  }
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1) {
+    s10 += __shfl_xor_sync(0xffffffffu, s10, o); s20 += __shfl_xor_sync(0xffffffffu, s20, o);
+    s11 += __shfl_xor_sync(0xffffffffu, s11, o); s21 += __shfl_xor_sync(0xffffffffu, s21, o);
+  }
+  s10 *= 1.0f / RS_H; s20 *= 1.0f / RS_H; s11 *= 1.0f / RS_H; s21 *= 1.0f / RS_H;
+  const bool v0 = i0 < rows_valid, v1 = i1 < rows_valid;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    D[nb][0] = v0 ? rstd0 * (D[nb][0] - s10 - xh[nb][0] * s20) : 0.f;
+    D[nb][1] = v0 ? rstd0 * (D[nb][1] - s10 - xh[nb][1] * s20) : 0.f;
+    D[nb][2] = v1 ? rstd1 * (D[nb][2] - s11 - xh[nb][2] * s21) : 0.f;
+    D[nb][3] = v1 ? rstd1 * (D[nb][3] - s11 - xh[nb][3] * s21) : 0.f;
+  }
+}
+
+struct PreBwdSmallSmem {
+  // halfword offsets
+  static constexpr int WT = 0;                       // Wt[3] : transposed weights  Wt[m][c][j] = W_m[j][c]
+  static constexpr int T = 3 * RS_TILE;              // T      : current dq*s / dk / dv tile, row-major
+  static constexpr int TT = T + RS_TILE;             // Tt     : transposed
+  static constexpr int XT = TT + RS_TILE;            // Xt     : transposed block input
+  static constexpr int NT_ = XT + RS_TILE;           // Nt     : transposed LayerNorm output
+  static constexpr int HALF_END = NT_ + RS_TILE;
+  static constexpr size_t XF_BYTES = (size_t)HALF_END * 2;               // Xf : fp32 [64][64] block input
+  static constexpr size_t STATS_BYTES = XF_BYTES + (size_t)64 * RS_LF * 4;  // stats : (mean, rstd) per row
+  static constexpr size_t TOTAL_BYTES = STATS_BYTES + 64 * 2 * 4;
+};
+
+__global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
+  using SM = PreBwdSmallSmem;
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
+  __nv_bfloat16* Wt = hb + SM::WT;
+  __nv_bfloat16* T = hb + SM::T;
+  __nv_bfloat16* Tt = hb + SM::TT;
+  __nv_bfloat16* Xt = hb + SM::XT;
+  __nv_bfloat16* Nt = hb + SM::NT_;
+  float* Xf = reinterpret_cast<float*>(rs_raw + SM::XF_BYTES);
+  float* stats = reinterpret_cast<float*>(rs_raw + SM::STATS_BYTES);
+  const int row0 = blockIdx.x * 64;
+  const int rows = min(64, p.M - row0);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  // ---- prologue: block input, dq, and the three weight matrices (transposed), all loads in flight together
+  {
+    const float* const src[2] = {p.x + (long long)row0 * RS_H, p.dq + (long long)row0 * RS_H};
+    const long long ld[2] = {RS_H, RS_H};
+    const int nr[2] = {rows, rows};
+    const float sc[2] = {1.f, p.qscale};
+    __nv_bfloat16* const d[2] = {nullptr, T};
+    __nv_bfloat16* const dT[2] = {Xt, Tt};
+    float* const dF[2] = {Xf, nullptr};
+    rs_load<2>(src, ld, nr, sc, d, dT, dF);
+  }
+  {
+    const float* const src[3] = {p.Win, p.Win + RS_H * RS_H, p.Win + 2 * RS_H * RS_H};
+    const long long ld[3] = {RS_H, RS_H, RS_H};
+    const int nr[3] = {64, 64, 64};
+    const float sc[3] = {1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[3] = {nullptr, nullptr, nullptr};
+    __nv_bfloat16* const dT[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
+    float* const dF[3] = {nullptr, nullptr, nullptr};
+    rs_load<3>(src, ld, nr, sc, d, dT, dF);
+  }
+  __syncthreads();
+  // ---- LayerNorm forward (two threads per row, two-pass statistics like ln_tile): stats + transposed bf16 N
+  {
+    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+    const float* xr = Xf + r * RS_LF + 32 * half;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    const float mean = s * (1.0f / RS_H);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / RS_H) + 1e-8f);
+    if (half == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const int col = 32 * half + c;
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), be = __ldg(reinterpret_cast<const float4*>(p.ln_b + col));
+      const bool ok = r < rows;
+      Nt[(col + 0) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.x - mean) * rstd * ga.x + be.x : 0.f);
+      Nt[(col + 1) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.y - mean) * rstd * ga.y + be.y : 0.f);
+      Nt[(col + 2) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.z - mean) * rstd * ga.z + be.z : 0.f);
+      Nt[(col + 3) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.w - mean) * rstd * ga.w + be.w : 0.f);
+    }
+  }
+  __syncthreads();
+  // ---- q projection: weight gradient against N, data gradient D = (dq*s) Wq (+ dnorm_extra)
+  float D[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) D[nb][0] = D[nb][1] = D[nb][2] = D[nb][3] = 0.f;
+  rs_wgrad(Tt, Nt, p.gWin, p.gbin);
+  rs_mma(D, T, Wt, 16 * w);
+  if (p.dnorm_extra) {
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int c = 8 * nb + 2 * t;
+      if (i0 < rows) { const float2 e = *reinterpret_cast<const float2*>(p.dnorm_extra + (long long)(row0 + i0) * RS_H + c); D[nb][0] += e.x; D[nb][1] += e.y; }
+      if (i1 < rows) { const float2 e = *reinterpret_cast<const float2*>(p.dnorm_extra + (long long)(row0 + i1) * RS_H + c); D[nb][2] += e.x; D[nb][3] += e.y; }
+    }
+  }
+  if (!p.kv_from_norm) rs_ln_bwd(D, Xf, stats, p.ln_g, p.gln_g, p.gln_b, rows);     // encoder: k, v are projected from x itself
+  // ---- k and v projections
+  const __nv_bfloat16* Xkv = p.kv_from_norm ? Nt : Xt;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    __syncthreads();                               // everybody is done with the previous T / Tt
+    {
+      const float* const src[1] = {(which == 0 ? p.dk : p.dv) + (long long)row0 * RS_H};
+      const long long ld[1] = {RS_H};
+      const int nr[1] = {rows};
+      const float sc[1] = {1.f};
+      __nv_bfloat16* const d[1] = {T};
+      __nv_bfloat16* const dT[1] = {Tt};
+      float* const dF[1] = {nullptr};
+      rs_load<1>(src, ld, nr, sc, d, dT, dF);
+    }
+    __syncthreads();
+    rs_wgrad(Tt, Xkv, p.gWin + (long long)(1 + which) * RS_H * RS_H, p.gbin + (1 + which) * RS_H);
+    rs_mma(D, T, Wt + (1 + which) * RS_TILE, 16 * w);
+  }
+  if (p.kv_from_norm) rs_ln_bwd(D, Xf, stats, p.ln_g, p.gln_g, p.gln_b, rows);      // decoder: q, k, v all come from LN(x)
+  // ---- dx = D (+ dx_extra)
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    if (i0 < rows) {
+      float2 o = make_float2(D[nb][0], D[nb][1]);
+      const long long gi = (long long)(row0 + i0) * RS_H + c;
+      if (p.dx_extra) { const float2 e = *reinterpret_cast<const float2*>(p.dx_extra + gi); o.x += e.x; o.y += e.y; }
+      *reinterpret_cast<float2*>(p.dx + gi) = o;
+    }
+    if (i1 < rows) {
+      float2 o = make_float2(D[nb][2], D[nb][3]);
+      const long long gi = (long long)(row0 + i1) * RS_H + c;
+      if (p.dx_extra) { const float2 e = *reinterpret_cast<const float2*>(p.dx_extra + gi); o.x += e.x; o.y += e.y; }
+      *reinterpret_cast<float2*>(p.dx + gi) = o;
+    }
+  }
+}
+
+}  // namespace adt

@@ -65,6 +65,7 @@ def test_bf16_tensor_core_mode_within_baseline_tolerance(T, name):
             if np.linalg.norm(b) > 1e-7:
                 cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
                 assert cos > 0.995, (k, cos)
+                assert np.abs(a - b).max() <= 1e-1 * np.abs(b).max() + 1e-6, (k, float(np.abs(a - b).max()), float(np.abs(b).max()))
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
