@@ -54,6 +54,85 @@ __device__ __forceinline__ void rs_load(const float* const (&src)[N], const long
   }
 }
 
+// ---- ldmatrix fragment loaders on row-major [64][72] bf16 tiles (144-byte rows: every 8x8 block load is bank-conflict free) ----
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* p) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(a));
+}
+// A fragment (rows m0..m0+15, k0..k0+15) of a row-major tile A[m][k]
+__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const __nv_bfloat16* A, int m0, int k0) {
+  const int l = threadIdx.x & 31;
+  ldsm_x4(a, A + (m0 + (l & 7) + 8 * ((l >> 3) & 1)) * RS_LD + k0 + 8 * (l >> 4));
+}
+// A fragment of the TRANSPOSE of a row-major tile S[k][m]: A[m][k] = S[k][m]
+__device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const __nv_bfloat16* S, int m0, int k0) {
+  const int l = threadIdx.x & 31;
+  ldsm_x4_t(a, S + (k0 + (l & 7) + 8 * (l >> 4)) * RS_LD + m0 + 8 * ((l >> 3) & 1));
+}
+// B fragment (k0..k0+15, n0..n0+7) of a row-major tile Bk[k][n]
+__device__ __forceinline__ void frag_b_t(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* Bk, int k0, int n0) {
+  const int l = threadIdx.x & 15;
+  ldsm_x2_t(b0, b1, Bk + (k0 + (l & 7) + 8 * (l >> 3)) * RS_LD + n0);
+}
+
+// D[nb] (rows 16w.. ; columns 8nb..) += T[rows][j] * W[j][c]   (T and W row-major; W used through transposing loads)
+__device__ __forceinline__ void rs_dgrad(float (&acc)[8][4], const __nv_bfloat16* __restrict__ T, const __nv_bfloat16* __restrict__ W, int r0) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    frag_a(a, T, r0, 16 * ks);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      uint32_t b0, b1;
+      frag_b_t(b0, b1, W, 16 * ks, 8 * nb);
+      mma16816(acc[nb], a, b0, b1);
+    }
+  }
+}
+
+// weight gradient of one projection from ROW-MAJOR tiles: gW[j][c] += sum_r T[r][j] X[r][c], gb[j] += sum_r T[r][j]
+__device__ __forceinline__ void rs_wgrad_rm(const __nv_bfloat16* __restrict__ T, const __nv_bfloat16* __restrict__ X, float* __restrict__ gW,
+                                            float* __restrict__ gb) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  float acc[8][4], ones[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    frag_a_t(a, T, 16 * w, 16 * ks);                 // A[m = j][k = r] = T[r][j]
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      uint32_t b0, b1;
+      frag_b_t(b0, b1, X, 16 * ks, 8 * nb);          // B[k = r][n = c] = X[r][c]
+      mma16816(acc[nb], a, b0, b1);
+    }
+    mma16816(ones, a, 0x3f803f80u, 0x3f803f80u);     // B = all ones (bf16 1.0): every column of `ones` is a row sum
+  }
+  const int j0 = 16 * w + g, j1 = j0 + 8;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const float x0 = __shfl_xor_sync(0xffffffffu, acc[nb][0], 1), x1 = __shfl_xor_sync(0xffffffffu, acc[nb][1], 1);
+    const float y0 = __shfl_xor_sync(0xffffffffu, acc[nb][2], 1), y1 = __shfl_xor_sync(0xffffffffu, acc[nb][3], 1);
+    if ((t & 1) == 0) {
+      atomicAdd(reinterpret_cast<float4*>(gW + (long long)j0 * RS_H + 8 * nb + 2 * t), make_float4(acc[nb][0], acc[nb][1], x0, x1));
+      atomicAdd(reinterpret_cast<float4*>(gW + (long long)j1 * RS_H + 8 * nb + 2 * t), make_float4(acc[nb][2], acc[nb][3], y0, y1));
+    }
+  }
+  if (t == 0) {
+    atomicAdd(gb + j0, ones[0]);
+    atomicAdd(gb + j1, ones[2]);
+  }
+}
+
 // acc[nb] (rows 16w+g, +8 ; columns 8nb+2t, +1) += A[16w.., k] * B[8nb.., k]^T over k = 0..63, both tiles [64][72] bf16 with k fast
 __device__ __forceinline__ void rs_mma(float (&acc)[8][4], const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int r0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -160,11 +239,10 @@ __device__ __forceinline__ void rs_ln_bwd(float (&D)[8][4], const float* __restr
 
 struct PreBwdSmallSmem {
   // halfword offsets
-  static constexpr int WT = 0;                       // Wt[3] : transposed weights  Wt[m][c][j] = W_m[j][c]
-  static constexpr int T = 3 * RS_TILE;              // T      : current dq*s / dk / dv tile, row-major
-  static constexpr int TT = T + RS_TILE;             // Tt     : transposed
-  static constexpr int XT = TT + RS_TILE;            // Xt     : transposed block input
-  static constexpr int NT_ = XT + RS_TILE;           // Nt     : transposed LayerNorm output
+  static constexpr int WT = 0;                       // W[3]  : the three projection matrices W_m[j][c], row-major bf16
+  static constexpr int T = 3 * RS_TILE;              // T     : current dq*s / dk / dv tile, row-major
+  static constexpr int XT = T + RS_TILE;             // X     : block input, row-major bf16
+  static constexpr int NT_ = XT + RS_TILE;           // N     : LayerNorm output, row-major bf16
   static constexpr int HALF_END = NT_ + RS_TILE;
   static constexpr size_t XF_BYTES = (size_t)HALF_END * 2;               // Xf : fp32 [64][64] block input
   static constexpr size_t STATS_BYTES = XF_BYTES + (size_t)64 * RS_LF * 4;  // stats : (mean, rstd) per row
@@ -177,7 +255,6 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
   __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
   __nv_bfloat16* Wt = hb + SM::WT;
   __nv_bfloat16* T = hb + SM::T;
-  __nv_bfloat16* Tt = hb + SM::TT;
   __nv_bfloat16* Xt = hb + SM::XT;
   __nv_bfloat16* Nt = hb + SM::NT_;
   float* Xf = reinterpret_cast<float*>(rs_raw + SM::XF_BYTES);
@@ -192,8 +269,8 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
     const long long ld[2] = {RS_H, RS_H};
     const int nr[2] = {rows, rows};
     const float sc[2] = {1.f, p.qscale};
-    __nv_bfloat16* const d[2] = {nullptr, T};
-    __nv_bfloat16* const dT[2] = {Xt, Tt};
+    __nv_bfloat16* const d[2] = {Xt, T};
+    __nv_bfloat16* const dT[2] = {nullptr, nullptr};
     float* const dF[2] = {Xf, nullptr};
     rs_load<2>(src, ld, nr, sc, d, dT, dF);
   }
@@ -202,8 +279,8 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
     const long long ld[3] = {RS_H, RS_H, RS_H};
     const int nr[3] = {64, 64, 64};
     const float sc[3] = {1.f, 1.f, 1.f};
-    __nv_bfloat16* const d[3] = {nullptr, nullptr, nullptr};
-    __nv_bfloat16* const dT[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
+    __nv_bfloat16* const d[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
+    __nv_bfloat16* const dT[3] = {nullptr, nullptr, nullptr};
     float* const dF[3] = {nullptr, nullptr, nullptr};
     rs_load<3>(src, ld, nr, sc, d, dT, dF);
   }
@@ -236,10 +313,9 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
       const float4 v = *reinterpret_cast<const float4*>(xr + c);
       const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), be = __ldg(reinterpret_cast<const float4*>(p.ln_b + col));
       const bool ok = r < rows;
-      Nt[(col + 0) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.x - mean) * rstd * ga.x + be.x : 0.f);
-      Nt[(col + 1) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.y - mean) * rstd * ga.y + be.y : 0.f);
-      Nt[(col + 2) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.z - mean) * rstd * ga.z + be.z : 0.f);
-      Nt[(col + 3) * RS_LD + r] = __float2bfloat16_rn(ok ? (v.w - mean) * rstd * ga.w + be.w : 0.f);
+      uint32_t* d = reinterpret_cast<uint32_t*>(Nt + r * RS_LD + col);
+      d[0] = ok ? pack_bf16((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y) : 0u;
+      d[1] = ok ? pack_bf16((v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w) : 0u;
     }
   }
   __syncthreads();
@@ -247,8 +323,8 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
   float D[8][4];
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) D[nb][0] = D[nb][1] = D[nb][2] = D[nb][3] = 0.f;
-  rs_wgrad(Tt, Nt, p.gWin, p.gbin);
-  rs_mma(D, T, Wt, 16 * w);
+  rs_wgrad_rm(T, Nt, p.gWin, p.gbin);
+  rs_dgrad(D, T, Wt, 16 * w);
   if (p.dnorm_extra) {
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
@@ -269,13 +345,13 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
       const int nr[1] = {rows};
       const float sc[1] = {1.f};
       __nv_bfloat16* const d[1] = {T};
-      __nv_bfloat16* const dT[1] = {Tt};
+      __nv_bfloat16* const dT[1] = {nullptr};
       float* const dF[1] = {nullptr};
       rs_load<1>(src, ld, nr, sc, d, dT, dF);
     }
     __syncthreads();
-    rs_wgrad(Tt, Xkv, p.gWin + (long long)(1 + which) * RS_H * RS_H, p.gbin + (1 + which) * RS_H);
-    rs_mma(D, T, Wt + (1 + which) * RS_TILE, 16 * w);
+    rs_wgrad_rm(T, Xkv, p.gWin + (long long)(1 + which) * RS_H * RS_H, p.gbin + (1 + which) * RS_H);
+    rs_dgrad(D, T, Wt + (1 + which) * RS_TILE, 16 * w);
   }
   if (p.kv_from_norm) rs_ln_bwd(D, Xf, stats, p.ln_g, p.gln_g, p.gln_b, rows);      // decoder: q, k, v all come from LN(x)
   // ---- dx = D (+ dx_extra)
