@@ -188,8 +188,22 @@ extern "C" int adt_embed_fwd(const adt_embed_fwd_args* a, adt_stream_t s_) {
 }
 
 // shared launch helpers -------------------------------------------------------------------------------------
+static bool use_row_small(int H, int mma) {
+  static int small = -1;
+  if (small < 0) { const char* e = getenv("ADT_ROW_SMALL"); small = e ? (atoi(e) != 0) : 1; }
+  return small && mma && H == RS_H;
+}
+
 static int launch_pre_fwd(const float* x, const float* ln_w, const float* ln_b, const adt_mha_w& w, float* q, float* k, float* v,
                           float* norm_out, int M, int H, int nh, int kv_from_norm, int mma, cudaStream_t s) {
+  if (use_row_small(H, mma)) {
+    const size_t sm = PreFwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(pre_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    TIMED("pre_fwd", s);
+    pre_fwd_small_kernel<<<(M + 63) / 64, AS_NT, sm, s>>>(x, ln_w, ln_b, w.in_w, w.in_b, q, k, v, norm_out, M, 1.0f / sqrtf((float)(H / nh)),
+                                                        kv_from_norm);
+    return check_launch("pre_fwd_small");
+  }
   size_t smem;
   const int pad = mma ? 8 : 4;
   const int tm = pick_tm(2 * (size_t)(H + pad), &smem);
@@ -272,10 +286,8 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
 
 // pre_bwd: narrow models (H == 64) in the bf16 mode take the weights-resident 128-thread kernel (ADT_ROW_SMALL=0 disables)
 static int launch_pre_bwd(const PreBwdArgs& r, int mma, cudaStream_t s) {
-  static int small = -1;
-  if (small < 0) { const char* e = getenv("ADT_ROW_SMALL"); small = e ? (atoi(e) != 0) : 1; }
   TIMED("pre_bwd", s);
-  if (small && mma && r.H == RS_H) {
+  if (use_row_small(r.H, mma)) {
     const size_t sm = PreBwdSmallSmem::TOTAL_BYTES;
     cudaFuncSetAttribute(pre_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     pre_bwd_small_kernel<<<(r.M + 63) / 64, AS_NT, sm, s>>>(r);
@@ -418,9 +430,16 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   m.Wo1 = a->slf.out_w; m.Win2 = a->enc.in_w; m.dfeats = a->dfeats; m.dctx1 = a->dctx;
   m.gWo1 = a->g_slf.out_w; m.gbo1 = a->g_slf.out_b; m.gWin2 = a->g_enc.in_w; m.gbin2 = a->g_enc.in_b;
   m.M = M; m.H = H; m.qscale = qscale;
+  if (use_row_small(H, mma)) {
+    const size_t sm = MidBwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(mid_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    TIMED("mid_bwd", s);
+    mid_bwd_small_kernel<<<(M + 63) / 64, AS_NT, sm, s>>>(m);
+  } else {
   tm = pick_tm(3 * (size_t)(H + pad) + (size_t)(2 * H + pad), &smem, 128, M >= 148 * 64 ? 128 : 64);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_bwd: tile does not fit shared memory");
   { TIMED("mid_bwd", s); LAUNCH_TM(tm, mma, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m); }
+  }
   if (int e = check_launch("mid_bwd")) return e;
   if (a->phase == 2) return ADT_OK;
   }

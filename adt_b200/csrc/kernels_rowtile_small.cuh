@@ -83,6 +83,27 @@ __device__ __forceinline__ void frag_b_t(uint32_t& b0, uint32_t& b1, const __nv_
   ldsm_x2_t(b0, b1, Bk + (k0 + (l & 7) + 8 * (l >> 3)) * RS_LD + n0);
 }
 
+// B fragment (k0..k0+15, n0..n0+7) of an n-major tile Bn[n][k] (nn.Linear weights W[out][in] as the B operand of x W^T)
+__device__ __forceinline__ void frag_b(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* Bn, int n0, int k0) {
+  const int l = threadIdx.x & 15;
+  const unsigned a = (unsigned)__cvta_generic_to_shared(Bn + (n0 + (l & 7)) * RS_LD + k0 + 8 * (l >> 3));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(a));
+}
+// Y[nb] (rows 16w.. ; columns 8nb..) += A[rows][k] * W[n][k]^T   (forward of nn.Linear, both tiles row-major)
+__device__ __forceinline__ void rs_fgemm(float (&acc)[8][4], const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W, int r0) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    frag_a(a, A, r0, 16 * ks);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      uint32_t b0, b1;
+      frag_b(b0, b1, W, 8 * nb, 16 * ks);
+      mma16816(acc[nb], a, b0, b1);
+    }
+  }
+}
+
 // D[nb] (rows 16w.. ; columns 8nb..) += T[rows][j] * W[j][c]   (T and W row-major; W used through transposing loads)
 __device__ __forceinline__ void rs_dgrad(float (&acc)[8][4], const __nv_bfloat16* __restrict__ T, const __nv_bfloat16* __restrict__ W, int r0) {
 #pragma unroll
@@ -370,6 +391,211 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
       if (p.dx_extra) { const float2 e = *reinterpret_cast<const float2*>(p.dx_extra + gi); o.x += e.x; o.y += e.y; }
       *reinterpret_cast<float2*>(p.dx + gi) = o;
     }
+  }
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// pre_fwd_small_kernel == pre_fwd_kernel (kernels_fwd.cuh): LayerNorm + packed in-projection, H == 64, bf16 mode.
+// -------------------------------------------------------------------------------------------------
+struct PreFwdSmallSmem {
+  static constexpr int W = 0, X = 3 * RS_TILE, N = X + RS_TILE, HALF_END = N + RS_TILE;
+  static constexpr size_t XF_BYTES = (size_t)HALF_END * 2;
+  static constexpr size_t TOTAL_BYTES = XF_BYTES + (size_t)64 * RS_LF * 4;
+};
+
+__global__ void __launch_bounds__(AS_NT) pre_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ ln_g,
+                                                              const float* __restrict__ ln_b, const float* __restrict__ Win,
+                                                              const float* __restrict__ bin, float* __restrict__ q, float* __restrict__ k,
+                                                              float* __restrict__ v, float* __restrict__ norm_out, int M, float qscale,
+                                                              int kv_from_norm) {
+  using SM = PreFwdSmallSmem;
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
+  __nv_bfloat16* Wt = hb + SM::W;
+  __nv_bfloat16* Xb = hb + SM::X;
+  __nv_bfloat16* Nb = hb + SM::N;
+  float* Xf = reinterpret_cast<float*>(rs_raw + SM::XF_BYTES);
+  const int row0 = blockIdx.x * 64;
+  const int rows = min(64, M - row0);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  {
+    const float* const src[1] = {x + (long long)row0 * RS_H};
+    const long long ld[1] = {RS_H};
+    const int nr[1] = {rows};
+    const float sc[1] = {1.f};
+    __nv_bfloat16* const d[1] = {Xb};
+    __nv_bfloat16* const dT[1] = {nullptr};
+    float* const dF[1] = {Xf};
+    rs_load<1>(src, ld, nr, sc, d, dT, dF);
+  }
+  {
+    const float* const src[3] = {Win, Win + RS_H * RS_H, Win + 2 * RS_H * RS_H};
+    const long long ld[3] = {RS_H, RS_H, RS_H};
+    const int nr[3] = {64, 64, 64};
+    const float sc[3] = {1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
+    __nv_bfloat16* const dT[3] = {nullptr, nullptr, nullptr};
+    float* const dF[3] = {nullptr, nullptr, nullptr};
+    rs_load<3>(src, ld, nr, sc, d, dT, dF);
+  }
+  __syncthreads();
+  {   // LayerNorm: two threads per row, two-pass statistics
+    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+    const float* xr = Xf + r * RS_LF + 32 * half;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const float4 u = *reinterpret_cast<const float4*>(xr + c);
+      s += (u.x + u.y) + (u.z + u.w);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    const float mean = s * (1.0f / RS_H);
+    float qq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const float4 u = *reinterpret_cast<const float4*>(xr + c);
+      const float a = u.x - mean, b = u.y - mean, cc = u.z - mean, d = u.w - mean;
+      qq += (a * a + b * b) + (cc * cc + d * d);
+    }
+    qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+    const float rstd = 1.0f / sqrtf(qq * (1.0f / RS_H) + 1e-8f);
+    const bool ok = r < rows;
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const int col = 32 * half + c;
+      const float4 u = *reinterpret_cast<const float4*>(xr + c);
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(ln_g + col)), be = __ldg(reinterpret_cast<const float4*>(ln_b + col));
+      const float4 n = make_float4((u.x - mean) * rstd * ga.x + be.x, (u.y - mean) * rstd * ga.y + be.y, (u.z - mean) * rstd * ga.z + be.z,
+                                   (u.w - mean) * rstd * ga.w + be.w);
+      uint32_t* d = reinterpret_cast<uint32_t*>(Nb + r * RS_LD + col);
+      d[0] = ok ? pack_bf16(n.x, n.y) : 0u;
+      d[1] = ok ? pack_bf16(n.z, n.w) : 0u;
+      if (norm_out && ok) *reinterpret_cast<float4*>(norm_out + (long long)(row0 + r) * RS_H + col) = n;
+    }
+  }
+  __syncthreads();
+  const __nv_bfloat16* Akv = kv_from_norm ? Nb : Xb;
+#pragma unroll 1
+  for (int m = 0; m < 3; ++m) {
+    float acc[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+    rs_fgemm(acc, m == 0 ? Nb : Akv, Wt + m * RS_TILE, 16 * w);
+    float* out = m == 0 ? q : m == 1 ? k : v;
+    const float sc = m == 0 ? qscale : 1.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int c = 8 * nb + 2 * t;
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bin + m * RS_H + c));
+      if (i0 < rows) *reinterpret_cast<float2*>(out + (long long)(row0 + i0) * RS_H + c) = make_float2((acc[nb][0] + b.x) * sc, (acc[nb][1] + b.y) * sc);
+      if (i1 < rows) *reinterpret_cast<float2*>(out + (long long)(row0 + i1) * RS_H + c) = make_float2((acc[nb][2] + b.x) * sc, (acc[nb][3] + b.y) * sc);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// mid_bwd_small_kernel == mid_bwd_kernel (kernels_bwd.cuh): adjoint of the decoder's self-attention out-projection and of the
+// cross-attention in-projection (q from the self-attention output a, k/v from the encoder features), H == 64, bf16 mode.
+// -------------------------------------------------------------------------------------------------
+struct MidBwdSmallSmem {
+  static constexpr int W = 0;                        // Wq2, Wk2, Wv2, Wo1 row-major
+  static constexpr int T = 4 * RS_TILE;              // dq2 * s
+  static constexpr int X = T + RS_TILE;              // a -> feats -> ctx1
+  static constexpr int K = X + RS_TILE;              // dk2
+  static constexpr int V = K + RS_TILE;              // dv2
+  static constexpr int DA = V + RS_TILE;             // grad wrt a
+  static constexpr size_t TOTAL_BYTES = (size_t)(DA + RS_TILE) * 2;
+};
+
+__device__ __forceinline__ void rs_load1(const float* src, int rows, float scale, __nv_bfloat16* dst) {
+  const float* const s[1] = {src};
+  const long long ld[1] = {RS_H};
+  const int nr[1] = {rows};
+  const float sc[1] = {scale};
+  __nv_bfloat16* const d[1] = {dst};
+  __nv_bfloat16* const dT[1] = {nullptr};
+  float* const dF[1] = {nullptr};
+  rs_load<1>(s, ld, nr, sc, d, dT, dF);
+}
+
+__global__ void __launch_bounds__(AS_NT) mid_bwd_small_kernel(MidBwdArgs p) {
+  using SM = MidBwdSmallSmem;
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
+  __nv_bfloat16* Wt = hb + SM::W;
+  __nv_bfloat16* T = hb + SM::T;
+  __nv_bfloat16* X = hb + SM::X;
+  __nv_bfloat16* Kt = hb + SM::K;
+  __nv_bfloat16* Vt = hb + SM::V;
+  __nv_bfloat16* DAs = hb + SM::DA;
+  const int row0 = blockIdx.x * 64;
+  const int rows = min(64, p.M - row0);
+  const long long g0 = (long long)row0 * RS_H;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  {
+    const float* const src[4] = {p.dq2 + g0, p.a + g0, p.dk2 + g0, p.dv2 + g0};
+    const long long ld[4] = {RS_H, RS_H, RS_H, RS_H};
+    const int nr[4] = {rows, rows, rows, rows};
+    const float sc[4] = {p.qscale, 1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[4] = {T, X, Kt, Vt};
+    __nv_bfloat16* const dT[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* const dF[4] = {nullptr, nullptr, nullptr, nullptr};
+    rs_load<4>(src, ld, nr, sc, d, dT, dF);
+  }
+  {
+    const float* const src[4] = {p.Win2, p.Win2 + RS_H * RS_H, p.Win2 + 2 * RS_H * RS_H, p.Wo1};
+    const long long ld[4] = {RS_H, RS_H, RS_H, RS_H};
+    const int nr[4] = {64, 64, 64, 64};
+    const float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[4] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE, Wt + 3 * RS_TILE};
+    __nv_bfloat16* const dT[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* const dF[4] = {nullptr, nullptr, nullptr, nullptr};
+    rs_load<4>(src, ld, nr, sc, d, dT, dF);
+  }
+  __syncthreads();
+  // 1. q projection of the cross attention: dWq2 += (dq2 s)^T a ; da = (dq2 s) Wq2
+  float D[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) D[nb][0] = D[nb][1] = D[nb][2] = D[nb][3] = 0.f;
+  rs_wgrad_rm(T, X, p.gWin2, p.gbin2);
+  rs_dgrad(D, T, Wt, 16 * w);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {          // da as a bf16 tile (operand of step 3), own rows only
+    *reinterpret_cast<uint32_t*>(DAs + i0 * RS_LD + 8 * nb + 2 * t) = pack_bf16(D[nb][0], D[nb][1]);
+    *reinterpret_cast<uint32_t*>(DAs + i1 * RS_LD + 8 * nb + 2 * t) = pack_bf16(D[nb][2], D[nb][3]);
+  }
+  __syncthreads();                          // everybody is done with X == a
+  rs_load1(p.feats + g0, rows, 1.f, X);
+  __syncthreads();
+  // 2. k/v projections of the encoder features: dWk2 += dk2^T feats, dWv2 += dv2^T feats ; dfeats += dk2 Wk2 + dv2 Wv2
+  rs_wgrad_rm(Kt, X, p.gWin2 + (long long)RS_H * RS_H, p.gbin2 + RS_H);
+  rs_wgrad_rm(Vt, X, p.gWin2 + 2ll * RS_H * RS_H, p.gbin2 + 2 * RS_H);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) D[nb][0] = D[nb][1] = D[nb][2] = D[nb][3] = 0.f;
+  rs_dgrad(D, Kt, Wt + RS_TILE, 16 * w);
+  rs_dgrad(D, Vt, Wt + 2 * RS_TILE, 16 * w);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    if (i0 < rows) { float2* d = reinterpret_cast<float2*>(p.dfeats + g0 + (long long)i0 * RS_H + c); const float2 o = *d; *d = make_float2(o.x + D[nb][0], o.y + D[nb][1]); }
+    if (i1 < rows) { float2* d = reinterpret_cast<float2*>(p.dfeats + g0 + (long long)i1 * RS_H + c); const float2 o = *d; *d = make_float2(o.x + D[nb][2], o.y + D[nb][3]); }
+  }
+  __syncthreads();                          // everybody is done with X == feats
+  rs_load1(p.ctx1 + g0, rows, 1.f, X);
+  __syncthreads();
+  // 3. self-attention out-projection: dWo1 += da^T ctx1 ; dctx1 = da Wo1
+  rs_wgrad_rm(DAs, X, p.gWo1, p.gbo1);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) D[nb][0] = D[nb][1] = D[nb][2] = D[nb][3] = 0.f;
+  rs_dgrad(D, DAs, Wt + 3 * RS_TILE, 16 * w);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    if (i0 < rows) *reinterpret_cast<float2*>(p.dctx1 + g0 + (long long)i0 * RS_H + c) = make_float2(D[nb][0], D[nb][1]);
+    if (i1 < rows) *reinterpret_cast<float2*>(p.dctx1 + g0 + (long long)i1 * RS_H + c) = make_float2(D[nb][2], D[nb][3]);
   }
 }
 
