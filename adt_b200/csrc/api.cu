@@ -382,9 +382,17 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   int tm = pick_tm(3 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "mid_fwd: tile does not fit shared memory");
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
-  { TIMED("mid_fwd", s);
-  LAUNCH_TM(tm, mma, mid_fwd_kernel, (M + tm - 1) / tm, smem, s, a->ctx1, a->feats, a->slf.out_w, a->slf.out_b, a->enc.in_w, a->enc.in_b, a->a,
-            a->q2, a->k2, a->v2, M, H, qscale); }
+  if (use_row_small(H, mma)) {
+    const size_t sm = MidFwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(mid_fwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    TIMED("mid_fwd", s);
+    mid_fwd_small_kernel<<<(M + 63) / 64, AS_NT, sm, s>>>(a->ctx1, a->feats, a->slf.out_w, a->slf.out_b, a->enc.in_w, a->enc.in_b, a->a,
+                                                        a->q2, a->k2, a->v2, M, qscale);
+  } else {
+    TIMED("mid_fwd", s);
+    LAUNCH_TM(tm, mma, mid_fwd_kernel, (M + tm - 1) / tm, smem, s, a->ctx1, a->feats, a->slf.out_w, a->slf.out_b, a->enc.in_w, a->enc.in_b, a->a,
+              a->q2, a->k2, a->v2, M, H, qscale);
+  }
   if (int e = check_launch("mid_fwd")) return e;
   if (int e = launch_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, a->precision, s))
     return e;

@@ -496,6 +496,109 @@ __global__ void __launch_bounds__(AS_NT) pre_fwd_small_kernel(const float* __res
 }
 
 // -------------------------------------------------------------------------------------------------
+// mid_fwd_small_kernel == mid_fwd_kernel (kernels_fwd.cuh): a = ctx1 Wo1^T + bo1 ; q2 = (a Wq2^T + bq2) s ; k2, v2 = feats Wkv2^T + bkv2.
+// `a` goes from the accumulator fragments of the first product straight into the A fragments of the second.
+// -------------------------------------------------------------------------------------------------
+struct MidFwdSmallSmem {
+  static constexpr int W = 0, C = 4 * RS_TILE, F = C + RS_TILE;       // Wo1, Wq2, Wk2, Wv2 | ctx1 | feats
+  static constexpr size_t TOTAL_BYTES = (size_t)(F + RS_TILE) * 2;
+};
+
+__global__ void __launch_bounds__(AS_NT) mid_fwd_small_kernel(const float* __restrict__ ctx1, const float* __restrict__ feats,
+                                                              const float* __restrict__ Wo1, const float* __restrict__ bo1,
+                                                              const float* __restrict__ Win2, const float* __restrict__ bin2,
+                                                              float* __restrict__ a_out, float* __restrict__ q2, float* __restrict__ k2,
+                                                              float* __restrict__ v2, int M, float qscale) {
+  using SM = MidFwdSmallSmem;
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
+  __nv_bfloat16* Wt = hb + SM::W;
+  __nv_bfloat16* Cs = hb + SM::C;
+  __nv_bfloat16* Fs = hb + SM::F;
+  const int row0 = blockIdx.x * 64;
+  const int rows = min(64, M - row0);
+  const long long g0 = (long long)row0 * RS_H;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  {
+    const float* const src[2] = {ctx1 + g0, feats + g0};
+    const long long ld[2] = {RS_H, RS_H};
+    const int nr[2] = {rows, rows};
+    const float sc[2] = {1.f, 1.f};
+    __nv_bfloat16* const d[2] = {Cs, Fs};
+    __nv_bfloat16* const dT[2] = {nullptr, nullptr};
+    float* const dF[2] = {nullptr, nullptr};
+    rs_load<2>(src, ld, nr, sc, d, dT, dF);
+  }
+  {
+    const float* const src[4] = {Wo1, Win2, Win2 + RS_H * RS_H, Win2 + 2 * RS_H * RS_H};
+    const long long ld[4] = {RS_H, RS_H, RS_H, RS_H};
+    const int nr[4] = {64, 64, 64, 64};
+    const float sc[4] = {1.f, 1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[4] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE, Wt + 3 * RS_TILE};
+    __nv_bfloat16* const dT[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* const dF[4] = {nullptr, nullptr, nullptr, nullptr};
+    rs_load<4>(src, ld, nr, sc, d, dT, dF);
+  }
+  __syncthreads();
+  float acc[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+  rs_fgemm(acc, Cs, Wt, 16 * w);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 b = __ldg(reinterpret_cast<const float2*>(bo1 + c));
+    acc[nb][0] += b.x; acc[nb][1] += b.y; acc[nb][2] += b.x; acc[nb][3] += b.y;
+    if (a_out) {
+      if (i0 < rows) *reinterpret_cast<float2*>(a_out + g0 + (long long)i0 * RS_H + c) = make_float2(acc[nb][0], acc[nb][1]);
+      if (i1 < rows) *reinterpret_cast<float2*>(a_out + g0 + (long long)i1 * RS_H + c) = make_float2(acc[nb][2], acc[nb][3]);
+    }
+  }
+  {   // q2 = (a Wq2^T + bq2) * s with a taken from the fragments
+    float o[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[4];
+      a[0] = pack_bf16(acc[2 * ks][0], acc[2 * ks][1]);
+      a[1] = pack_bf16(acc[2 * ks][2], acc[2 * ks][3]);
+      a[2] = pack_bf16(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+      a[3] = pack_bf16(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        uint32_t b0, b1;
+        frag_b(b0, b1, Wt + RS_TILE, 8 * nb, 16 * ks);
+        mma16816(o[nb], a, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int c = 8 * nb + 2 * t;
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bin2 + c));
+      if (i0 < rows) *reinterpret_cast<float2*>(q2 + g0 + (long long)i0 * RS_H + c) = make_float2((o[nb][0] + b.x) * qscale, (o[nb][1] + b.y) * qscale);
+      if (i1 < rows) *reinterpret_cast<float2*>(q2 + g0 + (long long)i1 * RS_H + c) = make_float2((o[nb][2] + b.x) * qscale, (o[nb][3] + b.y) * qscale);
+    }
+  }
+#pragma unroll 1
+  for (int m = 0; m < 2; ++m) {    // k2, v2 from the encoder features
+    float o[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+    rs_fgemm(o, Fs, Wt + (2 + m) * RS_TILE, 16 * w);
+    float* out = m == 0 ? k2 : v2;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int c = 8 * nb + 2 * t;
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bin2 + (1 + m) * RS_H + c));
+      if (i0 < rows) *reinterpret_cast<float2*>(out + g0 + (long long)i0 * RS_H + c) = make_float2(o[nb][0] + b.x, o[nb][1] + b.y);
+      if (i1 < rows) *reinterpret_cast<float2*>(out + g0 + (long long)i1 * RS_H + c) = make_float2(o[nb][2] + b.x, o[nb][3] + b.y);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // mid_bwd_small_kernel == mid_bwd_kernel (kernels_bwd.cuh): adjoint of the decoder's self-attention out-projection and of the
 // cross-attention in-projection (q from the self-attention output a, k/v from the encoder features), H == 64, bf16 mode.
 // -------------------------------------------------------------------------------------------------
