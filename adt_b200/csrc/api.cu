@@ -329,6 +329,13 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   size_t smem;
   const int tm = pick_tm(3 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_fwd: tile does not fit shared memory");
+  if (use_row_small(H, mma) && a->nh <= 8) {
+    const size_t sm = PostFwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(post_fwd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    TIMED("enc_post_fwd", s);
+    post_fwd_small_kernel<false><<<(M + 63) / 64, AS_NT, sm, s>>>(p);
+    return check_launch("enc post_fwd_small");
+  }
   { TIMED("enc_post_fwd", s); LAUNCH_TM2(tm, mma, post_fwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
   return check_launch("enc post_fwd");
 }
@@ -404,6 +411,13 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training));
   p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
+  if (use_row_small(H, mma)) {
+    const size_t sm = PostFwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(post_fwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    TIMED("dec_post_fwd", s);
+    post_fwd_small_kernel<true><<<(M + 63) / 64, AS_NT, sm, s>>>(p);
+    return check_launch("dec post_fwd_small");
+  }
   { TIMED("dec_post_fwd", s); LAUNCH_TM2(tm, mma, post_fwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
   return check_launch("dec post_fwd");
 }

@@ -395,6 +395,17 @@ __global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
 }
 
 
+__device__ __forceinline__ void rs_load1(const float* src, int rows, float scale, __nv_bfloat16* dst) {
+  const float* const s[1] = {src};
+  const long long ld[1] = {RS_H};
+  const int nr[1] = {rows};
+  const float sc[1] = {scale};
+  __nv_bfloat16* const d[1] = {dst};
+  __nv_bfloat16* const dT[1] = {nullptr};
+  float* const dF[1] = {nullptr};
+  rs_load<1>(s, ld, nr, sc, d, dT, dF);
+}
+
 // -------------------------------------------------------------------------------------------------
 // pre_fwd_small_kernel == pre_fwd_kernel (kernels_fwd.cuh): LayerNorm + packed in-projection, H == 64, bf16 mode.
 // -------------------------------------------------------------------------------------------------
@@ -493,6 +504,223 @@ __global__ void __launch_bounds__(AS_NT) pre_fwd_small_kernel(const float* __res
       if (i1 < rows) *reinterpret_cast<float2*>(out + (long long)(row0 + i1) * RS_H + c) = make_float2((acc[nb][2] + b.x) * sc, (acc[nb][3] + b.y) * sc);
     }
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// post_fwd_small_kernel == post_fwd_kernel (kernels_fwd.cuh), H == 64, bf16 mode.  Only the context tile and the three weight
+// matrices live in shared memory; LayerNorms, residuals, dropout, ReLU and the three chained products stay in MMA fragments
+// (accumulators of one product are re-packed as the A fragments of the next).
+// -------------------------------------------------------------------------------------------------
+struct PostFwdSmallSmem {
+  static constexpr int W = 0, C = 3 * RS_TILE;       // Wo, C1, C2 | ctx
+  static constexpr size_t TOTAL_BYTES = (size_t)(C + RS_TILE) * 2;
+};
+
+// LayerNorm (eps 1e-8, two-pass) of the two rows a thread co-owns with its quad, in place on fragments
+__device__ __forceinline__ void frag_ln(float (&v)[8][4], const float* __restrict__ gamma, const float* __restrict__ beta, int t) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) { s0 += v[nb][0] + v[nb][1]; s1 += v[nb][2] + v[nb][3]; }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float m0 = s0 * (1.0f / RS_H), m1 = s1 * (1.0f / RS_H);
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const float a = v[nb][0] - m0, b = v[nb][1] - m0, c = v[nb][2] - m1, d = v[nb][3] - m1;
+    q0 += a * a + b * b; q1 += c * c + d * d;
+  }
+  q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  const float r0 = 1.0f / sqrtf(q0 * (1.0f / RS_H) + 1e-8f), r1 = 1.0f / sqrtf(q1 * (1.0f / RS_H) + 1e-8f);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + 8 * nb + 2 * t)), be = __ldg(reinterpret_cast<const float2*>(beta + 8 * nb + 2 * t));
+    v[nb][0] = (v[nb][0] - m0) * r0 * ga.x + be.x; v[nb][1] = (v[nb][1] - m0) * r0 * ga.y + be.y;
+    v[nb][2] = (v[nb][2] - m1) * r1 * ga.x + be.x; v[nb][3] = (v[nb][3] - m1) * r1 * ga.y + be.y;
+  }
+}
+
+// out[nb] += A * W^T with A given as accumulator fragments (rows of this warp, k = 0..63) and W an n-major weight tile
+__device__ __forceinline__ void rs_fgemm_frag(float (&out)[8][4], const float (&a_in)[8][4], const __nv_bfloat16* __restrict__ W) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    a[0] = pack_bf16(a_in[2 * ks][0], a_in[2 * ks][1]);
+    a[1] = pack_bf16(a_in[2 * ks][2], a_in[2 * ks][3]);
+    a[2] = pack_bf16(a_in[2 * ks + 1][0], a_in[2 * ks + 1][1]);
+    a[3] = pack_bf16(a_in[2 * ks + 1][2], a_in[2 * ks + 1][3]);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      uint32_t b0, b1;
+      frag_b(b0, b1, W, 8 * nb, 16 * ks);
+      mma16816(out[nb], a, b0, b1);
+    }
+  }
+}
+
+// row-site dropout multipliers of this thread's fragment elements (rows r0 / r1 are GLOBAL row indices): element (row, col) draws
+// 32-bit word (col & 3) of philox(ctr = (base + row*64 + col) >> 2).  Lanes t and t^1 need the two halves of the same call: the
+// even lane evaluates the calls of even column blocks, the odd lane those of odd blocks, halves are exchanged by shuffle.
+__device__ __forceinline__ void frag_drop(float (&m)[8][4], const DropDesc& d, long long r0, long long r1, int t) {
+  const int odd = t & 1;
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    const int nb = 2 * np + odd;                                   // the block whose call this lane evaluates
+    const unsigned long long c0 = (d.base + (unsigned long long)(r0 * RS_H + 8 * nb + 2 * (t & 2))) >> 2;
+    const unsigned long long c1 = (d.base + (unsigned long long)(r1 * RS_H + 8 * nb + 2 * (t & 2))) >> 2;
+    const float4 a = drop_mul4(d, c0), b = drop_mul4(d, c1);
+    // partner needs: from an even lane (block 2np) the upper half (.z,.w); from an odd lane (block 2np+1) the lower half (.x,.y)
+    const float ax = __shfl_xor_sync(0xffffffffu, odd ? a.x : a.z, 1), ay = __shfl_xor_sync(0xffffffffu, odd ? a.y : a.w, 1);
+    const float bx = __shfl_xor_sync(0xffffffffu, odd ? b.x : b.z, 1), by = __shfl_xor_sync(0xffffffffu, odd ? b.y : b.w, 1);
+    // block 2np: even lane owns (.x,.y) of its own call, odd lane takes the partner's upper half
+    m[2 * np][0] = odd ? ax : a.x; m[2 * np][1] = odd ? ay : a.y; m[2 * np][2] = odd ? bx : b.x; m[2 * np][3] = odd ? by : b.y;
+    // block 2np+1: odd lane owns (.z,.w) of its own call, even lane takes the partner's lower half
+    m[2 * np + 1][0] = odd ? a.z : ax; m[2 * np + 1][1] = odd ? a.w : ay; m[2 * np + 1][2] = odd ? b.z : bx; m[2 * np + 1][3] = odd ? b.w : by;
+  }
+}
+
+__device__ __forceinline__ void cta128_accumulate(double v, double* dst, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(dst, (scratch[0] + scratch[1]) + (scratch[2] + scratch[3]));
+}
+
+template <bool IS_DEC>
+__global__ void __launch_bounds__(AS_NT) post_fwd_small_kernel(PostFwdArgs p) {
+  using SM = PostFwdSmallSmem;
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  __shared__ double red[4];
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
+  __nv_bfloat16* Wt = hb + SM::W;
+  __nv_bfloat16* Cs = hb + SM::C;
+  const int M = p.M;
+  const int row0 = blockIdx.x * 64;
+  const int rows = min(64, M - row0);
+  const long long g0 = (long long)row0 * RS_H;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  const bool v0 = i0 < rows, v1 = i1 < rows;
+  rs_load1(p.ctx + g0, rows, 1.f, Cs);
+  {
+    const float* const src[3] = {p.Wo, p.C1, p.C2};
+    const long long ld[3] = {RS_H, RS_H, RS_H};
+    const int nr[3] = {64, 64, 64};
+    const float sc[3] = {1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
+    __nv_bfloat16* const dT[3] = {nullptr, nullptr, nullptr};
+    float* const dF[3] = {nullptr, nullptr, nullptr};
+    rs_load<3>(src, ld, nr, sc, d, dT, dF);
+  }
+  // residual stream at the fragment positions (enc: block input x -> LN1 ; dec: d, added at the very end)
+  float res[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 a = v0 ? __ldg(reinterpret_cast<const float2*>(p.resid + g0 + (long long)i0 * RS_H + c)) : make_float2(0.f, 0.f);
+    const float2 b = v1 ? __ldg(reinterpret_cast<const float2*>(p.resid + g0 + (long long)i1 * RS_H + c)) : make_float2(0.f, 0.f);
+    res[nb][0] = a.x; res[nb][1] = a.y; res[nb][2] = b.x; res[nb][3] = b.y;
+  }
+  const int keep0 = v0 ? p.ids[row0 + i0] : 0, keep1 = v1 ? p.ids[row0 + i1] : 0;
+  if (!IS_DEC) frag_ln(res, p.ln1_g, p.ln1_b, t);          // Qn = LN1(x)
+  __syncthreads();
+  // y (enc) / c (dec) = ctx Wo^T + bo (+ Qn)
+  float u[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) u[nb][0] = u[nb][1] = u[nb][2] = u[nb][3] = 0.f;
+  rs_fgemm(u, Cs, Wt, 16 * w);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 b = __ldg(reinterpret_cast<const float2*>(p.bo + c));
+    u[nb][0] += b.x; u[nb][1] += b.y; u[nb][2] += b.x; u[nb][3] += b.y;
+    if (!IS_DEC) { u[nb][0] += res[nb][0]; u[nb][1] += res[nb][1]; u[nb][2] += res[nb][2]; u[nb][3] += res[nb][3]; }
+    if (p.u_save) {
+      if (v0) *reinterpret_cast<float2*>(p.u_save + g0 + (long long)i0 * RS_H + c) = make_float2(u[nb][0], u[nb][1]);
+      if (v1) *reinterpret_cast<float2*>(p.u_save + g0 + (long long)i1 * RS_H + c) = make_float2(u[nb][2], u[nb][3]);
+    }
+  }
+  if (!IS_DEC) {
+    // independence head on the per-head context slices (bf16 context tile): one thread per (row, head)
+    if (p.rec || p.acc) {
+      const int nh = p.nh, hd = RS_H / nh;
+      double nll = 0.0;
+      for (int i = threadIdx.x; i < 64 * nh; i += AS_NT) {
+        const int r = i / nh, c = i - r * nh;
+        if (r >= rows) continue;
+        float lg[8];
+        float mx = -INFINITY;
+        for (int j = 0; j < nh; ++j) {
+          float sacc = 0.f;
+          for (int dd = 0; dd < hd; ++dd) sacc = fmaf(__bfloat162float(Cs[r * RS_LD + c * hd + dd]), __ldg(p.Wsp + j * hd + dd), sacc);
+          lg[j] = sacc + __ldg(p.bsp + j);
+          mx = fmaxf(mx, lg[j]);
+        }
+        float se = 0.f;
+        for (int j = 0; j < nh; ++j) se += expf(lg[j] - mx);
+        const float lz = mx + logf(se);
+        if (p.rec)
+          for (int j = 0; j < nh; ++j) p.rec[((long long)(row0 + r) * nh + c) * nh + j] = lg[j] - lz;
+        nll -= (double)(lg[c] - lz);
+      }
+      if (p.acc) cta128_accumulate(nll, p.acc, red);
+    }
+    frag_ln(u, p.ln2_g, p.ln2_b, t);                       // z = LN2(y)
+  }
+  // h1 = z C1^T + c1 ; a = relu(drop1(h1))
+  float h[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) h[nb][0] = h[nb][1] = h[nb][2] = h[nb][3] = 0.f;
+  rs_fgemm_frag(h, u, Wt + RS_TILE);
+  float mk[8][4];
+  if (p.drop1.enabled) frag_drop(mk, p.drop1, row0 + i0, row0 + i1, t);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 b = __ldg(reinterpret_cast<const float2*>(p.c1 + c));
+    h[nb][0] += b.x; h[nb][1] += b.y; h[nb][2] += b.x; h[nb][3] += b.y;
+    if (p.h1_save) {
+      if (v0) *reinterpret_cast<float2*>(p.h1_save + g0 + (long long)i0 * RS_H + c) = make_float2(h[nb][0], h[nb][1]);
+      if (v1) *reinterpret_cast<float2*>(p.h1_save + g0 + (long long)i1 * RS_H + c) = make_float2(h[nb][2], h[nb][3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x = h[nb][e];
+      if (p.drop1.enabled) x *= mk[nb][e];
+      h[nb][e] = fmaxf(x, 0.f);
+    }
+  }
+  // h2 = a C2^T + c2 ; out = (drop2(h2) + z [+ d]) * keep
+  float o[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+  rs_fgemm_frag(o, h, Wt + 2 * RS_TILE);
+  if (p.drop2.enabled) frag_drop(mk, p.drop2, row0 + i0, row0 + i1, t);
+  double sq = 0.0;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 b = __ldg(reinterpret_cast<const float2*>(p.c2 + c));
+    float y[4] = {o[nb][0] + b.x, o[nb][1] + b.y, o[nb][2] + b.x, o[nb][3] + b.y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (p.drop2.enabled) y[e] *= mk[nb][e];
+      y[e] += u[nb][e];
+      if (IS_DEC) y[e] += res[nb][e];
+    }
+    if (keep0 == 0) { y[0] = 0.f; y[1] = 0.f; }
+    if (keep1 == 0) { y[2] = 0.f; y[3] = 0.f; }
+    if (v0) *reinterpret_cast<float2*>(p.out + g0 + (long long)i0 * RS_H + c) = make_float2(y[0], y[1]);
+    if (v1) *reinterpret_cast<float2*>(p.out + g0 + (long long)i1 * RS_H + c) = make_float2(y[2], y[3]);
+    if (IS_DEC && p.enc_in) {
+      if (v0) { const float2 e = *reinterpret_cast<const float2*>(p.enc_in + g0 + (long long)i0 * RS_H + c); sq += (double)((e.x - y[0]) * (e.x - y[0]) + (e.y - y[1]) * (e.y - y[1])); }
+      if (v1) { const float2 e = *reinterpret_cast<const float2*>(p.enc_in + g0 + (long long)i1 * RS_H + c); sq += (double)((e.x - y[2]) * (e.x - y[2]) + (e.y - y[3]) * (e.y - y[3])); }
+    }
+  }
+  if (IS_DEC && p.acc) cta128_accumulate(sq, p.acc, red);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -611,17 +839,6 @@ struct MidBwdSmallSmem {
   static constexpr int DA = V + RS_TILE;             // grad wrt a
   static constexpr size_t TOTAL_BYTES = (size_t)(DA + RS_TILE) * 2;
 };
-
-__device__ __forceinline__ void rs_load1(const float* src, int rows, float scale, __nv_bfloat16* dst) {
-  const float* const s[1] = {src};
-  const long long ld[1] = {RS_H};
-  const int nr[1] = {rows};
-  const float sc[1] = {scale};
-  __nv_bfloat16* const d[1] = {dst};
-  __nv_bfloat16* const dT[1] = {nullptr};
-  float* const dF[1] = {nullptr};
-  rs_load<1>(s, ld, nr, sc, d, dT, dF);
-}
 
 __global__ void __launch_bounds__(AS_NT) mid_bwd_small_kernel(MidBwdArgs p) {
   using SM = MidBwdSmallSmem;
