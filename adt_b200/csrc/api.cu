@@ -359,7 +359,14 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   size_t smem;
   int tm = pick_tm(4 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
-  { TIMED("enc_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p); }
+  if (use_row_small(H, mma) && a->nh <= 8) {
+    const size_t sm = PostBwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(post_bwd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    TIMED("enc_post_bwd", s);
+    post_bwd_small_kernel<false><<<(M + 63) / 64, AS_NT, sm, s>>>(p);
+  } else {
+    TIMED("enc_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p);
+  }
   if (int e = check_launch("enc post_bwd")) return e;
   if (int e = launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
                               a->drop_attn, a->precision, s))
@@ -440,7 +447,14 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   p.gWo = a->g_enc.out_w; p.gbo = a->g_enc.out_b; p.gC1 = a->g_ffn.w1; p.gc1 = a->g_ffn.b1; p.gC2 = a->g_ffn.w2; p.gc2 = a->g_ffn.b2;
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
-  { TIMED("dec_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p); }
+  if (use_row_small(H, mma)) {
+    const size_t sm = PostBwdSmallSmem::TOTAL_BYTES;
+    cudaFuncSetAttribute(post_bwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    TIMED("dec_post_bwd", s);
+    post_bwd_small_kernel<true><<<(M + 63) / 64, AS_NT, sm, s>>>(p);
+  } else {
+    TIMED("dec_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p);
+  }
   if (int e = check_launch("dec post_bwd")) return e;
   // cross attention (keys/values from the encoder features)
   if (int e = launch_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,

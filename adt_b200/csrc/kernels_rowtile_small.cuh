@@ -723,6 +723,309 @@ __global__ void __launch_bounds__(AS_NT) post_fwd_small_kernel(PostFwdArgs p) {
   if (IS_DEC && p.acc) cta128_accumulate(sq, p.acc, red);
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// post_bwd_small_kernel == post_bwd_kernel (kernels_bwd.cuh), H == 64, bf16 mode.  Weights C2, C1, Wo and the attention context
+// stay in shared memory; the gradient stream dO -> dh2 -> da -> dh1 -> dz -> dy -> dctx lives in fragments and is only parked in a
+// bf16 tile where a weight-gradient product needs all rows of the CTA.
+// -------------------------------------------------------------------------------------------------
+struct PostBwdSmallSmem {
+  static constexpr int W = 0, C = 3 * RS_TILE, T = C + RS_TILE, X = T + RS_TILE;     // C2, C1, Wo | ctx | T | X
+  static constexpr size_t LG_BYTES = (size_t)(X + RS_TILE) * 2;                       // logits / dlogits [64][nh*nh] fp32 (+ nh)
+  static constexpr size_t TOTAL_BYTES = LG_BYTES + (size_t)(64 * 64 + 8) * 4;
+};
+
+// D[nb] += A * W with A given as fragments (rows of this warp, k = j = 0..63) and W[j][c] a row-major weight tile
+__device__ __forceinline__ void rs_dgrad_frag(float (&out)[8][4], const float (&a_in)[8][4], const __nv_bfloat16* __restrict__ W) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    a[0] = pack_bf16(a_in[2 * ks][0], a_in[2 * ks][1]);
+    a[1] = pack_bf16(a_in[2 * ks][2], a_in[2 * ks][3]);
+    a[2] = pack_bf16(a_in[2 * ks + 1][0], a_in[2 * ks + 1][1]);
+    a[3] = pack_bf16(a_in[2 * ks + 1][2], a_in[2 * ks + 1][3]);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      uint32_t b0, b1;
+      frag_b_t(b0, b1, W, 16 * ks, 8 * nb);
+      mma16816(out[nb], a, b0, b1);
+    }
+  }
+}
+
+// fragments -> bf16 tile rows of this thread
+__device__ __forceinline__ void frag_store_tile(__nv_bfloat16* __restrict__ T, const float (&v)[8][4], int i0, int i1, int t) {
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    *reinterpret_cast<uint32_t*>(T + i0 * RS_LD + 8 * nb + 2 * t) = pack_bf16(v[nb][0], v[nb][1]);
+    *reinterpret_cast<uint32_t*>(T + i1 * RS_LD + 8 * nb + 2 * t) = pack_bf16(v[nb][2], v[nb][3]);
+  }
+}
+
+// fragment-position loads / stores of a row-major fp32 [M][64] tensor (rows of this thread: i0, i1; validity v0, v1)
+__device__ __forceinline__ void frag_load(float (&v)[8][4], const float* __restrict__ src, int i0, int i1, bool v0, bool v1, int t) {
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 a = (src && v0) ? __ldg(reinterpret_cast<const float2*>(src + (long long)i0 * RS_H + c)) : make_float2(0.f, 0.f);
+    const float2 b = (src && v1) ? __ldg(reinterpret_cast<const float2*>(src + (long long)i1 * RS_H + c)) : make_float2(0.f, 0.f);
+    v[nb][0] = a.x; v[nb][1] = a.y; v[nb][2] = b.x; v[nb][3] = b.y;
+  }
+}
+__device__ __forceinline__ void frag_store(float* __restrict__ dst, const float (&v)[8][4], int i0, int i1, bool v0, bool v1, int t) {
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    if (v0) *reinterpret_cast<float2*>(dst + (long long)i0 * RS_H + c) = make_float2(v[nb][0], v[nb][1]);
+    if (v1) *reinterpret_cast<float2*>(dst + (long long)i1 * RS_H + c) = make_float2(v[nb][2], v[nb][3]);
+  }
+}
+
+// LayerNorm adjoint entirely on fragments: Y = LN input rows (fragments), D = grad wrt LN output -> grad wrt LN input
+__device__ __forceinline__ void frag_ln_bwd(float (&D)[8][4], const float (&Y)[8][4], const float* __restrict__ gamma,
+                                            float* __restrict__ ggamma, float* __restrict__ gbeta, bool v0, bool v1, int g, int t) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) { s0 += Y[nb][0] + Y[nb][1]; s1 += Y[nb][2] + Y[nb][3]; }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float m0 = s0 * (1.0f / RS_H), m1 = s1 * (1.0f / RS_H);
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const float a = Y[nb][0] - m0, b = Y[nb][1] - m0, c = Y[nb][2] - m1, d = Y[nb][3] - m1;
+    q0 += a * a + b * b; q1 += c * c + d * d;
+  }
+  q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+  const float r0 = 1.0f / sqrtf(q0 * (1.0f / RS_H) + 1e-8f), r1 = 1.0f / sqrtf(q1 * (1.0f / RS_H) + 1e-8f);
+  float a10 = 0.f, a20 = 0.f, a11 = 0.f, a21 = 0.f;
+  float xh[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int c = 8 * nb + 2 * t;
+    const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c));
+    xh[nb][0] = (Y[nb][0] - m0) * r0; xh[nb][1] = (Y[nb][1] - m0) * r0;
+    xh[nb][2] = (Y[nb][2] - m1) * r1; xh[nb][3] = (Y[nb][3] - m1) * r1;
+    float dg0 = D[nb][0] * xh[nb][0] + D[nb][2] * xh[nb][2], dg1 = D[nb][1] * xh[nb][1] + D[nb][3] * xh[nb][3];
+    float db0 = D[nb][0] + D[nb][2], db1 = D[nb][1] + D[nb][3];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      dg0 += __shfl_xor_sync(0xffffffffu, dg0, o); dg1 += __shfl_xor_sync(0xffffffffu, dg1, o);
+      db0 += __shfl_xor_sync(0xffffffffu, db0, o); db1 += __shfl_xor_sync(0xffffffffu, db1, o);
+    }
+    if (g == 0) {
+      atomicAdd(ggamma + c, dg0); atomicAdd(ggamma + c + 1, dg1);
+      atomicAdd(gbeta + c, db0); atomicAdd(gbeta + c + 1, db1);
+    }
+    D[nb][0] *= ga.x; D[nb][1] *= ga.y; D[nb][2] *= ga.x; D[nb][3] *= ga.y;
+    a10 += D[nb][0] + D[nb][1]; a20 += D[nb][0] * xh[nb][0] + D[nb][1] * xh[nb][1];
+    a11 += D[nb][2] + D[nb][3]; a21 += D[nb][2] * xh[nb][2] + D[nb][3] * xh[nb][3];
+  }
+#pragma unroll
+  for (int o = 1; o < 4; o <<= 1) {
+    a10 += __shfl_xor_sync(0xffffffffu, a10, o); a20 += __shfl_xor_sync(0xffffffffu, a20, o);
+    a11 += __shfl_xor_sync(0xffffffffu, a11, o); a21 += __shfl_xor_sync(0xffffffffu, a21, o);
+  }
+  a10 *= 1.0f / RS_H; a20 *= 1.0f / RS_H; a11 *= 1.0f / RS_H; a21 *= 1.0f / RS_H;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    D[nb][0] = v0 ? r0 * (D[nb][0] - a10 - xh[nb][0] * a20) : 0.f;
+    D[nb][1] = v0 ? r0 * (D[nb][1] - a10 - xh[nb][1] * a20) : 0.f;
+    D[nb][2] = v1 ? r1 * (D[nb][2] - a11 - xh[nb][2] * a21) : 0.f;
+    D[nb][3] = v1 ? r1 * (D[nb][3] - a11 - xh[nb][3] * a21) : 0.f;
+  }
+}
+
+template <bool IS_DEC>
+__global__ void __launch_bounds__(AS_NT) post_bwd_small_kernel(PostBwdArgs p) {
+  using SM = PostBwdSmallSmem;
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
+  __nv_bfloat16* Wt = hb + SM::W;            // [0] C2, [1] C1, [2] Wo
+  __nv_bfloat16* Cs = hb + SM::C;
+  __nv_bfloat16* T = hb + SM::T;
+  __nv_bfloat16* X = hb + SM::X;
+  float* lgs = reinterpret_cast<float*>(rs_raw + SM::LG_BYTES);
+  const int M = p.M;
+  const int row0 = blockIdx.x * 64;
+  const int rows = min(64, M - row0);
+  const long long g0 = (long long)row0 * RS_H;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  const bool v0 = i0 < rows, v1 = i1 < rows;
+  rs_load1(p.ctx + g0, rows, 1.f, Cs);
+  {
+    const float* const src[3] = {p.C2, p.C1, p.Wo};
+    const long long ld[3] = {RS_H, RS_H, RS_H};
+    const int nr[3] = {64, 64, 64};
+    const float sc[3] = {1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
+    __nv_bfloat16* const dT[3] = {nullptr, nullptr, nullptr};
+    float* const dF[3] = {nullptr, nullptr, nullptr};
+    rs_load<3>(src, ld, nr, sc, d, dT, dF);
+  }
+  // ---- 1./2. dO, a = relu(h1 m1), dh2 = dO m2 on fragments
+  float G[8][4], A[8][4];
+  frag_load(G, p.dout ? p.dout + g0 : nullptr, i0, i1, v0, v1, t);
+  if (IS_DEC && p.enc_in) {
+    float O[8][4], E[8][4];
+    frag_load(O, p.out + g0, i0, i1, v0, v1, t);
+    frag_load(E, p.enc_in + g0, i0, i1, v0, v1, t);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { O[nb][e] = p.mse_coef * (O[nb][e] - E[nb][e]); G[nb][e] += O[nb][e]; O[nb][e] = -O[nb][e]; }
+    }
+    if (p.denc) frag_store(p.denc + g0, O, i0, i1, v0, v1, t);
+  }
+  {
+    const int k0 = v0 ? p.ids[row0 + i0] : 0, k1 = v1 ? p.ids[row0 + i1] : 0;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      if (k0 == 0) { G[nb][0] = 0.f; G[nb][1] = 0.f; }
+      if (k1 == 0) { G[nb][2] = 0.f; G[nb][3] = 0.f; }
+    }
+  }
+  frag_load(A, p.h1 + g0, i0, i1, v0, v1, t);
+  float mk[8][4];
+  uint32_t m1bits = 0u;                      // bit (4 nb + e): element kept by dropout 1 AND a > 0
+  {
+    if (p.drop1.enabled) frag_drop(mk, p.drop1, row0 + i0, row0 + i1, t);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x = A[nb][e];
+        if (p.drop1.enabled) x *= mk[nb][e];
+        A[nb][e] = fmaxf(x, 0.f);
+        if (A[nb][e] > 0.f) m1bits |= 1u << (4 * nb + e);
+      }
+    }
+  }
+  float D2[8][4];
+  if (p.drop2.enabled) frag_drop(mk, p.drop2, row0 + i0, row0 + i1, t);
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) D2[nb][e] = p.drop2.enabled ? G[nb][e] * mk[nb][e] : G[nb][e];
+  }
+  // ---- 3. dC2 += dh2^T a ; dc2 += colsum(dh2)
+  frag_store_tile(T, D2, i0, i1, t);
+  frag_store_tile(X, A, i0, i1, t);
+  __syncthreads();
+  rs_wgrad_rm(T, X, p.gC2, p.gc2);
+  // ---- 4. da = dh2 C2 ; dh1 = da [a>0] m1
+  float H1[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) H1[nb][0] = H1[nb][1] = H1[nb][2] = H1[nb][3] = 0.f;
+  rs_dgrad_frag(H1, D2, Wt);
+  {
+    const float sc1 = p.drop1.enabled ? p.drop1.scale : 1.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) H1[nb][e] = (m1bits >> (4 * nb + e)) & 1u ? H1[nb][e] * sc1 : 0.f;
+    }
+  }
+  // ---- 5. z = LN2(y) (enc) / c (dec) ; dC1 += dh1^T z ; dc1 += colsum(dh1)
+  float Y[8][4];
+  frag_load(Y, p.u + g0, i0, i1, v0, v1, t);
+  __syncthreads();                           // everybody is done with T / X of step 3
+  {
+    float Z[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { Z[nb][0] = Y[nb][0]; Z[nb][1] = Y[nb][1]; Z[nb][2] = Y[nb][2]; Z[nb][3] = Y[nb][3]; }
+    if (!IS_DEC) {
+      frag_ln(Z, p.ln2_g, p.ln2_b, t);
+      if (!v0) { for (int nb = 0; nb < 8; ++nb) { Z[nb][0] = 0.f; Z[nb][1] = 0.f; } }
+      if (!v1) { for (int nb = 0; nb < 8; ++nb) { Z[nb][2] = 0.f; Z[nb][3] = 0.f; } }
+    }
+    frag_store_tile(X, Z, i0, i1, t);
+  }
+  frag_store_tile(T, H1, i0, i1, t);
+  __syncthreads();
+  rs_wgrad_rm(T, X, p.gC1, p.gc1);
+  // ---- 6. dz (enc) / dc (dec) = dO + dh1 C1
+  float DZ[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) { DZ[nb][0] = G[nb][0]; DZ[nb][1] = G[nb][1]; DZ[nb][2] = G[nb][2]; DZ[nb][3] = G[nb][3]; }
+  rs_dgrad_frag(DZ, H1, Wt + RS_TILE);
+  if (!IS_DEC) {
+    // ---- 7. dy = LN2^T(dz) ; dres = dy
+    frag_ln_bwd(DZ, Y, p.ln2_g, p.gln2_g, p.gln2_b, v0, v1, g, t);
+    frag_store(p.dres + g0, DZ, i0, i1, v0, v1, t);
+  } else {
+    frag_store(p.dres + g0, G, i0, i1, v0, v1, t);     // dd = dO
+  }
+  // ---- 8. dWo += dy^T ctx ; dbo += colsum(dy) ; dctx = dy Wo
+  __syncthreads();                           // everybody is done with T / X of step 5
+  frag_store_tile(T, DZ, i0, i1, t);
+  __syncthreads();
+  rs_wgrad_rm(T, Cs, p.gWo, p.gbo);
+  float DC[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) DC[nb][0] = DC[nb][1] = DC[nb][2] = DC[nb][3] = 0.f;
+  rs_dgrad_frag(DC, DZ, Wt + 2 * RS_TILE);
+  if (!IS_DEC && (p.nll_coef != 0.f || p.drec)) {
+    // ---- 9. independence-head adjoint (per-head logits from the bf16 context tile)
+    const int nh = p.nh, hd = RS_H / nh, n2 = nh * nh;
+    float* dbs = lgs + 64 * n2;
+    for (int i = threadIdx.x; i < nh; i += AS_NT) dbs[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * nh; i += AS_NT) {
+      const int r = i / nh, c = i - r * nh;
+      float* lg = lgs + r * n2 + c * nh;
+      if (r >= rows) {
+        for (int j = 0; j < nh; ++j) lg[j] = 0.f;
+        continue;
+      }
+      float mx = -INFINITY;
+      for (int j = 0; j < nh; ++j) {
+        float sacc = 0.f;
+        for (int dd = 0; dd < hd; ++dd) sacc = fmaf(__bfloat162float(Cs[r * RS_LD + c * hd + dd]), __ldg(p.Wsp + j * hd + dd), sacc);
+        lg[j] = sacc + __ldg(p.bsp + j);
+        mx = fmaxf(mx, lg[j]);
+      }
+      float se = 0.f;
+      for (int j = 0; j < nh; ++j) se += expf(lg[j] - mx);
+      const float* dr = p.drec ? p.drec + ((long long)(row0 + r) * nh + c) * nh : nullptr;
+      float gsum = 0.f;
+      if (dr) for (int j = 0; j < nh; ++j) gsum += dr[j];
+      for (int j = 0; j < nh; ++j) {
+        const float pj = expf(lg[j] - mx) / se;
+        float dl = p.nll_coef * (pj - (j == c ? 1.f : 0.f));
+        if (dr) dl += dr[j] - pj * gsum;
+        lg[j] = dl;
+        atomicAdd(dbs + j, dl);
+      }
+    }
+    __syncthreads();
+    // dctx[r][c*hd+d] += sum_j dl[r][c][j] Wsp[j][d]   (on the fragments)
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = e < 2 ? i0 : i1, col = 8 * nb + 2 * t + (e & 1), c = col / hd, dd = col - c * hd;
+        const float* dl = lgs + r * n2 + c * nh;
+        float add = 0.f;
+        for (int j = 0; j < nh; ++j) add = fmaf(dl[j], __ldg(p.Wsp + j * hd + dd), add);
+        DC[nb][e] += add;
+      }
+    }
+    // dWsp[j][d] += sum_{r,c} dl[r][c][j] ctx[r][c*hd+d]
+    for (int i = threadIdx.x; i < nh * hd; i += AS_NT) {
+      const int j = i / hd, dd = i - j * hd;
+      float accw = 0.f;
+      for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < nh; ++c) accw = fmaf(lgs[r * n2 + c * nh + j], __bfloat162float(Cs[r * RS_LD + c * hd + dd]), accw);
+      atomicAdd(p.gWsp + i, accw);
+    }
+    for (int i = threadIdx.x; i < nh; i += AS_NT) atomicAdd(p.gbsp + i, dbs[i]);
+  }
+  frag_store(p.dctx + g0, DC, i0, i1, v0, v1, t);
+}
+
 // -------------------------------------------------------------------------------------------------
 // mid_fwd_small_kernel == mid_fwd_kernel (kernels_fwd.cuh): a = ctx1 Wo1^T + bo1 ; q2 = (a Wq2^T + bq2) s ; k2, v2 = feats Wkv2^T + bkv2.
 // `a` goes from the accumulator fragments of the first product straight into the A fragments of the second.
