@@ -610,7 +610,6 @@ __device__ __forceinline__ void gemm_stream(const float* __restrict__ A, int lda
     if (gi == 0 && t == 0) ADT_STAMP(19);
     if (rc == nrc - 1) {
       if constexpr (MMA) {
-#pragma unroll
         float4 v[NB];
         int rl = 0, cc[NB];
 #pragma unroll

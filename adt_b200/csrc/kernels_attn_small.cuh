@@ -240,7 +240,6 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
                                                                float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
                                                                int L, int H, int nh, int mask_mode, DropDesc drop) {
   using SM = AsBwdSmem<HD>;
-  constexpr int LD = SM::LD;
   extern __shared__ __align__(16) uint8_t as_raw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(as_raw);
   __nv_bfloat16* Ks = Qs + SM::ROW;

@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(TopkArgs a) {
   }
 }
 
-thread_local char g_err2[256] = "";
 
 }  // namespace
 
