@@ -86,3 +86,84 @@ def test_predict_large_shape_vs_oracle():
     from adt_b200.testing import rel_err
     assert rel_err(mc.predict(None, seq, cand), ref_c) < 5e-5
     assert rel_err(mc.predict(None, seq, None, True), ref_f) < 5e-5
+
+
+_SMALL_CASES = [
+    (7, 50, 2, 2, 0.5, [50, 49, 20, 10, 3, 1, 0]),     # C2-like: tail row tile (350 rows), empty and length-1 sequences
+    (3, 64, 4, 1, 0.3, [64, 63, 5]),                   # L = 64 boundary of the short-sequence attention kernels, head dim 16
+    (5, 10, 1, 2, 0.0, [10, 9, 4, 2, 1]),              # single head (head dim 64), no dropout
+    (2, 33, 8, 1, 0.5, [33, 17]),                      # eight heads: independence head with 64 logits per row
+]
+
+
+def _bf16_step_grads(case):
+    """one bf16-mode step on a seeded H=64 model -> (loss, grad norm, {name: flat grad})"""
+    from adt_b200.trainer import FusedTrainer
+    B, L, nh, nl, p, lens = case
+    H, I = 64, 300
+    m, sd0, cfg, O = _setup(B, L, H, nh, nl, I, p)
+    batch = _batch(np.random.default_rng(2), B, L, I, lens)
+    l1, l2, wd = [0.05, 0.1][:nl], [0.02, 0.07][:nl], 1e-3
+    out = {}
+    for prec in ("fp32", "bf16"):
+        mc = type(m)(10, I, m.args)
+        mc.load_state_dict(sd0)
+        mc = mc.cuda().train()
+        tr = FusedTrainer(mc, l1, l2, weight_decay=wd, seed=7, precision=prec)
+        tr.t = 5
+        tr.step(*batch)
+        eng = mc.engine
+        out[prec] = (tr.loss(), tr.grad_norm(), {k: eng.grad_view(k).detach().cpu().numpy().astype(np.float64).ravel() for k, _ in eng.order})
+    return out
+
+
+if __name__ == "__main__":      # helper process of test_bf16_small_kernels_match_generic_bf16 (the switches are read once per process)
+    import sys
+    res = _bf16_step_grads(_SMALL_CASES[int(sys.argv[1])])["bf16"]
+    np.savez(sys.argv[2], loss=res[0], gnorm=res[1], **{"g/" + k: v for k, v in res[2].items()})
+    sys.exit(0)
+
+
+@pytest.mark.parametrize("case", range(len(_SMALL_CASES)))
+def test_bf16_small_kernels_track_fp32_mode(case):
+    """H = 64 in the bf16 mode runs the specialised kernels (short-sequence attention, weights-resident row-tile kernels); the
+    fp32 mode runs the generic ones.  Same batch, same Philox streams: loss within 2e-2 (BASELINE tolerance for bf16) and every
+    gradient tensor parallel to the fp32 one (bf16 rounding noise at these tiny batches reaches ~20 % of a tensor's max on
+    single elements, with either set of kernels: the elementwise comparison is done bf16-vs-bf16 below)."""
+    out = _bf16_step_grads(_SMALL_CASES[case])
+    l0, g0, gr0 = out["fp32"]
+    l1_, g1, gr1 = out["bf16"]
+    assert abs(l1_ - l0) / abs(l0) < 2e-2 and abs(g1 - g0) / g0 < 3e-2
+    for k, a in gr0.items():
+        b = gr1[k]
+        if np.linalg.norm(a) < 1e-7:
+            continue
+        cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+        assert cos > 0.99, (k, cos)
+
+
+@pytest.mark.parametrize("case", [0, 1, 3])
+def test_bf16_small_kernels_match_generic_bf16(case, tmp_path):
+    """the specialised bf16 kernels against the generic bf16 row-tile kernels (ADT_ROW_SMALL=0 ADT_ATTN_SMALL=0, separate
+    process): same precision, different tiling -> gradients agree elementwise to 2 % of each tensor's max."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.abspath(__file__)
+    files = []
+    for tag, env in (("small", {}), ("generic", {"ADT_ROW_SMALL": "0", "ADT_ATTN_SMALL": "0"})):
+        f = str(tmp_path / f"{tag}.npz")
+        e = dict(os.environ, **env)
+        e["PYTHONPATH"] = os.path.dirname(os.path.dirname(here)) + os.pathsep + os.path.dirname(here) + os.pathsep + e.get("PYTHONPATH", "")
+        subprocess.run([sys.executable, here, str(case), f], check=True, env=e, timeout=600)
+        files.append(np.load(f))
+    a, b = files
+    assert abs(float(a["loss"]) - float(b["loss"])) / abs(float(b["loss"])) < 1e-4
+    assert abs(float(a["gnorm"]) - float(b["gnorm"])) / float(b["gnorm"]) < 5e-3
+    for k in a.files:
+        if not k.startswith("g/"):
+            continue
+        x, y = a[k], b[k]
+        if np.abs(y).max() < 1e-9:
+            continue
+        assert np.abs(x - y).max() <= 2e-2 * np.abs(y).max() + 1e-7, (k, float(np.abs(x - y).max()), float(np.abs(y).max()))
