@@ -16,6 +16,33 @@ constexpr int AS_LT = 72;         // row stride (halfwords) of the transposed [H
 
 __device__ __forceinline__ uint32_t ld_u32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
+// ldmatrix fragment loaders on row-major bf16 tiles with row stride LDT halfwords (LDT*2 bytes must be a multiple of 16; 40 and 72
+// halfwords give conflict-free 8x8 block loads)
+template <int LDT>
+__device__ __forceinline__ void lm_a(uint32_t (&a)[4], const __nv_bfloat16* A, int m0, int k0) {            // A[m][k]
+  const int l = threadIdx.x & 31;
+  const unsigned ad = (unsigned)__cvta_generic_to_shared(A + (m0 + (l & 7) + 8 * ((l >> 3) & 1)) * LDT + k0 + 8 * (l >> 4));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(ad));
+}
+template <int LDT>
+__device__ __forceinline__ void lm_a_t(uint32_t (&a)[4], const __nv_bfloat16* S, int m0, int k0) {          // A[m][k] = S[k][m]
+  const int l = threadIdx.x & 31;
+  const unsigned ad = (unsigned)__cvta_generic_to_shared(S + (k0 + (l & 7) + 8 * (l >> 4)) * LDT + m0 + 8 * ((l >> 3) & 1));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(ad));
+}
+template <int LDT>
+__device__ __forceinline__ void lm_b(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* Bn, int n0, int k0) {  // B[k][n] = Bn[n][k]
+  const int l = threadIdx.x & 15;
+  const unsigned ad = (unsigned)__cvta_generic_to_shared(Bn + (n0 + (l & 7)) * LDT + k0 + 8 * (l >> 3));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(ad));
+}
+template <int LDT>
+__device__ __forceinline__ void lm_b_t(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* Bk, int k0, int n0) {  // B[k][n] = Bk[k][n]
+  const int l = threadIdx.x & 15;
+  const unsigned ad = (unsigned)__cvta_generic_to_shared(Bk + (k0 + (l & 7) + 8 * (l >> 3)) * LDT + n0);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(ad));
+}
+
 // rows [0, L) x HD columns of N head slices (global row stride H) -> bf16 tiles [64][HD + 8] and/or transposed copies [HD][72].
 // All global loads of all N tensors are issued before the first conversion/store: one memory round trip for the whole prologue.
 template <int HD, int N>
@@ -99,6 +126,47 @@ __device__ __forceinline__ void as_mma_frag(float (&out)[HD / 8][4], const float
   }
 }
 
+// acc[nb] += A[16 rows r0..][0..HD) * Bn[8nb..][0..HD)^T with ldmatrix fragments (tiles [64][HD+8])
+template <int HD>
+__device__ __forceinline__ void as_mma_rows_lm(float (&acc)[8][4], const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bn,
+                                               int r0, int nbr) {
+  constexpr int LD = HD + 8;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    uint32_t a[4];
+    lm_a<LD>(a, A, r0, 16 * ks);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      if (nb < nbr) {
+        uint32_t b0, b1;
+        lm_b<LD>(b0, b1, Bn, 8 * nb, 16 * ks);
+        mma16816(acc[nb], a, b0, b1);
+      }
+    }
+  }
+}
+// out[db] += P (fragments, k = key index j) * Bk[j][8db..]   with Bk a row-major [64][HD+8] tile (V or K), via transposing loads
+template <int HD>
+__device__ __forceinline__ void as_mma_frag_lm(float (&out)[HD / 8][4], const float (&p)[8][4], const __nv_bfloat16* __restrict__ Bk, int nks) {
+  constexpr int LD = HD + 8;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    if (ks < nks) {
+      uint32_t a[4];
+      a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
+      a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
+      a[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+      a[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+#pragma unroll
+      for (int db = 0; db < HD / 8; ++db) {
+        uint32_t b0, b1;
+        lm_b_t<LD>(b0, b1, Bk, 16 * ks, 8 * db);
+        mma16816(out[db], a, b0, b1);
+      }
+    }
+  }
+}
+
 // masked scores -> (unnormalised) exponentials relative to `ref` (row max in fwd, log-sum-exp in bwd); returns nothing, updates s
 __device__ __forceinline__ float as_masked(float s, int i, int j, int L, int mask_mode, const int* __restrict__ kid) {
   if (i >= L || j >= L || (mask_mode == 0 && j > i)) return -INFINITY;
@@ -147,13 +215,13 @@ __global__ void __launch_bounds__(AS_NT) attn_small_fwd_kernel(const float* __re
                                                                float* __restrict__ lse, const int* __restrict__ key_ids, int L, int H,
                                                                int nh, int mask_mode, DropDesc drop) {
   constexpr int LD = HD + 8;
-  __shared__ __align__(16) __nv_bfloat16 Qs[64 * LD], Ks[64 * LD], Vt[HD * AS_LT];
+  __shared__ __align__(16) __nv_bfloat16 Qs[64 * LD], Ks[64 * LD], Vs[64 * LD];
   const int bh = blockIdx.x, b = bh / nh, h = bh - b * nh;
   const long long seq_off = (long long)b * L * H + (long long)h * HD;
   {   // rows >= L are written as zeros by the loader (every row of the 64-row tiles is covered)
     const float* const src[3] = {q + seq_off, k + seq_off, v + seq_off};
-    __nv_bfloat16* const dst[3] = {Qs, Ks, nullptr};
-    __nv_bfloat16* const dstT[3] = {nullptr, nullptr, Vt};
+    __nv_bfloat16* const dst[3] = {Qs, Ks, Vs};
+    __nv_bfloat16* const dstT[3] = {nullptr, nullptr, nullptr};
     as_load<HD, 3>(src, H, L, dst, dstT);
   }
   __syncthreads();
@@ -164,7 +232,7 @@ __global__ void __launch_bounds__(AS_NT) attn_small_fwd_kernel(const float* __re
   float s[8][4];
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-  as_mma_rows<HD>(s, Qs, Ks, 16 * w, nbr);
+  as_mma_rows_lm<HD>(s, Qs, Ks, 16 * w, nbr);
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) {
@@ -217,7 +285,7 @@ __global__ void __launch_bounds__(AS_NT) attn_small_fwd_kernel(const float* __re
   float o[HD / 8][4];
 #pragma unroll
   for (int db = 0; db < HD / 8; ++db) o[db][0] = o[db][1] = o[db][2] = o[db][3] = 0.f;
-  as_mma_frag<HD>(o, s, Vt, nks);
+  as_mma_frag_lm<HD>(o, s, Vs, nks);
 #pragma unroll
   for (int db = 0; db < HD / 8; ++db) {
     if (v0) *reinterpret_cast<float2*>(ctx + seq_off + (long long)i0 * H + 8 * db + 2 * t) = make_float2(o[db][0], o[db][1]);
@@ -229,8 +297,8 @@ __global__ void __launch_bounds__(AS_NT) attn_small_fwd_kernel(const float* __re
 template <int HD>
 struct AsBwdSmem {
   static constexpr int LD = HD + 8;
-  static constexpr int ROW = 64 * LD, TR = HD * AS_LT, SQ = 64 * AS_LT;
-  static constexpr int TOTAL = 4 * ROW + 3 * TR + 2 * SQ;     // Q, K, V, dC | Qt, Kt, dCt | dSt, Pt
+  static constexpr int ROW = 64 * LD, SQ = 64 * AS_LT;
+  static constexpr int TOTAL = 4 * ROW + 2 * SQ;              // Q, K, V, dC [64][HD+8] | dS, P~ [64][72]   (all row-major)
 };
 
 template <int HD>
@@ -240,16 +308,14 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
                                                                float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
                                                                int L, int H, int nh, int mask_mode, DropDesc drop) {
   using SM = AsBwdSmem<HD>;
+  constexpr int LD = SM::LD;
   extern __shared__ __align__(16) uint8_t as_raw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(as_raw);
   __nv_bfloat16* Ks = Qs + SM::ROW;
   __nv_bfloat16* Vs = Ks + SM::ROW;
   __nv_bfloat16* dCs = Vs + SM::ROW;
-  __nv_bfloat16* Qt = dCs + SM::ROW;
-  __nv_bfloat16* Kt = Qt + SM::TR;
-  __nv_bfloat16* dCt = Kt + SM::TR;
-  __nv_bfloat16* dSt = dCt + SM::TR;
-  __nv_bfloat16* Pt = dSt + SM::SQ;
+  __nv_bfloat16* dSt = dCs + SM::ROW;        // dS[i][j], row-major
+  __nv_bfloat16* Pt = dSt + SM::SQ;          // P~[i][j], row-major
   const int bh = blockIdx.x, b = bh / nh, h = bh - b * nh;
   const long long seq_off = (long long)b * L * H + (long long)h * HD;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -257,12 +323,10 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
   const bool v0 = i0 < L, v1 = i1 < L;
   const float ls0 = v0 ? lse[((long long)b * nh + h) * L + i0] : 0.f;     // issued early: consumed after the first product
   const float ls1 = v1 ? lse[((long long)b * nh + h) * L + i1] : 0.f;
-  for (int i = threadIdx.x; i < (3 * SM::TR + 2 * SM::SQ) / 2; i += AS_NT) reinterpret_cast<uint32_t*>(Qt)[i] = 0u;
-  __syncthreads();
   {
     const float* const src[4] = {q + seq_off, k + seq_off, v + seq_off, dctx + seq_off};
     __nv_bfloat16* const dst[4] = {Qs, Ks, Vs, dCs};
-    __nv_bfloat16* const dstT[4] = {Qt, Kt, nullptr, dCt};
+    __nv_bfloat16* const dstT[4] = {nullptr, nullptr, nullptr, nullptr};
     as_load<HD, 4>(src, H, L, dst, dstT);
   }
   __syncthreads();
@@ -274,8 +338,8 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
     p[nb][0] = p[nb][1] = p[nb][2] = p[nb][3] = 0.f;
     dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
   }
-  as_mma_rows<HD>(p, Qs, Ks, 16 * w, nbr);       // S = q k^T
-  as_mma_rows<HD>(dp, dCs, Vs, 16 * w, nbr);     // dP~ = dctx v^T
+  as_mma_rows_lm<HD>(p, Qs, Ks, 16 * w, nbr);       // S = q k^T
+  as_mma_rows_lm<HD>(dp, dCs, Vs, 16 * w, nbr);     // dP~ = dctx v^T
   const int lp8 = ((L + 7) & ~7) >> 3;
   const unsigned long long rb = drop.base + ((unsigned long long)b * nh + h) * L;
   float dl0 = 0.f, dl1 = 0.f;
@@ -310,15 +374,15 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
   for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int j = 8 * nb + 2 * t + e;
       const float ds0 = p[nb][e] * (dp[nb][e] - dl0), ds1 = p[nb][2 + e] * (dp[nb][2 + e] - dl1);
       dp[nb][e] = ds0; dp[nb][2 + e] = ds1;
-      if (nb < nbr) {
-        dSt[j * AS_LT + i0] = __float2bfloat16_rn(ds0);
-        dSt[j * AS_LT + i1] = __float2bfloat16_rn(ds1);
-        Pt[j * AS_LT + i0] = __float2bfloat16_rn(pt[nb][e]);
-        Pt[j * AS_LT + i1] = __float2bfloat16_rn(pt[nb][2 + e]);
-      }
+    }
+    if (nb < nbr) {
+      const int j = 8 * nb + 2 * t;
+      *reinterpret_cast<uint32_t*>(dSt + i0 * AS_LT + j) = pack_bf16(dp[nb][0], dp[nb][1]);
+      *reinterpret_cast<uint32_t*>(dSt + i1 * AS_LT + j) = pack_bf16(dp[nb][2], dp[nb][3]);
+      *reinterpret_cast<uint32_t*>(Pt + i0 * AS_LT + j) = pack_bf16(pt[nb][0], pt[nb][1]);
+      *reinterpret_cast<uint32_t*>(Pt + i1 * AS_LT + j) = pack_bf16(pt[nb][2], pt[nb][3]);
     }
   }
   // dq = dS k
@@ -326,7 +390,7 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
     float o[HD / 8][4];
 #pragma unroll
     for (int db = 0; db < HD / 8; ++db) o[db][0] = o[db][1] = o[db][2] = o[db][3] = 0.f;
-    as_mma_frag<HD>(o, dp, Kt, nks);
+    as_mma_frag_lm<HD>(o, dp, Ks, nks);
 #pragma unroll
     for (int db = 0; db < HD / 8; ++db) {
       if (v0) *reinterpret_cast<float2*>(dq + seq_off + (long long)i0 * H + 8 * db + 2 * t) = make_float2(o[db][0], o[db][1]);
@@ -337,8 +401,8 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
   // dk = dS^T q ; dv = P~^T dctx   (this warp owns key rows 16w .. 16w+15; plain stores: the CTA owns the whole head)
 #pragma unroll
   for (int which = 0; which < 2; ++which) {
-    const __nv_bfloat16* A = which == 0 ? dSt : Pt;
-    const __nv_bfloat16* Bt = which == 0 ? Qt : dCt;
+    const __nv_bfloat16* A = which == 0 ? dSt : Pt;       // [i][j]: used transposed, A[m = j][k = i]
+    const __nv_bfloat16* Bk = which == 0 ? Qs : dCs;      // [i][d]: B[k = i][n = d]
     float* out = which == 0 ? dk : dv;
     float o[HD / 8][4];
 #pragma unroll
@@ -347,14 +411,12 @@ __global__ void __launch_bounds__(AS_NT) attn_small_bwd_kernel(const float* __re
     for (int ks = 0; ks < 4; ++ks) {
       if (ks < nks) {
         uint32_t a[4];
-        a[0] = ld_u32(A + (16 * w + g) * AS_LT + 16 * ks + 2 * t);
-        a[1] = ld_u32(A + (16 * w + g + 8) * AS_LT + 16 * ks + 2 * t);
-        a[2] = ld_u32(A + (16 * w + g) * AS_LT + 16 * ks + 2 * t + 8);
-        a[3] = ld_u32(A + (16 * w + g + 8) * AS_LT + 16 * ks + 2 * t + 8);
+        lm_a_t<AS_LT>(a, A, 16 * w, 16 * ks);
 #pragma unroll
         for (int db = 0; db < HD / 8; ++db) {
-          const __nv_bfloat16* bp = Bt + (8 * db + g) * AS_LT + 16 * ks + 2 * t;
-          mma16816(o[db], a, ld_u32(bp), ld_u32(bp + 8));
+          uint32_t b0, b1;
+          lm_b_t<LD>(b0, b1, Bk, 16 * ks, 8 * db);
+          mma16816(o[db], a, b0, b1);
         }
       }
     }
