@@ -288,9 +288,9 @@ static int launch_attn_bwd(const float* q, const float* k, const float* v, const
 static int launch_pre_bwd(const PreBwdArgs& r, int mma, cudaStream_t s) {
   TIMED("pre_bwd", s);
   if (use_row_small(r.H, mma)) {
-    const size_t sm = PreBwdSmallSmem::TOTAL_BYTES;
-    cudaFuncSetAttribute(pre_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    pre_bwd_small_kernel<<<(r.M + 63) / 64, AS_NT, sm, s>>>(r);
+    const size_t sm = PreBwdSmall2Smem::TOTAL_BYTES;
+    cudaFuncSetAttribute(pre_bwd_small2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    pre_bwd_small2_kernel<<<(r.M + 63) / 64, AS_NT, sm, s>>>(r);
     return check_launch("pre_bwd_small");
   }
   const int pad = mma ? 8 : 4;

@@ -1,8 +1,8 @@
 // Narrow-model (H == 64) row-tile kernels for the bf16 tensor-core mode, built like kernels_attn_small.cuh: 128-thread CTAs,
 // every weight matrix of the kernel resident in shared memory as bf16 (no chunk ring, no per-chunk barriers), operands of all
 // products staged once as bf16 tiles (row-major and transposed), accumulators and LayerNorm adjoints kept in MMA fragments.
-//   pre_bwd_small_kernel == pre_bwd_kernel (kernels_bwd.cuh): adjoint of LayerNorm + packed QKV in-projection
-//   (sasrec/modules.py:646-647 / :668-670 with torch's packed in_proj, modules.py:124-130).
+// One kernel per generic row-tile kernel of kernels_fwd.cuh / kernels_bwd.cuh: pre_fwd, mid_fwd, post_fwd<enc|dec>, pre_bwd,
+// mid_bwd, post_bwd<enc|dec> (sasrec/modules.py:644-677 and their adjoints).
 #pragma once
 #include "common.cuh"
 #include "kernels_bwd.cuh"
@@ -153,247 +153,6 @@ __device__ __forceinline__ void rs_wgrad_rm(const __nv_bfloat16* __restrict__ T,
     atomicAdd(gb + j1, ones[2]);
   }
 }
-
-// acc[nb] (rows 16w+g, +8 ; columns 8nb+2t, +1) += A[16w.., k] * B[8nb.., k]^T over k = 0..63, both tiles [64][72] bf16 with k fast
-__device__ __forceinline__ void rs_mma(float (&acc)[8][4], const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, int r0) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a[4];
-    a[0] = ld_u32(A + (r0 + g) * RS_LD + 16 * ks + 2 * t);
-    a[1] = ld_u32(A + (r0 + g + 8) * RS_LD + 16 * ks + 2 * t);
-    a[2] = ld_u32(A + (r0 + g) * RS_LD + 16 * ks + 2 * t + 8);
-    a[3] = ld_u32(A + (r0 + g + 8) * RS_LD + 16 * ks + 2 * t + 8);
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const __nv_bfloat16* bp = B + (8 * nb + g) * RS_LD + 16 * ks + 2 * t;
-      mma16816(acc[nb], a, ld_u32(bp), ld_u32(bp + 8));
-    }
-  }
-}
-
-// weight gradient of one projection: gW[j][c] += sum_r Tt[j][r] * Xt[c][r], gb[j] += sum_r Tt[j][r]   (warp w owns rows j = 16w..16w+15)
-__device__ __forceinline__ void rs_wgrad(const __nv_bfloat16* __restrict__ Tt, const __nv_bfloat16* __restrict__ Xt, float* __restrict__ gW,
-                                         float* __restrict__ gb) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  float acc[8][4], ones[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a[4];
-    a[0] = ld_u32(Tt + (16 * w + g) * RS_LD + 16 * ks + 2 * t);
-    a[1] = ld_u32(Tt + (16 * w + g + 8) * RS_LD + 16 * ks + 2 * t);
-    a[2] = ld_u32(Tt + (16 * w + g) * RS_LD + 16 * ks + 2 * t + 8);
-    a[3] = ld_u32(Tt + (16 * w + g + 8) * RS_LD + 16 * ks + 2 * t + 8);
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const __nv_bfloat16* bp = Xt + (8 * nb + g) * RS_LD + 16 * ks + 2 * t;
-      mma16816(acc[nb], a, ld_u32(bp), ld_u32(bp + 8));
-    }
-    mma16816(ones, a, 0x3f803f80u, 0x3f803f80u);     // B = all ones (bf16 1.0): every column of `ones` is the row sum of Tt
-  }
-  const int j0 = 16 * w + g, j1 = j0 + 8;
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    // lanes t and t^1 hold adjacent column pairs: even t gathers four contiguous columns -> one 128-bit reduction per row
-    const float x0 = __shfl_xor_sync(0xffffffffu, acc[nb][0], 1), x1 = __shfl_xor_sync(0xffffffffu, acc[nb][1], 1);
-    const float y0 = __shfl_xor_sync(0xffffffffu, acc[nb][2], 1), y1 = __shfl_xor_sync(0xffffffffu, acc[nb][3], 1);
-    if ((t & 1) == 0) {
-      atomicAdd(reinterpret_cast<float4*>(gW + (long long)j0 * RS_H + 8 * nb + 2 * t), make_float4(acc[nb][0], acc[nb][1], x0, x1));
-      atomicAdd(reinterpret_cast<float4*>(gW + (long long)j1 * RS_H + 8 * nb + 2 * t), make_float4(acc[nb][2], acc[nb][3], y0, y1));
-    }
-  }
-  if (t == 0) {
-    atomicAdd(gb + j0, ones[0]);
-    atomicAdd(gb + j1, ones[2]);
-  }
-}
-
-// LayerNorm adjoint on accumulator fragments: D (grad wrt LN output) -> grad wrt LN input, plus dgamma / dbeta column sums
-__device__ __forceinline__ void rs_ln_bwd(float (&D)[8][4], const float* __restrict__ Xf, const float* __restrict__ stats,
-                                          const float* __restrict__ gamma, float* __restrict__ ggamma, float* __restrict__ gbeta,
-                                          int rows_valid) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int i0 = 16 * w + g, i1 = i0 + 8;
-  const float mean0 = stats[2 * i0], rstd0 = stats[2 * i0 + 1], mean1 = stats[2 * i1], rstd1 = stats[2 * i1 + 1];
-  float s10 = 0.f, s20 = 0.f, s11 = 0.f, s21 = 0.f;
-  float xh[8][4];
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    const int c = 8 * nb + 2 * t;
-    const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c));
-    const float2 x0 = *reinterpret_cast<const float2*>(Xf + i0 * RS_LF + c), x1 = *reinterpret_cast<const float2*>(Xf + i1 * RS_LF + c);
-    xh[nb][0] = (x0.x - mean0) * rstd0; xh[nb][1] = (x0.y - mean0) * rstd0;
-    xh[nb][2] = (x1.x - mean1) * rstd1; xh[nb][3] = (x1.y - mean1) * rstd1;
-    // dgamma / dbeta partials of this thread's two rows, reduced over the 8 row groups of the warp below
-    float dg0 = D[nb][0] * xh[nb][0] + D[nb][2] * xh[nb][2], dg1 = D[nb][1] * xh[nb][1] + D[nb][3] * xh[nb][3];
-    float db0 = D[nb][0] + D[nb][2], db1 = D[nb][1] + D[nb][3];
-#pragma unroll
-    for (int o = 4; o < 32; o <<= 1) {
-      dg0 += __shfl_xor_sync(0xffffffffu, dg0, o); dg1 += __shfl_xor_sync(0xffffffffu, dg1, o);
-      db0 += __shfl_xor_sync(0xffffffffu, db0, o); db1 += __shfl_xor_sync(0xffffffffu, db1, o);
-    }
-    if (g == 0) {
-      atomicAdd(ggamma + c, dg0); atomicAdd(ggamma + c + 1, dg1);
-      atomicAdd(gbeta + c, db0); atomicAdd(gbeta + c + 1, db1);
-    }
-    D[nb][0] *= ga.x; D[nb][1] *= ga.y; D[nb][2] *= ga.x; D[nb][3] *= ga.y;
-    s10 += D[nb][0] + D[nb][1]; s20 += D[nb][0] * xh[nb][0] + D[nb][1] * xh[nb][1];
-    s11 += D[nb][2] + D[nb][3]; s21 += D[nb][2] * xh[nb][2] + D[nb][3] * xh[nb][3];
-  }
-#pragma unroll
-  for (int o = 1; o < 4; o <<= 1) {
-    s10 += __shfl_xor_sync(0xffffffffu, s10, o); s20 += __shfl_xor_sync(0xffffffffu, s20, o);
-    s11 += __shfl_xor_sync(0xffffffffu, s11, o); s21 += __shfl_xor_sync(0xffffffffu, s21, o);
-  }
-  s10 *= 1.0f / RS_H; s20 *= 1.0f / RS_H; s11 *= 1.0f / RS_H; s21 *= 1.0f / RS_H;
-  const bool v0 = i0 < rows_valid, v1 = i1 < rows_valid;
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    D[nb][0] = v0 ? rstd0 * (D[nb][0] - s10 - xh[nb][0] * s20) : 0.f;
-    D[nb][1] = v0 ? rstd0 * (D[nb][1] - s10 - xh[nb][1] * s20) : 0.f;
-    D[nb][2] = v1 ? rstd1 * (D[nb][2] - s11 - xh[nb][2] * s21) : 0.f;
-    D[nb][3] = v1 ? rstd1 * (D[nb][3] - s11 - xh[nb][3] * s21) : 0.f;
-  }
-}
-
-struct PreBwdSmallSmem {
-  // halfword offsets
-  static constexpr int WT = 0;                       // W[3]  : the three projection matrices W_m[j][c], row-major bf16
-  static constexpr int T = 3 * RS_TILE;              // T     : current dq*s / dk / dv tile, row-major
-  static constexpr int XT = T + RS_TILE;             // X     : block input, row-major bf16
-  static constexpr int NT_ = XT + RS_TILE;           // N     : LayerNorm output, row-major bf16
-  static constexpr int HALF_END = NT_ + RS_TILE;
-  static constexpr size_t XF_BYTES = (size_t)HALF_END * 2;               // Xf : fp32 [64][64] block input
-  static constexpr size_t STATS_BYTES = XF_BYTES + (size_t)64 * RS_LF * 4;  // stats : (mean, rstd) per row
-  static constexpr size_t TOTAL_BYTES = STATS_BYTES + 64 * 2 * 4;
-};
-
-__global__ void __launch_bounds__(AS_NT) pre_bwd_small_kernel(PreBwdArgs p) {
-  using SM = PreBwdSmallSmem;
-  extern __shared__ __align__(16) uint8_t rs_raw[];
-  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
-  __nv_bfloat16* Wt = hb + SM::WT;
-  __nv_bfloat16* T = hb + SM::T;
-  __nv_bfloat16* Xt = hb + SM::XT;
-  __nv_bfloat16* Nt = hb + SM::NT_;
-  float* Xf = reinterpret_cast<float*>(rs_raw + SM::XF_BYTES);
-  float* stats = reinterpret_cast<float*>(rs_raw + SM::STATS_BYTES);
-  const int row0 = blockIdx.x * 64;
-  const int rows = min(64, p.M - row0);
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int i0 = 16 * w + g, i1 = i0 + 8;
-  // ---- prologue: block input, dq, and the three weight matrices (transposed), all loads in flight together
-  {
-    const float* const src[2] = {p.x + (long long)row0 * RS_H, p.dq + (long long)row0 * RS_H};
-    const long long ld[2] = {RS_H, RS_H};
-    const int nr[2] = {rows, rows};
-    const float sc[2] = {1.f, p.qscale};
-    __nv_bfloat16* const d[2] = {Xt, T};
-    __nv_bfloat16* const dT[2] = {nullptr, nullptr};
-    float* const dF[2] = {Xf, nullptr};
-    rs_load<2>(src, ld, nr, sc, d, dT, dF);
-  }
-  {
-    const float* const src[3] = {p.Win, p.Win + RS_H * RS_H, p.Win + 2 * RS_H * RS_H};
-    const long long ld[3] = {RS_H, RS_H, RS_H};
-    const int nr[3] = {64, 64, 64};
-    const float sc[3] = {1.f, 1.f, 1.f};
-    __nv_bfloat16* const d[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
-    __nv_bfloat16* const dT[3] = {nullptr, nullptr, nullptr};
-    float* const dF[3] = {nullptr, nullptr, nullptr};
-    rs_load<3>(src, ld, nr, sc, d, dT, dF);
-  }
-  __syncthreads();
-  // ---- LayerNorm forward (two threads per row, two-pass statistics like ln_tile): stats + transposed bf16 N
-  {
-    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
-    const float* xr = Xf + r * RS_LF + 32 * half;
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      s += (v.x + v.y) + (v.z + v.w);
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    const float mean = s * (1.0f / RS_H);
-    float q = 0.f;
-#pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
-      q += (a * a + b * b) + (cc * cc + d * d);
-    }
-    q += __shfl_xor_sync(0xffffffffu, q, 1);
-    const float rstd = 1.0f / sqrtf(q * (1.0f / RS_H) + 1e-8f);
-    if (half == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
-#pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      const int col = 32 * half + c;
-      const float4 v = *reinterpret_cast<const float4*>(xr + c);
-      const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_g + col)), be = __ldg(reinterpret_cast<const float4*>(p.ln_b + col));
-      const bool ok = r < rows;
-      uint32_t* d = reinterpret_cast<uint32_t*>(Nt + r * RS_LD + col);
-      d[0] = ok ? pack_bf16((v.x - mean) * rstd * ga.x + be.x, (v.y - mean) * rstd * ga.y + be.y) : 0u;
-      d[1] = ok ? pack_bf16((v.z - mean) * rstd * ga.z + be.z, (v.w - mean) * rstd * ga.w + be.w) : 0u;
-    }
-  }
-  __syncthreads();
-  // ---- q projection: weight gradient against N, data gradient D = (dq*s) Wq (+ dnorm_extra)
-  float D[8][4];
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) D[nb][0] = D[nb][1] = D[nb][2] = D[nb][3] = 0.f;
-  rs_wgrad_rm(T, Nt, p.gWin, p.gbin);
-  rs_dgrad(D, T, Wt, 16 * w);
-  if (p.dnorm_extra) {
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const int c = 8 * nb + 2 * t;
-      if (i0 < rows) { const float2 e = *reinterpret_cast<const float2*>(p.dnorm_extra + (long long)(row0 + i0) * RS_H + c); D[nb][0] += e.x; D[nb][1] += e.y; }
-      if (i1 < rows) { const float2 e = *reinterpret_cast<const float2*>(p.dnorm_extra + (long long)(row0 + i1) * RS_H + c); D[nb][2] += e.x; D[nb][3] += e.y; }
-    }
-  }
-  if (!p.kv_from_norm) rs_ln_bwd(D, Xf, stats, p.ln_g, p.gln_g, p.gln_b, rows);     // encoder: k, v are projected from x itself
-  // ---- k and v projections
-  const __nv_bfloat16* Xkv = p.kv_from_norm ? Nt : Xt;
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    __syncthreads();                               // everybody is done with the previous T / Tt
-    {
-      const float* const src[1] = {(which == 0 ? p.dk : p.dv) + (long long)row0 * RS_H};
-      const long long ld[1] = {RS_H};
-      const int nr[1] = {rows};
-      const float sc[1] = {1.f};
-      __nv_bfloat16* const d[1] = {T};
-      __nv_bfloat16* const dT[1] = {nullptr};
-      float* const dF[1] = {nullptr};
-      rs_load<1>(src, ld, nr, sc, d, dT, dF);
-    }
-    __syncthreads();
-    rs_wgrad_rm(T, Xkv, p.gWin + (long long)(1 + which) * RS_H * RS_H, p.gbin + (1 + which) * RS_H);
-    rs_dgrad(D, T, Wt + (1 + which) * RS_TILE, 16 * w);
-  }
-  if (p.kv_from_norm) rs_ln_bwd(D, Xf, stats, p.ln_g, p.gln_g, p.gln_b, rows);      // decoder: q, k, v all come from LN(x)
-  // ---- dx = D (+ dx_extra)
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    const int c = 8 * nb + 2 * t;
-    if (i0 < rows) {
-      float2 o = make_float2(D[nb][0], D[nb][1]);
-      const long long gi = (long long)(row0 + i0) * RS_H + c;
-      if (p.dx_extra) { const float2 e = *reinterpret_cast<const float2*>(p.dx_extra + gi); o.x += e.x; o.y += e.y; }
-      *reinterpret_cast<float2*>(p.dx + gi) = o;
-    }
-    if (i1 < rows) {
-      float2 o = make_float2(D[nb][2], D[nb][3]);
-      const long long gi = (long long)(row0 + i1) * RS_H + c;
-      if (p.dx_extra) { const float2 e = *reinterpret_cast<const float2*>(p.dx_extra + gi); o.x += e.x; o.y += e.y; }
-      *reinterpret_cast<float2*>(p.dx + gi) = o;
-    }
-  }
-}
-
 
 __device__ __forceinline__ void rs_load1(const float* src, int rows, float scale, __nv_bfloat16* dst) {
   const float* const s[1] = {src};
@@ -1024,6 +783,97 @@ __global__ void __launch_bounds__(AS_NT) post_bwd_small_kernel(PostBwdArgs p) {
     for (int i = threadIdx.x; i < nh; i += AS_NT) atomicAdd(p.gbsp + i, dbs[i]);
   }
   frag_store(p.dctx + g0, DC, i0, i1, v0, v1, t);
+}
+
+// -------------------------------------------------------------------------------------------------
+// pre_bwd_small2_kernel == pre_bwd_kernel (kernels_bwd.cuh): adjoint of LayerNorm + packed QKV in-projection.  The block input lives in fragments (LayerNorm forward and
+// adjoint without shared memory), all three upstream gradients (dq, dk, dv) are staged as bf16 tiles in the prologue, so the
+// kernel has ONE barrier and no global load on its critical path after the prologue.
+// -------------------------------------------------------------------------------------------------
+struct PreBwdSmall2Smem {
+  static constexpr int W = 0, TQ = 3 * RS_TILE, TK = TQ + RS_TILE, TV = TK + RS_TILE, X = TV + RS_TILE, N = X + RS_TILE;
+  static constexpr size_t TOTAL_BYTES = (size_t)(N + RS_TILE) * 2;
+};
+
+__global__ void __launch_bounds__(AS_NT) pre_bwd_small2_kernel(PreBwdArgs p) {
+  using SM = PreBwdSmall2Smem;
+  extern __shared__ __align__(16) uint8_t rs_raw[];
+  __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(rs_raw);
+  __nv_bfloat16* Wt = hb + SM::W;
+  __nv_bfloat16* Tq = hb + SM::TQ;
+  __nv_bfloat16* Tk = hb + SM::TK;
+  __nv_bfloat16* Tv = hb + SM::TV;
+  __nv_bfloat16* Xb = hb + SM::X;
+  __nv_bfloat16* Nb = hb + SM::N;
+  const int row0 = blockIdx.x * 64;
+  const int rows = min(64, p.M - row0);
+  const long long g0 = (long long)row0 * RS_H;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int i0 = 16 * w + g, i1 = i0 + 8;
+  const bool v0 = i0 < rows, v1 = i1 < rows;
+  {
+    const float* const src[3] = {p.dq + g0, p.dk + g0, p.dv + g0};
+    const long long ld[3] = {RS_H, RS_H, RS_H};
+    const int nr[3] = {rows, rows, rows};
+    const float sc[3] = {p.qscale, 1.f, 1.f};
+    __nv_bfloat16* const d[3] = {Tq, Tk, Tv};
+    __nv_bfloat16* const dT[3] = {nullptr, nullptr, nullptr};
+    float* const dF[3] = {nullptr, nullptr, nullptr};
+    rs_load<3>(src, ld, nr, sc, d, dT, dF);
+  }
+  {
+    const float* const src[3] = {p.Win, p.Win + RS_H * RS_H, p.Win + 2 * RS_H * RS_H};
+    const long long ld[3] = {RS_H, RS_H, RS_H};
+    const int nr[3] = {64, 64, 64};
+    const float sc[3] = {1.f, 1.f, 1.f};
+    __nv_bfloat16* const d[3] = {Wt, Wt + RS_TILE, Wt + 2 * RS_TILE};
+    __nv_bfloat16* const dT[3] = {nullptr, nullptr, nullptr};
+    float* const dF[3] = {nullptr, nullptr, nullptr};
+    rs_load<3>(src, ld, nr, sc, d, dT, dF);
+  }
+  float Xf[8][4];
+  frag_load(Xf, p.x + g0, i0, i1, v0, v1, t);
+  {
+    float Nf[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { Nf[nb][0] = Xf[nb][0]; Nf[nb][1] = Xf[nb][1]; Nf[nb][2] = Xf[nb][2]; Nf[nb][3] = Xf[nb][3]; }
+    frag_ln(Nf, p.ln_g, p.ln_b, t);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      if (!v0) { Nf[nb][0] = 0.f; Nf[nb][1] = 0.f; }
+      if (!v1) { Nf[nb][2] = 0.f; Nf[nb][3] = 0.f; }
+    }
+    frag_store_tile(Nb, Nf, i0, i1, t);
+    if (!p.kv_from_norm) frag_store_tile(Xb, Xf, i0, i1, t);
+  }
+  __syncthreads();
+  // ---- q projection
+  float D[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) D[nb][0] = D[nb][1] = D[nb][2] = D[nb][3] = 0.f;
+  rs_wgrad_rm(Tq, Nb, p.gWin, p.gbin);
+  rs_dgrad(D, Tq, Wt, 16 * w);
+  if (p.dnorm_extra) {
+    float E[8][4];
+    frag_load(E, p.dnorm_extra + g0, i0, i1, v0, v1, t);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { D[nb][0] += E[nb][0]; D[nb][1] += E[nb][1]; D[nb][2] += E[nb][2]; D[nb][3] += E[nb][3]; }
+  }
+  if (!p.kv_from_norm) frag_ln_bwd(D, Xf, p.ln_g, p.gln_g, p.gln_b, v0, v1, g, t);     // encoder: k, v come from x itself
+  // ---- k and v projections
+  const __nv_bfloat16* Xkv = p.kv_from_norm ? Nb : Xb;
+  rs_wgrad_rm(Tk, Xkv, p.gWin + (long long)RS_H * RS_H, p.gbin + RS_H);
+  rs_dgrad(D, Tk, Wt + RS_TILE, 16 * w);
+  rs_wgrad_rm(Tv, Xkv, p.gWin + 2ll * RS_H * RS_H, p.gbin + 2 * RS_H);
+  rs_dgrad(D, Tv, Wt + 2 * RS_TILE, 16 * w);
+  if (p.kv_from_norm) frag_ln_bwd(D, Xf, p.ln_g, p.gln_g, p.gln_b, v0, v1, g, t);      // decoder: q, k, v all come from LN(x)
+  if (p.dx_extra) {
+    float E[8][4];
+    frag_load(E, p.dx_extra + g0, i0, i1, v0, v1, t);
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) { D[nb][0] += E[nb][0]; D[nb][1] += E[nb][1]; D[nb][2] += E[nb][2]; D[nb][3] += E[nb][3]; }
+  }
+  frag_store(p.dx + g0, D, i0, i1, v0, v1, t);
 }
 
 // -------------------------------------------------------------------------------------------------
