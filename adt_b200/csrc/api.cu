@@ -567,8 +567,9 @@ extern "C" int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t s_) {
   TIMED("embed_bwd", s);
   if (a->d_pos_emb) {
     const int BS = (a->B + 148 * 4 - 1) / (148 * 4), pg = (a->B + BS - 1) / BS;   // sequences per CTA / CTAs
-    if (a->dx_enc) posgrad_kernel<<<pg, NT, 0, s>>>(a->dx_enc, a->seq, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_enc), BS);
-    if (a->dx_dec) posgrad_kernel<<<pg, NT, 0, s>>>(a->dx_dec, a->dec, a->d_pos_emb, a->B, a->L, a->H, mk_drop(a->drop_dec), BS);
+    if (a->dx_enc || a->dx_dec)
+      posgrad_kernel<<<dim3(pg, 2), NT, 0, s>>>(a->dx_enc, a->seq, mk_drop(a->drop_enc), a->dx_dec, a->dec, mk_drop(a->drop_dec), a->d_pos_emb,
+                                                a->B, a->L, a->H, BS);
   }
   ScatterArgs sa;
   memset(&sa, 0, sizeof(sa));

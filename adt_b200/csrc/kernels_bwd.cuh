@@ -620,8 +620,14 @@ __global__ void __launch_bounds__(NT) final_bwd_kernel(FinalBwdArgs p) {
 // One CTA per group of BS sequences: every thread walks the contiguous [L, H] slab of a sequence (fully coalesced 128-bit
 // reads), sums its (t, c4) position over the group in registers, then one vector atomic per position.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) posgrad_kernel(const float* __restrict__ dx, const int* __restrict__ ids, float* __restrict__ gP,
-                                                     int B, int L, int H, DropDesc drop, int BS) {
+__global__ void __launch_bounds__(NT) posgrad_kernel(const float* __restrict__ dx0, const int* __restrict__ ids0, DropDesc drop0,
+                                                     const float* __restrict__ dx1, const int* __restrict__ ids1, DropDesc drop1,
+                                                     float* __restrict__ gP, int B, int L, int H, int BS) {
+  // blockIdx.y selects the lookup (0: encoder sequence, 1: decoder sequence); a null dx skips it
+  const float* dx = blockIdx.y == 0 ? dx0 : dx1;
+  if (!dx) return;
+  const int* ids = blockIdx.y == 0 ? ids0 : ids1;
+  const DropDesc drop = blockIdx.y == 0 ? drop0 : drop1;
   const int h4 = H >> 2, n = L * h4;
   const int b0 = blockIdx.x * BS, b1 = min(B, b0 + BS);
   for (int s = threadIdx.x; s < n; s += NT) {

@@ -64,6 +64,11 @@ class FusedTrainer:
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
             eng.sort_ids(seq, dec, pos, neg, w)
+            if self.use_norm_decay and self.wd != 0.0:
+                # ||E||^2 of the weight-decay term (main.py:170) only depends on the parameters: also beside the forward pass
+                E = self.model.item_emb.weight
+                self._normsq.zero_()
+                L.check(self.lib.adt_sumsq(L.ptr(E), ctypes.c_int64(E.numel()), L.ptr(self._normsq), self._stream()), "adt_sumsq")
         w = eng.forward(seq, dec, pos, neg, training=True, fused_loss=True)
         cur.wait_stream(self.side)
         return w
@@ -80,8 +85,8 @@ class FusedTrainer:
         s = self._stream()
         E = m.item_emb.weight
         if self.use_norm_decay and self.wd != 0.0:
-            normsq = acc[3 + 2 * nl:]
-            L.check(self.lib.adt_sumsq(L.ptr(E), ctypes.c_int64(E.numel()), L.ptr(normsq), s), "adt_sumsq")
+            normsq = self._normsq
+            acc[3 + 2 * nl:4 + 2 * nl].copy_(normsq)      # kept in acc for loss()
             L.check(self.lib.adt_norm_decay_grad(L.ptr(eng.grad_view("item_emb.weight")), L.ptr(E), ctypes.c_int64(E.numel()),
                                                  ctypes.c_float(self.wd), L.ptr(normsq), s), "adt_norm_decay_grad")
         gn = acc[4 + 2 * nl:]
@@ -119,6 +124,7 @@ class FusedTrainer:
             # [0] dropout stream counter (step index of the NEXT step minus one), [1] Adam step count
             self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
             self.side = torch.cuda.Stream(device=dev)
+            self._normsq = torch.zeros(1, dtype=torch.float64, device=dev)
             if self.overlap:
                 eng.side_stream = torch.cuda.Stream(device=dev)
         eng.batch_offset = self.rank * B

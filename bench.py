@@ -232,17 +232,23 @@ def main():
         step_ms = [a.elapsed_time(b) for a, b in evs]
         total_ms = float(sum(step_ms))
         trace("e2e region")
-        # ---- end to end through the public API: pinned host ids in, loss scalar out, every step
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        # ---- end to end through the public API: pinned host ids in, loss scalar out, every step.  Every step synchronises with
+        # the host (loss read-back), so one scheduler hiccup on the box moves a K-step sum by >10 %: the K-step region is repeated
+        # E2E_REPS times and the MEDIAN repetition is reported.
+        E2E_REPS = 5
+        reps = []
         last_loss = None
-        for k in range(K):
-            tr.step(*host[k % POOL])
-            last_loss = tr.loss()
-        e1.record()
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
+        for _ in range(E2E_REPS):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(K):
+                tr.step(*host[k % POOL])
+                last_loss = tr.loss()
+            e1.record()
+            barrier()
+            reps.append(e0.elapsed_time(e1))
+        e2e_ms = float(np.median(reps))
     clocks = clk.summary()
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -365,7 +371,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args, cfg),
                        "parallelism": f"dp{world}", "global_batch": world * B, "l2": "flushed between timed steps (256 MB write)",
-                       "timing": "per-step CUDA events on the launch stream, max over ranks", "launch": "whole step replayed as one CUDA graph"},
+                       "timing": "per-step CUDA events on the launch stream, max over ranks", "launch": "whole step replayed as one CUDA graph",
+                       "e2e_timing": "median of 5 repetitions of the K-step region (each step: pinned H2D of the ids + loss read-back)"},
             "e2e": {"value": e2e_value, "unit": "seqs/s", "h2d_bytes_per_step": 4 * B * Lq * 4, "d2h_bytes_per_step": 8 * (8 + 2 * nl),
                     "ms_per_step": e2e_ms / K},
             "gpu_launches": int(round(launches_per_step * K)),
