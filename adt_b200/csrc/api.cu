@@ -593,6 +593,15 @@ extern "C" int adt_sumsq(const float* x, int64_t n, double* out, adt_stream_t s_
   return check_launch("adt_sumsq");
 }
 
+extern "C" int adt_sumsq_decay(float* g, const float* w, int64_t n, int64_t decay_off, float wd, const double* normsq, double* out,
+                               adt_stream_t s_) {
+  if (decay_off & 3) return fail(ADT_E_ALIGN, "%s", "sumsq_decay: decay_off must be a multiple of 4");
+  const int grid = (int)((n / 4 + 255) / 256 < 148 * 8 ? ((n / 4 + 255) / 256 > 0 ? (n / 4 + 255) / 256 : 1) : 148 * 8);
+  TIMED("sumsq", (cudaStream_t)s_);
+  sumsq_decay_kernel<<<grid, 256, 0, (cudaStream_t)s_>>>(g, w, (long long)n, (long long)decay_off, wd, normsq, out);
+  return check_launch("adt_sumsq_decay");
+}
+
 extern "C" int adt_norm_decay_grad(float* g, const float* w, int64_t n, float wd, const double* normsq, adt_stream_t s_) {
   const long long blocks = (n + 255) / 256;
   norm_decay_grad_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(g, w, (long long)n, wd, normsq);

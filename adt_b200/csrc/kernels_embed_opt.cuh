@@ -343,6 +343,32 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   cta_accumulate(s, out, red);
 }
 
+// fused: g[i] += (wd / sqrt(*normsq)) * w[i] for i >= decay_off (gradient of wd*||W||_F on the trailing table segment, main.py:170),
+// then out += sum g^2 over the whole buffer (clip_grad_norm_'s total norm).  decay_off is a multiple of 4.
+__global__ void __launch_bounds__(256) sumsq_decay_kernel(float* __restrict__ g, const float* __restrict__ w, long long n, long long decay_off,
+                                                          float wd, const double* __restrict__ normsq, double* __restrict__ out) {
+  __shared__ double red[8];
+  const float coef = wd / (float)sqrt(*normsq);
+  double s = 0.0;
+  const long long n4 = n >> 2, d4 = decay_off >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(g)[i];
+    if (i >= d4) {
+      const float4 p = reinterpret_cast<const float4*>(w)[i];
+      v = make_float4(fmaf(coef, p.x, v.x), fmaf(coef, p.y, v.y), fmaf(coef, p.z, v.z), fmaf(coef, p.w, v.w));
+      reinterpret_cast<float4*>(g)[i] = v;
+    }
+    s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float x = g[i];
+      if (i >= decay_off) { x = fmaf(coef, w[i], x); g[i] = x; }
+      s += (double)x * (double)x;
+    }
+  cta_accumulate(s, out, red);
+}
+
 // g += (wd / sqrt(*normsq)) * w     -- gradient of wd*||W||_F  (main.py:170)
 __global__ void __launch_bounds__(256) norm_decay_grad_kernel(float* __restrict__ g, const float* __restrict__ w, long long n, float wd,
                                                               const double* __restrict__ normsq) {

@@ -84,14 +84,14 @@ class FusedTrainer:
         acc = w["acc"]
         s = self._stream()
         E = m.item_emb.weight
-        if self.use_norm_decay and self.wd != 0.0:
-            normsq = self._normsq
-            acc[3 + 2 * nl:4 + 2 * nl].copy_(normsq)      # kept in acc for loss()
-            L.check(self.lib.adt_norm_decay_grad(L.ptr(eng.grad_view("item_emb.weight")), L.ptr(E), ctypes.c_int64(E.numel()),
-                                                 ctypes.c_float(self.wd), L.ptr(normsq), s), "adt_norm_decay_grad")
         gn = acc[4 + 2 * nl:]
         n = eng.gflat.numel()
-        L.check(self.lib.adt_sumsq(L.ptr(eng.gflat), ctypes.c_int64(n), L.ptr(gn), s), "adt_sumsq")
+        if self.use_norm_decay and self.wd != 0.0:
+            # wd * E / ||E|| into the table segment of the flat gradient and the global gradient norm, in ONE pass
+            L.check(self.lib.adt_sumsq_decay(L.ptr(eng.gflat), L.ptr(eng.pflat), ctypes.c_int64(n), ctypes.c_int64(eng.table_off),
+                                             ctypes.c_float(self.wd), L.ptr(self._normsq), L.ptr(gn), s), "adt_sumsq_decay")
+        else:
+            L.check(self.lib.adt_sumsq(L.ptr(eng.gflat), ctypes.c_int64(n), L.ptr(gn), s), "adt_sumsq")
         a = L.fill(L.adt_adam_args(), p=eng.pflat, g=eng.gflat, m=eng.adam_m, v=eng.adam_v, n=n, lr=self.lr, beta1=self.betas[0],
                    beta2=self.betas[1], eps=self.eps, weight_decay=self.adam_wd, step=0, max_norm=self.clip, gnormsq=gn,
                    step_dev=self.step_dev[1:])
@@ -210,8 +210,14 @@ class FusedTrainer:
         if h is None or h.numel() != a.numel():
             h = self._acc_host = torch.empty(a.numel(), dtype=a.dtype).pin_memory()
         h.copy_(a, non_blocking=True)
+        hn = getattr(self, "_normsq_host", None)
+        if hn is None:
+            hn = self._normsq_host = torch.empty(1, dtype=torch.float64).pin_memory()
+        hn.copy_(self._normsq, non_blocking=True)       # ||E||^2 lives in its own buffer (computed beside the forward pass)
         torch.cuda.current_stream(a.device).synchronize()
-        return h.tolist()
+        out = h.tolist()
+        out[3 + 2 * self.model.num_layers] = float(hn[0])
+        return out
 
     def grad_norm(self):
         return float(np.sqrt(self._read_acc(self._w)[4 + 2 * self.model.num_layers]))

@@ -171,6 +171,9 @@ int adt_embed_bwd(const adt_embed_bwd_args* a, adt_stream_t stream);
 /* K6. optimiser pieces -- sasrec/main.py:170-173 (wd*||E||, clip_grad_norm_, Adam). */
 int adt_sumsq(const float* x, int64_t n, double* out /* += */, adt_stream_t stream);
 int adt_norm_decay_grad(float* g, const float* w, int64_t n, float wd, const double* normsq, adt_stream_t stream);
+/* the two above in one pass over the FLAT gradient / parameter buffers: g[i] += wd/sqrt(*normsq) * w[i] for i >= decay_off (the item
+ * table is the trailing segment), then *out += sum g^2 over all n elements.  decay_off % 4 == 0. */
+int adt_sumsq_decay(float* g, const float* w, int64_t n, int64_t decay_off, float wd, const double* normsq, double* out, adt_stream_t stream);
 typedef struct {
   float* p; float* g; float* m; float* v; int64_t n;
   float lr, beta1, beta2, eps, weight_decay; int32_t step; float max_norm; const double* gnormsq;
