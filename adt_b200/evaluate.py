@@ -84,8 +84,9 @@ class CatalogScorer:
         self._tab = (tab, mx)
 
     @torch.no_grad()
-    def _topk_tc(self, feats, ip, ix, lo, hi):
-        """tensor-core path: tcgen05 candidate generation + exact fp32 re-score; exact-kernel fallback for flagged users."""
+    def _tc_launch(self, feats, ip, ix, lo, hi):
+        """tensor-core path, device side: tcgen05 candidate generation + exact fp32 re-score.  No host synchronisation
+        (capturable); users whose bf16 bound was inconclusive are marked in `flags` for _tc_fixup."""
         dev = feats.device
         U, H = feats.shape
         E = self.model.item_emb.weight
@@ -109,6 +110,12 @@ class CatalogScorer:
                    item_offset=lo, max_normsq=mx, seen_indptr=ip, seen_idx=ix, K=K, KC=KC, n_splits=S, part_scores=ps, part_ids=pi,
                    part_thr=pt, out_scores=os_, out_ids=oi, flags=flags)
         L.check(self.lib.adt_score_topk_tc(ctypes.byref(a), st), "adt_score_topk_tc")
+        return os_, oi, flags
+
+    @torch.no_grad()
+    def _tc_fixup(self, feats, ip, ix, lo, hi, os_, oi, flags):
+        """host side of the tensor-core path: re-run flagged users on the exact fp32 kernel (reads `flags`: synchronises)."""
+        dev = feats.device
         bad = torch.nonzero(flags, as_tuple=False).flatten()
         if bad.numel():
             self.fallback_users += int(bad.numel())
@@ -125,26 +132,33 @@ class CatalogScorer:
             oi[bad] = ei
         return os_, oi
 
+    def _uses_tc(self, H, lo, hi):
+        return self.use_tc and H % 64 == 0 and (hi - lo) >= self.tc_min_items
+
     @torch.no_grad()
-    def topk_from_feats(self, feats, seen_indptr=None, seen_idx=None):
-        m = self.model
-        dev = feats.device
-        U, H = feats.shape
-        E = m.item_emb.weight
-        lo, hi = shard_bounds(E.shape[0], self.world, self.rank)
-        ip = _as_ids(seen_indptr, dev) if seen_indptr is not None else None
-        ix = _as_ids(seen_idx, dev) if seen_idx is not None else None
-        if self.use_tc and H % 64 == 0 and (hi - lo) >= self.tc_min_items:
-            os_, oi = self._topk_tc(feats, ip, ix, lo, hi)
-        else:
-            os_, oi = self._topk_exact(feats, ip, ix, lo, hi)
+    def _merge(self, os_, oi):
+        """item-sharded mode: all-gather the per-shard lists and merge them on every rank."""
         if self.world == 1:
             return os_, oi
-        gs = torch.empty(self.world, U, self.K, device=dev)
-        gi = torch.empty(self.world, U, self.K, dtype=torch.int32, device=dev)
+        U = os_.shape[0]
+        gs = torch.empty(self.world, U, self.K, device=os_.device)
+        gi = torch.empty(self.world, U, self.K, dtype=torch.int32, device=os_.device)
         torch.distributed.all_gather_into_tensor(gs, os_.contiguous(), group=self.pg)
         torch.distributed.all_gather_into_tensor(gi, oi.contiguous(), group=self.pg)
         return merge_topk(gs, gi, self.K)
+
+    @torch.no_grad()
+    def topk_from_feats(self, feats, seen_indptr=None, seen_idx=None):
+        dev = feats.device
+        U, H = feats.shape
+        lo, hi = shard_bounds(self.model.item_emb.weight.shape[0], self.world, self.rank)
+        ip = _as_ids(seen_indptr, dev) if seen_indptr is not None else None
+        ix = _as_ids(seen_idx, dev) if seen_idx is not None else None
+        if self._uses_tc(H, lo, hi):
+            os_, oi = self._tc_fixup(feats, ip, ix, lo, hi, *self._tc_launch(feats, ip, ix, lo, hi))
+        else:
+            os_, oi = self._topk_exact(feats, ip, ix, lo, hi)
+        return self._merge(os_, oi)
 
     @torch.no_grad()
     def _topk_exact(self, feats, ip, ix, lo, hi):
@@ -160,6 +174,61 @@ class CatalogScorer:
                    seen_indptr=ip, seen_idx=ix, K=self.K, n_splits=S, part_scores=ps, part_ids=pi, out_scores=os_, out_ids=oi)
         L.check(self.lib.adt_score_topk(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "adt_score_topk")
         return os_, oi
+
+
+class GraphedScorer:
+    """Fixed-shape evaluation batch (U users x L positions, seen-set CSR of at most `max_seen` ids) replayed as ONE CUDA
+    graph: encoder forward + catalog scoring + fused top-K.  Per batch the host only copies the ids into the static
+    buffers and replays; the exact-kernel fix-up of the tensor-core path and the item-shard merge stay outside the graph
+    (one reads a device flag on the host, the other is a collective)."""
+
+    def __init__(self, scorer, U, L_, max_seen):
+        self.sc = scorer
+        m = scorer.model
+        dev = m.item_emb.weight.device
+        self.U, self.L = int(U), int(L_)
+        self.seq = torch.zeros(U, L_, dtype=torch.int32, device=dev)
+        self.ip = torch.zeros(U + 1, dtype=torch.int32, device=dev)
+        self.ix = torch.zeros(max(1, int(max_seen)), dtype=torch.int32, device=dev)
+        self.lo, self.hi = shard_bounds(m.item_emb.weight.shape[0], scorer.world, scorer.rank)
+        self.tc = scorer._uses_tc(m.hidden, self.lo, self.hi)
+        if self.tc:
+            scorer.refresh_table()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up outside capture (lazy allocations, cudaFuncSetAttribute)
+            for _ in range(2):
+                self._device_part()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._device_part()
+
+    @torch.no_grad()
+    def _device_part(self):
+        self.feats = self.sc.model.final_feats(self.seq)
+        if self.tc:
+            return self.sc._tc_launch(self.feats, self.ip, self.ix, self.lo, self.hi)
+        return self.sc._topk_exact(self.feats, self.ip, self.ix, self.lo, self.hi)
+
+    @torch.no_grad()
+    def topk(self, log_seqs, seen_indptr, seen_idx):
+        """same contract as CatalogScorer.topk for a [U, L] batch; the returned tensors are overwritten by the next call."""
+        def src(a):   # host numpy or torch tensor (any device) -> int32 tensor that copy_ can read
+            return a.to(torch.int32) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32))
+        seq, ip, ix = src(log_seqs), src(seen_indptr), src(seen_idx)
+        if tuple(seq.shape) != (self.U, self.L) or ip.numel() != self.U + 1 or ix.numel() > self.ix.numel():
+            raise ValueError(f"GraphedScorer was built for [{self.U},{self.L}] batches with at most {self.ix.numel()} seen ids")
+        self.seq.copy_(seq, non_blocking=True)
+        self.ip.copy_(ip, non_blocking=True)
+        self.ix[:ix.numel()].copy_(ix, non_blocking=True)
+        self.graph.replay()
+        if self.tc:
+            os_, oi = self.sc._tc_fixup(self.feats, self.ip, self.ix, self.lo, self.hi, *self.out)
+        else:
+            os_, oi = self.out
+        return self.sc._merge(os_, oi)
 
 
 def hit_ndcg_mrr(answers, topk_ids, ks=(5, 10)):

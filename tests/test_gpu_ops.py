@@ -163,6 +163,32 @@ def test_full_c2_shape_properties():
     assert np.allclose(np.take_along_axis(full, ids.astype(np.int64), axis=1), s, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_graphed_eval_matches_eager(use_tc):
+    """the evaluation batch replayed as one CUDA graph (static id buffers, seen-set CSR of varying size) must return
+    exactly the ids and scores of the eager path, batch after batch, on both the exact and the tensor-core scorer."""
+    import types
+    from adt_b200 import synth
+    from adt_b200.model import SASRecADT
+    from adt_b200.evaluate import CatalogScorer, GraphedScorer
+    cfg = synth.CONFIGS["C2"]
+    torch.manual_seed(3)
+    args = types.SimpleNamespace(device="cuda", num_heads=cfg["nh"], maxlen=cfg["L"], num_layers=cfg["nl"], hidden_units=cfg["H"], dropout=cfg["p"])
+    m = SASRecADT(1, cfg["items"], args).cuda().eval()
+    rng = np.random.default_rng(5)
+    U = 200
+    batches = [synth.make_eval_batch(rng, cfg, U) for _ in range(3)]
+    sc = CatalogScorer(m, K=10, use_tensor_cores=use_tc, tc_min_items=0)
+    gs = GraphedScorer(sc, U, cfg["L"], max_seen=max(len(b[3]) for b in batches))
+    for seq, _, ip, ix in batches + batches[:1]:
+        s_e, i_e = [t.clone() for t in sc.topk(seq, ip, ix)]
+        s_g, i_g = gs.topk(seq, ip, ix)
+        assert torch.equal(i_e, i_g)
+        assert torch.equal(s_e, s_g)
+    with pytest.raises(ValueError):
+        gs.topk(batches[0][0][:10], batches[0][2][:11], batches[0][3])
+
+
 def test_cuda_graph_step_matches_eager():
     """the captured-graph step (device-side dropout/Adam counters) must reproduce the eager step exactly up to the
     fp32 atomics of the weight gradients."""
