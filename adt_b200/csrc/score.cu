@@ -25,16 +25,20 @@ struct TopkArgs {
   int U, H, n_items, item_offset, K, n_splits;
 };
 
-__device__ __forceinline__ bool is_seen(const TopkArgs& a, int u, int item) {
-  if (!a.seen_indptr) return false;
-  int lo = a.seen_indptr[u], hi = a.seen_indptr[u + 1];
+// first position p in [lo, hi) of the sorted id list with idx[p] >= item
+__device__ __forceinline__ int seen_lower_bound(const int* __restrict__ idx, int lo, int hi, int item) {
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    const int v = a.seen_idx[mid];
-    if (v == item) return true;
-    if (v < item) lo = mid + 1; else hi = mid;
+    if (idx[mid] < item) lo = mid + 1; else hi = mid;
   }
-  return false;
+  return lo;
+}
+// [sb, se) = the part of the user's sorted seen list that falls into this CTA's catalog split (found once per CTA): for
+// most (user, split) pairs it is empty and the test costs no memory access at all
+__device__ __forceinline__ bool is_seen(const TopkArgs& a, int sb, int se, int item) {
+  if (sb >= se) return false;
+  const int p = seen_lower_bound(a.seen_idx, sb, se, item);
+  return p < se && a.seen_idx[p] == item;
 }
 
 // better(a,b): a ranks strictly before b  (score desc, then id asc -- deterministic under exact ties)
@@ -50,6 +54,8 @@ __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
   float* Ls = Ws + WS_FLOATS;             // [UT][K] scores
   int* Li = reinterpret_cast<int*>(Ls + UT * K);   // [UT][K] ids
   int* Ln = Li + UT * K;                  // [UT] fill counts
+  int* Sb = Ln + UT;                      // [UT] seen-list range of this split
+  int* Se = Sb + UT;
   const int split = blockIdx.x, u0 = blockIdx.y * UT;
   const int per = (a.n_items + a.n_splits - 1) / a.n_splits;
   const int it0 = split * per, it1 = min(a.n_items, it0 + per);
@@ -57,7 +63,17 @@ __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 
   load_tile<UT>(Fs, ld, a.feats, H, 0, H, u0, a.U);
-  for (int i = threadIdx.x; i < UT; i += NT) Ln[i] = 0;
+  for (int i = threadIdx.x; i < UT; i += NT) {
+    Ln[i] = 0;
+    int sb = 0, se = 0;
+    if (a.seen_indptr && u0 + i < a.U) {
+      const int hi = a.seen_indptr[u0 + i + 1];
+      sb = seen_lower_bound(a.seen_idx, a.seen_indptr[u0 + i], hi, a.item_offset + it0);
+      se = seen_lower_bound(a.seen_idx, sb, hi, a.item_offset + it1);
+    }
+    Sb[i] = sb;
+    Se[i] = se;
+  }
   __syncthreads();
 
   const int nrc = (H + CH - 1) / CH;
@@ -84,44 +100,47 @@ __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(Sc + (ty + 16 * i) * CHP + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     __syncthreads();
-    // selection: warp per user row, threshold filter, serial insert (rare once the list is warm)
+    // selection: warp per user row.  Lanes filter their two columns against the row's K-th best (and the seen list); the
+    // survivors are merged into the sorted list IN PARALLEL by rank counting -- every survivor and every list entry
+    // computes its position in the merged order ((score desc, id asc) is a strict total order, so positions are unique)
+    // and writes itself there.  Cost per merge ~ (#survivors + K) short steps instead of #survivors serial insertions,
+    // which matters because a split of a small catalog never gets a warm list.
     for (int r = w; r < UT; r += NT / 32) {
       const int u = u0 + r;
       if (u >= a.U) continue;
       float* ls = Ls + r * K;
       int* li = Li + r * K;
-#pragma unroll
+      const int sb = Sb[r], se = Se[r];
+#pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int col = l + 32 * half;
         const float s = Sc[r * CHP + col];
         const int item = a.item_offset + c0 + col;
-        int n = Ln[r];
-        const float thr_s = n == K ? ls[K - 1] : -INFINITY;
-        const int thr_i = n == K ? li[K - 1] : 0x7fffffff;
-        bool cand = col < ncols && (n < K || better(s, item, thr_s, thr_i));
-        unsigned ballot = __ballot_sync(0xffffffffu, cand);
-        while (ballot) {
-          const int src = __ffs(ballot) - 1;
-          ballot &= ballot - 1;
+        const int n = Ln[r];
+        const bool cand = col < ncols && (n < K || better(s, item, ls[K - 1], li[K - 1])) && !is_seen(a, sb, se, item);
+        const unsigned ballot = __ballot_sync(0xffffffffu, cand);
+        if (ballot == 0u) continue;
+        // this lane's list entries (K <= 64: slots l and l + 32), read before anything is overwritten
+        const bool h0 = l < n, h1 = l + 32 < n;
+        const float e0s = h0 ? ls[l] : 0.f, e1s = h1 ? ls[l + 32] : 0.f;
+        const int e0i = h0 ? li[l] : 0, e1i = h1 ? li[l + 32] : 0;
+        int pc = 0, p0 = l, p1 = l + 32;      // merged positions of: my survivor, my two list entries
+        for (unsigned b = ballot; b; b &= b - 1) {
+          const int src = __ffs(b) - 1;
           const float cs = __shfl_sync(0xffffffffu, s, src);
           const int ci = __shfl_sync(0xffffffffu, item, src);
-          if (l == 0) {
-            n = Ln[r];
-            const bool ok = (n < K || better(cs, ci, ls[K - 1], li[K - 1])) && !is_seen(a, u, ci);
-            if (ok) {
-              int p = n < K ? n : K - 1;
-              while (p > 0 && better(cs, ci, ls[p - 1], li[p - 1])) {
-                ls[p] = ls[p - 1];
-                li[p] = li[p - 1];
-                --p;
-              }
-              ls[p] = cs;
-              li[p] = ci;
-              if (n < K) Ln[r] = n + 1;
-            }
-          }
-          __syncwarp();
+          pc += better(cs, ci, s, item) ? 1 : 0;
+          p0 += better(cs, ci, e0s, e0i) ? 1 : 0;
+          p1 += better(cs, ci, e1s, e1i) ? 1 : 0;
         }
+        if (cand)
+          for (int j = 0; j < n; ++j) pc += better(ls[j], li[j], s, item) ? 1 : 0;   // same address in all lanes: broadcast
+        __syncwarp();
+        if (h0 && p0 < K) { ls[p0] = e0s; li[p0] = e0i; }
+        if (h1 && p1 < K) { ls[p1] = e1s; li[p1] = e1i; }
+        if (cand && pc < K) { ls[pc] = s; li[pc] = item; }
+        if (l == 0) Ln[r] = min(K, n + __popc(ballot));
+        __syncwarp();
       }
     }
     __syncthreads();
@@ -191,7 +210,7 @@ extern "C" int adt_score_topk(const adt_score_topk_args* a, adt_stream_t s_) {
   k.feats = a->feats; k.E = a->item_emb; k.seen_indptr = a->seen_indptr; k.seen_idx = a->seen_idx;
   k.part_scores = a->part_scores; k.part_ids = a->part_ids; k.out_scores = a->out_scores; k.out_ids = a->out_ids;
   k.U = a->U; k.H = a->H; k.n_items = a->n_items; k.item_offset = a->item_offset; k.K = a->K; k.n_splits = a->n_splits;
-  const size_t smem = ((size_t)UT * (a->H + 4) + (size_t)UT * CHP + WS_FLOATS + (size_t)UT * a->K * 2 + UT) * sizeof(float);
+  const size_t smem = ((size_t)UT * (a->H + 4) + (size_t)UT * CHP + WS_FLOATS + (size_t)UT * a->K * 2 + 3 * UT) * sizeof(float);
   cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(a->n_splits, (a->U + UT - 1) / UT);
   score_topk_kernel<<<grid, NT, smem, s>>>(k);

@@ -35,16 +35,19 @@ struct TcArgs {
   int U, n_items, item_offset, KC, n_splits, debug;
 };
 
-__device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int u, int item) {
-  if (!a.seen_indptr) return false;
-  int lo = a.seen_indptr[u], hi = a.seen_indptr[u + 1];
+// first position p in [lo, hi) of the sorted id list with idx[p] >= item
+__device__ __forceinline__ int tc_seen_lower_bound(const int* __restrict__ idx, int lo, int hi, int item) {
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    const int v = a.seen_idx[mid];
-    if (v == item) return true;
-    if (v < item) lo = mid + 1; else hi = mid;
+    if (idx[mid] < item) lo = mid + 1; else hi = mid;
   }
-  return false;
+  return lo;
+}
+// [sb, se): the part of the user's sorted seen list inside this CTA's catalog split, found once per row; usually empty
+__device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int sb, int se, int item) {
+  if (sb >= se) return false;
+  const int p = tc_seen_lower_bound(a.seen_idx, sb, se, item);
+  return p < se && a.seen_idx[p] == item;
 }
 
 // NS = depth of the TMA ring of catalog tiles (B operand); accumulators are double buffered in TMEM
@@ -141,6 +144,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       lk[k * BM + row] = 0u;                 // key 0 = "worse than anything"
       li[k * BM + row] = -1;
     }
+    int sb = 0, se = 0;                      // this row's seen ids inside [it0, it1)
+    if (a.seen_indptr && u < a.U) {
+      const int hi = a.seen_indptr[u + 1];
+      sb = tc_seen_lower_bound(a.seen_idx, a.seen_indptr[u], hi, a.item_offset + it0);
+      se = tc_seen_lower_bound(a.seen_idx, sb, hi, a.item_offset + it1);
+    }
     uint32_t mink = 0u;                      // smallest key in the list and its slot
     int minpos = 0;
     // rej: keys <= rej cannot be among the K' best of the WHOLE catalog: max of this split's K'-th best (mink) and the best
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       const uint32_t key = fkey(sc);
       if (key <= rej) return;
       const int item = a.item_offset + itl;
-      if (tc_is_seen(a, u, item)) return;
+      if (tc_is_seen(a, sb, se, item)) return;
       lk[minpos * BM + row] = key;
       li[minpos * BM + row] = item;
       uint32_t nm = 0xffffffffu;
