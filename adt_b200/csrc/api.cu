@@ -313,9 +313,13 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
-  if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, a->precision, s)) return e;
-  if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))
-    return e;
+  if (a->phase < 0 || a->phase > 2) return fail(ADT_E_SHAPE, "%s", "enc_block_fwd: phase must be 0, 1 or 2");
+  if (a->phase != 2) {
+    if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, a->precision, s)) return e;
+    if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))
+      return e;
+    if (a->phase == 1) return ADT_OK;
+  }
   PostFwdArgs p;
   memset(&p, 0, sizeof(p));
   p.ctx = a->ctx; p.resid = a->x; p.ids = a->ids; p.Wo = a->attn.out_w; p.bo = a->attn.out_b;

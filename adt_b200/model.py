@@ -211,8 +211,9 @@ class Engine:
                    drop=self._drop(site, "row", training, B, Lq))
         L.check(self.lib.adt_embed_fwd(L.ctypes.byref(a), self._stream()), "adt_embed_fwd")
 
-    def encode(self, seq, training, w, nll=False):
-        """embedding + encoder blocks (+ last LayerNorm into w['feats'] when pos is None handled by caller)."""
+    def encode(self, seq, training, w, nll=False, last_phase=0):
+        """embedding + encoder blocks (+ last LayerNorm into w['feats'] when pos is None handled by caller).
+        last_phase=1 stops the LAST block after its attention (see encode_last)."""
         m = self.m
         B, Lq = w["B"], w["L"]
         sites = self._sites()
@@ -220,7 +221,7 @@ class Engine:
         for l, layer in enumerate(m.encoder.encoder_layers):
             sv = w["enc"][l]
             sa, s1, s2 = sites[("enc", l)]
-            a = L.fill(L.adt_enc_block_fwd_args(), x=w["x"][l], ids=seq,
+            a = L.fill(L.adt_enc_block_fwd_args(), x=w["x"][l], ids=seq, phase=(last_phase if l == m.num_layers - 1 else 0),
                        ln1_w=layer.attention_layernorm.weight, ln1_b=layer.attention_layernorm.bias, attn=_mha_w(layer.attention_layer),
                        ln2_w=layer.forward_layernorm.weight, ln2_b=layer.forward_layernorm.bias, ffn=_ffn_w(layer.forward_layer),
                        sparse_w=layer.sparse.weight, sparse_b=layer.sparse.bias,
@@ -231,6 +232,32 @@ class Engine:
                        drop_attn=self._drop(sa, "attn", training, B, Lq), drop_ffn1=self._drop(s1, "row", training, B, Lq),
                        drop_ffn2=self._drop(s2, "row", training, B, Lq))
             L.check(self.lib.adt_enc_block_fwd(L.ctypes.byref(a), self._stream()), "adt_enc_block_fwd")
+
+    def encode_last(self, seq, w):
+        """eval-mode encoder + last LayerNorm for the LAST position of every sequence only (model.py:86-89 reads
+        log_feats[:, -1, :]).  Blocks 0..nl-2 run in full; the last block still projects and attends over all rows (its
+        keys/values are needed), but its row-wise tail (out-projection, residual, LayerNorms, FFN, pad mask) and the final
+        LayerNorm run on the B last rows instead of B*L.  Returns feats [B, H] (a workspace buffer)."""
+        m = self.m
+        B, Lq, H, nl = w["B"], w["L"], m.hidden, m.num_layers
+        self.encode(seq, False, w, last_phase=1)
+        ws = self.workspace(B, 1)
+        layer, sv, svs = m.encoder.encoder_layers[nl - 1], w["enc"][nl - 1], ws["enc"][nl - 1]
+        ws["x"][nl - 1].copy_(w["x"][nl - 1].view(B, Lq, H)[:, Lq - 1])      # strided gathers of the last position
+        svs["ctx"].copy_(sv["ctx"].view(B, Lq, H)[:, Lq - 1])
+        ids_last = seq[:, Lq - 1].contiguous()
+        nodrop = self._drop(0, "row", False, B, 1)
+        a = L.fill(L.adt_enc_block_fwd_args(), x=ws["x"][nl - 1], ids=ids_last, phase=2,
+                   ln1_w=layer.attention_layernorm.weight, ln1_b=layer.attention_layernorm.bias, attn=_mha_w(layer.attention_layer),
+                   ln2_w=layer.forward_layernorm.weight, ln2_b=layer.forward_layernorm.bias, ffn=_ffn_w(layer.forward_layer),
+                   sparse_w=layer.sparse.weight, sparse_b=layer.sparse.bias,
+                   q=svs["q"], k=svs["k"], v=svs["v"], ctx=svs["ctx"], lse=svs["lse"], y=svs["y"], h1=svs["h1"],
+                   out=ws["x"][nl], rec=svs["rec"], nll_acc=None,
+                   B=B, L=1, H=H, nh=m.num_heads, training=0, mask_mode=0, precision=self.precision,
+                   drop_attn=nodrop, drop_ffn1=nodrop, drop_ffn2=nodrop)
+        L.check(self.lib.adt_enc_block_fwd(L.ctypes.byref(a), self._stream()), "adt_enc_block_fwd")
+        self.final(ws, None, None, with_loss=False)
+        return ws["feats"]
 
     def final(self, w, pos, neg, with_loss):
         m = self.m
@@ -515,6 +542,8 @@ class SASRecADT(nn.Module):
         eng = self.engine
         B, Lq = seq.shape
         w = eng.workspace(B, Lq)
+        if Lq > 1 and self.num_layers >= 1:
+            return eng.encode_last(seq, w).clone()
         eng.encode(seq, False, w)
         eng.final(w, None, None, with_loss=False)
         return w["feats"].view(B, Lq, self.hidden)[:, -1, :].contiguous()

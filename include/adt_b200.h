@@ -68,6 +68,10 @@ typedef struct {
   int32_t B, L, H, nh, training, mask_mode;                /* mask_mode 0 causal, 1 key-padding (bidirectional) */
   adt_dropout drop_attn, drop_ffn1, drop_ffn2;
   int32_t precision;                                       /* 0: fp32 FFMA GEMM cores; 1: bf16 tensor-core cores (fp32 accumulate) */
+  int32_t phase;   /* 0: whole block; 1: LN + q/k/v projections + attention only (writes q, k, v, ctx, lse); 2: the rest of the
+                      block from ctx (out-projection, residual, LN, FFN, pad mask).  Phase 2 is row-wise, so it may be called on
+                      a row subset with B = rows, L = 1: predict() reads only the last position (sasrec/model.py:89) and runs
+                      the tail of the LAST block on those rows only */
 } adt_enc_block_fwd_args;
 int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t stream);
 
