@@ -24,6 +24,33 @@ def test_header_parses_and_library_exports_every_symbol():
     assert [n for n, _ in d._fields_] == ["enabled", "p", "seed", "step", "site", "base", "step_dev"]
 
 
+def test_ctypes_mirrors_match_the_c_struct_layouts(tmp_path):
+    """the Python side generates its ctypes.Structure classes from include/adt_b200.h; compile the same header with gcc
+    and compare sizeof / offsetof of EVERY field, so that a header edit can never silently shift the boundary."""
+    import ctypes
+    import subprocess
+    from adt_b200 import _lib
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{_lib.HEADER}"', 'int main(void) {']
+    for name, cls in _lib.STRUCTS.items():
+        lines.append(f'  printf("{name} . %zu\\n", sizeof({name}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{name} {fname} %zu\\n", offsetof({name}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in filter(None, out):
+        name, fname, val = ln.split()
+        cls = _lib.STRUCTS[name]
+        mine = ctypes.sizeof(cls) if fname == "." else getattr(cls, fname).offset
+        assert mine == int(val), (name, fname, mine, int(val))
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in _lib.STRUCTS.values()) and seen > 300
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_state_dict_matches_reference_names_and_shapes(name):
     """drop-in contract: reference checkpoints load into our module and vice versa."""
