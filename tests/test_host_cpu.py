@@ -217,3 +217,29 @@ def test_stosa_surface_on_cpu():
         m.finetune(z["seq"], z["dec"], np.arange(B))
     with pytest.raises(ValueError):      # stosa/modules.py:191-194
         DisenDistSAModel(types.SimpleNamespace(**{**vars(args), "num_heads": 5}))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): rank 0 prints ONE JSON line with the contract's
+    keys on the same workload string as our arm; every other rank exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "0"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    other = subprocess.run(cmd, env={**env, "RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, capture_output=True, text=True, timeout=300)
+    assert other.returncode == 0 and other.stdout.strip() == ""
+    r0 = subprocess.run(cmd, env={**env, "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, capture_output=True, text=True, timeout=600)
+    assert r0.returncode == 0, r0.stderr[-2000:]
+    lines = [ln for ln in r0.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "impl", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "train_seqs_per_sec" and d["unit"] == "seqs/s" and d["n_gpus"] == 2
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
+    assert d["config"]["workload"].startswith("SASRec-ADT C2: train step (items=12101, maxlen=50, hidden=64")
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["e2e"] == {"value": d["value"], "unit": "seqs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
