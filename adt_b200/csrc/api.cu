@@ -170,7 +170,27 @@ static void launch_pdl(void (*kern)(Exp...), dim3 grid, size_t smem, cudaStream_
     else LAUNCH_ONE((KERN<32, FLAG, true>), grid, smem, stream, __VA_ARGS__);                     \
   } while (0)
 
-extern "C" int adt_version(void) { return 100; }
+extern "C" int adt_version(void) { return 200; }
+
+// sizes of every buffer the caller allocates for one training step (the library allocates nothing); see include/adt_b200.h
+extern "C" int adt_workspace_bytes(const adt_workspace_query* q, adt_workspace_sizes* out) {
+  if (!q || !out) return fail(ADT_E_SHAPE, "%s", "workspace_bytes: null argument");
+  if (int e = check_dims(q->B, q->L, q->H, q->nh > 0 ? q->nh : 1)) return e;
+  const long long M = (long long)q->B * q->L, H = q->H, nh = q->nh > 0 ? q->nh : 1, nl = q->nl > 0 ? q->nl : 1, f = sizeof(float);
+  const long long MH = M * H * f, lse = (long long)q->B * nh * q->L * f;
+  // encoder block: q,k,v,ctx,y,h1 + lse + rec ; decoder block: d,q1,k1,v1,ctx1,a,q2,k2,v2,ctx2,c,h1 + 2 lse ; streams x[nl+1], xd[nl+1]
+  out->saved = nl * (6 * MH + lse + M * nh * nh * f) + nl * (12 * MH + 2 * lse) + 2 * (nl + 1) * MH + MH /*feats*/ + 2 * M * f;
+  // backward: dk,dv,dk2,dv2 + 10 row buffers + denc[nl] + 5 side buffers + cpos,cneg
+  out->scratch = 4 * MH + 10 * MH + nl * MH + 5 * MH + 2 * M * f;
+  const long long N = 4 * M;
+  out->sort_keys = 4 * N * (long long)sizeof(int);                       // keys, vals, keys_tmp, vals_tmp
+  out->sort_hist = 256 * ((N + 255) / 256) * (long long)sizeof(int);
+  const long long nb = (N + 31) / 32;
+  out->scatter_rows = 2 * nb * H * f;                                    // head, tail
+  out->scatter_flags = nb * (long long)sizeof(int);
+  out->score_part = (long long)(q->n_splits > 0 ? q->n_splits : 1) * q->B * (q->K > 0 ? q->K : 1) * 8;
+  return ADT_OK;
+}
 extern "C" const char* adt_last_error(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -625,6 +645,26 @@ extern "C" int adt_adam(const adt_adam_args* a, adt_stream_t s_) {
   TIMED("adam", (cudaStream_t)s_);
   adam_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)s_>>>(k);
   return check_launch("adt_adam");
+}
+
+extern "C" int adt_adam_segmented(const adt_adam_args* a, const adt_adam_segments* g, adt_stream_t s_) {
+  if (g->n_chunks <= 0) return ADT_OK;
+  AdamSegArgs k;
+  k.a.p = a->p; k.a.g = a->g; k.a.m = a->m; k.a.v = a->v; k.a.n = a->n;
+  k.a.lr = a->lr; k.a.beta1 = a->beta1; k.a.beta2 = a->beta2; k.a.eps = a->eps; k.a.weight_decay = a->weight_decay;
+  k.a.bc1 = k.a.bc2 = 1.f; k.a.max_norm = a->max_norm; k.a.gnormsq = a->gnormsq; k.a.step_dev = nullptr;
+  k.chunk_start = (const long long*)g->chunk_start; k.chunk_len = g->chunk_len; k.chunk_seg = g->chunk_seg; k.n_chunks = g->n_chunks;
+  k.seg_step = g->seg_step; k.active_seg = g->active_seg; k.n_active = g->n_active;
+  TIMED("adam", (cudaStream_t)s_);
+  if (g->n_active > 0) adam_seg_step_kernel<<<(g->n_active + 255) / 256, 256, 0, (cudaStream_t)s_>>>(k);
+  adam_seg_kernel<<<g->n_chunks < 148 * 8 ? g->n_chunks : 148 * 8, 256, 0, (cudaStream_t)s_>>>(k);
+  return check_launch("adt_adam_segmented");
+}
+
+extern "C" int adt_count_nonzero(const int32_t* ids, int32_t n, double* out, adt_stream_t s_) {
+  cudaMemsetAsync(out, 0, sizeof(double), (cudaStream_t)s_);
+  count_nonzero_kernel<<<min((n + 255) / 256, 148), 256, 0, (cudaStream_t)s_>>>(ids, n, out);
+  return check_launch("adt_count_nonzero");
 }
 
 extern "C" int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t s_) {

@@ -435,6 +435,63 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   }
 }
 
+// ---- segmented Adam: torch.optim.Adam's per-parameter semantics on the flat buffers ------------------------------------
+// torch skips parameters whose .grad is None (no moment decay, no weight decay, no step increment) and keeps one step count
+// PER PARAMETER (sasrec/evolution.py:111,316-318: the supernet only produces gradients for the 4 active candidate blocks of a
+// layer).  Work list: chunk c covers elements [chunk_start[c], chunk_start[c] + chunk_len[c]) of segment chunk_seg[c]; seg_step[s]
+// is that segment's own step count (already incremented for this step by adam_seg_step_kernel).
+struct AdamSegArgs {
+  AdamArgs a;
+  const long long* chunk_start; const int* chunk_len; const int* chunk_seg; int n_chunks;
+  int* seg_step; const int* active_seg; int n_active;
+};
+
+__global__ void adam_seg_step_kernel(AdamSegArgs s) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.n_active; i += gridDim.x * blockDim.x) s.seg_step[s.active_seg[i]] += 1;
+}
+
+__global__ void __launch_bounds__(256) adam_seg_kernel(AdamSegArgs s) {
+  const AdamArgs& a = s.a;
+  float coef = 1.f;
+  if (a.max_norm > 0.f) {
+    const float tn = (float)sqrt(*a.gnormsq);
+    coef = fminf(a.max_norm / (tn + 1e-6f), 1.0f);
+  }
+  const float ob1 = 1.f - a.beta1, ob2 = 1.f - a.beta2;
+  for (int c = blockIdx.x; c < s.n_chunks; c += gridDim.x) {
+    __shared__ float bc_s[2];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double t = (double)s.seg_step[s.chunk_seg[c]];
+      bc_s[0] = (float)(1.0 - pow((double)a.beta1, t));
+      bc_s[1] = (float)(1.0 - pow((double)a.beta2, t));
+    }
+    __syncthreads();
+    const float step = a.lr / bc_s[0];
+    const float isb2 = 1.0f / sqrtf(bc_s[1]);
+    const long long b = s.chunk_start[c];
+    const int n = s.chunk_len[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float g = a.g[b + i] * coef, p = a.p[b + i], m = a.m[b + i], v = a.v[b + i];
+      a.g[b + i] = g;
+      if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+      m = a.beta1 * m + ob1 * g;
+      v = a.beta2 * v + ob2 * g * g;
+      a.m[b + i] = m; a.v[b + i] = v;
+      a.p[b + i] = p - step * (m / (sqrtf(v) * isb2 + a.eps));
+    }
+  }
+}
+
+// out[0] = #{i : ids[i] != 0} as a double (the BCE normaliser of main.py:151-153 only depends on the batch: under data
+// parallelism it is all-reduced beside the forward pass instead of between forward and backward)
+__global__ void __launch_bounds__(256) count_nonzero_kernel(const int* __restrict__ ids, int n, double* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += ids[i] != 0 ? 1.0 : 0.0;
+  cta_accumulate(s, out, red);
+}
+
 // test helper: materialise the dropout keep-multipliers for elements [0, n) of a site
 __global__ void philox_mask_kernel(float* __restrict__ out, long long n, DropDesc d) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

@@ -22,8 +22,24 @@ constexpr int KMAX = 64;
 struct TopkArgs {
   const float* feats; const float* E; const int* seen_indptr; const int* seen_idx;
   float* part_scores; int* part_ids; float* out_scores; int* out_ids;
+  const int* user_mask;                        // optional [U]: only users with a non-zero entry are scored / written
+  const int* answers; double* metric_acc;      // optional fused HR/NDCG/MRR epilogue of the merge kernel
+  long long part_stride;                       // elements between two splits' lists in part_scores / part_ids (merge kernel)
+  float* dense_out; long long dense_ld;        // WRITE_ALL mode: the whole score row [U][dense_ld] (predict(full=True))
   int U, H, n_items, item_offset, K, n_splits;
 };
+
+// get_full_sort_score (sasrec/utils.py:686-708) for ONE held-out answer per user, accumulated over users:
+// acc[0] HIT@5, acc[1] NDCG@5, acc[2] HIT@10, acc[3] NDCG@10, acc[4] MRR (over the returned list), acc[5] #users.
+// `first` = 0-based position of the answer in the user's best-first list, or -1.
+__device__ __forceinline__ void metric_accumulate(double* acc, int first) {
+  atomicAdd(acc + 5, 1.0);
+  if (first < 0) return;
+  const double g = 1.0 / log2((double)first + 2.0);
+  if (first < 5) { atomicAdd(acc + 0, 1.0); atomicAdd(acc + 1, g); }
+  if (first < 10) { atomicAdd(acc + 2, 1.0); atomicAdd(acc + 3, g); }
+  atomicAdd(acc + 4, 1.0 / ((double)first + 1.0));
+}
 
 // first position p in [lo, hi) of the sorted id list with idx[p] >= item
 __device__ __forceinline__ int seen_lower_bound(const int* __restrict__ idx, int lo, int hi, int item) {
@@ -44,6 +60,7 @@ __device__ __forceinline__ bool is_seen(const TopkArgs& a, int sb, int se, int i
 // better(a,b): a ranks strictly before b  (score desc, then id asc -- deterministic under exact ties)
 __device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
 
+template <bool WRITE_ALL>
 __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int H = a.H, K = a.K;
@@ -62,6 +79,11 @@ __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 
+  if (a.user_mask) {     // fix-up launches of the tensor-core path: almost every tile has nothing to do
+    int any = 0;
+    for (int i = threadIdx.x; i < UT; i += NT) any |= (u0 + i < a.U && a.user_mask[u0 + i] != 0) ? 1 : 0;
+    if (!__syncthreads_or(any)) return;
+  }
   load_tile<UT>(Fs, ld, a.feats, H, 0, H, u0, a.U);
   for (int i = threadIdx.x; i < UT; i += NT) {
     Ln[i] = 0;
@@ -100,6 +122,14 @@ __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(Sc + (ty + 16 * i) * CHP + 4 * tx) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     __syncthreads();
+    if constexpr (WRITE_ALL) {     // predict(full=True): the score tile goes straight to HBM, coalesced along the item axis
+      for (int i = threadIdx.x; i < UT * CH; i += NT) {
+        const int r = i / CH, c = i - r * CH;
+        if (u0 + r < a.U && c < ncols) a.dense_out[(long long)(u0 + r) * a.dense_ld + a.item_offset + c0 + c] = Sc[r * CHP + c];
+      }
+      __syncthreads();
+      continue;
+    }
     // selection: warp per user row.  Lanes filter their two columns against the row's K-th best (and the seen list); the
     // survivors are merged into the sorted list IN PARALLEL by rank counting -- every survivor and every list entry
     // computes its position in the merged order ((score desc, id asc) is a strict total order, so positions are unique)
@@ -145,6 +175,7 @@ __global__ void __launch_bounds__(NT) score_topk_kernel(TopkArgs a) {
     }
     __syncthreads();
   }
+  if constexpr (WRITE_ALL) return;
   // write this split's lists (sorted, padded with -inf / -1)
   for (int i = threadIdx.x; i < UT * K; i += NT) {
     const int r = i / K, k = i - r * K;
@@ -162,11 +193,14 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(TopkArgs a) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int u = blockIdx.x * 8 + w;
   if (u >= a.U) return;
+  if (a.user_mask && a.user_mask[u] == 0) return;
   const int K = a.K, S = a.n_splits;
   // lane owns splits l, l+32, ... ; head pointer per owned split (S <= 32*8)
   int hp[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) hp[j] = 0;
+  const int answer = a.answers ? a.answers[u] : -1;
+  int first = -1;
   for (int k = 0; k < K; ++k) {
     float bs = -INFINITY;
     int bi = 0x7fffffff, bj = -1;
@@ -174,7 +208,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(TopkArgs a) {
     for (int j = 0; j < 8; ++j) {
       const int sp = l + 32 * j;
       if (sp < S && hp[j] < K) {
-        const long long o = ((long long)sp * a.U + u) * K + hp[j];
+        const long long o = (long long)sp * a.part_stride + (long long)u * K + hp[j];
         const float s = a.part_scores[o];
         const int id = a.part_ids[o];
         if (id >= 0 && better(s, id, bs, bi)) { bs = s; bi = id; bj = j; }
@@ -196,10 +230,72 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(TopkArgs a) {
     if (l == 0) {
       a.out_scores[(long long)u * K + k] = wl >= 0 ? ws : -INFINITY;
       a.out_ids[(long long)u * K + k] = wl >= 0 ? wi : -1;
+      if (wl >= 0 && wi == answer && first < 0) first = k;
     }
   }
+  if (l == 0 && a.answers && a.metric_acc) metric_accumulate(a.metric_acc, first);
 }
 
+// evaluate_loader's candidate ranking (sasrec/utils.py:407-410) without materialising item_embs [U,C,H] or sorting:
+// scores[u][c] = <feats[u], E[idx[u][c]]> (idx_stride = 0: one candidate list shared by all users, the 1-D `item_idx` of
+// utils.evaluate / evaluate_valid), rank[u] = #{c > 0 : s_c > s_0} = position of column 0 under a stable descending sort.
+// Warp per user; lanes stride over the candidates, 128-bit row loads.
+struct CandArgs {
+  const float* feats; const float* E; const int* idx; float* scores; int* rank; long long idx_stride; int U, H, C, n_rows;
+};
+__global__ void __launch_bounds__(256) candidate_scores_kernel(CandArgs a) {
+  extern __shared__ __align__(16) float cs_smem[];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int u = blockIdx.x * 8 + w;
+  if (u >= a.U) return;
+  float* f = cs_smem + w * a.H;
+  for (int h = l; h < a.H; h += 32) f[h] = a.feats[(long long)u * a.H + h];
+  __syncwarp();
+  const int* ix = a.idx + (long long)u * a.idx_stride;
+  float s0 = 0.f;
+  int cnt = 0;
+  for (int c0 = 0; c0 < a.C; c0 += 32) {
+    const int c = c0 + l;
+    float s = -INFINITY;
+    if (c < a.C) {
+      int id = ix[c];
+      id = id < 0 ? 0 : (id >= a.n_rows ? a.n_rows - 1 : id);     // ids are validated on the host; never read out of bounds
+      const float* e = a.E + (long long)id * a.H;
+      float acc = 0.f;
+      for (int h = 0; h < a.H; h += 4) {
+        const float4 ev = *reinterpret_cast<const float4*>(e + h);
+        const float4 fv = *reinterpret_cast<const float4*>(f + h);
+        acc = fmaf(fv.x, ev.x, acc); acc = fmaf(fv.y, ev.y, acc); acc = fmaf(fv.z, ev.z, acc); acc = fmaf(fv.w, ev.w, acc);
+      }
+      s = acc;
+      if (a.scores) a.scores[(long long)u * a.C + c] = s;
+    }
+    if (c0 == 0) s0 = __shfl_sync(0xffffffffu, s, 0);
+    cnt += __popc(__ballot_sync(0xffffffffu, c < a.C && c > 0 && s > s0));
+  }
+  if (l == 0 && a.rank) a.rank[u] = cnt;
+}
+
+// sampled-candidate metrics (utils.py:411-427) from the ranks: acc[0] HR@5, [1] NDCG@5, [2] HR@10, [3] NDCG@10, [4] sum 1/(rank+1),
+// [5] #users, [6] sum of (C1 - (rank+1)) / (C1 - 1) with the reference's C1 = 1 + C (quirk B7)
+__global__ void __launch_bounds__(256) rank_metrics_kernel(const int* __restrict__ rank, int U, int C, double* __restrict__ acc) {
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
+    const int r = rank[u];
+    const double g = 1.0 / log2((double)r + 2.0);
+    if (r < 5) { v[0] += 1.0; v[1] += g; }
+    if (r < 10) { v[2] += 1.0; v[3] += g; }
+    v[4] += 1.0 / ((double)r + 1.0);
+    v[5] += 1.0;
+    v[6] += ((double)(1 + C) - (double)(r + 1)) / (double)C;
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    if ((threadIdx.x & 31) == 0 && v[j] != 0.0) atomicAdd(acc + j, v[j]);
+  }
+}
 
 }  // namespace
 
@@ -210,11 +306,60 @@ extern "C" int adt_score_topk(const adt_score_topk_args* a, adt_stream_t s_) {
   k.feats = a->feats; k.E = a->item_emb; k.seen_indptr = a->seen_indptr; k.seen_idx = a->seen_idx;
   k.part_scores = a->part_scores; k.part_ids = a->part_ids; k.out_scores = a->out_scores; k.out_ids = a->out_ids;
   k.U = a->U; k.H = a->H; k.n_items = a->n_items; k.item_offset = a->item_offset; k.K = a->K; k.n_splits = a->n_splits;
+  k.answers = a->answers; k.metric_acc = a->metric_acc; k.dense_out = nullptr; k.dense_ld = 0; k.user_mask = a->user_mask;
+  k.part_stride = (long long)a->U * a->K;
   const size_t smem = ((size_t)UT * (a->H + 4) + (size_t)UT * CHP + WS_FLOATS + (size_t)UT * a->K * 2 + 3 * UT) * sizeof(float);
-  cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(score_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(a->n_splits, (a->U + UT - 1) / UT);
-  score_topk_kernel<<<grid, NT, smem, s>>>(k);
+  score_topk_kernel<false><<<grid, NT, smem, s>>>(k);
   if (a->out_ids) topk_merge_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(k);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+// predict(full=True) (sasrec/model.py:91-96): the whole fp32 score row, same FFMA tiles as the top-K path
+extern "C" int adt_score_full(const float* feats, int32_t U, int32_t H, const float* item_emb, int32_t n_items, int32_t item_offset,
+                              float* out, int64_t ld, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (H > 256 || (H & 3) || U <= 0 || n_items <= 0 || ld < (int64_t)item_offset + n_items) return ADT_E_SHAPE;
+  TopkArgs k;
+  memset(&k, 0, sizeof(k));
+  k.feats = feats; k.E = item_emb; k.U = U; k.H = H; k.n_items = n_items; k.item_offset = item_offset; k.K = 1;
+  const int tiles = (U + UT - 1) / UT;
+  int splits = (4 * 148 + tiles - 1) / tiles;
+  const int max_splits = (n_items + CH - 1) / CH;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  // splits must start on a CH boundary only for efficiency, not correctness: `per` is rounded up to CH
+  int per = (n_items + splits - 1) / splits;
+  per = (per + CH - 1) / CH * CH;
+  splits = (n_items + per - 1) / per;
+  k.n_splits = splits; k.dense_out = out; k.dense_ld = ld;
+  const size_t smem = ((size_t)UT * (H + 4) + (size_t)UT * CHP + WS_FLOATS + (size_t)UT * 2 + 3 * UT) * sizeof(float);
+  cudaFuncSetAttribute(score_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  score_topk_kernel<true><<<dim3(splits, tiles), NT, smem, s>>>(k);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+extern "C" int adt_candidate_scores(const adt_candidate_scores_args* a, adt_stream_t s_) {
+  if (a->U <= 0 || a->C <= 0 || a->H <= 0 || (a->H & 3) || a->H > 1024 || a->n_rows <= 0) return ADT_E_SHAPE;
+  CandArgs c;
+  c.feats = a->feats; c.E = a->item_emb; c.idx = a->idx; c.scores = a->scores; c.rank = a->rank;
+  c.idx_stride = a->idx_stride; c.U = a->U; c.H = a->H; c.C = a->C; c.n_rows = a->n_rows;
+  candidate_scores_kernel<<<(a->U + 7) / 8, 256, (size_t)8 * a->H * sizeof(float), (cudaStream_t)s_>>>(c);
+  if (a->rank && a->metric_acc) rank_metrics_kernel<<<min((a->U + 255) / 256, 148), 256, 0, (cudaStream_t)s_>>>(a->rank, a->U, a->C, a->metric_acc);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+// item-sharded evaluation: merge the all-gathered per-shard lists [n_lists][U][K] (each best first, -1 ids = padding) into the global
+// top-K, order (score desc, id asc), with the same fused metric epilogue as adt_score_topk.  list_stride = elements between lists.
+extern "C" int adt_topk_merge(const float* scores, const int32_t* ids, int32_t n_lists, int64_t list_stride, int32_t U, int32_t K,
+                              float* out_scores, int32_t* out_ids, const int32_t* answers, double* metric_acc, adt_stream_t s_) {
+  if (K <= 0 || K > KMAX || n_lists <= 0 || n_lists > 256 || U <= 0) return ADT_E_SHAPE;
+  TopkArgs k;
+  memset(&k, 0, sizeof(k));
+  k.part_scores = const_cast<float*>(scores); k.part_ids = const_cast<int*>(ids); k.out_scores = out_scores; k.out_ids = out_ids;
+  k.answers = answers; k.metric_acc = metric_acc; k.part_stride = list_stride; k.U = U; k.K = K; k.n_splits = n_lists;
+  topk_merge_kernel<<<(U + 7) / 8, 256, 0, (cudaStream_t)s_>>>(k);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }

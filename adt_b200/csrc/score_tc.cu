@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ 
 struct RescoreArgs {
   const float* feats; const float* E; const float* part_scores; const int* part_ids; const float* part_thr; const float* max_normsq;
   float* out_scores; int* out_ids; int* flags;
+  const int* answers; double* metric_acc;
   int U, H, item_offset, K, KC, n_splits;
 };
 
@@ -304,6 +305,8 @@ __global__ void __launch_bounds__(128) rescore_select_kernel(RescoreArgs a) {
   }
   __syncwarp();
   float kth = -INFINITY;
+  const int answer = a.answers ? a.answers[u] : -1;
+  int first = -1;
   for (int k = 0; k < a.K; ++k) {
     float bs = -INFINITY;
     int bi = 0x7fffffff, bp = -1;
@@ -324,12 +327,24 @@ __global__ void __launch_bounds__(128) rescore_select_kernel(RescoreArgs a) {
     if (l == 0) {
       a.out_scores[(long long)u * a.K + k] = bp >= 0 ? bs : -INFINITY;
       a.out_ids[(long long)u * a.K + k] = bp >= 0 ? bi : -1;
+      if (bp >= 0 && bi == answer && first < 0) first = k;
     }
     kth = bp >= 0 ? bs : -INFINITY;
   }
   if (l == 0) {
     const float eps = 0.0078125f * sqrtf(fn) * sqrtf(*a.max_normsq);   // 2^-7 |f| max|e|
-    a.flags[u] = (thr_max > -INFINITY && !(kth > thr_max + eps)) ? 1 : 0;
+    const int flag = (thr_max > -INFINITY && !(kth > thr_max + eps)) ? 1 : 0;
+    a.flags[u] = flag;
+    // fused get_full_sort_score epilogue (sasrec/utils.py:686-708) for the users whose list is proven exact
+    if (!flag && a.answers && a.metric_acc) {
+      atomicAdd(a.metric_acc + 5, 1.0);
+      if (first >= 0) {
+        const double g = 1.0 / log2((double)first + 2.0);
+        if (first < 5) { atomicAdd(a.metric_acc + 0, 1.0); atomicAdd(a.metric_acc + 1, g); }
+        if (first < 10) { atomicAdd(a.metric_acc + 2, 1.0); atomicAdd(a.metric_acc + 3, g); }
+        atomicAdd(a.metric_acc + 4, 1.0 / ((double)first + 1.0));
+      }
+    }
   }
 }
 
@@ -410,6 +425,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   int rc;
   if (KB == 1) rc = launch_tc<1, 128>(tmA, tmB, k, grid, s);
   else if (KB == 2) rc = launch_tc<2, 128>(tmA, tmB, k, grid, s);
+  else if (KB == 3) rc = launch_tc<3, 128>(tmA, tmB, k, grid, s);
   else if (KB == 4) rc = launch_tc<4, 64>(tmA, tmB, k, grid, s);
   else return ADT_E_SHAPE;
   if (rc) return rc;
@@ -417,6 +433,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   r.feats = a->feats; r.E = a->item_emb; r.part_scores = a->part_scores; r.part_ids = a->part_ids; r.part_thr = a->part_thr;
   r.max_normsq = a->max_normsq; r.out_scores = a->out_scores; r.out_ids = a->out_ids; r.flags = a->flags;
   r.U = a->U; r.H = a->H; r.item_offset = a->item_offset; r.K = a->K; r.KC = a->KC; r.n_splits = a->n_splits;
+  r.answers = a->answers; r.metric_acc = a->metric_acc;
   const size_t rs = (size_t)4 * 2 * RS_MAXC * sizeof(float);
   cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
   rescore_select_kernel<<<(a->U + 3) / 4, 128, rs, s>>>(r);

@@ -26,6 +26,14 @@ def _as_ids(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev, non_blocking=True)
 
 
+def _check_ids(t, item_num, what):
+    """ids feed raw-pointer kernels: an id outside [0, item_num] would be a silent out-of-bounds read where torch raises."""
+    if t.numel():
+        lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi > item_num:
+            raise IndexError(f"{what}: item ids must lie in [0, {item_num}], got [{lo}, {hi}]")
+
+
 class _MHA(nn.Module):
     """parameter holder with nn.MultiheadAttention's names/inits (sasrec/modules.py:168-218)."""
 
@@ -153,7 +161,11 @@ class Engine:
         H, nh, nl = m.hidden, m.num_heads, m.num_layers
         M = B * Lq
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        w = {"B": B, "L": Lq, "M": M}
+        w = {"B": B, "L": Lq, "M": M, "gen": 0}
+        q = L.fill(L.adt_workspace_query(), B=B, L=Lq, H=H, nh=nh, nl=nl, K=1, n_splits=1)
+        sz = L.adt_workspace_sizes()
+        L.check(self.lib.adt_workspace_bytes(L.ctypes.byref(q), L.ctypes.byref(sz)), "adt_workspace_bytes")
+        w["sizes"] = {k: int(getattr(sz, k)) for k, _ in sz._fields_}
         w["x"] = [f(M, H) for _ in range(nl + 1)]        # encoder stream: x[0]=embedding, x[l+1]=block l output
         w["xd"] = [f(M, H) for _ in range(nl + 1)]       # decoder stream
         w["enc"] = [{k: f(M, H) for k in ("q", "k", "v", "ctx", "y", "h1")} | {"lse": f(B, nh, Lq), "rec": f(M, nh, nh)}
@@ -172,8 +184,10 @@ class Engine:
         N = 4 * M
         i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
         w["keys"], w["vals"], w["keys_tmp"], w["vals_tmp"] = i32(N), i32(N), i32(N), i32(N)
-        w["hist"] = i32(256 * ((N + 255) // 256))   # >= 256 * ceil(N / SORT_WCH)
-        nb = (N + 31) // 32
+        assert w["sizes"]["sort_keys"] == 16 * N
+        w["hist"] = i32(w["sizes"]["sort_hist"] // 4)
+        nb = w["sizes"]["scatter_flags"] // 4
+        assert w["sizes"]["scatter_rows"] == 2 * nb * H * 4
         w["head"], w["tail"], w["has_tail"] = f(nb, H), f(nb, H), i32(nb)
         self.ws[key] = w
         return w
@@ -295,6 +309,7 @@ class Engine:
         """Full forward of model.py:67-81.  fused_loss=True also accumulates BCE / MSE / NLL sums into w['acc']."""
         B, Lq = seq.shape
         w = self.workspace(B, Lq)
+        w["gen"] += 1          # every forward of this shape overwrites the saved activations (see _CompatForward.backward)
         if fused_loss:
             w["acc"].zero_()
         side = self.side_stream
@@ -451,6 +466,7 @@ class _CompatForward(torch.autograd.Function):
         if training:
             eng.sort_ids(seq, dec, pos, neg, w)
         ctx.model, ctx.ids, ctx.w = model, (seq, dec, pos, neg), w
+        ctx.gen, ctx.drop_step = w["gen"], eng.drop_step
         nl, nh = model.num_layers, model.num_heads
         B, Lq = seq.shape
         H = model.hidden
@@ -475,7 +491,14 @@ class _CompatForward(torch.autograd.Function):
                "ddec_out": [c2(t) for t in gouts[2 + nl:2 + 2 * nl]], "drec": [c(t) for t in gouts[2 + 2 * nl:2 + 3 * nl]]}
         if model.num_heads == 1:
             ext["drec"] = None
-        eng.backward(seq, dec, pos, neg, w, grads, ext=ext)
+        if w["gen"] != ctx.gen:
+            raise L.AdtError("SASRecADT: the saved activations of this forward were overwritten by a later forward/predict of the same "
+                             "[B, L] shape before backward() ran (the engine keeps ONE workspace per shape): call backward() first")
+        cur_step, eng.drop_step = eng.drop_step, ctx.drop_step      # the adjoints re-draw the masks of THIS forward
+        try:
+            eng.backward(seq, dec, pos, neg, w, grads, ext=ext)
+        finally:
+            eng.drop_step = cur_step
         return (None, None, None, None, None) + tuple(grads[n] for n in names)
 
 
@@ -483,6 +506,7 @@ class SASRecADT(nn.Module):
     """Drop-in for /root/reference/sasrec/model.py:7 `SASRecADT(user_num, item_num, args)`."""
 
     has_last_ln = True
+    check_ids = True      # host-side range check of the ids (one min/max reduction per call); the fused trainer never pays it
 
     def __init__(self, user_num, item_num, args):
         super().__init__()
@@ -514,8 +538,14 @@ class SASRecADT(nn.Module):
         """model.py:67-81 -> (pos_logits, neg_logits, enc_inputs[nl], dec_outputs[nl] reversed, rec_ind[nl])."""
         dev = self.item_emb.weight.device
         seq, dec, pos, neg = (_as_ids(a, dev) for a in (log_seqs, dec_seqs, pos_seqs, neg_seqs))
+        if self.check_ids:
+            for t, what in ((seq, "log_seqs"), (dec, "dec_seqs"), (pos, "pos_seqs"), (neg, "neg_seqs")):
+                _check_ids(t, self.item_num, what)
         params = [p for _, p in self.named_parameters()]
         outs = _CompatForward.apply(self, seq, dec, pos, neg, *params)
+        eng = self.engine
+        if self.training and eng.step_dev is None:
+            eng.drop_step += 1     # a fresh dropout stream for every training forward (the fused trainer advances step_dev instead)
         nl = self.num_layers
         B, Lq = seq.shape
         enc_in = list(outs[2:2 + nl])
@@ -527,14 +557,15 @@ class SASRecADT(nn.Module):
 
     @torch.no_grad()
     def predict(self, user_ids, log_seqs, item_indices, full=False):
-        """model.py:83-97: logits of the last position against candidates [B,C] or the whole table [B,I+1]."""
+        """model.py:83-97: logits of the last position against candidates ([B,C], or one shared 1-D list [C] as utils.evaluate /
+        evaluate_valid pass it) or against the whole table [B,I+1].  Scoring runs in libadt_b200.so (adt_score_full /
+        adt_candidate_scores), not in a torch matmul."""
         dev = self.item_emb.weight.device
         seq = _as_ids(log_seqs, dev)
+        if self.check_ids:
+            _check_ids(seq, self.item_num, "log_seqs")
         final = self.final_feats(seq)
-        if full:
-            return final @ self.item_emb.weight.t()
-        idx = _as_ids(item_indices, dev).long()
-        return torch.bmm(self.item_emb.weight[idx], final.unsqueeze(-1)).squeeze(-1)
+        return score_candidates(self.item_emb.weight, final, item_indices, full, check=self.check_ids)
 
     @torch.no_grad()
     def final_feats(self, seq):
@@ -547,3 +578,34 @@ class SASRecADT(nn.Module):
         eng.encode(seq, False, w)
         eng.final(w, None, None, with_loss=False)
         return w["feats"].view(B, Lq, self.hidden)[:, -1, :].contiguous()
+
+
+@torch.no_grad()
+def score_candidates(E, final, item_indices, full, check=True, want_rank=False, metric_acc=None):
+    """shared tail of predict(): final [B,H] against the table E [I+1,H].  Returns logits [B,C] / [B,I+1]
+    (and the rank of column 0 when want_rank)."""
+    lib = L.lib()
+    dev = E.device
+    B, H = final.shape
+    st = L.ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    final = final.contiguous()
+    if full:
+        out = torch.empty(B, E.shape[0], dtype=torch.float32, device=dev)
+        L.check(lib.adt_score_full(L.ptr(final), L.ctypes.c_int32(B), L.ctypes.c_int32(H), L.ptr(E), L.ctypes.c_int32(E.shape[0]),
+                                   L.ctypes.c_int32(0), L.ptr(out), L.ctypes.c_int64(E.shape[0]), st), "adt_score_full")
+        return out
+    idx = _as_ids(item_indices, dev)
+    if check:
+        _check_ids(idx, E.shape[0] - 1, "item_indices")
+    if idx.dim() == 1:
+        stride, C = 0, idx.shape[0]
+    else:
+        if idx.shape[0] != B:
+            raise ValueError(f"item_indices must be [C] or [{B}, C], got {tuple(idx.shape)}")
+        stride, C = idx.shape[1], idx.shape[1]
+    out = torch.empty(B, C, dtype=torch.float32, device=dev)
+    rank = torch.empty(B, dtype=torch.int32, device=dev) if want_rank else None
+    a = L.fill(L.adt_candidate_scores_args(), feats=final, item_emb=E, idx=idx, scores=out, rank=rank, metric_acc=metric_acc,
+               idx_stride=stride, U=B, H=H, C=C, n_rows=E.shape[0])
+    L.check(lib.adt_candidate_scores(L.ctypes.byref(a), st), "adt_candidate_scores")
+    return (out, rank) if want_rank else out

@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from .blocks import DEC_KEYS, ENC_KEYS, DecBlockFn, DropCfg, EmbedFn, EncBlockFn, LogitsFn, layer_params
-from .model import _as_ids, _DecoderLayer, _EncoderLayer
+from .model import _as_ids, _DecoderLayer, _EncoderLayer, score_candidates
 
 
 def get_position(weight, choice):
@@ -135,8 +135,5 @@ class SuperSASRecModel(nn.Module):
         seq = _as_ids(log_seqs, dev)
         B, Lq = seq.shape
         x, _, _ = self.log2feats(seq, DropCfg(0.0, 0, 0, False))
-        final = x.view(B, Lq, self.hidden)[:, -1, :]
-        if full:
-            return final @ self.item_emb.weight.t()
-        idx = _as_ids(item_indices, dev).long()
-        return torch.bmm(self.item_emb.weight[idx], final.unsqueeze(-1)).squeeze(-1)
+        final = x.view(B, Lq, self.hidden)[:, -1, :].contiguous()
+        return score_candidates(self.item_emb.weight, final, item_indices, full)

@@ -1,8 +1,9 @@
 """Fused SASRec-ADT training step (the reference's sasrec/main.py:142-175 inner loop) on one or more B200s.
 
     forward (CUDA blocks, losses fused into the epilogues)
- -> [DP] allreduce of the 8+2*nl loss accumulators (global BCE count: main.py:151-153 takes the mean over the
-         valid positions of the WHOLE batch, so ranks must agree on n before the backward)
+    [DP] beside it: count(pos != 0) of the local batch -> all-reduce of that ONE double (main.py:151-153 takes the BCE mean
+         over the valid positions of the WHOLE batch; the count depends on the batch only, so the exchange overlaps the
+         forward pass instead of sitting between forward and backward)
  -> backward (CUDA blocks; weight grads by vector atomics into ONE flat buffer)
  -> sort-then-segmented embedding backward into the flat buffer's table segment
  -> [DP] ONE NCCL allreduce(sum) of the flat gradient buffer (dense params || item table)
@@ -10,6 +11,9 @@
  -> global grad-norm, clip (main.py:172) and Adam(b1=.9, b2=.98) (main.py:122,173) in one pass over the flat buffer.
 
 Every rank applies the identical update to its replica, so parameters stay bit-identical across ranks.
+With world > 1 the WHOLE step, both NCCL collectives included, is captured into one CUDA graph (capture_collectives=True;
+if the NCCL build refuses capture the trainer falls back to three graph segments with eager collectives between them).
+The loss accumulators are all-reduced lazily, only when loss() is called.
 """
 import ctypes
 import numpy as np
@@ -22,7 +26,7 @@ from .model import _as_ids
 class FusedTrainer:
     def __init__(self, model, lambdas1, lambdas2, weight_decay=0.0, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, clip=5.0,
                  adam_weight_decay=0.0, seed=0, process_group=None, use_norm_decay=True, use_graph=False, precision="fp32",
-                 overlap=True):
+                 overlap=True, capture_collectives=True):
         self.model = model
         self.eng = model.engine
         self.l1, self.l2 = [float(x) for x in lambdas1], [float(x) for x in lambdas2]
@@ -43,6 +47,8 @@ class FusedTrainer:
         self.use_graph = use_graph
         self.overlap = overlap        # run the encoder-independent decoder kernels on a second stream (fork/join inside the step)
         self._graphs = {}
+        self.capture_collectives = capture_collectives
+        self.launch_mode = "eager"     # how the last step was issued (reported by bench.py)
         self.step_dev = None
         self._counter_t = None
         self.lib = L.lib()
@@ -63,6 +69,10 @@ class FusedTrainer:
         # the radix sort of the lookup ids only depends on the batch: run it beside the forward pass
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
+            if self.world > 1:    # global BCE normaliser: one double, exchanged beside the forward pass
+                L.check(self.lib.adt_count_nonzero(L.ptr(pos), ctypes.c_int32(pos.numel()), L.ptr(self._nvalid), self._stream()),
+                        "adt_count_nonzero")
+                torch.distributed.all_reduce(self._nvalid, group=self.pg)
             eng.sort_ids(seq, dec, pos, neg, w)
             if self.use_norm_decay and self.wd != 0.0:
                 # ||E||^2 of the weight-decay term (main.py:170) only depends on the parameters: also beside the forward pass
@@ -76,7 +86,8 @@ class FusedTrainer:
     def _seg_backward(self, seq, dec, pos, neg, w):
         eng = self.eng
         grads = {n: eng.grad_view(n) for n, _ in eng.order}
-        eng.backward(seq, dec, pos, neg, w, grads, lambdas1=self.l1, lambdas2=self.l2)
+        eng.backward(seq, dec, pos, neg, w, grads, lambdas1=self.l1, lambdas2=self.l2,
+                     n_valid=self._nvalid if self.world > 1 else None)
 
     def _seg_optimizer(self, w):
         eng, m = self.eng, self.model
@@ -100,8 +111,6 @@ class FusedTrainer:
     def _step_impl(self, seq, dec, pos, neg):
         """eager step on int32 device ids; every launch goes to the current stream."""
         w = self._seg_forward(seq, dec, pos, neg)
-        if self.world > 1:
-            torch.distributed.all_reduce(w["acc"], group=self.pg)
         self._seg_backward(seq, dec, pos, neg, w)
         if self.world > 1:
             torch.distributed.all_reduce(self.eng.gflat, group=self.pg)
@@ -125,6 +134,7 @@ class FusedTrainer:
             self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
             self.side = torch.cuda.Stream(device=dev)
             self._normsq = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._nvalid = torch.zeros(1, dtype=torch.float64, device=dev)
             if self.overlap:
                 eng.side_stream = torch.cuda.Stream(device=dev)
         eng.batch_offset = self.rank * B
@@ -145,6 +155,9 @@ class FusedTrainer:
         self.t += 1
         eng.adam_t += 1
         self._counter_t = self.t
+        # the Adam kernel rewrites the flat buffer through raw pointers (torch's tensor versions do not move): tell anything that
+        # caches derived copies of the parameters (CatalogScorer's bf16 table) that they are stale now
+        self.model._adt_param_version = getattr(self.model, "_adt_param_version", 0) + 1
         if not self.use_graph:
             ids = [_as_ids(a, dev) for a in (seq, dec, pos, neg)]
             self._w = self._step_impl(*ids)
@@ -165,18 +178,30 @@ class FusedTrainer:
                 self.step_dev.copy_(saved)
             torch.cuda.current_stream().wait_stream(cap)
             w = eng.workspace(B, Lq)
-            if self.world == 1:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step_impl(*static)
-                graphs = [g]
-            else:
+            graphs = None
+            if self.world == 1 or self.capture_collectives:
+                try:
+                    g = torch.cuda.CUDAGraph(keep_graph=True)
+                    with torch.cuda.graph(g):
+                        self._step_impl(*static)
+                    g.instantiate()
+                    graphs = [g]
+                    self.launch_mode = "whole step replayed as one CUDA graph" + (" (NCCL all-reduces captured inside)" if self.world > 1 else "")
+                except Exception as e:   # noqa: BLE001 -- an NCCL build that refuses stream capture: keep the collectives eager
+                    if self.world == 1:
+                        raise
+                    import warnings
+                    warnings.warn(f"adt_b200: capturing the NCCL all-reduces failed ({e}); using three graph segments")
+                    torch.cuda.synchronize(dev)
+            if graphs is None:
                 graphs = []
                 for seg in (lambda: self._seg_forward(*static), lambda: self._seg_backward(*static, w), lambda: self._seg_optimizer(w)):
-                    g = torch.cuda.CUDAGraph()
+                    g = torch.cuda.CUDAGraph(keep_graph=True)
                     with torch.cuda.graph(g):
                         seg()
+                    g.instantiate()
                     graphs.append(g)
+                self.launch_mode = "three CUDA graph segments, the gradient all-reduce issued eagerly between them"
             self.step_dev.copy_(saved)   # capture does not execute, but keep the counters explicit
             self._graphs[key] = (graphs, static, w)
         graphs, static, w = self._graphs[key]
@@ -189,7 +214,6 @@ class FusedTrainer:
             graphs[0].replay()
         else:
             graphs[0].replay()
-            torch.distributed.all_reduce(w["acc"], group=self.pg)
             graphs[1].replay()
             torch.distributed.all_reduce(eng.gflat, group=self.pg)
             graphs[2].replay()
@@ -215,9 +239,21 @@ class FusedTrainer:
             hn = self._normsq_host = torch.empty(1, dtype=torch.float64).pin_memory()
         hn.copy_(self._normsq, non_blocking=True)       # ||E||^2 lives in its own buffer (computed beside the forward pass)
         torch.cuda.current_stream(a.device).synchronize()
+        if self.world > 1:        # loss sums of the global batch: exchanged only when somebody asks for the loss
+            t = h.clone().to(a.device)
+            torch.distributed.all_reduce(t, group=self.pg)
+            h = t.cpu()
         out = h.tolist()
         out[3 + 2 * self.model.num_layers] = float(hn[0])
         return out
+
+    def kernel_nodes(self):
+        """number of kernel nodes of the captured step graph(s) of the last shape = kernels launched per replayed step."""
+        from .graphs import count_kernel_nodes
+        if not self._graphs or self._w is None:
+            return None
+        graphs = self._graphs[(self._w["B"], self._w["L"])][0]
+        return sum(count_kernel_nodes(g) for g in graphs)
 
     def grad_norm(self):
         return float(np.sqrt(self._read_acc(self._w)[4 + 2 * self.model.num_layers]))

@@ -42,6 +42,14 @@ typedef struct {
 int adt_version(void);
 const char* adt_last_error(void);
 
+/* Scratch / saved-activation sizes (bytes) the caller must allocate for one (B, L, H, nh, nl) training step: the library allocates
+ * nothing itself.  saved = activations kept from forward for backward; scratch = backward temporaries; sort = keys/vals/tmp/hist of
+ * adt_embed_sort; scatter = head/tail/has_tail of adt_embed_bwd; score_part = part_scores + part_ids of adt_score_topk for
+ * (U = B, K, n_splits). */
+typedef struct { int32_t B, L, H, nh, nl, K, n_splits; } adt_workspace_query;
+typedef struct { int64_t saved, scratch, sort_keys, sort_hist, scatter_rows, scatter_flags, score_part; } adt_workspace_sizes;
+int adt_workspace_bytes(const adt_workspace_query* q, adt_workspace_sizes* out);
+
 /* K1. x = dropout(E[ids]*sqrt(H) + P[t]) * (ids != 0)            -- sasrec/model.py:34-41 and :53-58 */
 typedef struct {
   const int32_t* ids; const float* item_emb; const float* pos_emb; float* x;
@@ -184,6 +192,18 @@ typedef struct {
   const int32_t* step_dev;  /* optional DEVICE step count t (overrides `step`; for CUDA-graph replay) */
 } adt_adam_args;
 int adt_adam(const adt_adam_args* a, adt_stream_t stream);
+/* torch.optim.Adam's PER-PARAMETER semantics on the flat buffers (sasrec/evolution.py:111,316-318): parameters whose .grad is None
+ * are skipped entirely (no moment decay, no weight decay, no step increment) and every parameter keeps its own step count.  The
+ * caller lists the active segments (active_seg[n_active], indices into seg_step) and a work list of chunks of those segments
+ * (chunk_start / chunk_len in elements, chunk_seg = owning segment); seg_step[] (device int32, one per segment) is incremented for
+ * the active segments and then read for the bias corrections.  a->step / a->step_dev are ignored; clipping uses a->gnormsq. */
+typedef struct {
+  const int64_t* chunk_start; const int32_t* chunk_len; const int32_t* chunk_seg; int32_t n_chunks;
+  int32_t* seg_step; const int32_t* active_seg; int32_t n_active;
+} adt_adam_segments;
+int adt_adam_segmented(const adt_adam_args* a, const adt_adam_segments* g, adt_stream_t stream);
+/* *out = #{i < n : ids[i] != 0} (double): the BCE normaliser of sasrec/main.py:151-153, which depends on the batch only */
+int adt_count_nonzero(const int32_t* ids, int32_t n, double* out, adt_stream_t stream);
 
 /* K7. full-catalog scoring with fused per-user top-K -- replaces predict(full=True) + the host-side
  * mask / argpartition / sort of the whole score row (sasrec/model.py:91-96, sasrec/utils.py:718-731,
@@ -198,8 +218,35 @@ typedef struct {
   int32_t n_splits;                                      /* catalog splits per 64-user tile (<= 256) */
   float* part_scores; int32_t* part_ids;                 /* scratch [n_splits][U][K] */
   float* out_scores; int32_t* out_ids;                   /* [U][K], best first; -inf / -1 padded */
+  /* optional fused metric epilogue (get_full_sort_score, sasrec/utils.py:686-708, :530-569, :629-648): answers[u] = the held-out
+   * item of user u; metric_acc[6] += {HIT@5, NDCG@5, HIT@10, NDCG@10, MRR over the K-list, #users}.  Both NULL = off. */
+  const int32_t* answers; double* metric_acc;
+  const int32_t* user_mask;   /* optional [U]: only users with a non-zero entry are scored and written (the exact re-run of the users
+                                 adt_score_topk_tc flagged, issued unconditionally so that the whole evaluation stays capturable) */
 } adt_score_topk_args;
 int adt_score_topk(const adt_score_topk_args* a, adt_stream_t stream);
+
+/* item-sharded evaluation: merge n_lists per-shard top-K lists (all-gathered, [n_lists][U][K] with `list_stride`
+ * elements between lists, each best first, id -1 = padding) into the global top-K, order (score desc, id asc); optional fused metric
+ * epilogue as in adt_score_topk.  Replaces the host-side concatenate + sort of a sharded evaluate_loader_full. */
+int adt_topk_merge(const float* scores, const int32_t* ids, int32_t n_lists, int64_t list_stride, int32_t U, int32_t K,
+                   float* out_scores, int32_t* out_ids, const int32_t* answers, double* metric_acc, adt_stream_t stream);
+
+/* predict(full=True), sasrec/model.py:91-96: out[u][item_offset + i] = <feats[u], item_emb[i]> for i < n_items, fp32 FFMA
+ * (row stride ld floats).  Replaces `item_emb.weight.matmul(final_feat)`. */
+int adt_score_full(const float* feats, int32_t U, int32_t H, const float* item_emb, int32_t n_items, int32_t item_offset,
+                   float* out, int64_t ld, adt_stream_t stream);
+
+/* predict(full=False) + evaluate_loader's ranking, sasrec/model.py:91-96 and sasrec/utils.py:407-427:
+ * scores[u][c] = <feats[u], item_emb[idx[u*idx_stride + c]]> (idx_stride 0 = one candidate list for all users),
+ * rank[u] = #{c > 0 : scores[u][c] > scores[u][0]} (= `(-pred).argsort().argsort()[:,0]` without ties),
+ * metric_acc[7] += {HR@5, NDCG@5, HR@10, NDCG@10, sum 1/(rank+1), #users, sum (C+1-(rank+1))/C}  (AUC with the reference's
+ * candidates_size = 1 + C, quirk B7).  scores / rank / metric_acc may be NULL. */
+typedef struct {
+  const float* feats; const float* item_emb; const int32_t* idx; float* scores; int32_t* rank; double* metric_acc;
+  int64_t idx_stride; int32_t U, H, C, n_rows;
+} adt_candidate_scores_args;
+int adt_candidate_scores(const adt_candidate_scores_args* a, adt_stream_t stream);
 
 /* K7 on the tensor cores (H % 64 == 0): bf16 TMA-fed tcgen05.mma GEMM (fp32 accumulators in TMEM) with a fused
  * streaming top-KC epilogue per (catalog split, user), then an exact fp32 re-score of the <= n_splits*KC candidates
@@ -215,6 +262,8 @@ typedef struct {
   int32_t K, KC, n_splits;
   float* part_scores; int32_t* part_ids; float* part_thr;            /* scratch [n_splits][U][KC], [n_splits][U] */
   float* out_scores; int32_t* out_ids; int32_t* flags;               /* [U][K], [U][K], [U] */
+  const int32_t* answers; double* metric_acc;   /* fused metric epilogue as in adt_score_topk, for the users whose result is proven
+                                                   exact (flags[u] == 0); flagged users are accumulated by the exact re-run */
 } adt_score_topk_tc_args;
 int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t stream);
 
