@@ -13,6 +13,7 @@
 #include "kernels_stosa.cuh"
 #include "kernels_attn_small.cuh"
 #include "kernels_rowtile_small.cuh"
+#include "kernels_seq.cuh"
 
 using namespace adt;
 
@@ -327,6 +328,123 @@ static adt_dropout row_drop(const adt_dropout& d, int training) {
   return r;
 }
 
+// ---- sequence-resident block kernels (kernels_seq.cuh): one CTA per sequence, a whole block per launch ------------------------
+static bool use_seq(int L, int H, int nh, int mma) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_SEQ_FUSED"); v = e ? (atoi(e) != 0) : 1; }
+  return v && mma && H == RS_H && L <= 64 && (nh == 1 || nh == 2 || nh == 4);
+}
+extern "C" int adt_seq_kernels_apply(int32_t L, int32_t H, int32_t nh, int32_t precision) { return use_seq(L, H, nh, precision ? 1 : 0) ? 1 : 0; }
+
+static SeqW mk_seqw(const adt_wmirror& m) {
+  SeqW w;
+  w.base32 = m.base32; w.base16 = reinterpret_cast<const __nv_bfloat16*>(m.bf16);
+  return w;
+}
+#define SEQ_LAUNCH(KERN, nh, grid, smem, stream, arg)                                                                  \
+  do {                                                                                                                 \
+    if ((nh) == 1) { cudaFuncSetAttribute(KERN<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); KERN<64><<<grid, SQ_NT, smem, stream>>>(arg); } \
+    else if ((nh) == 2) { cudaFuncSetAttribute(KERN<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); KERN<32><<<grid, SQ_NT, smem, stream>>>(arg); } \
+    else { cudaFuncSetAttribute(KERN<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); KERN<16><<<grid, SQ_NT, smem, stream>>>(arg); } \
+  } while (0)
+
+static int seq_enc_fwd(const adt_enc_block_fwd_args* a, cudaStream_t s) {
+  EncSeqFwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.x = a->x; p.ids = a->ids; p.ln1_g = a->ln1_w; p.ln1_b = a->ln1_b; p.Win = a->attn.in_w; p.bin = a->attn.in_b; p.Wo = a->attn.out_w;
+  p.bo = a->attn.out_b; p.ln2_g = a->ln2_w; p.ln2_b = a->ln2_b; p.C1 = a->ffn.w1; p.c1 = a->ffn.b1; p.C2 = a->ffn.w2; p.c2 = a->ffn.b2;
+  p.Wsp = a->sparse_w; p.bsp = a->sparse_b;
+  const bool save = a->training != 0;
+  p.q = save ? a->q : nullptr; p.k = save ? a->k : nullptr; p.v = save ? a->v : nullptr; p.ctx = save ? a->ctx : nullptr;
+  p.lse = save ? a->lse : nullptr; p.y = save ? a->y : nullptr; p.h1 = save ? a->h1 : nullptr;
+  p.out = a->out; p.out_last = a->out_last; p.rec = a->rec; p.nll_acc = a->nll_acc;
+  if (a->nh == 1) { p.rec = nullptr; p.nll_acc = nullptr; }   // a single head has no independence term (main.py:160)
+  p.B = a->B; p.L = a->L; p.mask_mode = a->mask_mode; p.qscale = 1.0f / sqrtf((float)(a->H / a->nh));
+  adt_dropout da = a->drop_attn;
+  if (!a->training) da.enabled = 0;
+  p.drop_attn = mk_drop(da); p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training)); p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
+  p.w = mk_seqw(a->wm);
+  TIMED("enc_block_fwd", s);
+  SEQ_LAUNCH(enc_seq_fwd_kernel, a->nh, a->B, EncSeqFwdSmem::TOTAL_BYTES, s, p);
+  return check_launch("enc_seq_fwd");
+}
+
+static int seq_enc_bwd(const adt_enc_block_bwd_args* a, cudaStream_t s) {
+  EncSeqBwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.x = a->x; p.ids = a->ids; p.q = a->q; p.k = a->k; p.v = a->v; p.ctx = a->ctx; p.lse = a->lse; p.y = a->y; p.h1 = a->h1;
+  p.ln1_g = a->ln1_w; p.ln1_b = a->ln1_b; p.Win = a->attn.in_w; p.Wo = a->attn.out_w; p.ln2_g = a->ln2_w; p.ln2_b = a->ln2_b;
+  p.C1 = a->ffn.w1; p.C2 = a->ffn.w2; p.Wsp = a->sparse_w; p.bsp = a->sparse_b;
+  p.dout = a->dout; p.dx_extra = a->dx_extra; p.drec = a->nh > 1 ? a->drec : nullptr; p.nll_coef = a->nh > 1 ? a->nll_coef : 0.f; p.dx = a->dx;
+  p.gln1_g = a->g_ln1_w; p.gln1_b = a->g_ln1_b; p.gWin = a->g_attn.in_w; p.gbin = a->g_attn.in_b; p.gWo = a->g_attn.out_w; p.gbo = a->g_attn.out_b;
+  p.gln2_g = a->g_ln2_w; p.gln2_b = a->g_ln2_b; p.gC1 = a->g_ffn.w1; p.gc1 = a->g_ffn.b1; p.gC2 = a->g_ffn.w2; p.gc2 = a->g_ffn.b2;
+  p.gWsp = a->g_sparse_w; p.gbsp = a->g_sparse_b;
+  p.B = a->B; p.L = a->L; p.mask_mode = a->mask_mode; p.qscale = 1.0f / sqrtf((float)(a->H / a->nh));
+  p.drop_attn = mk_drop(a->drop_attn); p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
+  p.w = mk_seqw(a->wm);
+  TIMED("enc_block_bwd", s);
+  SEQ_LAUNCH(enc_seq_bwd_kernel, a->nh, a->B, SeqBwdSmem::TOTAL_BYTES, s, p);
+  return check_launch("enc_seq_bwd");
+}
+
+static int seq_dec_fwd(const adt_dec_block_fwd_args* a, cudaStream_t s) {
+  DecSeqFwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.x = a->x; p.feats = a->feats; p.ids = a->ids; p.ln_g = a->ln_w; p.ln_b = a->ln_b;
+  p.Win1 = a->slf.in_w; p.bin1 = a->slf.in_b; p.Wo1 = a->slf.out_w; p.bo1 = a->slf.out_b;
+  p.Win2 = a->enc.in_w; p.bin2 = a->enc.in_b; p.Wo2 = a->enc.out_w; p.bo2 = a->enc.out_b;
+  p.C1 = a->ffn.w1; p.c1 = a->ffn.b1; p.C2 = a->ffn.w2; p.c2 = a->ffn.b2; p.enc_in = a->enc_in;
+  p.d = a->d; p.q1 = a->q1; p.k1 = a->k1; p.v1 = a->v1; p.ctx1 = a->ctx1; p.lse1 = a->lse1; p.a = a->a;
+  p.q2 = a->q2; p.k2 = a->k2; p.v2 = a->v2; p.ctx2 = a->ctx2; p.lse2 = a->lse2; p.c = a->c; p.h1 = a->h1;
+  p.out = a->out; p.mse_acc = a->mse_acc;
+  p.B = a->B; p.L = a->L; p.mask_mode = a->mask_mode; p.qscale = 1.0f / sqrtf((float)(a->H / a->nh));
+  adt_dropout ds = a->drop_slf, de = a->drop_enc;
+  if (!a->training) { ds.enabled = 0; de.enabled = 0; }
+  p.drop_slf = mk_drop(ds); p.drop_enc = mk_drop(de);
+  p.drop1 = mk_drop(row_drop(a->drop_ffn1, a->training)); p.drop2 = mk_drop(row_drop(a->drop_ffn2, a->training));
+  p.w = mk_seqw(a->wm);
+  if (a->phase != 2) {
+    TIMED("dec_block_fwd_p1", s);
+    SEQ_LAUNCH(dec_seq_fwd1_kernel, a->nh, a->B, DecSeqFwd1Smem::TOTAL_BYTES, s, p);
+    if (int e = check_launch("dec_seq_fwd1")) return e;
+  }
+  if (a->phase != 1) {
+    TIMED("dec_block_fwd_p2", s);
+    SEQ_LAUNCH(dec_seq_fwd2_kernel, a->nh, a->B, DecSeqFwd2Smem::TOTAL_BYTES, s, p);
+    if (int e = check_launch("dec_seq_fwd2")) return e;
+  }
+  return ADT_OK;
+}
+
+static int seq_dec_bwd(const adt_dec_block_bwd_args* a, cudaStream_t s) {
+  DecSeqBwdArgs p;
+  memset(&p, 0, sizeof(p));
+  p.x = a->x; p.feats = a->feats; p.ids = a->ids;
+  p.d = a->d; p.q1 = a->q1; p.k1 = a->k1; p.v1 = a->v1; p.ctx1 = a->ctx1; p.lse1 = a->lse1; p.a = a->a;
+  p.q2 = a->q2; p.k2 = a->k2; p.v2 = a->v2; p.ctx2 = a->ctx2; p.lse2 = a->lse2; p.c = a->c; p.h1 = a->h1;
+  p.out = a->out; p.enc_in = a->enc_in; p.mse_coef = a->mse_coef;
+  p.ln_g = a->ln_w; p.ln_b = a->ln_b; p.Win1 = a->slf.in_w; p.Wo1 = a->slf.out_w; p.Win2 = a->enc.in_w; p.Wo2 = a->enc.out_w;
+  p.C1 = a->ffn.w1; p.C2 = a->ffn.w2;
+  p.dout = a->dout; p.denc = a->denc; p.dd = a->dd; p.dctx1 = a->dctx; p.dfeats = a->dfeats; p.dx = a->dx;
+  p.gln_g = a->g_ln_w; p.gln_b = a->g_ln_b; p.gWin1 = a->g_slf.in_w; p.gbin1 = a->g_slf.in_b; p.gWo1 = a->g_slf.out_w; p.gbo1 = a->g_slf.out_b;
+  p.gWin2 = a->g_enc.in_w; p.gbin2 = a->g_enc.in_b; p.gWo2 = a->g_enc.out_w; p.gbo2 = a->g_enc.out_b;
+  p.gC1 = a->g_ffn.w1; p.gc1 = a->g_ffn.b1; p.gC2 = a->g_ffn.w2; p.gc2 = a->g_ffn.b2;
+  p.B = a->B; p.L = a->L; p.mask_mode = a->mask_mode; p.qscale = 1.0f / sqrtf((float)(a->H / a->nh));
+  p.drop_slf = mk_drop(a->drop_slf); p.drop_enc = mk_drop(a->drop_enc); p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
+  p.w = mk_seqw(a->wm);
+  if (a->phase != 1) {
+    TIMED("dec_block_bwd_p2", s);
+    SEQ_LAUNCH(dec_seq_bwd2_kernel, a->nh, a->B, SeqBwdSmem::TOTAL_BYTES, s, p);
+    if (int e = check_launch("dec_seq_bwd2")) return e;
+  }
+  if (a->phase != 2) {
+    TIMED("dec_block_bwd_p1", s);
+    SEQ_LAUNCH(dec_seq_bwd1_kernel, a->nh, a->B, SeqBwdSmem::TOTAL_BYTES, s, p);
+    if (int e = check_launch("dec_seq_bwd1")) return e;
+  }
+  return ADT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s_) {
   cudaStream_t s = (cudaStream_t)s_;
@@ -334,6 +452,7 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   if (a->phase < 0 || a->phase > 2) return fail(ADT_E_SHAPE, "%s", "enc_block_fwd: phase must be 0, 1 or 2");
+  if (a->phase == 0 && use_seq(a->L, H, a->nh, mma)) return seq_enc_fwd(a, s);
   if (a->phase != 2) {
     if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, a->precision, s)) return e;
     if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))
@@ -369,6 +488,7 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
+  if (use_seq(a->L, H, a->nh, mma)) return seq_enc_bwd(a, s);
   PostBwdArgs p;
   memset(&p, 0, sizeof(p));
   p.dout = a->dout; p.ids = a->ids; p.ctx = a->ctx; p.u = a->y; p.h1 = a->h1;
@@ -410,6 +530,7 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
+  if (use_seq(a->L, H, a->nh, mma)) return seq_dec_fwd(a, s);
   if (a->phase != 2) {
     if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, a->precision, s)) return e;
     if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
@@ -459,6 +580,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  if (use_seq(a->L, H, a->nh, mma)) return seq_dec_bwd(a, s);
   size_t smem;
   int tm = pick_tm(4 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
@@ -639,6 +761,7 @@ extern "C" int adt_adam(const adt_adam_args* a, adt_stream_t s_) {
   k.bc1 = (float)(1.0 - pow((double)a->beta1, (double)a->step));
   k.bc2 = (float)(1.0 - pow((double)a->beta2, (double)a->step));
   k.max_norm = a->max_norm; k.gnormsq = a->gnormsq; k.step_dev = a->step_dev;
+  k.mirror = reinterpret_cast<__nv_bfloat16*>(a->mirror); k.mirror_n = a->mirror ? (a->mirror_n & ~3ll) : 0;
   if ((((uintptr_t)a->p | (uintptr_t)a->g | (uintptr_t)a->m | (uintptr_t)a->v) & 15) != 0)
     return fail(ADT_E_ALIGN, "%s", "adam: buffers must be 16-byte aligned");
   const long long blocks = (a->n / 4 + 255) / 256 + 1;
@@ -653,6 +776,7 @@ extern "C" int adt_adam_segmented(const adt_adam_args* a, const adt_adam_segment
   k.a.p = a->p; k.a.g = a->g; k.a.m = a->m; k.a.v = a->v; k.a.n = a->n;
   k.a.lr = a->lr; k.a.beta1 = a->beta1; k.a.beta2 = a->beta2; k.a.eps = a->eps; k.a.weight_decay = a->weight_decay;
   k.a.bc1 = k.a.bc2 = 1.f; k.a.max_norm = a->max_norm; k.a.gnormsq = a->gnormsq; k.a.step_dev = nullptr;
+  k.a.mirror = nullptr; k.a.mirror_n = 0;
   k.chunk_start = (const long long*)g->chunk_start; k.chunk_len = g->chunk_len; k.chunk_seg = g->chunk_seg; k.n_chunks = g->n_chunks;
   k.seg_step = g->seg_step; k.active_seg = g->active_seg; k.n_active = g->n_active;
   TIMED("adam", (cudaStream_t)s_);

@@ -384,6 +384,7 @@ struct AdamArgs {
   float max_norm;                              // <=0: no clipping
   const double* gnormsq;                       // device scalar: sum of squares of ALL grads
   const int* step_dev;                         // optional device step count (overrides bc1/bc2)
+  __nv_bfloat16* mirror; long long mirror_n;   // optional bf16 copy of p[0 .. mirror_n) (mirror_n % 4 == 0)
 };
 
 // torch.nn.utils.clip_grad_norm_ + torch.optim.Adam (single tensor semantics), fused.  g is left holding the
@@ -427,6 +428,11 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     float4 g = g4[i], p = p4[i], m = m4[i], v = v4[i];
     upd(g.x, p.x, m.x, v.x); upd(g.y, p.y, m.y, v.y); upd(g.z, p.z, m.z, v.z); upd(g.w, p.w, m.w, v.w);
     g4[i] = g; m4[i] = m; v4[i] = v; p4[i] = p;
+    if (a.mirror && 4 * i < a.mirror_n) {
+      uint2 pk;
+      pk.x = pack_bf16(p.x, p.y); pk.y = pack_bf16(p.z, p.w);
+      *reinterpret_cast<uint2*>(a.mirror + 4 * i) = pk;
+    }
   }
   for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
     float g = a.g[i], p = a.p[i], m = a.m[i], v = a.v[i];

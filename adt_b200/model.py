@@ -112,6 +112,9 @@ class Engine:
         self.side_stream = None    # optional second stream: decoder work that is independent of the encoder runs beside it
         self.step_dev = None       # optional int32 device tensor: [0] is added to the dropout step at run time
         self.precision = 0         # 0: fp32 FFMA GEMM cores (reference precision) ; 1: bf16 tensor-core cores, fp32 accumulate
+        self.use_mirror = True     # keep a bf16 mirror of the dense weights for the sequence-resident kernels (bf16 mode only)
+        self.pflat = None
+        self.mirror, self._mirror_key = None, None
 
     # ------------------------------------------------------------------ parameters / flat buffers
     def dev(self):
@@ -129,7 +132,7 @@ class Engine:
         offs, off = {}, 0
         for n, p in order:
             offs[n] = off
-            off += (p.numel() + 3) // 4 * 4
+            off += (p.numel() + 7) // 8 * 8          # 8-element segments: 16-byte aligned in the bf16 mirror too (cp.async)
         dev = self.dev()
         ok = self.gflat is not None and self.pflat.device == dev and self.pflat.numel() == off and all(
             p.data_ptr() == self.pflat.data_ptr() + 4 * offs[n] for n, p in order)
@@ -144,7 +147,45 @@ class Engine:
             self.adam_t = 0
             self.offs, self.order = offs, order
             self.table_off = offs["item_emb.weight"]
+            # bf16 mirror of the dense parameters (everything before the item table): the sequence-resident block kernels cp.async
+            # their weight tiles from it; the fused trainer's Adam kernel keeps it current, everybody else through ensure_mirror()
+            self.mirror = torch.zeros(self.table_off, dtype=torch.bfloat16, device=dev)
+            self._mirror_key = None
         return self.offs
+
+    def _param_key(self):
+        return (self.pflat.data_ptr(), getattr(self.m, "_adt_param_version", 0), sum(p._version for _, p in self.order))
+
+    def refresh_mirror(self):
+        n = self.table_off
+        L.check(self.lib.adt_to_bf16(L.ptr(self.pflat), L.ptr(self.mirror), L.ctypes.c_int64(n // 8), L.ctypes.c_int32(8), None, self._stream()),
+                "adt_to_bf16")
+        self._mirror_key = self._param_key()
+
+    def ensure_mirror(self):
+        """make the bf16 weight mirror current (host-side version check; not callable during graph capture).  Models that were
+        never given a flat parameter buffer get one here (parameters become views of it; values unchanged)."""
+        if not self.use_mirror:
+            return
+        self.ensure_flat()
+        if self._mirror_key != self._param_key():
+            self.refresh_mirror()
+
+    def mirror_marked_current(self):
+        """the fused trainer's Adam kernel has just rewritten the mirror together with the parameters"""
+        self._mirror_key = self._param_key()
+
+    def wm(self):
+        """adt_wmirror for the kernels: the mirror when it is known to be current, else NULL (kernels convert from fp32)"""
+        w = L.adt_wmirror()
+        if self.use_mirror and self.gflat is not None and self._mirror_key is not None and (
+                torch.cuda.is_current_stream_capturing() or self._mirror_key == self._param_key()):
+            w.base32, w.bf16 = self.pflat.data_ptr(), self.mirror.data_ptr()
+        return w
+
+    def seq_kernels(self, Lq):
+        m = self.m
+        return bool(self.lib.adt_seq_kernels_apply(int(Lq), int(m.hidden), int(m.num_heads), int(self.precision)))
 
     def grad_view(self, name):
         p = dict(self.order)[name]
@@ -225,22 +266,26 @@ class Engine:
                    drop=self._drop(site, "row", training, B, Lq))
         L.check(self.lib.adt_embed_fwd(L.ctypes.byref(a), self._stream()), "adt_embed_fwd")
 
-    def encode(self, seq, training, w, nll=False, last_phase=0):
+    def encode(self, seq, training, w, nll=False, last_phase=0, out_last=None):
         """embedding + encoder blocks (+ last LayerNorm into w['feats'] when pos is None handled by caller).
-        last_phase=1 stops the LAST block after its attention (see encode_last)."""
+        last_phase=1 stops the LAST block after its attention (see encode_last); out_last: [B,H] buffer that receives the LAST
+        block's output at the last position only (sequence-resident kernels)."""
         m = self.m
         B, Lq = w["B"], w["L"]
         sites = self._sites()
+        wm = self.wm()
         self.embed(seq, w["x"][0], sites["enc_emb"], training, B, Lq)
         for l, layer in enumerate(m.encoder.encoder_layers):
             sv = w["enc"][l]
             sa, s1, s2 = sites[("enc", l)]
+            last = l == m.num_layers - 1
             a = L.fill(L.adt_enc_block_fwd_args(), x=w["x"][l], ids=seq, phase=(last_phase if l == m.num_layers - 1 else 0),
+                       wm=wm, out_last=(out_last if last else None),
                        ln1_w=layer.attention_layernorm.weight, ln1_b=layer.attention_layernorm.bias, attn=_mha_w(layer.attention_layer),
                        ln2_w=layer.forward_layernorm.weight, ln2_b=layer.forward_layernorm.bias, ffn=_ffn_w(layer.forward_layer),
                        sparse_w=layer.sparse.weight, sparse_b=layer.sparse.bias,
                        q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"],
-                       out=w["x"][l + 1], rec=sv["rec"],
+                       out=(None if (last and out_last is not None) else w["x"][l + 1]), rec=(sv["rec"] if training or out_last is None else None),
                        nll_acc=(w["acc"][3 + m.num_layers + l:] if (nll and m.num_heads > 1) else None),
                        B=B, L=Lq, H=m.hidden, nh=m.num_heads, training=int(training), mask_mode=0, precision=self.precision,
                        drop_attn=self._drop(sa, "attn", training, B, Lq), drop_ffn1=self._drop(s1, "row", training, B, Lq),
@@ -254,8 +299,13 @@ class Engine:
         LayerNorm run on the B last rows instead of B*L.  Returns feats [B, H] (a workspace buffer)."""
         m = self.m
         B, Lq, H, nl = w["B"], w["L"], m.hidden, m.num_layers
-        self.encode(seq, False, w, last_phase=1)
         ws = self.workspace(B, 1)
+        if self.seq_kernels(Lq):
+            # sequence-resident kernels: every block is one launch over whole sequences; the last one writes position L-1 only
+            self.encode(seq, False, w, out_last=ws["x"][nl])
+            self.final(ws, None, None, with_loss=False)
+            return ws["feats"]
+        self.encode(seq, False, w, last_phase=1)
         layer, sv, svs = m.encoder.encoder_layers[nl - 1], w["enc"][nl - 1], ws["enc"][nl - 1]
         ws["x"][nl - 1].copy_(w["x"][nl - 1].view(B, Lq, H)[:, Lq - 1])      # strided gathers of the last position
         svs["ctx"].copy_(sv["ctx"].view(B, Lq, H)[:, Lq - 1])
@@ -294,7 +344,7 @@ class Engine:
                 break
             sv = w["dec"][j]
             ss, se, s1, s2 = sites[("dec", j)]
-            a = L.fill(L.adt_dec_block_fwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec,
+            a = L.fill(L.adt_dec_block_fwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec, wm=self.wm(),
                        ln_w=layer.layer_norm.weight, ln_b=layer.layer_norm.bias, slf=_mha_w(layer.slf_attn), enc=_mha_w(layer.enc_attn),
                        ffn=_ffn_w(layer.pos_ffn), enc_in=w["x"][nl - 1 - j] if fused_mse else None,
                        out=w["xd"][j + 1], mse_acc=(w["acc"][3 + j:] if fused_mse else None),
@@ -369,7 +419,7 @@ class Engine:
             out_dx = bufs[j % 2]
             split = side is not None and j == 0
             sb = w["side"] if split else None
-            a = L.fill(L.adt_dec_block_bwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec,
+            a = L.fill(L.adt_dec_block_bwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec, wm=self.wm(),
                        ln_w=layer.layer_norm.weight, ln_b=layer.layer_norm.bias, slf=_mha_w(layer.slf_attn), enc=_mha_w(layer.enc_attn),
                        ffn=_ffn_w(layer.pos_ffn), out=w["xd"][j + 1], enc_in=w["x"][i_enc] if fused else None,
                        mse_coef=(float(lambdas1[i_enc]) * 2.0 / (Mg * H)) if fused else 0.0,
@@ -412,7 +462,7 @@ class Engine:
             dout = dx   # already contains the external grad wrt x[l+1] (added as dx_extra of block l+1)
             dx_extra = w["denc"][l] if fused else (ei[l] if ei is not None else None)
             dr = ext.get("drec")
-            a = L.fill(L.adt_enc_block_bwd_args(), x=w["x"][l], ids=seq,
+            a = L.fill(L.adt_enc_block_bwd_args(), x=w["x"][l], ids=seq, wm=self.wm(),
                        ln1_w=layer.attention_layernorm.weight, ln1_b=layer.attention_layernorm.bias, attn=_mha_w(layer.attention_layer),
                        ln2_w=layer.forward_layernorm.weight, ln2_b=layer.forward_layernorm.bias, ffn=_ffn_w(layer.forward_layer),
                        sparse_w=layer.sparse.weight, sparse_b=layer.sparse.bias,
@@ -573,6 +623,8 @@ class SASRecADT(nn.Module):
         eng = self.engine
         B, Lq = seq.shape
         w = eng.workspace(B, Lq)
+        if eng.precision and eng.seq_kernels(Lq) and not torch.cuda.is_current_stream_capturing():
+            eng.ensure_mirror()
         if Lq > 1 and self.num_layers >= 1:
             return eng.encode_last(seq, w).clone()
         eng.encode(seq, False, w)

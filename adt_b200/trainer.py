@@ -47,6 +47,7 @@ class FusedTrainer:
         self.use_graph = use_graph
         self.overlap = overlap        # run the encoder-independent decoder kernels on a second stream (fork/join inside the step)
         self._graphs = {}
+        self._mirror_on = False
         self.capture_collectives = capture_collectives
         self.launch_mode = "eager"     # how the last step was issued (reported by bench.py)
         self.step_dev = None
@@ -105,7 +106,7 @@ class FusedTrainer:
             L.check(self.lib.adt_sumsq(L.ptr(eng.gflat), ctypes.c_int64(n), L.ptr(gn), s), "adt_sumsq")
         a = L.fill(L.adt_adam_args(), p=eng.pflat, g=eng.gflat, m=eng.adam_m, v=eng.adam_v, n=n, lr=self.lr, beta1=self.betas[0],
                    beta2=self.betas[1], eps=self.eps, weight_decay=self.adam_wd, step=0, max_norm=self.clip, gnormsq=gn,
-                   step_dev=self.step_dev[1:])
+                   step_dev=self.step_dev[1:], mirror=(eng.mirror if self._mirror_on else None), mirror_n=eng.table_off)
         L.check(self.lib.adt_adam(ctypes.byref(a), s), "adt_adam")
 
     def _step_impl(self, seq, dec, pos, neg):
@@ -129,6 +130,10 @@ class FusedTrainer:
             self._graphs.clear()        # parameters were re-homed (e.g. .to() / re-init): rebuild buffers and re-capture
         dev = eng.dev()
         eng.ensure_flat()
+        # bf16 weight mirror for the sequence-resident block kernels: refreshed here, then rewritten by every Adam launch
+        self._mirror_on = bool(eng.use_mirror and eng.precision and eng.seq_kernels(Lq))
+        if self._mirror_on:
+            eng.refresh_mirror()
         if self.step_dev is None or self.step_dev.device != dev:
             # [0] dropout stream counter (step index of the NEXT step minus one), [1] Adam step count
             self.step_dev = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -146,6 +151,20 @@ class FusedTrainer:
         """One optimisation step on this rank's shard of the batch.  ids: [B_local, L] host arrays or device tensors.
         Asynchronous; call loss() to read the step's (global) loss."""
         eng = self.eng
+        B, Lq = seq.shape
+        self._prepare(B, Lq)
+        if self._mirror_on and eng._mirror_key != eng._param_key():
+            eng.refresh_mirror()       # somebody changed the parameters behind the trainer's back (load_state_dict, manual edits)
+        w = self._step_body(seq, dec, pos, neg)
+        # the Adam kernel rewrites the flat buffer (and the bf16 mirror) through raw pointers (torch's tensor versions do not move):
+        # tell anything that caches derived copies of the parameters (CatalogScorer's bf16 table) that they are stale now
+        self.model._adt_param_version = getattr(self.model, "_adt_param_version", 0) + 1
+        if self._mirror_on:
+            eng.mirror_marked_current()
+        return w
+
+    def _step_body(self, seq, dec, pos, neg):
+        eng = self.eng
         dev = eng.dev()
         B, Lq = seq.shape
         self._prepare(B, Lq)
@@ -155,9 +174,6 @@ class FusedTrainer:
         self.t += 1
         eng.adam_t += 1
         self._counter_t = self.t
-        # the Adam kernel rewrites the flat buffer through raw pointers (torch's tensor versions do not move): tell anything that
-        # caches derived copies of the parameters (CatalogScorer's bf16 table) that they are stale now
-        self.model._adt_param_version = getattr(self.model, "_adt_param_version", 0) + 1
         if not self.use_graph:
             ids = [_as_ids(a, dev) for a in (seq, dec, pos, neg)]
             self._w = self._step_impl(*ids)
@@ -176,6 +192,8 @@ class FusedTrainer:
                 self._step_impl(*static)
                 eng.pflat.copy_(snap[0]); eng.adam_m.copy_(snap[1]); eng.adam_v.copy_(snap[2])
                 self.step_dev.copy_(saved)
+                if self._mirror_on:
+                    eng.refresh_mirror()     # the warm-up step's Adam launch advanced the mirror together with the weights
             torch.cuda.current_stream().wait_stream(cap)
             w = eng.workspace(B, Lq)
             graphs = None

@@ -274,7 +274,8 @@ def alg_bytes_table(cfg):
     M, H, nh, e = cfg["B"] * cfg["L"], cfg["H"], cfg["nh"], 4
     return {
         "enc_block_fwd": M * (2 * H * e + nh * nh * e), "enc_block_bwd": M * (3 * H * e + nh * nh * e),
-        "dec_block_fwd": M * 3 * H * e, "dec_block_bwd": M * 5 * H * e,
+        # decoder block, SURVEY 8d: fwd 3 L H e (x, feats in; out), bwd 5 L H e (dout, x, feats in; dx, dfeats out), split over its two launches
+        "dec_block_fwd_p1": M * 1 * H * e, "dec_block_fwd_p2": M * 2 * H * e, "dec_block_bwd_p2": M * 3 * H * e, "dec_block_bwd_p1": M * 2 * H * e,
         "enc_post_bwd": M * (3 * H * e + nh * nh * e), "dec_post_bwd": M * 5 * H * e // 2, "attn_bwd": M * 7 * H * e, "attn_fwd": M * 4 * H * e,
         "pre_bwd": M * 5 * H * e, "mid_bwd": M * 8 * H * e, "enc_post_fwd": M * (2 * H * e + nh * nh * e), "dec_post_fwd": M * 3 * H * e,
         "pre_fwd": M * 4 * H * e, "mid_fwd": M * 6 * H * e,

@@ -62,6 +62,12 @@ typedef struct { const float* in_w; const float* in_b; const float* out_w; const
 typedef struct { float* in_w; float* in_b; float* out_w; float* out_b; } adt_mha_g;
 typedef struct { const float* w1; const float* b1; const float* w2; const float* b2; } adt_ffn_w; /* Conv1d k=1 == [H,H] */
 typedef struct { float* w1; float* b1; float* w2; float* b2; } adt_ffn_g;
+/* Optional bf16 mirror of the flat fp32 parameter buffer: the bf16 copy of a weight W lives at bf16 + (W - base32).  Kept current by
+ * adt_adam (mirror / mirror_n) or adt_to_bf16; base32 segments must start on 8-element boundaries.  bf16 == NULL: kernels convert the
+ * fp32 weights on the fly. */
+typedef struct { const float* base32; const void* bf16; } adt_wmirror;
+/* 1 when the sequence-resident block kernels (one CTA per sequence, a whole block per launch) serve this shape / precision */
+int adt_seq_kernels_apply(int32_t L, int32_t H, int32_t nh, int32_t precision);
 
 /* Encoder block -- EncoderLayer.forward, sasrec/modules.py:644-655 (+ MultiheadAttentionADT :270-527,
  * PointWiseFeedForward :629-633, SparseInputLinear :696-703).  rec is written in TRUE [B,L,nh,nh] layout. */
@@ -80,6 +86,10 @@ typedef struct {
                       block from ctx (out-projection, residual, LN, FFN, pad mask).  Phase 2 is row-wise, so it may be called on
                       a row subset with B = rows, L = 1: predict() reads only the last position (sasrec/model.py:89) and runs
                       the tail of the LAST block on those rows only */
+  adt_wmirror wm;  /* optional bf16 mirror of the parameters (see adt_wmirror) */
+  float* out_last; /* optional [B][H]: the block output of the LAST position of every sequence (predict reads nothing else,
+                      sasrec/model.py:89); `out` may then be NULL.  Only honoured by the sequence-resident kernels (phase 0, precision 1,
+                      H == 64, L <= 64, nh in {1,2,4}); otherwise ignored, so callers must check adt_seq_kernels_apply() first */
 } adt_enc_block_fwd_args;
 int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t stream);
 
@@ -99,6 +109,7 @@ typedef struct {
   int32_t B, L, H, nh, mask_mode;
   adt_dropout drop_attn, drop_ffn1, drop_ffn2;
   int32_t precision;
+  adt_wmirror wm;
 } adt_enc_block_bwd_args;
 int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t stream);
 
@@ -116,6 +127,7 @@ typedef struct {
   int32_t precision;
   int32_t phase;   /* 0: whole block; 1: only LN + self-attention (independent of the encoder -> may run beside it on another
                     * stream); 2: the rest (cross-attention on `feats`, FFN) */
+  adt_wmirror wm;
 } adt_dec_block_fwd_args;
 int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t stream);
 
@@ -136,6 +148,7 @@ typedef struct {
   int32_t precision;
   int32_t phase;   /* 0: whole block; 2: FFN + cross-attention adjoints (produce dfeats, dctx, dd); 1: self-attention + LN adjoints
                     * (produce dx; nothing the encoder backward needs -> may run beside it on another stream) */
+  adt_wmirror wm;
 } adt_dec_block_bwd_args;
 int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t stream);
 
@@ -190,6 +203,7 @@ typedef struct {
   float* p; float* g; float* m; float* v; int64_t n;
   float lr, beta1, beta2, eps, weight_decay; int32_t step; float max_norm; const double* gnormsq;
   const int32_t* step_dev;  /* optional DEVICE step count t (overrides `step`; for CUDA-graph replay) */
+  void* mirror; int64_t mirror_n;   /* optional: bf16 copy of p[0 .. mirror_n) written in the same pass (adt_wmirror) */
 } adt_adam_args;
 int adt_adam(const adt_adam_args* a, adt_stream_t stream);
 /* torch.optim.Adam's PER-PARAMETER semantics on the flat buffers (sasrec/evolution.py:111,316-318): parameters whose .grad is None

@@ -102,7 +102,7 @@ def test_predict_accepts_shared_candidate_list_and_checks_ids():
     instead of reading out of bounds; full=True equals the candidate scores of every id."""
     from adt_b200 import testing as T
     g = T.load_golden("tiny_p5")
-    m = T.model_from_golden(g).eval()
+    m = T.model_from_golden(g, prefix="sd1/").eval()      # the fixture's predictions were taken after its optimisation step
     B = g["seq"].shape[0]
     I = g["dims"]["I"]
     full = m.predict(None, g["seq"], None, True)
@@ -286,3 +286,26 @@ def test_reference_staging_runs_on_this_box():
     rng = np.random.default_rng(0)
     l0 = tr.step(*synth.make_batch(rng, cfg))
     assert np.isfinite(l0)
+
+
+@pytest.mark.parametrize("nh,Lq", [(2, 50), (4, 64), (1, 33)])
+def test_sequence_resident_block_kernels_match_row_tile_kernels(nh, Lq):
+    """the one-CTA-per-sequence block kernels (kernels_seq.cuh) against the 3 / 5-kernel row-tile path they replace: same bf16
+    operands, same Philox streams -> three training steps and an evaluation pass agree to fp32-atomics level."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for fused in ("0", "1"):
+        env = dict(os.environ, ADT_SEQ_FUSED=fused)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "seq_ab.py"), str(nh), str(Lq)], capture_output=True, text=True, env=env,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = res
+    for k in range(3):
+        assert abs(a["loss"][k] - b["loss"][k]) / abs(a["loss"][k]) < 2e-5, (k, a["loss"], b["loss"])
+        assert abs(a["gnorm"][k] - b["gnorm"][k]) / a["gnorm"][k] < 1e-3, (k, a["gnorm"], b["gnorm"])
+        assert abs(a["gsum"][k] - b["gsum"][k]) / a["gsum"][k] < 1e-3
+    assert abs(a["psum"] - b["psum"]) / a["psum"] < 1e-4
+    same = np.mean(np.array(a["ids"]) == np.array(b["ids"]))
+    assert same > 0.98, same
