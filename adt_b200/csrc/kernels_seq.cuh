@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(SQ_NT, 2) enc_seq_fwd_kernel(EncSeqFwdArgs p) 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int i0 = 16 * w + g, i1 = i0 + 8;
   const bool v0 = i0 < L, v1 = i1 < L;
+  ADT_STAMP(48);
   {
     const float* const w6a[3] = {p.Win, p.Win + RS_H * RS_H, p.Win + 2 * RS_H * RS_H};
     const float* const w6b[3] = {p.Wo, p.C1, p.C2};
@@ -410,8 +411,10 @@ __global__ void __launch_bounds__(SQ_NT, 2) enc_seq_fwd_kernel(EncSeqFwdArgs p) 
   for (int nb = 0; nb < 8; ++nb) { Nf[nb][0] = Xf[nb][0]; Nf[nb][1] = Xf[nb][1]; Nf[nb][2] = Xf[nb][2]; Nf[nb][3] = Xf[nb][3]; }
   frag_ln(Nf, p.ln1_g, p.ln1_b, t);                   // Qn = LN1(x)
   frag_mask_rows(Nf, v0, v1);
+  ADT_STAMP(49);
   sq_weights_wait();
   __syncthreads();
+  ADT_STAMP(50);
   // ---- packed in-projection: q from Qn, k / v from the un-normalised x (modules.py:124-130)
   {
     float o[8][4];
@@ -431,10 +434,13 @@ __global__ void __launch_bounds__(SQ_NT, 2) enc_seq_fwd_kernel(EncSeqFwdArgs p) 
     if (p.v) frag_store(p.v + g0, o, i0, i1, v0, v1, t);
     frag_store_tile(Vs, o, i0, i1, t);
   }
+  ADT_STAMP(51);
   __syncthreads();
+  ADT_STAMP(52);
   // ---- attention, all heads
   float Cf[8][4];
   sq_attn_fwd<HD>(Cf, Qs, Ks, Vs, L, b, p.mask_mode, p.ids + grow0, p.drop_attn, p.lse);
+  ADT_STAMP(53);
   if (p.ctx) frag_store(p.ctx + g0, Cf, i0, i1, v0, v1, t);
   // ---- y = ctx Wo^T + bo + Qn ; independence head on the per-head context slices
   float u[8][4];
@@ -446,6 +452,7 @@ __global__ void __launch_bounds__(SQ_NT, 2) enc_seq_fwd_kernel(EncSeqFwdArgs p) 
     u[nb][0] += bb.x + Nf[nb][0]; u[nb][1] += bb.y + Nf[nb][1]; u[nb][2] += bb.x + Nf[nb][2]; u[nb][3] += bb.y + Nf[nb][3];
   }
   if (p.y) frag_store(p.y + g0, u, i0, i1, v0, v1, t);
+  ADT_STAMP(54);
   if (p.rec || p.nll_acc) {
     __syncthreads();                                  // every warp is done with Q as the attention operand
     frag_store_tile(Qs, Cf, i0, i1, t);               // context tile (bf16, as the row-tile kernels see it)
@@ -476,15 +483,18 @@ __global__ void __launch_bounds__(SQ_NT, 2) enc_seq_fwd_kernel(EncSeqFwdArgs p) 
     }
     if (p.nll_acc) warp_accumulate(nll, p.nll_acc);
   }
+  ADT_STAMP(55);
   frag_ln(u, p.ln2_g, p.ln2_b, t);                    // z = LN2(y)
   float o[8][4];
   sq_ffn_fwd(o, u, Wt + 4 * RS_TILE, Wt + 5 * RS_TILE, p.c1, p.c2, p.drop1, p.drop2, p.h1, grow0, i0, i1, v0, v1, t);
+  ADT_STAMP(56);
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) {
     if (keep0 == 0) { o[nb][0] = 0.f; o[nb][1] = 0.f; }
     if (keep1 == 0) { o[nb][2] = 0.f; o[nb][3] = 0.f; }
   }
   if (p.out) frag_store(p.out + g0, o, i0, i1, v0, v1, t);
+  ADT_STAMP(57);
   if (p.out_last) frag_store(p.out_last + (long long)b * RS_H - (long long)(L - 1) * RS_H, o, i0, i1, i0 == L - 1, i1 == L - 1, t);
 }
 

@@ -32,8 +32,32 @@ struct TcArgs {
   const int* seen_indptr; const int* seen_idx;
   float* part_scores; int* part_ids; float* part_thr;
   unsigned int* gthr;   // [U] best K'-th-best key published by any catalog split of this launch (order-preserving keys, 0 = none)
+  const float* tau;     // MODE 1: [U] per-user score threshold (from the sample pass): everything above it is a candidate
   int U, n_items, item_offset, KC, n_splits, debug;
+  int sstride;          // MODE 2: every sstride-th catalog tile belongs to the sample
 };
+
+// Which catalog tiles (BN items each) a CTA walks:
+//   MODE 0  streaming top-K' lists over a CONTIGUOUS tile range per split (small catalogs: one pass, thresholds exchanged through gthr)
+//   MODE 1  append-only candidate lists against a FIXED per-user threshold tau, tiles interleaved over the splits (tile s, s+S, ...)
+//           so that every split sees the same score distribution whatever the id order of the catalog
+//   MODE 2  sample pass: streaming top-K' lists over every sstride-th tile (interleaved), from which tau is chosen
+template <int MODE>
+__device__ __forceinline__ void tc_tile_walk(const TcArgs& a, int BN, int split, int& first, int& step, int& count) {
+  const int ntt = (a.n_items + BN - 1) / BN;
+  if (MODE == 0) {
+    const int tps = (ntt + a.n_splits - 1) / a.n_splits;
+    first = split * tps; step = 1;
+    count = max(0, min(tps, ntt - first));
+  } else if (MODE == 1) {
+    first = split; step = a.n_splits;
+    count = split < ntt ? (ntt - split + a.n_splits - 1) / a.n_splits : 0;
+  } else {
+    const int nst = (ntt + a.sstride - 1) / a.sstride;
+    first = split * a.sstride; step = a.n_splits * a.sstride;
+    count = split < nst ? (nst - split + a.n_splits - 1) / a.n_splits : 0;
+  }
+}
 
 // first position p in [lo, hi) of the sorted id list with idx[p] >= item
 __device__ __forceinline__ int tc_seen_lower_bound(const int* __restrict__ idx, int lo, int hi, int item) {
@@ -51,7 +75,7 @@ __device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int sb, int se, int 
 }
 
 // NS = depth of the TMA ring of catalog tiles (B operand); accumulators are double buffered in TMEM
-template <int KB, int BN, int NS>
+template <int KB, int BN, int NS, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -75,10 +99,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, u0 = blockIdx.y * BM;
-  int per = (a.n_items + a.n_splits - 1) / a.n_splits;
-  per = (per + 7) & ~7;
-  const int it0 = min(a.n_items, split * per), it1 = min(a.n_items, it0 + per);
-  const int ntiles = (it1 - it0 + BN - 1) / BN;
+  int tfirst, tstep, ntiles;
+  tc_tile_walk<MODE>(a, BN, split, tfirst, tstep, ntiles);
+  const int it0 = min(a.n_items, tfirst * BN), it1 = min(a.n_items, (tfirst + (ntiles > 0 ? (ntiles - 1) * tstep + 1 : 0)) * BN);   // item span touched
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -108,7 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         const int st = t % NS;
         tc::mbar_wait(empty + st, ((t / NS) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(full + st, B_STAGE);
-        for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sB + st * B_STAGE + kb * BN * 128, &tmB, kb * 64, it0 + t * BN, full + st);
+        for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sB + st * B_STAGE + kb * BN * 128, &tmB, kb * 64, (tfirst + t * tstep) * BN, full + st);
       }
     }
   } else if (warp == 1) {
@@ -144,28 +167,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       lk[k * BM + row] = 0u;                 // key 0 = "worse than anything"
       li[k * BM + row] = -1;
     }
-    int sb = 0, se = 0;                      // this row's seen ids inside [it0, it1)
+    int sb = 0, se = 0;                      // this row's seen ids inside the item span this CTA touches
     if (a.seen_indptr && u < a.U) {
       const int hi = a.seen_indptr[u + 1];
       sb = tc_seen_lower_bound(a.seen_idx, a.seen_indptr[u], hi, a.item_offset + it0);
       se = tc_seen_lower_bound(a.seen_idx, sb, hi, a.item_offset + it1);
     }
-    uint32_t mink = 0u;                      // smallest key in the list and its slot
-    int minpos = 0;
-    // rej: keys <= rej cannot be among the K' best of the WHOLE catalog: max of this split's K'-th best (mink) and the best
-    // K'-th best any other split has published so far (K' items of one split beat it, so the global K'-th best does too)
-    uint32_t rej = 0u, published = 0u;
-    float thr = u < a.U ? -INFINITY : INFINITY;   // rej as a float (-inf while nothing is known)
     auto unkey = [](uint32_t k) -> float { return k == 0u ? -INFINITY : __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); };
     auto fkey = [](float f) -> uint32_t {
       const uint32_t b = __float_as_uint(f);
       return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
     };
+    float thr;
+    if constexpr (MODE == 1) {
+      // ---- fixed threshold, append only: no list maintenance in the hot loop at all
+      thr = u < a.U ? a.tau[u] : INFINITY;
+      int cnt = 0;
+      bool overflow = false;
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t & 1;
+        tc::mbar_wait(tfull + st, (t >> 1) & 1);
+        tc::tc_fence_after();
+        const int tb = (tfirst + t * tstep) * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
+          if (c0 + 32 == BN) {               // accumulator fully read: hand it back to the MMA warp
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty + st);
+          }
+          const int ib = tb + c0;
+          const int nvalid = a.n_items - ib;
+          if (nvalid < 32) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c >= nvalid) v[c] = -INFINITY;
+          }
+          if (a.debug == 1) continue;
+          float mx = v[0];
+#pragma unroll
+          for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
+          const bool fire = mx > thr;
+          if (__ballot_sync(0xffffffffu, fire) == 0u || a.debug == 2) continue;
+          float* vs = vsm + q * 1024;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) vs[c * 32 + lane] = v[c];
+          __syncwarp();
+          if (fire) {
+            for (int c = 0; c < 32; ++c) {
+              const float x = vs[c * 32 + lane];
+              if (x > thr) {
+                const int item = a.item_offset + ib + c;
+                if (!tc_is_seen(a, sb, se, item)) {
+                  if (cnt < KC) { lk[cnt * BM + row] = fkey(x); li[cnt * BM + row] = item; ++cnt; }
+                  else overflow = true;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (overflow) thr = INFINITY;          // candidates were dropped: the caller must re-run this user exactly
+    } else {
+    uint32_t mink = 0u;                      // smallest key in the list and its slot
+    int minpos = 0;
+    // rej: keys <= rej cannot be among the K' best of the WHOLE catalog: max of this split's K'-th best (mink) and the best
+    // K'-th best any other split has published so far (K' items of one split beat it, so the global K'-th best does too)
+    uint32_t rej = 0u, published = 0u;
+    thr = u < a.U ? -INFINITY : INFINITY;    // rej as a float (-inf while nothing is known)
     auto insert = [&](float sc, int itl) {
       const uint32_t key = fkey(sc);
       if (key <= rej) return;
       const int item = a.item_offset + itl;
-      if (tc_is_seen(a, sb, se, item)) return;
+      if (MODE == 0 && tc_is_seen(a, sb, se, item)) return;    // the sample pass only needs score quantiles: seen items may stay
       lk[minpos * BM + row] = key;
       li[minpos * BM + row] = item;
       uint32_t nm = 0xffffffffu;
@@ -180,9 +257,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     for (int t = 0; t < ntiles; ++t) {
       const int st = t & 1;
       // thresholds of the other splits: issue the (L2) load now, consume it after this tile
-      const uint32_t gnext = (a.gthr && u < a.U) ? __ldcg(a.gthr + u) : 0u;
+      const uint32_t gnext = (MODE == 0 && a.gthr && u < a.U) ? __ldcg(a.gthr + u) : 0u;
       tc::mbar_wait(tfull + st, (t >> 1) & 1);
       tc::tc_fence_after();
+      const int tb = (tfirst + t * tstep) * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -192,8 +270,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(tempty + st);
         }
-        const int ib = it0 + t * BN + c0;
-        const int nvalid = it1 - ib;
+        const int ib = tb + c0;
+        const int nvalid = a.n_items - ib;
         if (nvalid < 32) {
 #pragma unroll
           for (int c = 0; c < 32; ++c)
@@ -218,10 +296,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         }
         __syncwarp();
       }
-      if (a.gthr && u < a.U) {
+      if (MODE == 0 && a.gthr && u < a.U) {
         if (mink > published) { atomicMax(a.gthr + u, mink); published = mink; }   // rare once the list is warm
         if (gnext > rej) { rej = gnext; thr = unkey(gnext); }
       }
+    }
     }
     if (u < a.U) {
       const long long o = ((long long)split * a.U + u) * KC;
@@ -376,21 +455,71 @@ int make_map(CUtensorMap* m, const void* base, long long rows, int H, int box_ro
   return r == CUDA_SUCCESS ? ADT_OK : ADT_E_CUDA;
 }
 
-template <int KB, int BN, int NS>
+template <int KB, int BN, int NS, int MODE>
 int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s, size_t smem) {
-  cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  score_tc_kernel<KB, BN, NS><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
+  cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  score_tc_kernel<KB, BN, NS, MODE><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }
 // deepest catalog-tile ring (2..4 stages) that fits the 227 KB of shared memory next to the user tile and the top-K lists
-template <int KB, int BN>
+template <int KB, int BN, int MODE>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
   const size_t fixed = 1024 + (size_t)KB * BM * 128 + (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 + BM * 4 + 4 * 1024 * 4 + 256;
   const size_t stage = (size_t)KB * BN * 128, cap = 227 * 1024;
-  if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4>(tmA, tmB, k, grid, s, fixed + 4 * stage);
-  if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3>(tmA, tmB, k, grid, s, fixed + 3 * stage);
-  if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2>(tmA, tmB, k, grid, s, fixed + 2 * stage);
+  if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4, MODE>(tmA, tmB, k, grid, s, fixed + 4 * stage);
+  if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3, MODE>(tmA, tmB, k, grid, s, fixed + 3 * stage);
+  if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2, MODE>(tmA, tmB, k, grid, s, fixed + 2 * stage);
   return ADT_E_SHAPE;
+}
+template <int MODE>
+int launch_tc_h(int KB, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
+  if (KB == 1) return launch_tc<1, 128, MODE>(tmA, tmB, k, grid, s);
+  if (KB == 2) return launch_tc<2, 128, MODE>(tmA, tmB, k, grid, s);
+  if (KB == 3) return launch_tc<3, 128, MODE>(tmA, tmB, k, grid, s);
+  if (KB == 4) return launch_tc<4, 64, MODE>(tmA, tmB, k, grid, s);
+  return ADT_E_SHAPE;
+}
+
+// tau[u] = the R-th largest score among the sample pass's per-split lists [S][U][KCA] (-inf when the sample holds fewer than R
+// scores): with a sample of 1/sstride of the catalog, about R*sstride catalog items score above it.  Warp per user.
+__global__ void __launch_bounds__(256) tau_select_kernel(const float* __restrict__ part_scores, const int* __restrict__ part_ids, int S, int U,
+                                                         int KCA, int R, float* __restrict__ tau) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int u = blockIdx.x * 8 + w;
+  if (u >= U) return;
+  const int n = S * KCA;                      // <= 2048 (checked by the launcher)
+  float mine[64];                             // lane l owns entries l, l+32, ...
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const int c = l + 32 * j;
+    float v = -INFINITY;
+    if (c < n) {
+      const int sp = c / KCA, k = c - sp * KCA;
+      const long long o = ((long long)sp * U + u) * KCA + k;
+      if (part_ids[o] >= 0) v = part_scores[o];
+    }
+    mine[j] = v;
+  }
+  float kth = -INFINITY;
+  for (int r = 0; r < R; ++r) {
+    float bm = -INFINITY;
+    int bj = -1;
+#pragma unroll
+    for (int j = 0; j < 64; ++j)
+      if (mine[j] > bm) { bm = mine[j]; bj = j; }
+    float wm = bm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    const unsigned who = __ballot_sync(0xffffffffu, bj >= 0 && bm == wm);
+    if (who == 0u) { kth = -INFINITY; break; }     // fewer than R scores in the sample
+    if (l == __ffs(who) - 1) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j)
+        if (j == bj) mine[j] = -INFINITY;
+    }
+    kth = wm;
+  }
+  if (l == 0) tau[u] = kth;
 }
 
 }  // namespace
@@ -401,6 +530,35 @@ extern "C" int adt_to_bf16(const float* x, void* y, int64_t rows, int32_t H, flo
   to_bf16_kernel<<<(int)(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16), 256, 0, (cudaStream_t)s_>>>(
       x, reinterpret_cast<__nv_bfloat16*>(y), (long long)rows, H, max_normsq);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+// launch plan of adt_score_topk_tc for (U users, n_items catalog rows, top-K): list capacity KC per (split, user) and the number of
+// catalog splits.  Returns 1 when the two-pass (sample threshold + append-only) scheme applies, else 0 (single streaming pass).
+static const int TC_TWO_PASS_MIN_ITEMS = 65536, TC_SSTRIDE = 16;
+static int tc_target(int K) { return K * 6 > 192 ? K * 6 : 192; }
+extern "C" int adt_score_tc_plan(int32_t U, int32_t n_items, int32_t K, int32_t* KC_out, int32_t* n_splits_out) {
+  static int two_pass = -1;
+  if (two_pass < 0) { const char* e = getenv("ADT_TC_TWO_PASS"); two_pass = e ? atoi(e) : 1; }
+  const int tiles = (U + BM - 1) / BM;
+  const int item_tiles = (n_items + 127) / 128;
+  int S = 148 / tiles > 1 ? 148 / tiles : 1;
+  if (S > item_tiles) S = item_tiles;
+  int KC, mode = 0;
+  if (two_pass && n_items >= TC_TWO_PASS_MIN_ITEMS && K <= 48) {
+    // capacity >= 4x the expected number of candidates per split (they are spread evenly: tiles are interleaved over the splits)
+    const int target = tc_target(K);
+    int need = (4 * target + S - 1) / S + 8;
+    if (need > 64) { S = (4 * target + 55) / 56; need = (4 * target + S - 1) / S + 8; }
+    KC = need <= 32 ? 32 : 64;
+    mode = 1;
+  } else {
+    KC = K + 8 > 2 * K ? K + 8 : 2 * K;
+    if (KC > 64) KC = 64;
+  }
+  if (S * KC > RS_MAXC) S = RS_MAXC / KC;
+  if (S < 1) S = 1;
+  *KC_out = KC; *n_splits_out = S;
+  return mode;
 }
 
 extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s_) {
@@ -423,11 +581,27 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   { const char* dbg = getenv("ADT_TC_DEBUG"); k.debug = dbg ? atoi(dbg) : 0; }
   dim3 grid(a->n_splits, (a->U + BM - 1) / BM);
   int rc;
-  if (KB == 1) rc = launch_tc<1, 128>(tmA, tmB, k, grid, s);
-  else if (KB == 2) rc = launch_tc<2, 128>(tmA, tmB, k, grid, s);
-  else if (KB == 3) rc = launch_tc<3, 128>(tmA, tmB, k, grid, s);
-  else if (KB == 4) rc = launch_tc<4, 64>(tmA, tmB, k, grid, s);
-  else return ADT_E_SHAPE;
+  k.tau = nullptr; k.sstride = 1;
+  // Large catalogs: two passes.  (1) a SAMPLE of every 16th catalog tile is scored with streaming top-R lists; the R-th best sample
+  // score of a user becomes her threshold tau, so about 16 R (>= 6 K) catalog items score above it.  (2) the whole catalog is scored
+  // against that FIXED threshold: the epilogue only appends (no sorted-list maintenance, no warm-up phase per split).  Everything
+  // above tau is a candidate, so the exactness test of the re-score kernel is unchanged (thr = tau, or +inf after an overflow).
+  static int two_pass = -1;
+  if (two_pass < 0) { const char* e = getenv("ADT_TC_TWO_PASS"); two_pass = e ? atoi(e) : 1; }
+  const int sstride = TC_SSTRIDE;
+  const int R = (tc_target(a->K) + sstride - 1) / sstride;
+  if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && R <= a->KC && a->n_splits * R <= RS_MAXC) {
+    TcArgs ks = k;
+    ks.KC = R; ks.sstride = sstride; ks.gthr = nullptr;
+    rc = launch_tc_h<2>(KB, tmA, tmB, ks, grid, s);
+    if (rc) return rc;
+    float* tau = a->out_scores;            // U floats of scratch: overwritten by the re-score kernel at the end
+    tau_select_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(a->part_scores, a->part_ids, a->n_splits, a->U, R, R, tau);
+    k.tau = tau; k.gthr = nullptr;
+    rc = launch_tc_h<1>(KB, tmA, tmB, k, grid, s);
+  } else {
+    rc = launch_tc_h<0>(KB, tmA, tmB, k, grid, s);
+  }
   if (rc) return rc;
   RescoreArgs r;
   r.feats = a->feats; r.E = a->item_emb; r.part_scores = a->part_scores; r.part_ids = a->part_ids; r.part_thr = a->part_thr;

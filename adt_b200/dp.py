@@ -169,7 +169,7 @@ class GraphedStep:
         for d, a in zip(self.static, arrays):
             d.copy_(_to_i32(a, dev))
         m.step_dev = self.counters[0:1]
-        snap = (opt.pflat.clone(), opt.m.clone(), opt.v.clone(), self.counters.clone(), m.drop_step, opt.t)
+        snap = (opt.pflat.clone(), opt.m.clone(), opt.v.clone(), self.counters.clone(), m.drop_step, opt.t, opt.seg_step.clone())
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                      # warm-up outside capture (lazy allocations, function attributes)
@@ -180,6 +180,7 @@ class GraphedStep:
         def restore():
             opt.pflat.copy_(snap[0]); opt.m.copy_(snap[1]); opt.v.copy_(snap[2]); self.counters.copy_(snap[3])
             m.drop_step, opt.t = snap[4], snap[5]
+            opt.seg_step.copy_(snap[6])          # per-parameter step counts (segmented Adam) advanced during the warm-up too
         restore()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

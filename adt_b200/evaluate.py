@@ -154,9 +154,9 @@ class CatalogScorer:
         tab, mx = self._tab
         n_items = hi - lo
         K = self.K
-        KC = min(64, max(K + 8, 2 * K))
-        tiles = (U + 127) // 128
-        S = max(1, min(2048 // KC, max(1, 148 // tiles), (n_items + 127) // 128))
+        kc, ns = ctypes.c_int32(0), ctypes.c_int32(0)
+        self.lib.adt_score_tc_plan(ctypes.c_int32(U), ctypes.c_int32(n_items), ctypes.c_int32(K), ctypes.byref(kc), ctypes.byref(ns))
+        KC, S = kc.value, ns.value
         key = ("tc", U, S, KC)
         if key not in self._buf:
             pk = torch.empty(2, U, K, dtype=torch.int32, device=dev)        # [0] scores (float bits), [1] ids: one all-gather payload

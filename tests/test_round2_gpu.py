@@ -131,7 +131,7 @@ def test_sampled_rank_and_fused_metrics_match_reference_protocol():
     m = T.model_from_golden(g).eval()
     rng = np.random.default_rng(3)
     U, C = g["seq"].shape[0], 101
-    item_idx = rng.integers(1, g["dims"]["I"] + 1, size=(U, C))
+    item_idx = np.stack([rng.permutation(g["dims"]["I"])[:C] + 1 for _ in range(U)])      # distinct candidates: no exact score ties
     acc = torch.zeros(7, dtype=torch.float64, device="cuda")
     rank, scores = sampled_rank(m, g["seq"], item_idx, metric_acc=acc)
     pred = -scores.cpu()
