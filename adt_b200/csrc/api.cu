@@ -329,10 +329,13 @@ static adt_dropout row_drop(const adt_dropout& d, int training) {
 }
 
 // ---- sequence-resident block kernels (kernels_seq.cuh): one CTA per sequence, a whole block per launch ------------------------
-static bool use_seq(int L, int H, int nh, int mma) {
+// ADT_SEQ_FUSED is a bit mask of the launches served by the sequence-resident kernels: 1 encoder fwd, 2 decoder fwd, 4 encoder bwd,
+// 8 decoder bwd (default below; 0 = the row-tile kernels everywhere)
+enum { SEQ_ENC_FWD = 1, SEQ_DEC_FWD = 2, SEQ_ENC_BWD = 4, SEQ_DEC_BWD = 8, SEQ_DEFAULT = 15 };
+static bool use_seq(int L, int H, int nh, int mma, int which = SEQ_ENC_FWD) {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("ADT_SEQ_FUSED"); v = e ? (atoi(e) != 0) : 1; }
-  return v && mma && H == RS_H && L <= 64 && (nh == 1 || nh == 2 || nh == 4);
+  if (v < 0) { const char* e = getenv("ADT_SEQ_FUSED"); v = e ? atoi(e) : SEQ_DEFAULT; }
+  return (v & which) && mma && H == RS_H && L <= 64 && (nh == 1 || nh == 2 || nh == 4);
 }
 extern "C" int adt_seq_kernels_apply(int32_t L, int32_t H, int32_t nh, int32_t precision) { return use_seq(L, H, nh, precision ? 1 : 0) ? 1 : 0; }
 
@@ -488,7 +491,7 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
-  if (use_seq(a->L, H, a->nh, mma)) return seq_enc_bwd(a, s);
+  if (use_seq(a->L, H, a->nh, mma, SEQ_ENC_BWD)) return seq_enc_bwd(a, s);
   PostBwdArgs p;
   memset(&p, 0, sizeof(p));
   p.dout = a->dout; p.ids = a->ids; p.ctx = a->ctx; p.u = a->y; p.h1 = a->h1;
@@ -530,7 +533,7 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
-  if (use_seq(a->L, H, a->nh, mma)) return seq_dec_fwd(a, s);
+  if (use_seq(a->L, H, a->nh, mma, SEQ_DEC_FWD)) return seq_dec_fwd(a, s);
   if (a->phase != 2) {
     if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, a->precision, s)) return e;
     if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
@@ -580,7 +583,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
-  if (use_seq(a->L, H, a->nh, mma)) return seq_dec_bwd(a, s);
+  if (use_seq(a->L, H, a->nh, mma, SEQ_DEC_BWD)) return seq_dec_bwd(a, s);
   size_t smem;
   int tm = pick_tm(4 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");

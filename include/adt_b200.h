@@ -378,6 +378,32 @@ int adt_sqdiff_bwd(const float* a, const float* b, const float* g, float scale, 
  * so that <user row, catalog row> = -distance(u, i) + const(u): the largest dot product is the smallest distance. */
 int adt_wcatalog_rows(const float* mean, const float* cov, float* out, int32_t n, int32_t H, int32_t is_user, adt_stream_t stream);
 
+/* ---- device-side batch assembly and sampling ---------------------------------------------------------------------
+ * User histories live in HBM as CSR (hist_indptr [n_users+2] indexed by user id, hist_items in interaction order, hist_sorted the same
+ * rows sorted ascending for membership tests).  Every random draw is Philox4x32-10 of (seed, epoch, user, position, draw index), so
+ * a sample does not depend on its batch and oracle/sampler_oracle.py reproduces it bit for bit.
+ * adt_assemble_train_batch == WarpDataset.sample_data + random_neq (sasrec/utils.py:288-307, :73-77): right-aligned seq / pos,
+ * dec = seq shifted right by one, neg uniform over 1..itemnum outside the user's history. */
+typedef struct {
+  const int32_t* users; const int32_t* hist_indptr; const int32_t* hist_items; const int32_t* hist_sorted;
+  int32_t* seq; int32_t* dec; int32_t* pos; int32_t* neg;      /* out [B][L] */
+  int32_t B, L, itemnum; uint64_t seed; uint32_t epoch;
+} adt_train_batch_args;
+int adt_assemble_train_batch(const adt_train_batch_args* a, adt_stream_t stream);
+/* adt_assemble_eval_batch == EvalDataset.sample_data (sasrec/utils.py:162-191) + PopularSampler.get_negative_samples (:57-69):
+ * seq = the last L history items (+ last_item[u] appended when non-zero: test mode), item_idx[u] = [answers[u], n_candidates ids drawn
+ * by popularity WITHOUT replacement over ids 0..itemnum-1 (quirk B8) outside the user's seen set].  alias_prob / alias_idx: Vose alias
+ * table of popular_p.  n_candidates == 0: sequences only. */
+typedef struct {
+  const int32_t* users; const int32_t* hist_indptr; const int32_t* hist_items;
+  const int32_t* seen_indptr; const int32_t* seen_sorted;       /* per-user seen set (sorted ids), CSR by user id */
+  const int32_t* last_item; const int32_t* answers;
+  const float* alias_prob; const int32_t* alias_idx;
+  int32_t* seq; int32_t* item_idx;                              /* out [U][L], [U][1 + n_candidates] */
+  int32_t U, L, itemnum, n_candidates; uint64_t seed; uint32_t epoch;
+} adt_eval_batch_args;
+int adt_assemble_eval_batch(const adt_eval_batch_args* a, adt_stream_t stream);
+
 /* optional per-kernel CUDA-event timing (used by bench.py for the live roofline number; off by default) */
 int adt_timing_enable(int on);
 int adt_debug_read(long long* out, int n);   /* clock64() phase stamps of CTA 0 of the instrumented kernels (debug) */

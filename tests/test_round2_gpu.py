@@ -295,7 +295,7 @@ def test_sequence_resident_block_kernels_match_row_tile_kernels(nh, Lq):
     import json, os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = []
-    for fused in ("0", "1"):
+    for fused in ("0", "15"):
         env = dict(os.environ, ADT_SEQ_FUSED=fused)
         r = subprocess.run([sys.executable, os.path.join(root, "tools", "seq_ab.py"), str(nh), str(Lq)], capture_output=True, text=True, env=env,
                            timeout=600)
@@ -307,5 +307,7 @@ def test_sequence_resident_block_kernels_match_row_tile_kernels(nh, Lq):
         assert abs(a["gnorm"][k] - b["gnorm"][k]) / a["gnorm"][k] < 1e-3, (k, a["gnorm"], b["gnorm"])
         assert abs(a["gsum"][k] - b["gsum"][k]) / a["gsum"][k] < 1e-3
     assert abs(a["psum"] - b["psum"]) / a["psum"] < 1e-4
+    # three optimisation steps with fp32-atomic weight gradients later, near-ties of a 12k-item catalog may swap places
     same = np.mean(np.array(a["ids"]) == np.array(b["ids"]))
-    assert same > 0.98, same
+    assert same > 0.9, same
+    assert np.abs(np.array(a["scores"]) - np.array(b["scores"])).max() < 2e-3
