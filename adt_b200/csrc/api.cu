@@ -329,13 +329,19 @@ static adt_dropout row_drop(const adt_dropout& d, int training) {
 }
 
 // ---- sequence-resident block kernels (kernels_seq.cuh): one CTA per sequence, a whole block per launch ------------------------
-// ADT_SEQ_FUSED is a bit mask of the launches served by the sequence-resident kernels: 1 encoder fwd, 2 decoder fwd, 4 encoder bwd,
-// 8 decoder bwd (default below; 0 = the row-tile kernels everywhere)
-enum { SEQ_ENC_FWD = 1, SEQ_DEC_FWD = 2, SEQ_ENC_BWD = 4, SEQ_DEC_BWD = 8, SEQ_DEFAULT = 15 };
-static bool use_seq(int L, int H, int nh, int mma, int which = SEQ_ENC_FWD) {
+// ADT_SEQ_FUSED is a bit mask of the launches served by the sequence-resident kernels: 1 encoder fwd in evaluation mode, 2 decoder
+// fwd, 4 encoder bwd, 8 decoder bwd, 16 encoder fwd in training mode too (0 = the row-tile kernels everywhere).  Default = 1: measured
+// on B200 at the C2 shape (profiles/r02_seq_kernel_variants.md) the one-launch-per-block kernels win where a block runs alone
+// (evaluation: +6 % users/s) but lose inside the training step, whose row-tile kernels overlap across the two streams of the step
+// graph while a sequence-resident CTA pins 83-110 KB of shared memory per SM (0.533 ms -> 0.622 ms with all of them on).
+enum { SEQ_ENC_FWD = 1, SEQ_DEC_FWD = 2, SEQ_ENC_BWD = 4, SEQ_DEC_BWD = 8, SEQ_ENC_FWD_TRAIN = 16, SEQ_DEFAULT = 1 };
+static int seq_mask() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("ADT_SEQ_FUSED"); v = e ? atoi(e) : SEQ_DEFAULT; }
-  return (v & which) && mma && H == RS_H && L <= 64 && (nh == 1 || nh == 2 || nh == 4);
+  return v;
+}
+static bool use_seq(int L, int H, int nh, int mma, int which = SEQ_ENC_FWD) {
+  return (seq_mask() & which) && mma && H == RS_H && L <= 64 && (nh == 1 || nh == 2 || nh == 4);
 }
 extern "C" int adt_seq_kernels_apply(int32_t L, int32_t H, int32_t nh, int32_t precision) { return use_seq(L, H, nh, precision ? 1 : 0) ? 1 : 0; }
 
@@ -455,7 +461,7 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   if (a->phase < 0 || a->phase > 2) return fail(ADT_E_SHAPE, "%s", "enc_block_fwd: phase must be 0, 1 or 2");
-  if (a->phase == 0 && use_seq(a->L, H, a->nh, mma)) return seq_enc_fwd(a, s);
+  if (a->phase == 0 && use_seq(a->L, H, a->nh, mma, a->training ? SEQ_ENC_FWD_TRAIN : SEQ_ENC_FWD)) return seq_enc_fwd(a, s);
   if (a->phase != 2) {
     if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, a->precision, s)) return e;
     if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))

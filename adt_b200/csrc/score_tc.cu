@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   constexpr int B_STAGE = KB * BN * 128;
   uint8_t* sA = smem;
   uint8_t* sB = sA + A_BYTES;
-  const int KCP = a.KC <= 32 ? 32 : 64;                       // list slots reserved per user row
+  const int KCP = MODE == 0 ? (a.KC <= 32 ? 32 : 64) : 0;     // list slots reserved per user row (the two-pass modes keep no lists on chip)
   uint32_t* lk = reinterpret_cast<uint32_t*>(sB + NS * B_STAGE);  // [KCP][128] order-preserving score keys, slot-major: the
   int* li = reinterpret_cast<int*>(lk + BM * KCP);                // [KCP][128] item ids      thread that owns a row scans it conflict-free
   float* thr_s = reinterpret_cast<float*>(li + BM * KCP);         // [128] (unused scratch)
@@ -163,9 +163,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     const int row = 32 * q + lane;
     const int u = u0 + row;
     const int KC = a.KC;
-    for (int k = 0; k < KC; ++k) {
-      lk[k * BM + row] = 0u;                 // key 0 = "worse than anything"
-      li[k * BM + row] = -1;
+    if (MODE == 0) {
+      for (int k = 0; k < KC; ++k) {
+        lk[k * BM + row] = 0u;               // key 0 = "worse than anything"
+        li[k * BM + row] = -1;
+      }
     }
     int sb = 0, se = 0;                      // this row's seen ids inside the item span this CTA touches
     if (a.seen_indptr && u < a.U) {
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       thr = u < a.U ? a.tau[u] : INFINITY;
       int cnt = 0;
       bool overflow = false;
+      const long long obase = ((long long)split * a.U + (u < a.U ? u : 0)) * KC;
       for (int t = 0; t < ntiles; ++t) {
         const int st = t & 1;
         tc::mbar_wait(tfull + st, (t >> 1) & 1);
@@ -220,8 +223,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
               const float x = vs[c * 32 + lane];
               if (x > thr) {
                 const int item = a.item_offset + ib + c;
-                if (!tc_is_seen(a, sb, se, item)) {
-                  if (cnt < KC) { lk[cnt * BM + row] = fkey(x); li[cnt * BM + row] = item; ++cnt; }
+                if (!tc_is_seen(a, sb, se, item)) {       // rare: candidates go straight to HBM, no list on chip
+                  if (cnt < KC) { a.part_scores[obase + cnt] = x; a.part_ids[obase + cnt] = item; ++cnt; }
                   else overflow = true;
                 }
               }
@@ -231,6 +234,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         }
       }
       if (overflow) thr = INFINITY;          // candidates were dropped: the caller must re-run this user exactly
+      if (u < a.U) {
+        for (int k = cnt; k < KC; ++k) { a.part_scores[obase + k] = -INFINITY; a.part_ids[obase + k] = -1; }
+        a.part_thr[(long long)split * a.U + u] = thr;
+      }
+    } else if constexpr (MODE == 2) {
+      // ---- sample pass: only the maximum of every sampled tile is kept, [sample tile][user] in part_scores (tau_select_kernel picks the
+      // R-th largest of them): no lists, no shared memory, one store per (row, tile)
+      thr = 0.f;
+      for (int t = 0; t < ntiles; ++t) {
+        const int st = t & 1;
+        tc::mbar_wait(tfull + st, (t >> 1) & 1);
+        tc::tc_fence_after();
+        const int tb = (tfirst + t * tstep) * BN;
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
+          if (c0 + 32 == BN) {
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty + st);
+          }
+          const int nvalid = a.n_items - (tb + c0);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, c < nvalid ? v[c] : -INFINITY);
+        }
+        if (u < a.U) a.part_scores[(long long)(split + t * a.n_splits) * a.U + u] = mx;
+      }
     } else {
     uint32_t mink = 0u;                      // smallest key in the list and its slot
     int minpos = 0;
@@ -302,7 +334,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       }
     }
     }
-    if (u < a.U) {
+    if (MODE == 0 && u < a.U) {
       const long long o = ((long long)split * a.U + u) * KC;
       for (int k = 0; k < KC; ++k) {
         const uint32_t key = lk[k * BM + row];
@@ -464,7 +496,7 @@ int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k
 // deepest catalog-tile ring (2..4 stages) that fits the 227 KB of shared memory next to the user tile and the top-K lists
 template <int KB, int BN, int MODE>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
-  const size_t fixed = 1024 + (size_t)KB * BM * 128 + (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 + BM * 4 + 4 * 1024 * 4 + 256;
+  const size_t fixed = 1024 + (size_t)KB * BM * 128 + (MODE == 0 ? (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 : 0) + BM * 4 + 4 * 1024 * 4 + 256;
   const size_t stage = (size_t)KB * BN * 128, cap = 227 * 1024;
   if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4, MODE>(tmA, tmB, k, grid, s, fixed + 4 * stage);
   if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3, MODE>(tmA, tmB, k, grid, s, fixed + 3 * stage);
@@ -480,25 +512,18 @@ int launch_tc_h(int KB, const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
   return ADT_E_SHAPE;
 }
 
-// tau[u] = the R-th largest score among the sample pass's per-split lists [S][U][KCA] (-inf when the sample holds fewer than R
-// scores): with a sample of 1/sstride of the catalog, about R*sstride catalog items score above it.  Warp per user.
-__global__ void __launch_bounds__(256) tau_select_kernel(const float* __restrict__ part_scores, const int* __restrict__ part_ids, int S, int U,
-                                                         int KCA, int R, float* __restrict__ tau) {
+// tau[u] = the R-th largest of the nst sampled-tile maxima of user u (layout [sample tile][U]; -inf when there are fewer than R).
+// The R largest tile maxima are R distinct catalog scores >= tau, so with a sample of 1/sstride of the tiles about R*sstride (or a few
+// more) catalog items score above tau.  Warp per user, nst <= 2048.
+__global__ void __launch_bounds__(256) tau_select_kernel(const float* __restrict__ tile_max, int nst, int U, int R, float* __restrict__ tau) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   const int u = blockIdx.x * 8 + w;
   if (u >= U) return;
-  const int n = S * KCA;                      // <= 2048 (checked by the launcher)
   float mine[64];                             // lane l owns entries l, l+32, ...
 #pragma unroll
   for (int j = 0; j < 64; ++j) {
     const int c = l + 32 * j;
-    float v = -INFINITY;
-    if (c < n) {
-      const int sp = c / KCA, k = c - sp * KCA;
-      const long long o = ((long long)sp * U + u) * KCA + k;
-      if (part_ids[o] >= 0) v = part_scores[o];
-    }
-    mine[j] = v;
+    mine[j] = c < nst ? tile_max[(long long)c * U + u] : -INFINITY;
   }
   float kth = -INFINITY;
   for (int r = 0; r < R; ++r) {
@@ -582,21 +607,31 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   dim3 grid(a->n_splits, (a->U + BM - 1) / BM);
   int rc;
   k.tau = nullptr; k.sstride = 1;
-  // Large catalogs: two passes.  (1) a SAMPLE of every 16th catalog tile is scored with streaming top-R lists; the R-th best sample
-  // score of a user becomes her threshold tau, so about 16 R (>= 6 K) catalog items score above it.  (2) the whole catalog is scored
-  // against that FIXED threshold: the epilogue only appends (no sorted-list maintenance, no warm-up phase per split).  Everything
-  // above tau is a candidate, so the exactness test of the re-score kernel is unchanged (thr = tau, or +inf after an overflow).
+  // Large catalogs: two passes.  (1) a SAMPLE of every 16th catalog tile is scored and only the maximum of each sampled tile is kept
+  // per user; the R-th largest of those maxima becomes the user's threshold tau, so about 16 R (>= 6 K) catalog items score above it.
+  // (2) the whole catalog is scored against that FIXED threshold: the epilogue is one max-reduction and one compare per 32 scores, the
+  // rare candidates are appended straight to HBM (no sorted lists, no warm-up phase per split, no list storage on chip -> a deeper
+  // TMA ring).  Everything above tau is a candidate, so the exactness test of the re-score kernel is unchanged (thr = tau, or +inf
+  // after an overflow of a split's KC slots).
   static int two_pass = -1;
   if (two_pass < 0) { const char* e = getenv("ADT_TC_TWO_PASS"); two_pass = e ? atoi(e) : 1; }
-  const int sstride = TC_SSTRIDE;
-  const int R = (tc_target(a->K) + sstride - 1) / sstride;
-  if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && R <= a->KC && a->n_splits * R <= RS_MAXC) {
+  // sample stride: every 16th catalog tile, coarser when the tile maxima would not fit the scratch (part_scores holds
+  // n_splits*KC floats per user) or the selection kernel (2048 values per user)
+  const int BNk = KB == 4 ? 64 : 128;
+  const int ntt = (a->n_items + BNk - 1) / BNk;
+  int cap = a->n_splits * a->KC < 2048 ? a->n_splits * a->KC : 2048;
+  int sstride = TC_SSTRIDE;
+  while ((ntt + sstride - 1) / sstride > cap) sstride *= 2;
+  const int nst = (ntt + sstride - 1) / sstride;
+  int R = (tc_target(a->K) + sstride - 1) / sstride;
+  if (R < 4) R = 4;
+  if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && a->K <= 48 && nst >= 4 * R) {
     TcArgs ks = k;
-    ks.KC = R; ks.sstride = sstride; ks.gthr = nullptr;
+    ks.sstride = sstride; ks.gthr = nullptr;
     rc = launch_tc_h<2>(KB, tmA, tmB, ks, grid, s);
     if (rc) return rc;
     float* tau = a->out_scores;            // U floats of scratch: overwritten by the re-score kernel at the end
-    tau_select_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(a->part_scores, a->part_ids, a->n_splits, a->U, R, R, tau);
+    tau_select_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(a->part_scores, nst, a->U, R, tau);
     k.tau = tau; k.gthr = nullptr;
     rc = launch_tc_h<1>(KB, tmA, tmB, k, grid, s);
   } else {

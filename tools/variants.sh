@@ -1,6 +1,6 @@
 #!/bin/bash
 # bench variants of the C2 step with different sets of sequence-resident kernels (ADT_SEQ_FUSED bit mask) -> gpurun_out/variants.txt
-for m in 0 1 3 5 7 15; do
+for m in 0 1 17 19 21 23 31; do
   ADT_SEQ_FUSED=$m python bench.py --steps 20 --warmup 5 --skip c1,c5,refgpu,fp32,selfcheck --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
