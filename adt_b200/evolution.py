@@ -8,7 +8,7 @@ given the frozen supernet weights, so candidate c goes to rank c mod G; ranks ga
 import numpy as np
 import torch
 
-from .evaluate import rank_of_first_candidate, sampled_metrics
+from .evaluate import rank_of_first_candidate, sampled_metrics, sampled_rank, sampled_metrics_from_acc
 from .lambdas import candidate_to_lambdas
 
 
@@ -40,15 +40,17 @@ def assign(n_candidates, world, rank):
     return list(range(rank, n_candidates, world))
 
 
-def evaluate_population(candidates, fitness_fn, process_group=None):
+def evaluate_population(candidates, fitness_fn, process_group=None, local=None):
     """Evaluate `candidates` (list of vectors) in parallel over the ranks of `process_group`.
-    fitness_fn(cand) -> tuple of floats is called only for this rank's candidates.
+    fitness_fn(cand) -> tuple of floats is called only for this rank's candidates (or `local` = their already computed tuples).
     Returns an array [n_candidates, n_metrics] identical on every rank."""
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
     world = torch.distributed.get_world_size(process_group) if dist_on else 1
     rank = torch.distributed.get_rank(process_group) if dist_on else 0
     mine = assign(len(candidates), world, rank)
-    local = [tuple(float(x) for x in fitness_fn(candidates[c])) for c in mine]
+    if local is None:
+        local = [tuple(float(x) for x in fitness_fn(candidates[c])) for c in mine]
+    local = [tuple(float(x) for x in t) for t in local]
     nm = len(local[0]) if local else 0
     if world == 1:
         return np.array(local, dtype=np.float64).reshape(len(candidates), -1)
@@ -69,3 +71,65 @@ def evaluate_population(candidates, fitness_fn, process_group=None):
         for j, c in enumerate(assign(len(candidates), world, r)):
             res[c] = out[r, j]
     return res
+
+
+
+class PopulationEvaluator:
+    """Fitness of a whole population of lambda candidates against ONE frozen supernet (the reference walks the population
+    strictly sequentially, sasrec/evolution.py:172-206, re-sampling the validation negatives on the CPU for every candidate).
+
+      * the validation batches (sequences + 1 + C sampled candidates per user) are assembled ONCE on the device
+        (adt_b200.sampler.DeviceSampler.eval_batch) and shared by every candidate -- every candidate is ranked on the same negatives;
+      * per candidate the host only flips `set_choice` and enqueues the encoder blocks + ONE gather-dot / rank / metric launch per
+        batch (adt_candidate_scores): AUC / NDCG@10 / HR@10 accumulate on the device, nothing is read back per batch;
+      * `in_flight` candidates are enqueued on separate CUDA streams: their evaluations are independent given the frozen weights, and
+        one candidate's latency-bound kernels leave most of a B200 idle;
+      * with a process group the candidates are dealt round-robin to the ranks (candidate c -> rank c mod G) and the fitness triples
+        are all-gathered (evaluate_population)."""
+
+    def __init__(self, model, val_batches, rec_choice, ind_choice, process_group=None, in_flight=4):
+        self.model, self.batches = model, list(val_batches)
+        self.rec_choice, self.ind_choice = rec_choice, ind_choice
+        self.pg = process_group
+        dev = model.item_emb.weight.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, int(in_flight)))]
+        self.evaluated = 0
+
+    @torch.no_grad()
+    def _enqueue(self, cand, stream):
+        dev = self.model.item_emb.weight.device
+        acc = torch.zeros(7, dtype=torch.float64, device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            set_choice_from_candidate(self.model, cand, self.rec_choice, self.ind_choice)
+            for seq, item_idx in self.batches:
+                sampled_rank(self.model, seq, item_idx, metric_acc=acc)
+        return acc
+
+    @torch.no_grad()
+    def fitness_many(self, cands):
+        """[(AUC, NDCG@10, HR@10)] for this process's candidates, `in_flight` of them enqueued at a time"""
+        self.model.eval()
+        out, pending = [], []
+        for i, cand in enumerate(cands):
+            pending.append(self._enqueue(cand, self.streams[i % len(self.streams)]))
+            if len(pending) == len(self.streams) or i == len(cands) - 1:
+                for s in self.streams:
+                    torch.cuda.current_stream().wait_stream(s)
+                for acc in pending:
+                    (ndcg, hr), auc, _ = sampled_metrics_from_acc(acc)
+                    out.append((auc, ndcg[10], hr[10]))
+                pending = []
+        self.evaluated += len(cands)
+        return out
+
+    def fitness(self, cand):
+        return self.fitness_many([cand])[0]
+
+    def evaluate(self, candidates):
+        """-> array [n_candidates, 3] identical on every rank"""
+        dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+        world = torch.distributed.get_world_size(self.pg) if dist_on else 1
+        rank = torch.distributed.get_rank(self.pg) if dist_on else 0
+        mine = assign(len(candidates), world, rank)
+        return evaluate_population(candidates, None, self.pg, local=self.fitness_many([candidates[c] for c in mine]))

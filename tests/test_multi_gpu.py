@@ -41,7 +41,8 @@ def _worker(rank, world, port, ret):
     same = bool(torch.equal(flat, other))
     # item-sharded eval == unsharded exact eval
     m.eval()
-    sc = CatalogScorer(m, K=5, use_tensor_cores=True, tc_min_items=0)
+    sc = CatalogScorer(m, K=5, use_tensor_cores=True, tc_min_items=0, shard=True)
+    assert sc.sharded
     s, i = sc.topk(seq)
     ref = m.predict(None, seq, None, True)
     rs, ri = torch.topk(ref, 5, dim=1)
