@@ -123,7 +123,59 @@ __global__ void __launch_bounds__(256) assemble_eval_kernel(EvalBatchArgs a) {
   }
 }
 
+// ---- Bert4Rec cloze instances (bert4rec/datasets/dataset.py:70-158) -------------------------------------------------------------
+struct ClozeArgs {
+  const int* users; const int* win_start; const int* win_len; const int* dup;     // per instance; dup < 0: the "mask last" instance
+  const int* indptr; const int* items;
+  int* tokens; int* dec_tokens; int* labels;
+  int B, L, itemnum, mask_token; float mask_prob; uint32_t seed_lo, seed_hi, epoch;
+};
+
+// one thread per (instance, position).  Window w = history[start, start + len) right aligned in L slots; position j of the window:
+//   p = U[0,1) ; p < mask_prob: label = item, token = MASK (p/mask_prob < 0.8) | random item in 1..itemnum (< 0.9) | item ; else token = item
+// the decoder copy equals the tokens except that the LAST position is always the mask token (dataset.py:150); the mask-last instance
+// masks only the last position (dataset.py:99-121).  Draw = Philox(ctr = (user, start + j, dup, epoch)).
+__global__ void __launch_bounds__(256) cloze_kernel(ClozeArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * a.L) return;
+  const int b = i / a.L, idx = i - b * a.L;
+  const int user = a.users[b], start = a.win_start[b], len = a.win_len[b], dup = a.dup[b];
+  const int j = idx - (a.L - len);          // position inside the window (negative: left padding)
+  int tok = 0, dtok = 0, lab = 0;
+  if (j >= 0) {
+    const int item = a.items[a.indptr[user] + start + j];
+    tok = dtok = item;
+    if (dup < 0) {
+      if (j == len - 1) { tok = dtok = a.mask_token; lab = item; }
+    } else {
+      const uint4 r = philox4x32_10((uint32_t)user, (uint32_t)(start + j), (uint32_t)dup, a.epoch, a.seed_lo, a.seed_hi);
+      float p = (float)(r.x >> 8) * (1.0f / 16777216.0f);
+      if (p < a.mask_prob) {
+        p = p / a.mask_prob;
+        if (p < 0.8f) tok = a.mask_token;
+        else if (p < 0.9f) tok = 1 + (int)bounded(r.y, (uint32_t)a.itemnum);
+        dtok = tok;
+        lab = item;
+      }
+      if (j == len - 1) dtok = a.mask_token;
+    }
+  }
+  a.tokens[i] = tok; a.dec_tokens[i] = dtok; a.labels[i] = lab;
+}
+
 }  // namespace
+
+extern "C" int adt_cloze_batch(const adt_cloze_batch_args* a, adt_stream_t s_) {
+  if (a->B <= 0 || a->L <= 0 || a->itemnum <= 0) return ADT_E_SHAPE;
+  ClozeArgs k;
+  k.users = a->users; k.win_start = a->win_start; k.win_len = a->win_len; k.dup = a->dup; k.indptr = a->hist_indptr; k.items = a->hist_items;
+  k.tokens = a->tokens; k.dec_tokens = a->dec_tokens; k.labels = a->labels; k.B = a->B; k.L = a->L; k.itemnum = a->itemnum;
+  k.mask_token = a->mask_token; k.mask_prob = a->mask_prob;
+  k.seed_lo = (uint32_t)(a->seed & 0xffffffffull); k.seed_hi = (uint32_t)(a->seed >> 32); k.epoch = a->epoch;
+  const int n = a->B * a->L;
+  cloze_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)s_>>>(k);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
 
 extern "C" int adt_assemble_train_batch(const adt_train_batch_args* a, adt_stream_t s_) {
   if (a->B <= 0 || a->L <= 0 || a->itemnum <= 0) return ADT_E_SHAPE;

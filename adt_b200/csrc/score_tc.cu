@@ -212,25 +212,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
           float mx = v[0];
 #pragma unroll
           for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
-          const bool fire = mx > thr;
-          if (__ballot_sync(0xffffffffu, fire) == 0u || a.debug == 2) continue;
-          float* vs = vsm + q * 1024;
+          if (a.debug == 2) continue;
+          if (mx > thr) {                    // rare (about one row in 150 per chunk): walk the 32 registers, no staging through smem
 #pragma unroll
-          for (int c = 0; c < 32; ++c) vs[c * 32 + lane] = v[c];
-          __syncwarp();
-          if (fire) {
             for (int c = 0; c < 32; ++c) {
-              const float x = vs[c * 32 + lane];
-              if (x > thr) {
+              if (v[c] > thr) {
                 const int item = a.item_offset + ib + c;
-                if (!tc_is_seen(a, sb, se, item)) {       // rare: candidates go straight to HBM, no list on chip
-                  if (cnt < KC) { a.part_scores[obase + cnt] = x; a.part_ids[obase + cnt] = item; ++cnt; }
+                if (!tc_is_seen(a, sb, se, item)) {       // candidates go straight to HBM, no list on chip
+                  if (cnt < KC) { a.part_scores[obase + cnt] = v[c]; a.part_ids[obase + cnt] = item; ++cnt; }
                   else overflow = true;
                 }
               }
             }
           }
-          __syncwarp();
         }
       }
       if (overflow) thr = INFINITY;          // candidates were dropped: the caller must re-run this user exactly
@@ -376,78 +370,87 @@ struct RescoreArgs {
   int U, H, item_offset, K, KC, n_splits;
 };
 
-constexpr int RS_MAXC = 2048;   // candidates per user (n_splits * KC)
+constexpr int RS_MAXC = 2048;   // candidate slots per user (n_splits * KC)
+constexpr int RS_NT = 256;
 
-__global__ void __launch_bounds__(128) rescore_select_kernel(RescoreArgs a) {
-  extern __shared__ float rs_smem[];
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  const int u = blockIdx.x * 4 + w;
-  if (u >= a.U) return;
-  float* cs = rs_smem + w * 2 * RS_MAXC;
-  int* ci = reinterpret_cast<int*>(cs + RS_MAXC);
+// One CTA per user: (1) compact the valid candidates of all splits, (2) one THREAD per candidate recomputes its score in fp32 with
+// the same sequential fmaf order as the exact kernel (bit-identical scores, so the two paths can be mixed and compared), 16 row
+// loads in flight per thread, (3) rank counting under the total order (score desc, id asc) places the K best, (4) the exactness flag
+// and the fused get_full_sort_score sums.
+__global__ void __launch_bounds__(RS_NT) rescore_select_kernel(RescoreArgs a) {
+  __shared__ int cid[RS_MAXC];
+  __shared__ float csc[RS_MAXC];
+  __shared__ int cnt_s, first_s;
+  __shared__ float red[RS_NT / 32];
+  __shared__ float kth_s;
+  const int u = blockIdx.x, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   const int n = a.n_splits * a.KC;
+  if (tid == 0) { cnt_s = 0; first_s = -1; kth_s = -INFINITY; }
   const float* f = a.feats + (long long)u * a.H;
   float fn = 0.f;
-  for (int c = l; c < a.H; c += 32) fn = fmaf(f[c], f[c], fn);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) fn += __shfl_xor_sync(0xffffffffu, fn, o);
+  for (int c = tid; c < a.H; c += RS_NT) fn = fmaf(f[c], f[c], fn);
   float thr_max = -INFINITY;
-  for (int s = l; s < a.n_splits; s += 32) thr_max = fmaxf(thr_max, a.part_thr[(long long)s * a.U + u]);
+  for (int s = tid; s < a.n_splits; s += RS_NT) thr_max = fmaxf(thr_max, a.part_thr[(long long)s * a.U + u]);
+  __syncthreads();
+  for (int c = tid; c < n; c += RS_NT) {
+    const int sp = c / a.KC, k = c - sp * a.KC;
+    const int id = a.part_ids[((long long)sp * a.U + u) * a.KC + k];
+    if (id >= 0) cid[atomicAdd(&cnt_s, 1)] = id;
+  }
+  // |f|^2 and max threshold over the CTA
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) thr_max = fmaxf(thr_max, __shfl_xor_sync(0xffffffffu, thr_max, o));
-  // exact fp32 re-score, lane per candidate
-  for (int c = l; c < n; c += 32) {
-    const int s = c / a.KC, k = c - s * a.KC;
-    const long long o = ((long long)s * a.U + u) * a.KC + k;
-    const int id = a.part_ids[o];
-    float sc = -INFINITY;
-    if (id >= 0) {
-      const float* e = a.E + (long long)(id - a.item_offset) * a.H;
-      float acc = 0.f;
-      for (int h = 0; h < a.H; h += 4) {
-        const float4 ev = *reinterpret_cast<const float4*>(e + h);
-        const float4 fv = *reinterpret_cast<const float4*>(f + h);
-        acc = fmaf(fv.x, ev.x, acc); acc = fmaf(fv.y, ev.y, acc); acc = fmaf(fv.z, ev.z, acc); acc = fmaf(fv.w, ev.w, acc);
+  for (int o = 16; o > 0; o >>= 1) { fn += __shfl_xor_sync(0xffffffffu, fn, o); thr_max = fmaxf(thr_max, __shfl_xor_sync(0xffffffffu, thr_max, o)); }
+  __shared__ float fn_s[RS_NT / 32], tm_s[RS_NT / 32];
+  if (l == 0) { fn_s[w] = fn; tm_s[w] = thr_max; }
+  __syncthreads();
+  const int m = cnt_s;
+  fn = 0.f; thr_max = -INFINITY;
+  for (int i = 0; i < RS_NT / 32; ++i) { fn += fn_s[i]; thr_max = fmaxf(thr_max, tm_s[i]); }
+  for (int c = tid; c < m; c += RS_NT) {
+    const float* e = a.E + (long long)(cid[c] - a.item_offset) * a.H;
+    float acc = 0.f;
+    for (int h0 = 0; h0 < a.H; h0 += 64) {
+      float4 ev[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ev[j] = __ldg(reinterpret_cast<const float4*>(e + h0) + j);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 fv = *reinterpret_cast<const float4*>(f + h0 + 4 * j);
+        acc = fmaf(fv.x, ev[j].x, acc); acc = fmaf(fv.y, ev[j].y, acc); acc = fmaf(fv.z, ev[j].z, acc); acc = fmaf(fv.w, ev[j].w, acc);
       }
-      sc = acc;
     }
-    cs[c] = sc;
-    ci[c] = id;
+    csc[c] = acc;
   }
-  __syncwarp();
-  float kth = -INFINITY;
+  __syncthreads();
   const int answer = a.answers ? a.answers[u] : -1;
-  int first = -1;
-  for (int k = 0; k < a.K; ++k) {
-    float bs = -INFINITY;
-    int bi = 0x7fffffff, bp = -1;
-    for (int c = l; c < n; c += 32) {
-      const float s = cs[c];
-      const int id = ci[c];
-      if (id >= 0 && (s > bs || (s == bs && id < bi))) { bs = s; bi = id; bp = c; }
+  for (int c = tid; c < m; c += RS_NT) {
+    const float s = csc[c];
+    const int id = cid[c];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const float sj = csc[j];
+      rank += (sj > s || (sj == s && cid[j] < id)) ? 1 : 0;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (op >= 0 && (bp < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; bp = op; }
+    if (rank < a.K) {
+      a.out_scores[(long long)u * a.K + rank] = s;
+      a.out_ids[(long long)u * a.K + rank] = id;
+      if (id == answer) first_s = rank;
+      if (rank == a.K - 1) kth_s = s;
     }
-    if (bp >= 0 && (bp & 31) == l) ci[bp] = -1;   // consumed (owner lane of slot bp is bp % 32)
-    __syncwarp();
-    if (l == 0) {
-      a.out_scores[(long long)u * a.K + k] = bp >= 0 ? bs : -INFINITY;
-      a.out_ids[(long long)u * a.K + k] = bp >= 0 ? bi : -1;
-      if (bp >= 0 && bi == answer && first < 0) first = k;
-    }
-    kth = bp >= 0 ? bs : -INFINITY;
   }
-  if (l == 0) {
+  for (int k = m + tid; k < a.K; k += RS_NT) {          // fewer than K candidates: pad (the user is flagged below)
+    a.out_scores[(long long)u * a.K + k] = -INFINITY;
+    a.out_ids[(long long)u * a.K + k] = -1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float kth = m >= a.K ? kth_s : -INFINITY;
     const float eps = 0.0078125f * sqrtf(fn) * sqrtf(*a.max_normsq);   // 2^-7 |f| max|e|
     const int flag = (thr_max > -INFINITY && !(kth > thr_max + eps)) ? 1 : 0;
     a.flags[u] = flag;
     // fused get_full_sort_score epilogue (sasrec/utils.py:686-708) for the users whose list is proven exact
     if (!flag && a.answers && a.metric_acc) {
+      const int first = first_s;
       atomicAdd(a.metric_acc + 5, 1.0);
       if (first >= 0) {
         const double g = 1.0 / log2((double)first + 2.0);
@@ -498,6 +501,9 @@ template <int KB, int BN, int MODE>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
   const size_t fixed = 1024 + (size_t)KB * BM * 128 + (MODE == 0 ? (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 : 0) + BM * 4 + 4 * 1024 * 4 + 256;
   const size_t stage = (size_t)KB * BN * 128, cap = 227 * 1024;
+  // the ring must hold more than one DRAM round trip (~1 us) of tensor work: a [128 x 128 x 64] tile is only 256 cycles
+  if (fixed + 8 * stage <= cap) return launch_tc_ns<KB, BN, 8, MODE>(tmA, tmB, k, grid, s, fixed + 8 * stage);
+  if (fixed + 6 * stage <= cap) return launch_tc_ns<KB, BN, 6, MODE>(tmA, tmB, k, grid, s, fixed + 6 * stage);
   if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4, MODE>(tmA, tmB, k, grid, s, fixed + 4 * stage);
   if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3, MODE>(tmA, tmB, k, grid, s, fixed + 3 * stage);
   if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2, MODE>(tmA, tmB, k, grid, s, fixed + 2 * stage);
@@ -560,7 +566,7 @@ extern "C" int adt_to_bf16(const float* x, void* y, int64_t rows, int32_t H, flo
 // launch plan of adt_score_topk_tc for (U users, n_items catalog rows, top-K): list capacity KC per (split, user) and the number of
 // catalog splits.  Returns 1 when the two-pass (sample threshold + append-only) scheme applies, else 0 (single streaming pass).
 static const int TC_TWO_PASS_MIN_ITEMS = 65536, TC_SSTRIDE = 16;
-static int tc_target(int K) { return K * 6 > 192 ? K * 6 : 192; }
+static int tc_target(int K) { return K * 6 > 96 ? K * 6 : 96; }    // catalog items expected above a user's threshold tau
 extern "C" int adt_score_tc_plan(int32_t U, int32_t n_items, int32_t K, int32_t* KC_out, int32_t* n_splits_out) {
   static int two_pass = -1;
   if (two_pass < 0) { const char* e = getenv("ADT_TC_TWO_PASS"); two_pass = e ? atoi(e) : 1; }
@@ -624,7 +630,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   while ((ntt + sstride - 1) / sstride > cap) sstride *= 2;
   const int nst = (ntt + sstride - 1) / sstride;
   int R = (tc_target(a->K) + sstride - 1) / sstride;
-  if (R < 4) R = 4;
+  if (R < 6) R = 6;
   if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && a->K <= 48 && nst >= 4 * R) {
     TcArgs ks = k;
     ks.sstride = sstride; ks.gthr = nullptr;
@@ -643,8 +649,6 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   r.max_normsq = a->max_normsq; r.out_scores = a->out_scores; r.out_ids = a->out_ids; r.flags = a->flags;
   r.U = a->U; r.H = a->H; r.item_offset = a->item_offset; r.K = a->K; r.KC = a->KC; r.n_splits = a->n_splits;
   r.answers = a->answers; r.metric_acc = a->metric_acc;
-  const size_t rs = (size_t)4 * 2 * RS_MAXC * sizeof(float);
-  cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
-  rescore_select_kernel<<<(a->U + 3) / 4, 128, rs, s>>>(r);
+  rescore_select_kernel<<<a->U, RS_NT, 0, s>>>(r);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }

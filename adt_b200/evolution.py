@@ -30,7 +30,7 @@ def candidate_fitness(model, val_batches, k=10):
     ranks, C = [], None
     for u, seq, item_idx in val_batches:
         ranks.append(rank_of_first_candidate(model, u, seq, item_idx).cpu())
-        C = np.asarray(item_idx).shape[1]
+        C = item_idx.shape[1] if hasattr(item_idx, "shape") else np.asarray(item_idx).shape[1]
     (ndcg, hr), auc = sampled_metrics(torch.cat(ranks), C, ks=(k,))
     return auc, ndcg[k], hr[k]
 

@@ -117,3 +117,59 @@ class DeviceSampler:
                    itemnum=self.itemnum, n_candidates=int(n_candidates), seed=self.seed, epoch=int(epoch))
         L.check(self.lib.adt_assemble_eval_batch(ctypes.byref(a), self._stream()), "adt_assemble_eval_batch")
         return seq, idx
+
+
+class ClozeSampler:
+    """Bert4Rec-ADT training instances on the device (BertTrainDataset._generate_data / sample_data / _mask_last,
+    /root/reference/bert4rec/datasets/dataset.py:70-158).  The reference materialises dupe_factor masked copies of every window of
+    every user as Python lists of tensors before training; here only the instance TABLE (user, window start, window length, copy
+    index) is built once (integer arithmetic on the host, same window enumeration), and the masked token / decoder / label tensors of a
+    batch are generated by one kernel launch from the resident histories, with fresh masks every epoch if wanted."""
+
+    def __init__(self, user_train, usernum, itemnum, maxlen, mask_prob, dupe_factor=10, prop_sliding_window=0.1, device="cuda", seed=23):
+        self.usernum, self.itemnum, self.L = int(usernum), int(itemnum), int(maxlen)
+        self.mask_prob, self.seed, self.mask_token = float(mask_prob), int(seed), int(itemnum) + 1
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise L.AdtError("adt_b200.ClozeSampler generates batches on a CUDA device (no CPU fallback)")
+        self.lib = L.lib()
+        ip, it = _csr(user_train, usernum)
+        self.table = self.instance_table(user_train, usernum, maxlen, dupe_factor, prop_sliding_window)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        self.hist_indptr, self.hist_items = t(ip), t(it)
+        self.tab_dev = t(self.table)
+
+    @staticmethod
+    def instance_table(user_train, usernum, maxlen, dupe_factor, prop_sliding_window):
+        """dataset.py:70-98 -> int32 [n_instances, 4] = (user, window start, window length, copy index | -1 for mask-last)"""
+        rows = []
+        for user in range(1, usernum + 1):
+            seqs = user_train.get(user, []) if isinstance(user_train, dict) else user_train[user]
+            n = len(seqs)
+            if n < 1:
+                continue
+            if n <= maxlen:
+                rows += [(user, 0, n, d) for d in range(dupe_factor)]
+            else:
+                step = int(prop_sliding_window * maxlen) if prop_sliding_window != -1 else maxlen
+                beg = list(range(n - maxlen, 0, -step)) + [0]
+                for i in beg[::-1]:
+                    rows += [(user, i, min(maxlen, n - i), d) for d in range(dupe_factor)]
+            ln = min(n, maxlen)
+            rows.append((user, n - ln, ln, -1))
+        return np.asarray(rows, np.int32).reshape(-1, 4)
+
+    def __len__(self):
+        return len(self.table)
+
+    def batch(self, idx, epoch=0):
+        """idx: int array / tensor of instance indices -> (tokens, dec_tokens, labels) int32 device tensors [B, L]"""
+        ix = idx.to(self.dev, torch.long) if isinstance(idx, torch.Tensor) else torch.from_numpy(np.asarray(idx, np.int64)).to(self.dev)
+        rows = self.tab_dev[ix].t().contiguous()
+        B = ix.numel()
+        out = [torch.empty(B, self.L, dtype=torch.int32, device=self.dev) for _ in range(3)]
+        a = L.fill(L.adt_cloze_batch_args(), users=rows[0], win_start=rows[1], win_len=rows[2], dup=rows[3], hist_indptr=self.hist_indptr,
+                   hist_items=self.hist_items, tokens=out[0], dec_tokens=out[1], labels=out[2], B=B, L=self.L, itemnum=self.itemnum,
+                   mask_token=self.mask_token, mask_prob=self.mask_prob, seed=self.seed, epoch=int(epoch))
+        L.check(self.lib.adt_cloze_batch(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)), "adt_cloze_batch")
+        return tuple(out)

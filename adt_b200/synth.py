@@ -67,3 +67,15 @@ def make_eval_batch(rng, cfg, U):
         seen.append(s.astype(np.int32))
         indptr[u + 1] = indptr[u] + len(s)
     return seq, answers, indptr, (np.concatenate(seen) if seen else np.zeros(0, np.int32))
+
+
+def make_histories(rng, cfg, n_users):
+    """per-user interaction histories of the configured shape, split like data_partition (/root/reference/sasrec/utils.py:124-160):
+    the last item is the test item, the one before the validation item, the rest is training history -> (train, valid, test) dicts"""
+    I = cfg["items"]
+    lens = np.clip(rng.geometric(cfg["geo"], size=n_users) + cfg["add"] + 2, cfg["lo"] + 2, 4 * cfg["L"])
+    train, valid, test = {}, {}, {}
+    for u in range(1, n_users + 1):
+        items = [int(x) for x in zipf_items(rng, int(lens[u - 1]), I)]
+        train[u], valid[u], test[u] = items[:-2], [items[-2]], [items[-1]]
+    return train, valid, test

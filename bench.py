@@ -16,6 +16,7 @@ backward, clip + Adam) over one synthetic batch of the C2 shape (configs[1]: ~12
   c1 {...}                                   configs[0]'s shape (ml-1m: L 200, H 256) through the same trainer
   c5 {...}                                   catalog scoring at 1M items (H 64 / 256): tensor-pipe roofline
   reference_gpu_eager {...}                  the unmodified reference in PyTorch eager on the same B200 (the kernel bar)
+  evolution {...}                            evolution.py's population evaluation on the supernet, candidates dealt to the ranks
   selfcheck {...}                            N > 1: data-parallel and item-sharded results against the 1-GPU fixture
 """
 import argparse
@@ -326,6 +327,32 @@ def train_section(cx, args, cfg, name, precision, K, W, with_e2e=True, with_kern
     if with_kernels:
         kern = kernel_breakdown(cx, tr, resident, min(K, 20))
         out["kernels"] = kern
+    if with_e2e and with_kernels and name == "C2":
+        # end to end WITHOUT any host batch: the batch is assembled on the device from resident user histories (SURVEY 8f-1:
+        # adt_assemble_train_batch = WarpDataset.sample_data + random_neq), then the same step, loss read back every step
+        from adt_b200.sampler import DeviceSampler
+        n_users = 4096
+        tr_h, va_h, te_h = synth.make_histories(np.random.default_rng(5), cfg, n_users)
+        ds = DeviceSampler(tr_h, va_h, te_h, n_users, cfg["items"], cfg["L"], device=cx.dev, seed=23)
+        users = [torch.from_numpy(np.random.default_rng(7 + cx.rank + i).integers(1, n_users + 1, size=B).astype(np.int32)).to(cx.dev) for i in range(8)]
+        bufs = [torch.empty(B, cfg["L"], dtype=torch.int32, device=cx.dev) for _ in range(4)]
+        for i in range(3):
+            tr.step(*ds.train_batch(users[i % 8], epoch=i, out=bufs))
+        rr = []
+        for _ in range(3):
+            cx.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(K):
+                tr.step(*ds.train_batch(users[k % 8], epoch=k, out=bufs))
+                last_loss = tr.loss()
+            e1.record()
+            cx.barrier()
+            rr.append(e0.elapsed_time(e1))
+        (dms,) = reduce_max(cx, float(np.median(rr)))
+        out["e2e_device_batches"] = {"value": cx.world * B * K / (dms / 1e3), "unit": "seqs/s", "ms_per_step": dms / K, "h2d_bytes_per_step": 0,
+                                     "what": "batch assembled on the GPU (history CSR resident, Philox negatives) + step + loss read-back; "
+                                             "the reference feeds this step from 4 CPU DataLoader workers"}
     out["_tr"], out["_model"] = tr, model
     return out
 
@@ -483,6 +510,44 @@ def refgpu_section(cx, cfg):
         return {"unavailable": str(e)[:200]}
 
 
+def evolution_section(cx, cfg):
+    """evolution.py's population evaluation on the frozen supernet: candidates dealt round-robin to the ranks,
+    validation batches assembled once on the device, fused rank metrics; serial (one candidate at a time) vs 4 candidates in flight."""
+    import types
+    from adt_b200.supernet import SuperSASRecModel
+    from adt_b200.sampler import DeviceSampler
+    from adt_b200.evolution import PopulationEvaluator
+    rec_choice = [0, 0.0001, 0.0005, 0.001, 0.005, 0.01]          # sasrec/evolution.py:95-96
+    ind_choice = [0, 0.0001, 0.0005, 0.001, 0.0015, 0.002]
+    n_users, n_val, C = 4096, 2048, 100
+    tr_h, va_h, te_h = synth.make_histories(np.random.default_rng(5), cfg, n_users)
+    torch.manual_seed(3)
+    args = types.SimpleNamespace(device=cx.dev, num_heads=cfg["nh"], maxlen=cfg["L"], num_layers=cfg["nl"], hidden_units=cfg["H"], dropout=cfg["p"])
+    m = SuperSASRecModel(n_users, cfg["items"], rec_choice, ind_choice, args).to(cx.dev).eval()
+    ds = DeviceSampler(tr_h, va_h, te_h, n_users, cfg["items"], cfg["L"], device=cx.dev, seed=23)
+    users = np.arange(1, n_val + 1, dtype=np.int32)
+    batches = [ds.eval_batch(users[i:i + 512], mode="val", n_candidates=C) for i in range(0, n_val, 512)]
+    rng = np.random.default_rng(11)
+    n_cand = 8 * cx.world
+    cands = [list(rng.random(2 * cfg["nl"]) * 0.98) for _ in range(n_cand)]
+    res = {}
+    fit = None
+    for name, inflight in (("serial", 1), ("in_flight_4", 4)):
+        pe = PopulationEvaluator(m, batches, rec_choice, ind_choice, in_flight=inflight)
+        pe.evaluate(cands[:cx.world * 2])
+        cx.barrier()
+        t0 = time.time()
+        fit = pe.evaluate(cands)
+        cx.barrier()
+        dt = time.time() - t0
+        (dt,) = reduce_max(cx, dt)
+        res[name] = {"candidates_per_sec": n_cand / dt, "seconds": dt}
+    res.update({"candidates": n_cand, "val_users": n_val, "sampled_negatives": C, "ranks": cx.world,
+                "best_auc": float(np.max(fit[:, 0])), "what": "set_choice + supernet encoder (4 blended candidate blocks per layer) + "
+                "gather-dot / rank / AUC-NDCG-HR sums per 512-user batch; candidates c -> rank c mod G"})
+    return res
+
+
 def selfcheck_section(cx):
     """N > 1: (a) the data-parallel step on the c2mini_p5 fixture (6 sequences split across 2 ranks... all ranks take a slice) against
     the unmodified reference's loss / updated weights; (b) item-sharded top-K against the single-GPU exact scorer."""
@@ -603,6 +668,14 @@ def main():
         except Exception as e:   # noqa: BLE001
             c5 = {"error": str(e)[:300]}
 
+    evo = None
+    if "evo" not in skip:
+        trace("evolution")
+        try:
+            evo = evolution_section(cx, cfg)
+        except Exception as e:   # noqa: BLE001
+            evo = {"error": str(e)[:300]}
+
     selfcheck = None
     if world > 1 and "selfcheck" not in skip:
         trace("selfcheck")
@@ -638,12 +711,12 @@ def main():
             "metric": "train_seqs_per_sec", "value": main_tr["value"], "unit": "seqs/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": main_tr["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic", "config": config_dict(args, cfg, world), "launch": main_tr["launch"],
-            "e2e": main_tr["e2e"], "gpu_launches": (lps * K) if lps else None, "gpu_launches_per_step": lps,
+            "e2e": main_tr["e2e"], "e2e_device_batches": main_tr.get("e2e_device_batches"), "gpu_launches": (lps * K) if lps else None, "gpu_launches_per_step": lps,
             "gpu_launches_how": "kernel nodes of the captured step graph (cuGraphGetNodes) x timed steps",
             "loss": main_tr["loss"], "roofline": roofline, "step_roofline": main_tr["step_roofline"],
             "kernels_us": {k_: round(v["avg_us"], 2) for k_, v in sorted(kern.items())},
             "eval_users_per_sec": ev["value"] if ev else None, "eval": ev,
-            ("fp32" if other == "fp32" else "bf16"): other_mode, "c1": c1, "c5": c5, "selfcheck": selfcheck, "reference_gpu_eager": refgpu,
+            ("fp32" if other == "fp32" else "bf16"): other_mode, "c1": c1, "c5": c5, "evolution": evo, "selfcheck": selfcheck, "reference_gpu_eager": refgpu,
             "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))

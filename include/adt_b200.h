@@ -404,6 +404,19 @@ typedef struct {
 } adt_eval_batch_args;
 int adt_assemble_eval_batch(const adt_eval_batch_args* a, adt_stream_t stream);
 
+/* adt_cloze_batch == Bert4Rec's cloze instances (bert4rec/datasets/dataset.py:70-158) generated on the device instead of
+ * a pre-generated Python list of dupe_factor x users tensors: instance b = window [win_start, win_start + win_len) of the user's
+ * history, right aligned; per position p ~ U[0,1): p < mask_prob -> label = item and token = mask_token (p/mask_prob < 0.8), a random
+ * item in 1..itemnum (< 0.9) or the item itself; the decoder copy always ends in mask_token; dup[b] < 0 = the "mask last" instance.
+ * Draws are Philox(user, position in the history, dup, epoch): independent of the batch. */
+typedef struct {
+  const int32_t* users; const int32_t* win_start; const int32_t* win_len; const int32_t* dup;
+  const int32_t* hist_indptr; const int32_t* hist_items;
+  int32_t* tokens; int32_t* dec_tokens; int32_t* labels;         /* out [B][L] */
+  int32_t B, L, itemnum, mask_token; float mask_prob; uint64_t seed; uint32_t epoch;
+} adt_cloze_batch_args;
+int adt_cloze_batch(const adt_cloze_batch_args* a, adt_stream_t stream);
+
 /* optional per-kernel CUDA-event timing (used by bench.py for the live roofline number; off by default) */
 int adt_timing_enable(int on);
 int adt_debug_read(long long* out, int n);   /* clock64() phase stamps of CTA 0 of the instrumented kernels (debug) */

@@ -66,3 +66,35 @@ def eval_sample(hist, seen, answer, last_item, user, L, itemnum, S, alias_prob, 
             out.append(cand)
         k += 1
     return seq, np.asarray(out, np.int32)
+
+
+def cloze_sample(hist, user, start, length, dup, L, itemnum, mask_prob, seed, epoch):
+    """BertTrainDataset.sample_data / _mask_last (/root/reference/bert4rec/datasets/dataset.py:99-158) for one instance, with the
+    reference's random.Random draws replaced by the kernel's Philox counters -> tokens, dec_tokens, labels (int32 [L])"""
+    mask_token = itemnum + 1
+    tokens, dec, labels = (np.zeros(L, np.int32) for _ in range(3))
+    win = list(hist[start:start + length])
+    for j, s in enumerate(win):
+        idx = L - length + j
+        tok = dtok = s
+        lab = 0
+        if dup < 0:
+            if j == length - 1:
+                tok = dtok = mask_token
+                lab = s
+        else:
+            r = philox.philox4x32_10(np.uint32([user]), np.uint32(start + j), np.uint32(dup), np.uint32(epoch),
+                                     np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
+            p = np.float32(int(r[0][0]) >> 8) * np.float32(1.0 / 16777216.0)
+            if p < np.float32(mask_prob):
+                p = np.float32(p / np.float32(mask_prob))
+                if p < np.float32(0.8):
+                    tok = mask_token
+                elif p < np.float32(0.9):
+                    tok = 1 + _bounded(int(r[1][0]), itemnum)
+                dtok = tok
+                lab = s
+            if j == length - 1:
+                dtok = mask_token
+        tokens[idx], dec[idx], labels[idx] = tok, dtok, lab
+    return tokens, dec, labels

@@ -188,6 +188,10 @@ def _gloo_worker(rank, world, port, ret):
     fit = lambda c: (float(c.sum()), float(c[0] * 2), float(c[1] - 1))
     res = evaluate_population(cands, fit)
     ok3 = bool(np.allclose(res, np.array([fit(c) for c in cands])))
+    # ... and with the local fitness tuples computed up front (PopulationEvaluator: several candidates in flight per rank)
+    from adt_b200.evolution import assign
+    res2 = evaluate_population(cands, None, local=[fit(cands[c]) for c in assign(len(cands), world, rank)])
+    ok3 = ok3 and bool(np.allclose(res2, res))
     ret[rank] = (ok1, ok2, ok3)
     dist.destroy_process_group()
 
@@ -239,6 +243,8 @@ def test_bench_reference_arm_contract():
               "dtype", "data", "impl", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "train_seqs_per_sec" and d["unit"] == "seqs/s" and d["n_gpus"] == 2
+    assert d["steps"] == 2 and d["warmup"] == 0                      # the arm honours --steps / --warmup
+    assert d["cpu_baseline"]["kind"] == "reference"                   # the staged UNMODIFIED reference, torch's own dropout
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert d["config"]["workload"].startswith("SASRec-ADT C2: train step (items=12101, maxlen=50, hidden=64")
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("port", "reference")

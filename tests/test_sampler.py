@@ -139,3 +139,59 @@ def test_device_candidates_follow_popularity():
     p /= p.sum()
     assert counts[[i for i in range(itemnum) if p[i] == 0]].sum() == 0
     assert np.abs(counts / counts.sum() - p).max() < 0.08
+
+
+def test_cloze_instance_table_and_layout_match_reference_dataset():
+    """the window enumeration of BertTrainDataset._generate_data and the deterministic layout of sample_data / _mask_last
+    (right alignment, decoder copy ending in the mask token, labels) against the UNMODIFIED reference dataset class."""
+    if not os.path.isdir("/root/reference/bert4rec"):
+        pytest.skip("/root/reference not present on this box")
+    import importlib
+    pkg = types.ModuleType("refbert_datasets")          # the reference's `datasets/` has no __init__.py: mount it as a package
+    pkg.__path__ = ["/root/reference/bert4rec/datasets"]
+    sys.modules["refbert_datasets"] = pkg
+    try:
+        mod = importlib.import_module("refbert_datasets.dataset")
+    except Exception as e:   # noqa: BLE001
+        pytest.skip(f"reference dataset module not importable here: {e}")
+    from adt_b200.sampler import ClozeSampler
+    from oracle import sampler_oracle as S
+    rng = np.random.default_rng(2)
+    usernum, itemnum, L = 25, 80, 10
+    train = {u: [int(x) for x in rng.integers(1, itemnum + 1, size=int(rng.integers(0, 35)))] for u in range(1, usernum + 1)}
+    d = mod.BertTrainDataset(train, {}, {}, usernum, itemnum, L, None, 0.0, 1, generate=True, dupe_factor=2, prop_sliding_window=0.5)
+    tab = ClozeSampler.instance_table(train, usernum, L, 2, 0.5)
+    assert len(tab) == len(d.datas)
+    # with mask_prob = 0 nothing is masked: tokens = window, decoder copy = window with the last position masked, labels = 0
+    for row, (data, label) in zip(tab, zip(d.datas, d.labels)):
+        u, st, ln, dup = [int(x) for x in row]
+        tok, dec, lab = S.cloze_sample(train[u], u, st, ln, dup, L, itemnum, 0.0, seed=1, epoch=0)
+        assert np.array_equal(tok, data[0].numpy()) and np.array_equal(dec, data[1].numpy()) and np.array_equal(lab, label.numpy()), row
+
+
+@pytest.mark.gpu
+def test_device_cloze_batches_match_oracle_and_mask_rates():
+    from adt_b200.sampler import ClozeSampler
+    from oracle import sampler_oracle as S
+    rng = np.random.default_rng(4)
+    usernum, itemnum, L = 60, 500, 40
+    train = {u: [int(x) for x in rng.integers(1, itemnum + 1, size=int(rng.integers(0, 120)))] for u in range(1, usernum + 1)}
+    cs = ClozeSampler(train, usernum, itemnum, L, mask_prob=0.2, dupe_factor=3, prop_sliding_window=0.5, seed=(3 << 32) | 5)
+    idx = np.arange(len(cs))
+    tok, dec, lab = [t.cpu().numpy() for t in cs.batch(idx, epoch=2)]
+    for b in range(0, len(cs), 7):
+        u, st, ln, dup = [int(x) for x in cs.table[b]]
+        o = S.cloze_sample(train[u], u, st, ln, dup, L, itemnum, 0.2, seed=(3 << 32) | 5, epoch=2)
+        assert np.array_equal(tok[b], o[0]) and np.array_equal(dec[b], o[1]) and np.array_equal(lab[b], o[2]), b
+    reg = cs.table[:, 3] >= 0
+    valid = tok[reg] != 0
+    masked = lab[reg] != 0
+    rate = masked.sum() / valid.sum()
+    assert abs(rate - 0.2) < 0.02
+    m = masked
+    frac_mask = (tok[reg][m] == itemnum + 1).mean()
+    assert abs(frac_mask - 0.8) < 0.05
+    # different epochs -> different masks; same epoch -> identical (counter based)
+    tok2 = cs.batch(idx, epoch=3)[0].cpu().numpy()
+    assert not np.array_equal(tok, tok2)
+    assert np.array_equal(tok, cs.batch(idx, epoch=2)[0].cpu().numpy())
