@@ -566,27 +566,40 @@ extern "C" int adt_to_bf16(const float* x, void* y, int64_t rows, int32_t H, flo
 // launch plan of adt_score_topk_tc for (U users, n_items catalog rows, top-K): list capacity KC per (split, user) and the number of
 // catalog splits.  Returns 1 when the two-pass (sample threshold + append-only) scheme applies, else 0 (single streaming pass).
 static const int TC_TWO_PASS_MIN_ITEMS = 65536, TC_SSTRIDE = 16;
-static int tc_target(int K) { return K * 6 > 96 ? K * 6 : 96; }    // catalog items expected above a user's threshold tau
-extern "C" int adt_score_tc_plan(int32_t U, int32_t n_items, int32_t K, int32_t* KC_out, int32_t* n_splits_out) {
+static int tc_target(int K) { return K * 6 > 192 ? K * 6 : 192; }    // catalog items expected above a user's threshold tau
+extern "C" int adt_score_tc_plan(int32_t U, int32_t H, int32_t n_items, int32_t K, int32_t* KC_out, int32_t* n_splits_out) {
   static int two_pass = -1;
   if (two_pass < 0) { const char* e = getenv("ADT_TC_TWO_PASS"); two_pass = e ? atoi(e) : 1; }
   const int tiles = (U + BM - 1) / BM;
-  const int item_tiles = (n_items + 127) / 128;
+  const int BN = H == 256 ? 64 : 128;
+  const int ntt = (n_items + BN - 1) / BN;
   int S = 148 / tiles > 1 ? 148 / tiles : 1;
-  if (S > item_tiles) S = item_tiles;
+  if (S > ntt) S = ntt;
   int KC, mode = 0;
   if (two_pass && n_items >= TC_TWO_PASS_MIN_ITEMS && K <= 48) {
-    // capacity >= 4x the expected number of candidates per split (they are spread evenly: tiles are interleaved over the splits)
-    const int target = tc_target(K);
-    int need = (4 * target + S - 1) / S + 8;
-    if (need > 64) { S = (4 * target + 55) / 56; need = (4 * target + S - 1) / S + 8; }
-    KC = need <= 32 ? 32 : 64;
-    mode = 1;
-  } else {
+    // the sample pass parks one maximum per sampled tile in the candidate scratch (n_splits*KC floats per user, <= 2048) and the
+    // threshold pass needs >= 4x the expected number of candidates per split (tiles are interleaved over the splits: even spread)
+    int sstride = TC_SSTRIDE;
+    while ((ntt + sstride - 1) / sstride > RS_MAXC) sstride *= 2;
+    const int nst = (ntt + sstride - 1) / sstride;
+    int R = (tc_target(K) + sstride - 1) / sstride;
+    if (R < 6) R = 6;
+    const int eff = R * sstride;
+    int best_s = 0, best_kc = 0;
+    for (int kc = 32; kc <= 64; kc *= 2) {      // the capacity that needs the fewest extra splits (ties: the smaller lists)
+      int s2 = S;
+      if (s2 * kc < nst) s2 = (nst + kc - 1) / kc;
+      const int per = kc - 8;
+      if (s2 * per < 4 * eff) s2 = (4 * eff + per - 1) / per;
+      if (s2 * kc <= RS_MAXC && s2 <= ntt && (!best_s || s2 < best_s)) { best_s = s2; best_kc = kc; }
+    }
+    if (best_s) { S = best_s; KC = best_kc; mode = 1; } else KC = 64;
+  }
+  if (!mode) {
     KC = K + 8 > 2 * K ? K + 8 : 2 * K;
     if (KC > 64) KC = 64;
+    if (S * KC > RS_MAXC) S = RS_MAXC / KC;
   }
-  if (S * KC > RS_MAXC) S = RS_MAXC / KC;
   if (S < 1) S = 1;
   *KC_out = KC; *n_splits_out = S;
   return mode;
@@ -631,7 +644,8 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   const int nst = (ntt + sstride - 1) / sstride;
   int R = (tc_target(a->K) + sstride - 1) / sstride;
   if (R < 6) R = 6;
-  if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && a->K <= 48 && nst >= 4 * R) {
+  // two passes only when the caller's scratch follows adt_score_tc_plan: room for 4x the expected candidates of a split
+  if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && a->K <= 48 && nst >= 4 * R && (long long)a->n_splits * (a->KC - 8) >= 4ll * R * sstride) {
     TcArgs ks = k;
     ks.sstride = sstride; ks.gthr = nullptr;
     rc = launch_tc_h<2>(KB, tmA, tmB, ks, grid, s);

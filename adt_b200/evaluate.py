@@ -155,7 +155,7 @@ class CatalogScorer:
         n_items = hi - lo
         K = self.K
         kc, ns = ctypes.c_int32(0), ctypes.c_int32(0)
-        self.lib.adt_score_tc_plan(ctypes.c_int32(U), ctypes.c_int32(n_items), ctypes.c_int32(K), ctypes.byref(kc), ctypes.byref(ns))
+        self.lib.adt_score_tc_plan(ctypes.c_int32(U), ctypes.c_int32(H), ctypes.c_int32(n_items), ctypes.c_int32(K), ctypes.byref(kc), ctypes.byref(ns))
         KC, S = kc.value, ns.value
         key = ("tc", U, S, KC)
         if key not in self._buf:

@@ -284,7 +284,7 @@ int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t stream);
  * Returns 1 when the call will run as two passes (catalogs of >= 65,536 rows): a sample of every 16th catalog tile fixes a per-user
  * score threshold tau with about max(192, 6K) catalog items above it, then the whole catalog is filtered against tau with an
  * append-only epilogue (tiles interleaved over the splits); 0: one streaming top-KC pass with cross-split threshold exchange. */
-int adt_score_tc_plan(int32_t U, int32_t n_items, int32_t K, int32_t* KC, int32_t* n_splits);
+int adt_score_tc_plan(int32_t U, int32_t H, int32_t n_items, int32_t K, int32_t* KC, int32_t* n_splits);
 
 /* test helper: out[i] = keep-multiplier (0 or 1/(1-p)) of element base+i of a dropout site */
 int adt_philox_mask(float* out, int64_t n, const adt_dropout* d, adt_stream_t stream);
