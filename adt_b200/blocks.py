@@ -109,7 +109,7 @@ class EncBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ids, cfg, *p):
-        nh, training, d_attn, d_f1, d_f2 = cfg
+        nh, training, d_attn, d_f1, d_f2, prec = cfg
         B, Lq = ids.shape
         M, H = x.shape
         x = x.contiguous()
@@ -119,7 +119,7 @@ class EncBlockFn(torch.autograd.Function):
                    ln2_b=p[7], ffn=L.fill(L.adt_ffn_w(), w1=p[8], b1=p[9], w2=p[10], b2=p[11]), sparse_w=p[12], sparse_b=p[13],
                    q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"], out=sv["out"], rec=sv["rec"],
                    nll_acc=None, B=B, L=Lq, H=H, nh=nh, training=int(training), mask_mode=0, drop_attn=d_attn, drop_ffn1=d_f1,
-                   drop_ffn2=d_f2)
+                   drop_ffn2=d_f2, precision=int(prec))
         L.check(L.lib().adt_enc_block_fwd(ctypes.byref(a), _stream(x.device)), "adt_enc_block_fwd")
         ctx.sv, ctx.x, ctx.ids, ctx.cfg, ctx.p = sv, x, ids, cfg, p
         return sv["out"], sv["rec"]
@@ -127,7 +127,7 @@ class EncBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout, drec):
         sv, x, ids, p = ctx.sv, ctx.x, ctx.ids, ctx.p
-        nh, training, d_attn, d_f1, d_f2 = ctx.cfg
+        nh, training, d_attn, d_f1, d_f2, prec = ctx.cfg
         B, Lq = ids.shape
         M, H = x.shape
         g = [torch.zeros_like(t) for t in p]
@@ -140,7 +140,7 @@ class EncBlockFn(torch.autograd.Function):
                    dq=sc["dq"], dk=sc["dk"], dv=sc["dv"], dctx=sc["dctx"], dy=sc["dy"], dx=sc["dx"],
                    g_ln1_w=g[0], g_ln1_b=g[1], g_attn=_mha_g(g[2], g[3], g[4], g[5]), g_ln2_w=g[6], g_ln2_b=g[7],
                    g_ffn=L.fill(L.adt_ffn_g(), w1=g[8], b1=g[9], w2=g[10], b2=g[11]), g_sparse_w=g[12], g_sparse_b=g[13],
-                   B=B, L=Lq, H=H, nh=nh, mask_mode=0, drop_attn=d_attn, drop_ffn1=d_f1, drop_ffn2=d_f2)
+                   B=B, L=Lq, H=H, nh=nh, mask_mode=0, drop_attn=d_attn, drop_ffn1=d_f1, drop_ffn2=d_f2, precision=int(prec))
         L.check(L.lib().adt_enc_block_bwd(ctypes.byref(a), _stream(x.device)), "adt_enc_block_bwd")
         return (sc["dx"], None, None) + tuple(g)
 
@@ -152,7 +152,7 @@ class DecBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, feats, ids, cfg, *p):
-        nh, training, d_s, d_e, d_f1, d_f2 = cfg
+        nh, training, d_s, d_e, d_f1, d_f2, prec = cfg
         B, Lq = ids.shape
         M, H = x.shape
         x, feats = x.contiguous(), feats.contiguous()
@@ -161,7 +161,7 @@ class DecBlockFn(torch.autograd.Function):
         a = L.fill(L.adt_dec_block_fwd_args(), x=x, feats=feats, ids=ids, ln_w=p[0], ln_b=p[1], slf=_mha_w(p[2], p[3], p[4], p[5]),
                    enc=_mha_w(p[6], p[7], p[8], p[9]), ffn=L.fill(L.adt_ffn_w(), w1=p[10], b1=p[11], w2=p[12], b2=p[13]), enc_in=None,
                    out=sv["out"], mse_acc=None, B=B, L=Lq, H=H, nh=nh, training=int(training), mask_mode=0, drop_slf=d_s, drop_enc=d_e,
-                   drop_ffn1=d_f1, drop_ffn2=d_f2, lse1=sv["lse1"], lse2=sv["lse2"], **{k: sv[k] for k in DecBlockFn.SAVED})
+                   drop_ffn1=d_f1, drop_ffn2=d_f2, precision=int(prec), lse1=sv["lse1"], lse2=sv["lse2"], **{k: sv[k] for k in DecBlockFn.SAVED})
         L.check(L.lib().adt_dec_block_fwd(ctypes.byref(a), _stream(x.device)), "adt_dec_block_fwd")
         ctx.sv, ctx.x, ctx.feats, ctx.ids, ctx.cfg, ctx.p = sv, x, feats, ids, cfg, p
         return sv["out"]
@@ -169,7 +169,7 @@ class DecBlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         sv, x, feats, ids, p = ctx.sv, ctx.x, ctx.feats, ctx.ids, ctx.p
-        nh, training, d_s, d_e, d_f1, d_f2 = ctx.cfg
+        nh, training, d_s, d_e, d_f1, d_f2, prec = ctx.cfg
         B, Lq = ids.shape
         M, H = x.shape
         g = [torch.zeros_like(t) for t in p]
@@ -181,7 +181,7 @@ class DecBlockFn(torch.autograd.Function):
                    dq=sc["dq"], dk=sc["dk"], dv=sc["dv"], dctx=sc["dctx"], dd=sc["dd"], dq2=sc["dq2"], dk2=sc["dk2"], dv2=sc["dv2"],
                    dctx2=sc["dctx2"], dfeats=dfeats, dx=sc["dx"], g_ln_w=g[0], g_ln_b=g[1], g_slf=_mha_g(g[2], g[3], g[4], g[5]),
                    g_enc=_mha_g(g[6], g[7], g[8], g[9]), g_ffn=L.fill(L.adt_ffn_g(), w1=g[10], b1=g[11], w2=g[12], b2=g[13]),
-                   B=B, L=Lq, H=H, nh=nh, mask_mode=0, drop_slf=d_s, drop_enc=d_e, drop_ffn1=d_f1, drop_ffn2=d_f2,
+                   B=B, L=Lq, H=H, nh=nh, mask_mode=0, drop_slf=d_s, drop_enc=d_e, drop_ffn1=d_f1, drop_ffn2=d_f2, precision=int(prec),
                    lse1=sv["lse1"], lse2=sv["lse2"], **{k: sv[k] for k in DecBlockFn.SAVED})
         L.check(L.lib().adt_dec_block_bwd(ctypes.byref(a), _stream(x.device)), "adt_dec_block_bwd")
         return (sc["dx"], dfeats, None, None) + tuple(g)

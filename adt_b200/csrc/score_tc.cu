@@ -75,7 +75,9 @@ __device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int sb, int se, int 
 }
 
 // NS = depth of the TMA ring of catalog tiles (B operand); accumulators are double buffered in TMEM
-template <int KB, int BN, int NS, int MODE>
+// MC: the CTA is one of a 2-CTA cluster that walks the SAME catalog tiles for two different user tiles; each CTA fetches half of every
+// catalog tile and TMA multicasts it into both CTAs' rings, so every catalog byte leaves L2 once per pair (tmB's box is BN/2 rows then)
+template <int KB, int BN, int NS, int MODE, bool MC>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -98,7 +100,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x, u0 = blockIdx.y * BM;
+  const int split = MC ? blockIdx.y : blockIdx.x, u0 = (MC ? blockIdx.x : blockIdx.y) * BM;
+  const uint32_t crank = MC ? tc::cluster_ctarank() : 0u;
   int tfirst, tstep, ntiles;
   tc_tile_walk<MODE>(a, BN, split, tfirst, tstep, ntiles);
   const int it0 = min(a.n_items, tfirst * BN), it1 = min(a.n_items, (tfirst + (ntiles > 0 ? (ntiles - 1) * tstep + 1 : 0)) * BN);   // item span touched
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     tc::tma_prefetch_desc(&tmB);
     for (int i = 0; i < NS; ++i) {
       tc::mbar_init(full + i, 1);
-      tc::mbar_init(empty + i, 1);
+      tc::mbar_init(empty + i, MC ? 2 : 1);      // multicast ring: both CTAs of the pair must have consumed a stage
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(tfull + i, 1);
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   if (warp == 1) tc::tmem_alloc<2 * BN>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
+  if (MC) tc::cluster_sync();                    // the peer's barriers exist before anything is multicast into this CTA
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -131,7 +135,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         const int st = t % NS;
         tc::mbar_wait(empty + st, ((t / NS) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(full + st, B_STAGE);
-        for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sB + st * B_STAGE + kb * BN * 128, &tmB, kb * 64, (tfirst + t * tstep) * BN, full + st);
+        if (MC) {
+          for (int kb = 0; kb < KB; ++kb)
+            tc::tma_load_2d_mc(sB + st * B_STAGE + kb * BN * 128 + crank * (BN / 2) * 128, &tmB, kb * 64,
+                               (tfirst + t * tstep) * BN + (int)crank * (BN / 2), full + st, (uint16_t)3);
+        } else {
+          for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sB + st * B_STAGE + kb * BN * 128, &tmB, kb * 64, (tfirst + t * tstep) * BN, full + st);
+        }
       }
     }
   } else if (warp == 1) {
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
           for (int k4 = 0; k4 < 4; ++k4)   // 4 x K=16 per 64-wide swizzle atom: +32 bytes on the start address
             tc::mma_bf16_ss(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
         }
-        tc::mma_commit(empty + st);
+        if (MC) tc::mma_commit_mc(empty + st, (uint16_t)3); else tc::mma_commit(empty + st);
         tc::mma_commit(tfull + acc);
       }
     }
@@ -341,6 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (MC) tc::cluster_sync();                    // nobody leaves while the peer may still multicast into / arrive on this CTA
   if (warp == 1) tc::tmem_dealloc<2 * BN>(tmem_base);
 }
 
@@ -491,30 +502,42 @@ int make_map(CUtensorMap* m, const void* base, long long rows, int H, int box_ro
 }
 
 template <int KB, int BN, int NS, int MODE>
-int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s, size_t smem) {
-  cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  score_tc_kernel<KB, BN, NS, MODE><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
+int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s, size_t smem) {
+  if (tmBh) {      // 2-CTA clusters over pairs of user tiles, grid = (user tiles, splits)
+    if (MODE == 0) return ADT_E_SHAPE;
+    cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid.y, grid.x); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, score_tc_kernel<KB, BN, NS, MODE, true>, tmA, *tmBh, k) == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+  }
+  cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  score_tc_kernel<KB, BN, NS, MODE, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }
 // deepest catalog-tile ring (2..4 stages) that fits the 227 KB of shared memory next to the user tile and the top-K lists
 template <int KB, int BN, int MODE>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s) {
   const size_t fixed = 1024 + (size_t)KB * BM * 128 + (MODE == 0 ? (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 : 0) + BM * 4 + 4 * 1024 * 4 + 256;
   const size_t stage = (size_t)KB * BN * 128, cap = 227 * 1024;
   // the ring must hold more than one DRAM round trip (~1 us) of tensor work: a [128 x 128 x 64] tile is only 256 cycles
-  if (fixed + 8 * stage <= cap) return launch_tc_ns<KB, BN, 8, MODE>(tmA, tmB, k, grid, s, fixed + 8 * stage);
-  if (fixed + 6 * stage <= cap) return launch_tc_ns<KB, BN, 6, MODE>(tmA, tmB, k, grid, s, fixed + 6 * stage);
-  if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4, MODE>(tmA, tmB, k, grid, s, fixed + 4 * stage);
-  if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3, MODE>(tmA, tmB, k, grid, s, fixed + 3 * stage);
-  if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2, MODE>(tmA, tmB, k, grid, s, fixed + 2 * stage);
+  if (fixed + 8 * stage <= cap) return launch_tc_ns<KB, BN, 8, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 8 * stage);
+  if (fixed + 6 * stage <= cap) return launch_tc_ns<KB, BN, 6, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 6 * stage);
+  if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 4 * stage);
+  if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 3 * stage);
+  if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 2 * stage);
   return ADT_E_SHAPE;
 }
 template <int MODE>
-int launch_tc_h(int KB, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& k, dim3 grid, cudaStream_t s) {
-  if (KB == 1) return launch_tc<1, 128, MODE>(tmA, tmB, k, grid, s);
-  if (KB == 2) return launch_tc<2, 128, MODE>(tmA, tmB, k, grid, s);
-  if (KB == 3) return launch_tc<3, 128, MODE>(tmA, tmB, k, grid, s);
-  if (KB == 4) return launch_tc<4, 64, MODE>(tmA, tmB, k, grid, s);
+int launch_tc_h(int KB, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s) {
+  if (KB == 1) return launch_tc<1, 128, MODE>(tmA, tmB, tmBh, k, grid, s);
+  if (KB == 2) return launch_tc<2, 128, MODE>(tmA, tmB, tmBh, k, grid, s);
+  if (KB == 3) return launch_tc<3, 128, MODE>(tmA, tmB, tmBh, k, grid, s);
+  if (KB == 4) return launch_tc<4, 64, MODE>(tmA, tmB, tmBh, k, grid, s);
   return ADT_E_SHAPE;
 }
 
@@ -651,14 +674,23 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && a->K <= 48 && nst >= 4 * R && (long long)a->n_splits * (a->KC - 8) >= 4ll * R * sstride) {
     TcArgs ks = k;
     ks.sstride = sstride; ks.gthr = nullptr;
-    rc = launch_tc_h<2>(KB, tmA, tmB, ks, grid, s);
+    // pairs of user tiles share every catalog tile through TMA multicast (ADT_TC_MULTICAST=0 disables)
+    static int mc = -1;
+    if (mc < 0) { const char* e = getenv("ADT_TC_MULTICAST"); mc = e ? atoi(e) : 1; }
+    CUtensorMap tmBhalf;
+    const CUtensorMap* tmBh = nullptr;
+    if (mc && (grid.y % 2) == 0) {
+      if (int e = make_map(&tmBhalf, a->item_emb_bf16, a->n_items, a->H, BN / 2)) return e;
+      tmBh = &tmBhalf;
+    }
+    rc = launch_tc_h<2>(KB, tmA, tmB, tmBh, ks, grid, s);
     if (rc) return rc;
     float* tau = a->out_scores;            // U floats of scratch: overwritten by the re-score kernel at the end
     tau_select_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(a->part_scores, nst, a->U, R, tau);
     k.tau = tau; k.gthr = nullptr;
-    rc = launch_tc_h<1>(KB, tmA, tmB, k, grid, s);
+    rc = launch_tc_h<1>(KB, tmA, tmB, tmBh, k, grid, s);
   } else {
-    rc = launch_tc_h<0>(KB, tmA, tmB, k, grid, s);
+    rc = launch_tc_h<0>(KB, tmA, tmB, nullptr, k, grid, s);
   }
   if (rc) return rc;
   RescoreArgs r;

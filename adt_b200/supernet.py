@@ -71,6 +71,7 @@ class SuperSASRecModel(nn.Module):
         self.encoder = _SuperStack("enc", args.num_layers, H, args.num_heads, rec_choice, ind_choice)
         self.decoder = _SuperStack("dec", args.num_layers, H, args.num_heads, rec_choice, ind_choice)
         self.drop_seed, self.drop_step = 0, 0
+        self.precision = 0     # GEMM cores of the blocks: 0 fp32 (parity mode), 1 bf16 tensor cores (evaluation / fitness passes)
         L.lib()
 
     def set_choice(self, cand):
@@ -92,7 +93,7 @@ class SuperSASRecModel(nn.Module):
             enc_inputs.append(x)
             out = rec = None
             for idx, w in zip(idxs, weights):
-                cfg = (nh, drop.training, drop.next("attn", nh, Lq, H), drop.next("row", nh, Lq, H), drop.next("row", nh, Lq, H))
+                cfg = (nh, drop.training, drop.next("attn", nh, Lq, H), drop.next("row", nh, Lq, H), drop.next("row", nh, Lq, H), self.precision)
                 o, r = EncBlockFn.apply(x, seq, cfg, *layer_params(layer[idx], ENC_KEYS))
                 out = o * w if out is None else out + o * w
                 rec = r * w if rec is None else rec + r * w
@@ -116,7 +117,7 @@ class SuperSASRecModel(nn.Module):
             out = None
             for idx, w in zip(idxs, weights):
                 cfg = (nh, drop.training, drop.next("attn", nh, Lq, H), drop.next("attn", nh, Lq, H), drop.next("row", nh, Lq, H),
-                       drop.next("row", nh, Lq, H))
+                       drop.next("row", nh, Lq, H), self.precision)
                 o = DecBlockFn.apply(xd, feats, dec, cfg, *layer_params(layer[idx], DEC_KEYS))
                 out = o * w if out is None else out + o * w
             xd = out

@@ -258,9 +258,11 @@ class FusedTrainer:
         hn.copy_(self._normsq, non_blocking=True)       # ||E||^2 lives in its own buffer (computed beside the forward pass)
         torch.cuda.current_stream(a.device).synchronize()
         if self.world > 1:        # loss sums of the global batch: exchanged only when somebody asks for the loss
-            t = h.clone().to(a.device)
+            n_loss = 3 + 2 * self.model.num_layers          # BCE sums, valid count, MSE / NLL sums are per-rank partial sums;
+            t = h[:n_loss].clone().to(a.device)              # ||E||^2 and the gradient norm behind them are already global
             torch.distributed.all_reduce(t, group=self.pg)
-            h = t.cpu()
+            h = h.clone()
+            h[:n_loss] = t.cpu()
         out = h.tolist()
         out[3 + 2 * self.model.num_layers] = float(hn[0])
         return out

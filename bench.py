@@ -524,6 +524,7 @@ def evolution_section(cx, cfg):
     torch.manual_seed(3)
     args = types.SimpleNamespace(device=cx.dev, num_heads=cfg["nh"], maxlen=cfg["L"], num_layers=cfg["nl"], hidden_units=cfg["H"], dropout=cfg["p"])
     m = SuperSASRecModel(n_users, cfg["items"], rec_choice, ind_choice, args).to(cx.dev).eval()
+    m.precision = 1          # bf16 GEMM cores for the fitness pass (ranking metrics; BASELINE tolerance 2e-2): one launch per candidate block
     ds = DeviceSampler(tr_h, va_h, te_h, n_users, cfg["items"], cfg["L"], device=cx.dev, seed=23)
     users = np.arange(1, n_val + 1, dtype=np.int32)
     batches = [ds.eval_batch(users[i:i + 512], mode="val", n_candidates=C) for i in range(0, n_val, 512)]
@@ -719,9 +720,15 @@ def main():
             ("fp32" if other == "fp32" else "bf16"): other_mode, "c1": c1, "c5": c5, "evolution": evo, "selfcheck": selfcheck, "reference_gpu_eager": refgpu,
             "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # the step / evaluation graphs hold captured NCCL work: tearing the communicator down underneath them can block at interpreter
+        # exit, so every rank synchronises, agrees that the line is out, and leaves without running destructors
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
