@@ -532,12 +532,16 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap*
   if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 2 * stage);
   return ADT_E_SHAPE;
 }
+// catalog tile width: 128 items, except that the single-pass H = 256 kernel (user tile 64 KB + lists 32-64 KB on chip) only has room
+// for 64-item tiles.  Wider is better there: a [128 x 64 x 16] MMA re-reads its 4 KB A fragment for 2 KB of B, 192 B/clk of a
+// 128 B/clk shared-memory port; with 128 columns it is 128 B/clk (measured 512 x 1M x 256: 0.77 -> 0.66 ms).
+static int tc_bn(int KB, int two_pass_mode) { return (KB == 4 && !two_pass_mode) ? 64 : 128; }
 template <int MODE>
-int launch_tc_h(int KB, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s) {
+int launch_tc_h(int KB, int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s) {
   if (KB == 1) return launch_tc<1, 128, MODE>(tmA, tmB, tmBh, k, grid, s);
   if (KB == 2) return launch_tc<2, 128, MODE>(tmA, tmB, tmBh, k, grid, s);
   if (KB == 3) return launch_tc<3, 128, MODE>(tmA, tmB, tmBh, k, grid, s);
-  if (KB == 4) return launch_tc<4, 64, MODE>(tmA, tmB, tmBh, k, grid, s);
+  if (KB == 4) return BN == 64 ? launch_tc<4, 64, MODE>(tmA, tmB, tmBh, k, grid, s) : launch_tc<4, 128, MODE>(tmA, tmB, tmBh, k, grid, s);
   return ADT_E_SHAPE;
 }
 
@@ -589,13 +593,15 @@ extern "C" int adt_to_bf16(const float* x, void* y, int64_t rows, int32_t H, flo
 // launch plan of adt_score_topk_tc for (U users, n_items catalog rows, top-K): list capacity KC per (split, user) and the number of
 // catalog splits.  Returns 1 when the two-pass (sample threshold + append-only) scheme applies, else 0 (single streaming pass).
 static const int TC_TWO_PASS_MIN_ITEMS = 65536, TC_SSTRIDE = 16;
+
 static int tc_target(int K) { return K * 6 > 192 ? K * 6 : 192; }    // catalog items expected above a user's threshold tau
 extern "C" int adt_score_tc_plan(int32_t U, int32_t H, int32_t n_items, int32_t K, int32_t* KC_out, int32_t* n_splits_out) {
   static int two_pass = -1;
   if (two_pass < 0) { const char* e = getenv("ADT_TC_TWO_PASS"); two_pass = e ? atoi(e) : 1; }
   const int tiles = (U + BM - 1) / BM;
-  const int BN = H == 256 ? 64 : 128;
-  const int ntt = (n_items + BN - 1) / BN;
+  const int KBp = (H + 63) / 64;
+  int BN = tc_bn(KBp, 1);
+  int ntt = (n_items + BN - 1) / BN;
   int S = 148 / tiles > 1 ? 148 / tiles : 1;
   if (S > ntt) S = ntt;
   int KC, mode = 0;
@@ -622,6 +628,8 @@ extern "C" int adt_score_tc_plan(int32_t U, int32_t H, int32_t n_items, int32_t 
     if (best_s) { S = best_s; KC = best_kc; mode = 1; } else KC = 64;
   }
   if (!mode) {
+    BN = tc_bn(KBp, 0);
+    ntt = (n_items + BN - 1) / BN;
     KC = K + 8 > 2 * K ? K + 8 : 2 * K;
     if (KC > 64) KC = 64;
     if (S * KC > RS_MAXC) S = RS_MAXC / KC;
@@ -637,9 +645,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
     return ADT_E_SHAPE;
   CUtensorMap tmA, tmB;
   const int KB = a->H / 64;
-  const int BN = KB == 4 ? 64 : 128;
   if (int e = make_map(&tmA, a->feats_bf16, a->U, a->H, BM)) return e;
-  if (int e = make_map(&tmB, a->item_emb_bf16, a->n_items, a->H, BN)) return e;
   TcArgs k;
   k.seen_indptr = a->seen_indptr; k.seen_idx = a->seen_idx; k.part_scores = a->part_scores; k.part_ids = a->part_ids; k.part_thr = a->part_thr;
   k.U = a->U; k.n_items = a->n_items; k.item_offset = a->item_offset; k.KC = a->KC; k.n_splits = a->n_splits;
@@ -662,8 +668,8 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   if (two_pass < 0) { const char* e = getenv("ADT_TC_TWO_PASS"); two_pass = e ? atoi(e) : 1; }
   // sample stride: every 16th catalog tile, coarser when the tile maxima would not fit the scratch (part_scores holds
   // n_splits*KC floats per user) or the selection kernel (2048 values per user)
-  const int BNk = KB == 4 ? 64 : 128;
-  const int ntt = (a->n_items + BNk - 1) / BNk;
+  int BN = tc_bn(KB, 1);
+  const int ntt = (a->n_items + BN - 1) / BN;
   int cap = a->n_splits * a->KC < 2048 ? a->n_splits * a->KC : 2048;
   int sstride = TC_SSTRIDE;
   while ((ntt + sstride - 1) / sstride > cap) sstride *= 2;
@@ -672,6 +678,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   if (R < 6) R = 6;
   // two passes only when the caller's scratch follows adt_score_tc_plan: room for 4x the expected candidates of a split
   if (two_pass && a->n_items >= TC_TWO_PASS_MIN_ITEMS && a->K <= 48 && nst >= 4 * R && (long long)a->n_splits * (a->KC - 8) >= 4ll * R * sstride) {
+    if (int e = make_map(&tmB, a->item_emb_bf16, a->n_items, a->H, BN)) return e;
     TcArgs ks = k;
     ks.sstride = sstride; ks.gthr = nullptr;
     // pairs of user tiles share every catalog tile through TMA multicast (ADT_TC_MULTICAST=0 disables)
@@ -683,14 +690,16 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
       if (int e = make_map(&tmBhalf, a->item_emb_bf16, a->n_items, a->H, BN / 2)) return e;
       tmBh = &tmBhalf;
     }
-    rc = launch_tc_h<2>(KB, tmA, tmB, tmBh, ks, grid, s);
+    rc = launch_tc_h<2>(KB, BN, tmA, tmB, tmBh, ks, grid, s);
     if (rc) return rc;
     float* tau = a->out_scores;            // U floats of scratch: overwritten by the re-score kernel at the end
     tau_select_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(a->part_scores, nst, a->U, R, tau);
     k.tau = tau; k.gthr = nullptr;
-    rc = launch_tc_h<1>(KB, tmA, tmB, tmBh, k, grid, s);
+    rc = launch_tc_h<1>(KB, BN, tmA, tmB, tmBh, k, grid, s);
   } else {
-    rc = launch_tc_h<0>(KB, tmA, tmB, nullptr, k, grid, s);
+    BN = tc_bn(KB, 0);
+    if (int e = make_map(&tmB, a->item_emb_bf16, a->n_items, a->H, BN)) return e;
+    rc = launch_tc_h<0>(KB, BN, tmA, tmB, nullptr, k, grid, s);
   }
   if (rc) return rc;
   RescoreArgs r;
