@@ -1,0 +1,263 @@
+// nn.Linear on the 5th-generation tensor cores: C[M,N] (fp32) = act((A[M,K] . B[N,K]^T + bias[N]) * scale)  with A, B bf16 K-major.
+// One GEMM serves the three products of a linear layer (bert4rec/model/modules.py:57-72, :128-139, bert.py:80-90; the wide
+// contractions of the H = 256 shapes):
+//   forward   y  = x W^T        A = x   [M,K]      B = W    [N,K]
+//   dgrad     dx = dy W         A = dy  [M,N]      B = W^T  [K,N]      (transposed bf16 copy made by adt_to_bf16_t)
+//   wgrad     dW = dy^T x       A = dy^T [N,M]     B = x^T  [K,M]
+// Structure: one 128 x BN output tile per CTA; warp 0 = TMA producer (A and B K-slabs of 64 through an NS-stage ring), warp 1 =
+// tcgen05.mma issuer (accumulator 128 x BN fp32 in TMEM), warps 2-5 = epilogue (tcgen05.ld -> bias / scale / activation -> fp32
+// rows to HBM, thread == output row).  K, M, N are arbitrary: TMA zero-fills out-of-bounds rows / columns, stores are masked.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/adt_b200.h"
+#include "tc.cuh"
+
+using namespace adt;
+
+namespace {
+
+constexpr int GM = 128;            // output rows per CTA (= TMEM lanes)
+constexpr int G_THREADS = 192;
+
+struct GemmTcArgs {
+  float* C; float* pre; const float* bias; long long ldc;
+  int M, N, K, act, accumulate; float scale;
+};
+
+__device__ __forceinline__ float g_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float g_act(float x, int act) {
+  return act == 1 ? fmaxf(x, 0.f) : act == 2 ? g_gelu(x) : act == 3 ? (x > 0.f ? x : expm1f(x)) : act == 4 ? (x > 0.f ? x : expm1f(x)) + 1.f : x;
+}
+
+template <int BN, int NS>
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                               GemmTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int A_STAGE = GM * 128, B_STAGE = BN * 128;        // one 64-wide K slab (128 bytes per row)
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NS * A_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NS * B_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NS;
+  uint64_t* tfull = bars + 2 * NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM;
+  const int nkb = (a.K + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int i = 0; i < NS; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+    tc::mbar_init(tfull, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<BN>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % NS;
+        tc::mbar_wait(empty + st, ((kb / NS) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(full + st, A_STAGE + B_STAGE);
+        tc::tma_load_2d(sA + st * A_STAGE, &tmA, kb * 64, m0, full + st);
+        tc::tma_load_2d(sB + st * B_STAGE, &tmB, kb * 64, n0, full + st);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::idesc_bf16_f32(GM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % NS;
+        tc::mbar_wait(full + st, (kb / NS) & 1);
+        tc::tc_fence_after();
+        const uint64_t ad = tc::smem_desc_k_sw128(tc::smem_u32(sA + st * A_STAGE));
+        const uint64_t bd = tc::smem_desc_k_sw128(tc::smem_u32(sB + st * B_STAGE));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          tc::mma_bf16_ss(tmem_base, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+        tc::mma_commit(empty + st);
+      }
+      tc::mma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + 32 * q + lane;
+    tc::mbar_wait(tfull, 0);
+    tc::tc_fence_after();
+    const bool vec = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && (!a.pre || (reinterpret_cast<uintptr_t>(a.pre) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + c0, v);
+      const int nb = n0 + c0;
+      if (row >= a.M || nb >= a.N) continue;
+      float* crow = a.C + (long long)row * a.ldc + nb;
+      float* prow = a.pre ? a.pre + (long long)row * a.ldc + nb : nullptr;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float x = v[c];
+        if (a.bias && nb + c < a.N) x += __ldg(a.bias + nb + c);
+        v[c] = x * a.scale;
+      }
+      if (vec && nb + 32 <= a.N) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          if (prow) *reinterpret_cast<float4*>(prow + c) = o;
+          o = make_float4(g_act(o.x, a.act), g_act(o.y, a.act), g_act(o.z, a.act), g_act(o.w, a.act));
+          if (a.accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(crow + c);
+            o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w);
+          }
+          *reinterpret_cast<float4*>(crow + c) = o;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (nb + c < a.N) {
+            if (prow) prow[c] = v[c];
+            float o = g_act(v[c], a.act);
+            if (a.accumulate) o += crow[c];
+            crow[c] = o;
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<BN>(tmem_base);
+}
+
+// fp32 [R][C] (row stride ld) -> bf16 TRANSPOSE [C][ldt] (ldt >= R, multiple of 8), through a 32 x 32 smem tile
+__global__ void __launch_bounds__(256) to_bf16_t_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ y, long long ldt,
+                                                        int R, int C) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < R && c < C) ? x[(long long)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < C && r < R) y[(long long)c * ldt + r] = __float2bfloat16_rn(tile[tx][j]);
+  }
+}
+
+// fp32 [R][C] (row stride ld) -> bf16 [R][ldy]
+__global__ void __launch_bounds__(256) to_bf16_ld_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ y, long long ldy,
+                                                         long long R, int C) {
+  const long long n = R * (long long)C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    y[r * ldy + c] = __float2bfloat16_rn(x[r * ld + c]);
+  }
+}
+
+// out[c] (+)= sum_r x[r][c]   (bias gradient): 32 columns x 8 row groups per CTA, atomics across the row blocks
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ld, int R, int C, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < C)
+    for (int r = blockIdx.y * 8 + ty; r < R; r += gridDim.y * 8) s += x[(long long)r * ld + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// bf16 row-major [rows][cols] with row stride ld elements; box = [box_rows][64 cols], 128-byte swizzle, zero fill out of bounds
+int g_make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = g_encode();
+  if (!enc) return ADT_E_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? ADT_OK : ADT_E_CUDA;
+}
+
+template <int BN, int NS>
+int g_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& k, cudaStream_t s) {
+  const size_t smem = 1024 + (size_t)NS * (GM * 128 + BN * 128) + 256;
+  cudaFuncSetAttribute(gemm_tc_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((k.N + BN - 1) / BN, (k.M + GM - 1) / GM);
+  gemm_tc_kernel<BN, NS><<<grid, G_THREADS, smem, s>>>(tmA, tmB, k);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+}  // namespace
+
+extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
+  cudaStream_t s = (cudaStream_t)s_;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->lda & 7) || (a->ldb & 7) || a->lda < a->K || a->ldb < a->K || a->ldc < a->N) return ADT_E_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(a->a_bf16) | reinterpret_cast<uintptr_t>(a->b_bf16)) & 15) return ADT_E_ALIGN;
+  CUtensorMap tmA, tmB;
+  GemmTcArgs k;
+  k.C = a->c; k.pre = a->pre; k.bias = a->bias; k.ldc = a->ldc; k.M = a->M; k.N = a->N; k.K = a->K; k.act = a->act; k.accumulate = a->accumulate;
+  k.scale = a->scale == 0.f ? 1.f : a->scale;
+  if (int e = g_make_map(&tmA, a->a_bf16, a->M, a->K, a->lda, GM)) return e;
+  // narrow outputs waste less of the tile with 64 columns; wide ones amortise the A slab over 128
+  if (a->N <= 64) {
+    if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, 64)) return e;
+    return g_launch<64, 6>(tmA, tmB, k, s);
+  }
+  if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, 128)) return e;
+  return g_launch<128, 6>(tmA, tmB, k, s);
+}
+
+extern "C" int adt_to_bf16_t(const float* x, int64_t ld, void* y_bf16, int64_t ldt, int32_t R, int32_t C, adt_stream_t s_) {
+  if (R <= 0 || C <= 0 || ldt < R || ld < C) return ADT_E_SHAPE;
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  to_bf16_t_kernel<<<grid, 256, 0, (cudaStream_t)s_>>>(x, ld, reinterpret_cast<__nv_bfloat16*>(y_bf16), ldt, R, C);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+extern "C" int adt_to_bf16_ld(const float* x, int64_t ld, void* y_bf16, int64_t ldy, int64_t R, int32_t C, adt_stream_t s_) {
+  if (R <= 0 || C <= 0 || ldy < C || ld < C) return ADT_E_SHAPE;
+  const long long blocks = (R * (long long)C + 255) / 256;
+  to_bf16_ld_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)s_>>>(x, ld, reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, R, C);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}
+
+extern "C" int adt_colsum(const float* x, int64_t ld, int32_t R, int32_t C, float* out, adt_stream_t s_) {
+  if (R <= 0 || C <= 0) return ADT_E_SHAPE;
+  int gy = (R + 255) / 256;
+  if (gy > 64) gy = 64;
+  colsum_kernel<<<dim3((C + 31) / 32, gy), 256, 0, (cudaStream_t)s_>>>(x, ld, R, C, out);
+  return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+}

@@ -19,6 +19,45 @@ def no_drop():
     return L.adt_dropout()
 
 
+TC_MIN_WORK = 1 << 22     # M*N*K below this: the row-tile kernel's single launch beats convert + GEMM
+
+
+def _ceil8(n):
+    return (n + 7) // 8 * 8
+
+
+def _bf16(x, transpose=False):
+    """bf16 operand copy of a contiguous fp32 matrix [R, C] (leading dimension padded to a multiple of 8 for TMA), or of its transpose"""
+    lib = L.lib()
+    R, C = x.shape
+    st = _st(x.device)
+    if transpose:
+        ld = _ceil8(R)
+        y = torch.empty(C, ld, dtype=torch.bfloat16, device=x.device)
+        if ld != R:
+            y[:, R:].zero_()
+        L.check(lib.adt_to_bf16_t(L.ptr(x), ctypes.c_int64(x.stride(0)), L.ptr(y), ctypes.c_int64(ld), ctypes.c_int32(R), ctypes.c_int32(C), st),
+                "adt_to_bf16_t")
+        return y, ld
+    ld = _ceil8(C)
+    y = torch.empty(R, ld, dtype=torch.bfloat16, device=x.device)
+    if ld != C:
+        y[:, C:].zero_()
+    L.check(lib.adt_to_bf16_ld(L.ptr(x), ctypes.c_int64(x.stride(0)), L.ptr(y), ctypes.c_int64(ld), ctypes.c_int64(R), ctypes.c_int32(C), st),
+            "adt_to_bf16_ld")
+    return y, ld
+
+
+def _gemm_tc(a16, lda, b16, ldb, c, M, N, K, bias=None, act=0, scale=1.0, pre=None, accumulate=False):
+    a = L.fill(L.adt_gemm_tc_args(), a_bf16=a16, b_bf16=b16, lda=lda, ldb=ldb, c=c, pre=pre, bias=bias, ldc=c.stride(0), M=M, N=N, K=K,
+               act=act, accumulate=int(accumulate), scale=scale)
+    L.check(L.lib().adt_gemm_tc(ctypes.byref(a), _st(c.device)), "adt_gemm_tc")
+
+
+def _use_tc(precision, M, N, K):
+    return bool(precision) and M >= 128 and M * N * K >= TC_MIN_WORK and torch.cuda.get_device_capability()[0] >= 10
+
+
 class LinearFn(torch.autograd.Function):
     """y = act((x W^T + b) * scale), x [M,K], W [N,K]  (act: 0 none, 1 relu, 2 gelu)."""
 
@@ -29,6 +68,13 @@ class LinearFn(torch.autograd.Function):
         N = W.shape[0]
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
         pre = torch.empty_like(y) if act else None
+        if _use_tc(precision, M, N, K):   # tcgen05 GEMM on bf16 operand copies (fp32 accumulate, fp32 bias / activation epilogue)
+            x16, lda = _bf16(x)
+            w16, ldb = _bf16(W)
+            _gemm_tc(x16, lda, w16, ldb, y, M, N, K, bias=b, act=act, scale=scale, pre=pre)
+            ctx.save_for_backward(x, W, pre if pre is not None else y)
+            ctx.cfg = (act, scale, precision, b is not None)
+            return y
         for n0 in range(0, N, NBLK):      # wide outputs (the vocabulary head) are produced in column blocks
             n1 = min(N, n0 + NBLK)
             a = L.fill(L.adt_linear_fwd_args(), x=x, w=W[n0:n1], b=b[n0:n1] if b is not None else None, y=y[:, n0:n1],
@@ -54,6 +100,20 @@ class LinearFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         gW = torch.zeros_like(W)
         gb = torch.zeros(N, dtype=torch.float32, device=x.device) if has_b else None
+        if _use_tc(precision, M, N, K):
+            # dx = scale * dy W ; dW = scale * dy^T x ; db = scale * colsum(dy): three more products on the tensor cores
+            dy16, ldd = _bf16(dy)
+            wt16, ldw = _bf16(W, transpose=True)            # [K, N]
+            _gemm_tc(dy16, ldd, wt16, ldw, dx, M, K, N, scale=scale)
+            dyt16, ldt = _bf16(dy, transpose=True)          # [N, M]
+            xt16, ldx = _bf16(x, transpose=True)            # [K, M]
+            _gemm_tc(dyt16, ldt, xt16, ldx, gW, N, K, M, scale=scale)
+            if has_b:
+                L.check(lib.adt_colsum(L.ptr(dy), ctypes.c_int64(dy.stride(0)), ctypes.c_int32(M), ctypes.c_int32(N), L.ptr(gb), _st(x.device)),
+                        "adt_colsum")
+                if scale != 1.0:
+                    gb.mul_(scale)
+            return dx, gW, gb, None, None, None
         for n0 in range(0, N, NBLK):
             n1 = min(N, n0 + NBLK)
             a = L.fill(L.adt_linear_bwd_args(), x=x, w=W[n0:n1], dy=dy[:, n0:n1], dx=dx, g_w=gW[n0:n1], g_b=gb[n0:n1] if has_b else None,

@@ -306,6 +306,22 @@ typedef struct {
 } adt_linear_bwd_args;
 int adt_linear_bwd(const adt_linear_bwd_args* a, adt_stream_t stream);
 int adt_act_bwd(const float* dy, const float* pre, float* dpre, int64_t n, int32_t act, adt_stream_t stream);
+/* nn.Linear on tcgen05 (bert4rec/model/modules.py:57-72, :128-139, bert.py:80-90 and their autograd): c[M,N] (fp32, row stride ldc)
+ * (+)= act((A[M,K] . B[N,K]^T + bias[N]) * scale), A / B bf16 row-major with row strides lda / ldb (multiples of 8 elements; use
+ * adt_to_bf16_ld / adt_to_bf16_t to make the operand copies: forward A = x, B = W; dgrad A = dy, B = W^T; wgrad A = dy^T, B = x^T).
+ * TMA-fed 128 x 128 (or x 64) tiles, fp32 accumulators in TMEM; M, N, K arbitrary (zero-filled edges, masked stores).
+ * pre (optional, same layout as c) receives the pre-activation values; accumulate != 0 adds into c. */
+typedef struct {
+  const void* a_bf16; const void* b_bf16; int64_t lda, ldb;
+  float* c; float* pre; const float* bias; int64_t ldc;
+  int32_t M, N, K, act, accumulate; float scale;
+} adt_gemm_tc_args;
+int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t stream);
+/* operand copies for adt_gemm_tc: fp32 [R][C] (row stride ld) -> bf16 [R][ldy], or -> its bf16 transpose [C][ldt] */
+int adt_to_bf16_ld(const float* x, int64_t ld, void* y_bf16, int64_t ldy, int64_t R, int32_t C, adt_stream_t stream);
+int adt_to_bf16_t(const float* x, int64_t ld, void* y_bf16, int64_t ldt, int32_t R, int32_t C, adt_stream_t stream);
+/* out[c] += sum_r x[r][c]  (bias gradient of a linear layer) */
+int adt_colsum(const float* x, int64_t ld, int32_t R, int32_t C, float* out, adt_stream_t stream);
 /* mode 0: y = LN(dropout(a) + r)  (DropResidualNormalizeLayer, modules.py:104-117)
  * mode 1: y = dropout(LN(a + r))  (BertEmbedding, modules.py:42-48).   r may be NULL. */
 typedef struct {

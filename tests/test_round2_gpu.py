@@ -311,3 +311,38 @@ def test_sequence_resident_block_kernels_match_row_tile_kernels(nh, Lq):
     same = np.mean(np.array(a["ids"]) == np.array(b["ids"]))
     assert same > 0.9, same
     assert np.abs(np.array(a["scores"]) - np.array(b["scores"])).max() < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,act", [(256, 256, 256, 0), (1000, 768, 256, 2), (333, 200, 1024, 1), (2048, 26844, 256, 0), (130, 64, 72, 3)])
+def test_tcgen05_linear_matches_fp32_linear(M, N, K, act):
+    """adt_gemm_tc (TMA + tcgen05.mma, bf16 operands, fp32 accumulate) behind ops.linear(precision=1): forward, input gradient,
+    weight gradient and bias gradient against torch fp32 on the bf16-rounded operands (the rounding is the only difference)."""
+    from adt_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x = (torch.randn(M, K, generator=g) * 0.5).cuda().requires_grad_(True)
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda().requires_grad_(True)
+    b = (torch.randn(N, generator=g) * 0.1).cuda().requires_grad_(True)
+    dy = torch.randn(M, N, generator=g).cuda()
+    old = ops.TC_MIN_WORK
+    ops.TC_MIN_WORK = 0
+    try:
+        y = ops.linear(x, W, b, act=act, scale=0.5, precision=1)
+        gx, gW, gb = torch.autograd.grad(y, (x, W, b), dy)
+    finally:
+        ops.TC_MIN_WORK = old
+    r = lambda t: t.detach().to(torch.bfloat16).float()
+    xr, Wr = r(x).requires_grad_(True), r(W).requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    pre = (xr @ Wr.t() + br) * 0.5
+    fn = {0: lambda t: t, 1: torch.relu, 2: lambda t: torch.nn.functional.gelu(t), 3: torch.nn.functional.elu}[act]
+    yr = fn(pre)
+    assert torch.allclose(y, yr, rtol=2e-3, atol=2e-3), float((y - yr).abs().max())
+    # backward products round dy / x / W to bf16 too: compare against the same rounding
+    dpre = torch.autograd.grad(yr, pre, dy, retain_graph=True)[0]
+    dq = r(dpre)
+    gx_ref = (dq @ Wr.detach()) * 0.5
+    gW_ref = (dq.t() @ xr.detach()) * 0.5
+    gb_ref = dpre.sum(0) * 0.5
+    for got, ref, name in ((gx, gx_ref, "dx"), (gW, gW_ref, "dW"), (gb, gb_ref, "db")):
+        err = float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
+        assert err < 5e-3, (name, err)
