@@ -32,6 +32,7 @@ struct TcArgs {
   const int* seen_indptr; const int* seen_idx;
   float* part_scores; int* part_ids; float* part_thr;
   unsigned int* gthr;   // [U] best K'-th-best key published by any catalog split of this launch (order-preserving keys, 0 = none)
+  const __nv_bfloat16* feats_bf16;   // [U][H] user features (ATM kernels load them straight into tensor memory)
   const float* tau;     // MODE 1: [U] per-user score threshold (from the sample pass): everything above it is a candidate
   int U, n_items, item_offset, KC, n_splits, debug;
   int sstride;          // MODE 2: every sstride-th catalog tile belongs to the sample
@@ -77,12 +78,17 @@ __device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int sb, int se, int 
 // NS = depth of the TMA ring of catalog tiles (B operand); accumulators are double buffered in TMEM
 // MC: the CTA is one of a 2-CTA cluster that walks the SAME catalog tiles for two different user tiles; each CTA fetches half of every
 // catalog tile and TMA multicasts it into both CTAs' rings, so every catalog byte leaves L2 once per pair (tmB's box is BN/2 rows then)
-template <int KB, int BN, int NS, int MODE, bool MC>
+// ATM: the user tile (A operand, reused by every MMA of the kernel) lives in TENSOR MEMORY instead of shared memory: the epilogue
+// threads store their own feature row with tcgen05.st once, the MMAs read it from TMEM (tcgen05.mma, A from TMEM).  Frees
+// KB*16 KB of shared memory for a deeper TMA ring and takes the A fragment reads off the shared-memory port.
+template <int KB, int BN, int NS, int MODE, bool MC, bool ATM>
 __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int A_BYTES = KB * BM * 128;
+  constexpr int A_BYTES = ATM ? 0 : KB * BM * 128;
+  constexpr int TM_COLS = ATM ? 512 : 2 * BN;                 // accumulators 2 x BN (+ KB*32 columns of A behind them)
+  constexpr uint32_t A_COL = 2 * BN;
   constexpr int B_STAGE = KB * BN * 128;
   uint8_t* sA = smem;
   uint8_t* sB = sA + A_BYTES;
@@ -117,10 +123,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       tc::mbar_init(tfull + i, 1);
       tc::mbar_init(tempty + i, 4);
     }
-    tc::mbar_init(abar, 1);
+    tc::mbar_init(abar, ATM ? 4 : 1);            // A in TMEM: one arrival per epilogue warp after its tcgen05.st completed
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tc::tmem_alloc<TM_COLS>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   if (MC) tc::cluster_sync();                    // the peer's barriers exist before anything is multicast into this CTA
@@ -129,8 +135,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(abar, A_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sA + kb * BM * 128, &tmA, kb * 64, u0, abar);
+      if (!ATM) {
+        tc::mbar_arrive_expect_tx(abar, A_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sA + kb * BM * 128, &tmA, kb * 64, u0, abar);
+      }
       for (int t = 0; t < ntiles; ++t) {
         const int st = t % NS;
         tc::mbar_wait(empty + st, ((t / NS) & 1) ^ 1);
@@ -156,11 +164,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         const uint32_t d_tmem = tmem_base + acc * BN;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
-          const uint64_t ad = tc::smem_desc_k_sw128(tc::smem_u32(sA + kb * BM * 128));
           const uint64_t bd = tc::smem_desc_k_sw128(tc::smem_u32(sB + st * B_STAGE + kb * BN * 128));
+          if (ATM) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)   // 4 x K=16 per 64-wide swizzle atom: +32 bytes on the start address
-            tc::mma_bf16_ss(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+            for (int k4 = 0; k4 < 4; ++k4)   // K = 16 per MMA = 8 TMEM columns of A
+              tc::mma_bf16_ts(d_tmem, tmem_base + A_COL + kb * 32 + k4 * 8, bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+          } else {
+            const uint64_t ad = tc::smem_desc_k_sw128(tc::smem_u32(sA + kb * BM * 128));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)   // 4 x K=16 per 64-wide swizzle atom: +32 bytes on the start address
+              tc::mma_bf16_ss(d_tmem, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+          }
         }
         if (MC) tc::mma_commit_mc(empty + st, (uint16_t)3); else tc::mma_commit(empty + st);
         tc::mma_commit(tfull + acc);
@@ -173,6 +187,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     const int row = 32 * q + lane;
     const int u = u0 + row;
     const int KC = a.KC;
+    if (ATM) {     // this thread's feature row (bf16, KB*32 words) -> TMEM columns A_COL.. of its lane
+      const uint4* frow = reinterpret_cast<const uint4*>(a.feats_bf16 + (long long)(u < a.U ? u : 0) * (KB * 64));
+#pragma unroll 1
+      for (int i = 0; i < KB; ++i) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 x = u < a.U ? __ldg(frow + i * 8 + j) : make_uint4(0u, 0u, 0u, 0u);
+          r[4 * j] = x.x; r[4 * j + 1] = x.y; r[4 * j + 2] = x.z; r[4 * j + 3] = x.w;
+        }
+        tc::tmem_st32(tmem_base + ((uint32_t)(32 * q) << 16) + A_COL + 32 * i, r);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(abar);
+    }
     if (MODE == 0) {
       for (int k = 0; k < KC; ++k) {
         lk[k * BM + row] = 0u;               // key 0 = "worse than anything"
@@ -197,44 +228,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       int cnt = 0;
       bool overflow = false;
       const long long obase = ((long long)split * a.U + (u < a.U ? u : 0)) * KC;
+      // one chunk = 32 score columns of this thread's row.  The TMEM load of chunk c+1 is in flight while chunk c is filtered.
+      auto process = [&](const uint32_t (&r)[32], int ib) {
+        const int nvalid = a.n_items - ib;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, c < nvalid ? __uint_as_float(r[c]) : -INFINITY);
+        if (a.debug != 0) return;
+        if (mx > thr) {                      // rare (about one row in 150 per chunk): walk the 32 registers, no staging through smem
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float x = __uint_as_float(r[c]);
+            if (c < nvalid && x > thr) {
+              const int item = a.item_offset + ib + c;
+              if (!tc_is_seen(a, sb, se, item)) {       // candidates go straight to HBM, no list on chip
+                if (cnt < KC) { a.part_scores[obase + cnt] = x; a.part_ids[obase + cnt] = item; ++cnt; }
+                else overflow = true;
+              }
+            }
+          }
+        }
+      };
+      constexpr int NCH = BN / 32;           // 2 or 4 chunks per tile
       for (int t = 0; t < ntiles; ++t) {
         const int st = t & 1;
         tc::mbar_wait(tfull + st, (t >> 1) & 1);
         tc::tc_fence_after();
         const int tb = (tfirst + t * tstep) * BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
-          if (c0 + 32 == BN) {               // accumulator fully read: hand it back to the MMA warp
+        const uint32_t tad = tmem_base + ((uint32_t)(32 * q) << 16) + st * BN;
+        uint32_t r0[32], r1[32];
+        tc::tmem_ld32_issue(tad, r0);
+        tc::tmem_ld_wait(r0);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ch += 2) {
+          tc::tmem_ld32_issue(tad + 32 * (ch + 1), r1);
+          process(r0, tb + 32 * ch);
+          tc::tmem_ld_wait(r1);
+          if (ch + 2 < NCH) {
+            tc::tmem_ld32_issue(tad + 32 * (ch + 2), r0);
+          } else {                           // accumulator fully read: hand it back to the MMA warp
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty + st);
           }
-          const int ib = tb + c0;
-          const int nvalid = a.n_items - ib;
-          if (nvalid < 32) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (c >= nvalid) v[c] = -INFINITY;
-          }
-          if (a.debug == 1) continue;
-          float mx = v[0];
-#pragma unroll
-          for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
-          if (a.debug == 2) continue;
-          if (mx > thr) {                    // rare (about one row in 150 per chunk): walk the 32 registers, no staging through smem
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              if (v[c] > thr) {
-                const int item = a.item_offset + ib + c;
-                if (!tc_is_seen(a, sb, se, item)) {       // candidates go straight to HBM, no list on chip
-                  if (cnt < KC) { a.part_scores[obase + cnt] = v[c]; a.part_ids[obase + cnt] = item; ++cnt; }
-                  else overflow = true;
-                }
-              }
-            }
-          }
+          process(r1, tb + 32 * (ch + 1));
+          if (ch + 2 < NCH) tc::tmem_ld_wait(r0);
         }
       }
       if (overflow) thr = INFINITY;          // candidates were dropped: the caller must re-run this user exactly
@@ -352,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   tc::tc_fence_before();
   __syncthreads();
   if (MC) tc::cluster_sync();                    // nobody leaves while the peer may still multicast into / arrive on this CTA
-  if (warp == 1) tc::tmem_dealloc<2 * BN>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<TM_COLS>(tmem_base);
 }
 
 // fp32 -> bf16 rows (round to nearest even) + max squared row norm (atomicMax on the float bits; values >= 0)
@@ -501,11 +539,16 @@ int make_map(CUtensorMap* m, const void* base, long long rows, int H, int box_ro
   return r == CUDA_SUCCESS ? ADT_OK : ADT_E_CUDA;
 }
 
-template <int KB, int BN, int NS, int MODE>
+static bool tc_atmem() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_TC_ATMEM"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+template <int KB, int BN, int NS, int MODE, bool ATM>
 int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s, size_t smem) {
   if (tmBh) {      // 2-CTA clusters over pairs of user tiles, grid = (user tiles, splits)
     if (MODE == 0) return ADT_E_SHAPE;
-    cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, true, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid.y, grid.x); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -513,24 +556,29 @@ int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, score_tc_kernel<KB, BN, NS, MODE, true>, tmA, *tmBh, k) == cudaSuccess ? ADT_OK : ADT_E_CUDA;
+    return cudaLaunchKernelEx(&cfg, score_tc_kernel<KB, BN, NS, MODE, true, ATM>, tmA, *tmBh, k) == cudaSuccess ? ADT_OK : ADT_E_CUDA;
   }
-  cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  score_tc_kernel<KB, BN, NS, MODE, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
+  cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, false, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  score_tc_kernel<KB, BN, NS, MODE, false, ATM><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }
 // deepest catalog-tile ring (2..4 stages) that fits the 227 KB of shared memory next to the user tile and the top-K lists
-template <int KB, int BN, int MODE>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s) {
-  const size_t fixed = 1024 + (size_t)KB * BM * 128 + (MODE == 0 ? (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 : 0) + BM * 4 + 4 * 1024 * 4 + 256;
+template <int KB, int BN, int MODE, bool ATM>
+int launch_tc_a(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s) {
+  const size_t fixed = 1024 + (ATM ? 0 : (size_t)KB * BM * 128) + (MODE == 0 ? (size_t)(k.KC <= 32 ? 32 : 64) * BM * 8 : 0) + BM * 4 + 4 * 1024 * 4 + 256;
   const size_t stage = (size_t)KB * BN * 128, cap = 227 * 1024;
   // the ring must hold more than one DRAM round trip (~1 us) of tensor work: a [128 x 128 x 64] tile is only 256 cycles
-  if (fixed + 8 * stage <= cap) return launch_tc_ns<KB, BN, 8, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 8 * stage);
-  if (fixed + 6 * stage <= cap) return launch_tc_ns<KB, BN, 6, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 6 * stage);
-  if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 4 * stage);
-  if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 3 * stage);
-  if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2, MODE>(tmA, tmB, tmBh, k, grid, s, fixed + 2 * stage);
+  if (fixed + 8 * stage <= cap) return launch_tc_ns<KB, BN, 8, MODE, ATM>(tmA, tmB, tmBh, k, grid, s, fixed + 8 * stage);
+  if (fixed + 6 * stage <= cap) return launch_tc_ns<KB, BN, 6, MODE, ATM>(tmA, tmB, tmBh, k, grid, s, fixed + 6 * stage);
+  if (fixed + 4 * stage <= cap) return launch_tc_ns<KB, BN, 4, MODE, ATM>(tmA, tmB, tmBh, k, grid, s, fixed + 4 * stage);
+  if (fixed + 3 * stage <= cap) return launch_tc_ns<KB, BN, 3, MODE, ATM>(tmA, tmB, tmBh, k, grid, s, fixed + 3 * stage);
+  if (fixed + 2 * stage <= cap) return launch_tc_ns<KB, BN, 2, MODE, ATM>(tmA, tmB, tmBh, k, grid, s, fixed + 2 * stage);
   return ADT_E_SHAPE;
+}
+template <int KB, int BN, int MODE>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmBh, const TcArgs& k, dim3 grid, cudaStream_t s) {
+  if (MODE != 0 && tc_atmem()) return launch_tc_a<KB, BN, MODE, true>(tmA, tmB, tmBh, k, grid, s);
+  return launch_tc_a<KB, BN, MODE, false>(tmA, tmB, tmBh, k, grid, s);
 }
 // catalog tile width: 128 items, except that the single-pass H = 256 kernel (user tile 64 KB + lists 32-64 KB on chip) only has room
 // for 64-item tiles.  Wider is better there: a [128 x 64 x 16] MMA re-reads its 4 KB A fragment for 2 KB of B, 192 B/clk of a
@@ -649,6 +697,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   TcArgs k;
   k.seen_indptr = a->seen_indptr; k.seen_idx = a->seen_idx; k.part_scores = a->part_scores; k.part_ids = a->part_ids; k.part_thr = a->part_thr;
   k.U = a->U; k.n_items = a->n_items; k.item_offset = a->item_offset; k.KC = a->KC; k.n_splits = a->n_splits;
+  k.feats_bf16 = reinterpret_cast<const __nv_bfloat16*>(a->feats_bf16);
   k.gthr = nullptr;
   if (a->n_splits > 1 && a->flags) {     // `flags` doubles as the threshold exchange buffer until the re-score kernel overwrites it
     k.gthr = reinterpret_cast<unsigned int*>(a->flags);

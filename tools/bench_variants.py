@@ -34,6 +34,7 @@ def bert():
                                  inner_units=inner, type_vocab_size=2)
     torch.manual_seed(0)
     m = BertModel(100, I, args).cuda().train()
+    m.precision = int(os.environ.get("BERT_PREC", "1"))     # 1: bf16 GEMM cores -- the linear layers run on tcgen05 (adt_gemm_tc)
     rng = np.random.default_rng(23)
     dec = seqs(rng, B, L, I, 144)
     mask = (rng.random((B, L)) < 0.2) & (dec > 0)
@@ -49,7 +50,8 @@ def bert():
         opt.step()
         out["loss"] = loss
     ms = timed(step)
-    print(json.dumps({"model": "Bert4Rec-ADT C3 (B=256, L=200, H=256, nh=4, inner=1024, items=26744, mask_prob=0.2)", "ms_per_step": ms,
+    print(json.dumps({"model": "Bert4Rec-ADT C3 (B=256, L=200, H=256, nh=4, inner=1024, items=26744, mask_prob=0.2)", "precision": m.precision,
+                      "ms_per_step": ms,
                       "seqs_per_sec": B / ms * 1e3, "loss": float(out["loss"]), "labelled_positions": int(mask.sum())}), flush=True)
 
 
