@@ -212,7 +212,7 @@ class BertModel(nn.Module):
         pos_ids = torch.arange(Lq, dtype=torch.int32, device=dev).repeat(B, 1)
         sent = torch.zeros(B, Lq, dtype=torch.int32, device=dev)
         feats, enc_inputs, dec_outs, inds = self._body(src_ids, dec_ids, pos_ids, sent, pos_ids, sent)
-        lab = torch.as_tensor(np.asarray(labels.cpu() if isinstance(labels, torch.Tensor) else labels)).to(dev).view(-1).long()
+        lab = (labels.to(dev) if isinstance(labels, torch.Tensor) else torch.as_tensor(np.asarray(labels)).to(dev)).view(-1).long()
         rows = torch.nonzero(lab != 0, as_tuple=False).flatten()
         logits = self.downstream(feats.index_select(0, rows))
         total = MaskedCE.apply(logits, lab[rows].int())

@@ -26,7 +26,8 @@ using namespace adt;
 namespace {
 
 constexpr int BM = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;          // single streaming pass: TMA warp, MMA warp, 4 epilogue warps (thread == user row, lists in smem)
+constexpr int TC_THREADS2 = 320;         // two-pass kernels: 8 epilogue warps, two per TMEM lane quarter, each filters half of a tile's columns
 
 struct TcArgs {
   const int* seen_indptr; const int* seen_idx;
@@ -82,8 +83,8 @@ __device__ __forceinline__ bool tc_is_seen(const TcArgs& a, int sb, int se, int 
 // threads store their own feature row with tcgen05.st once, the MMAs read it from TMEM (tcgen05.mma, A from TMEM).  Frees
 // KB*16 KB of shared memory for a deeper TMA ring and takes the A fragment reads off the shared-memory port.
 template <int KB, int BN, int NS, int MODE, bool MC, bool ATM>
-__global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                 const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = ATM ? 0 : KB * BM * 128;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(tfull + i, 1);
-      tc::mbar_init(tempty + i, 4);
+      tc::mbar_init(tempty + i, MODE == 0 ? 4 : 8);
     }
     tc::mbar_init(abar, ATM ? 4 : 1);            // A in TMEM: one arrival per epilogue warp after its tcgen05.st completed
     tc::fence_barrier_init();
@@ -183,11 +184,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
   } else {
     // epilogue: thread == user row, for the threshold filter AND for the maintenance of that row's candidate list: every lane
     // inserts its own candidates into its own slot-major list (no cross-lane traffic, all 32 rows of a warp progress in parallel)
-    const int q = warp & 3;
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;        // two-pass kernels: which half of a tile's columns this warp filters (0 in the single pass)
     const int row = 32 * q + lane;
     const int u = u0 + row;
-    const int KC = a.KC;
-    if (ATM) {     // this thread's feature row (bf16, KB*32 words) -> TMEM columns A_COL.. of its lane
+    const int KC = MODE == 0 ? a.KC : a.KC / 2;      // two-pass: every (row, column half) owns KC/2 candidate slots = one virtual split
+    const int CB = MODE == 0 ? 0 : half * (BN / 2), CE = MODE == 0 ? BN : CB + BN / 2;
+    if (ATM && half == 0) {     // this thread's feature row (bf16, KB*32 words) -> TMEM columns A_COL.. of its lane
       const uint4* frow = reinterpret_cast<const uint4*>(a.feats_bf16 + (long long)(u < a.U ? u : 0) * (KB * 64));
 #pragma unroll 1
       for (int i = 0; i < KB; ++i) {
@@ -227,58 +230,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
       thr = u < a.U ? a.tau[u] : INFINITY;
       int cnt = 0;
       bool overflow = false;
-      const long long obase = ((long long)split * a.U + (u < a.U ? u : 0)) * KC;
-      // one chunk = 32 score columns of this thread's row.  The TMEM load of chunk c+1 is in flight while chunk c is filtered.
-      auto process = [&](const uint32_t (&r)[32], int ib) {
-        const int nvalid = a.n_items - ib;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, c < nvalid ? __uint_as_float(r[c]) : -INFINITY);
-        if (a.debug != 0) return;
-        if (mx > thr) {                      // rare (about one row in 150 per chunk): walk the 32 registers, no staging through smem
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float x = __uint_as_float(r[c]);
-            if (c < nvalid && x > thr) {
-              const int item = a.item_offset + ib + c;
-              if (!tc_is_seen(a, sb, se, item)) {       // candidates go straight to HBM, no list on chip
-                if (cnt < KC) { a.part_scores[obase + cnt] = x; a.part_ids[obase + cnt] = item; ++cnt; }
-                else overflow = true;
-              }
-            }
-          }
-        }
-      };
-      constexpr int NCH = BN / 32;           // 2 or 4 chunks per tile
+      const long long vsplit = (long long)split * 2 + half;
+      const long long obase = (vsplit * a.U + (u < a.U ? u : 0)) * KC;
       for (int t = 0; t < ntiles; ++t) {
         const int st = t & 1;
         tc::mbar_wait(tfull + st, (t >> 1) & 1);
         tc::tc_fence_after();
         const int tb = (tfirst + t * tstep) * BN;
-        const uint32_t tad = tmem_base + ((uint32_t)(32 * q) << 16) + st * BN;
-        uint32_t r0[32], r1[32];
-        tc::tmem_ld32_issue(tad, r0);
-        tc::tmem_ld_wait(r0);
-#pragma unroll
-        for (int ch = 0; ch < NCH; ch += 2) {
-          tc::tmem_ld32_issue(tad + 32 * (ch + 1), r1);
-          process(r0, tb + 32 * ch);
-          tc::tmem_ld_wait(r1);
-          if (ch + 2 < NCH) {
-            tc::tmem_ld32_issue(tad + 32 * (ch + 2), r0);
-          } else {                           // accumulator fully read: hand it back to the MMA warp
+#pragma unroll 1
+        for (int c0 = CB; c0 < CE; c0 += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
+          if (c0 + 32 == CE) {               // accumulator fully read: hand it back to the MMA warp
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty + st);
           }
-          process(r1, tb + 32 * (ch + 1));
-          if (ch + 2 < NCH) tc::tmem_ld_wait(r0);
+          const int ib = tb + c0;
+          const int nvalid = a.n_items - ib;
+          if (nvalid < 32) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c >= nvalid) v[c] = -INFINITY;
+          }
+          if (a.debug == 1) continue;
+          float mx = v[0];
+#pragma unroll
+          for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
+          if (a.debug == 2) continue;
+          if (mx > thr) {                    // rare (about one row in 150 per chunk): walk the 32 registers, no staging through smem
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (v[c] > thr) {
+                const int item = a.item_offset + ib + c;
+                if (!tc_is_seen(a, sb, se, item)) {       // candidates go straight to HBM, no list on chip
+                  if (cnt < KC) { a.part_scores[obase + cnt] = v[c]; a.part_ids[obase + cnt] = item; ++cnt; }
+                  else overflow = true;
+                }
+              }
+            }
+          }
         }
       }
       if (overflow) thr = INFINITY;          // candidates were dropped: the caller must re-run this user exactly
       if (u < a.U) {
         for (int k = cnt; k < KC; ++k) { a.part_scores[obase + k] = -INFINITY; a.part_ids[obase + k] = -1; }
-        a.part_thr[(long long)split * a.U + u] = thr;
+        a.part_thr[vsplit * a.U + u] = thr;
       }
     } else if constexpr (MODE == 2) {
       // ---- sample pass: only the maximum of every sampled tile is kept, [sample tile][user] in part_scores (tau_select_kernel picks the
@@ -291,10 +288,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
         const int tb = (tfirst + t * tstep) * BN;
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = CB; c0 < CE; c0 += 32) {
           float v[32];
           tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
-          if (c0 + 32 == BN) {
+          if (c0 + 32 == CE) {
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty + st);
@@ -303,7 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_tc_kernel(const __grid_co
 #pragma unroll
           for (int c = 0; c < 32; ++c) mx = fmaxf(mx, c < nvalid ? v[c] : -INFINITY);
         }
-        if (u < a.U) a.part_scores[(long long)(split + t * a.n_splits) * a.U + u] = mx;
+        if (u < a.U) a.part_scores[((long long)(split + t * a.n_splits) * 2 + half) * a.U + u] = mx;
       }
     } else {
     uint32_t mink = 0u;                      // smallest key in the list and its slot
@@ -551,7 +548,7 @@ int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, true, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid.y, grid.x); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cfg.gridDim = dim3(grid.y, grid.x); cfg.blockDim = dim3(MODE == 0 ? TC_THREADS : TC_THREADS2); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -559,7 +556,7 @@ int launch_tc_ns(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
     return cudaLaunchKernelEx(&cfg, score_tc_kernel<KB, BN, NS, MODE, true, ATM>, tmA, *tmBh, k) == cudaSuccess ? ADT_OK : ADT_E_CUDA;
   }
   cudaFuncSetAttribute(score_tc_kernel<KB, BN, NS, MODE, false, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  score_tc_kernel<KB, BN, NS, MODE, false, ATM><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, k);
+  score_tc_kernel<KB, BN, NS, MODE, false, ATM><<<grid, MODE == 0 ? TC_THREADS : TC_THREADS2, smem, s>>>(tmA, tmB, k);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }
 // deepest catalog-tile ring (2..4 stages) that fits the 227 KB of shared memory next to the user tile and the top-K lists
@@ -660,16 +657,16 @@ extern "C" int adt_score_tc_plan(int32_t U, int32_t H, int32_t n_items, int32_t 
     // the sample pass parks one maximum per sampled tile in the candidate scratch (n_splits*KC floats per user, <= 2048) and the
     // threshold pass needs >= 4x the expected number of candidates per split (tiles are interleaved over the splits: even spread)
     int sstride = TC_SSTRIDE;
-    while ((ntt + sstride - 1) / sstride > RS_MAXC) sstride *= 2;
-    const int nst = (ntt + sstride - 1) / sstride;
+    while (2 * ((ntt + sstride - 1) / sstride) > RS_MAXC) sstride *= 2;
+    const int nst = 2 * ((ntt + sstride - 1) / sstride);      // one maximum per sampled half tile
     int R = (tc_target(K) + sstride - 1) / sstride;
     if (R < 6) R = 6;
     const int eff = R * sstride;
     int best_s = 0, best_kc = 0;
     for (int kc = 32; kc <= 64; kc *= 2) {      // the capacity that needs the fewest extra splits (ties: the smaller lists)
-      int s2 = S;
+      int s2 = S < RS_MAXC / kc ? S : RS_MAXC / kc;
       if (s2 * kc < nst) s2 = (nst + kc - 1) / kc;
-      const int per = kc - 8;
+      const int per = kc - 8;               // >= 4x the expected candidates overall; each (split, column half) owns kc/2 of the slots
       if (s2 * per < 4 * eff) s2 = (4 * eff + per - 1) / per;
       if (s2 * kc <= RS_MAXC && s2 <= ntt && (!best_s || s2 < best_s)) { best_s = s2; best_kc = kc; }
     }
@@ -706,6 +703,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   { const char* dbg = getenv("ADT_TC_DEBUG"); k.debug = dbg ? atoi(dbg) : 0; }
   dim3 grid(a->n_splits, (a->U + BM - 1) / BM);
   int rc;
+  bool two = false;
   k.tau = nullptr; k.sstride = 1;
   // Large catalogs: two passes.  (1) a SAMPLE of every 16th catalog tile is scored and only the maximum of each sampled tile is kept
   // per user; the R-th largest of those maxima becomes the user's threshold tau, so about 16 R (>= 6 K) catalog items score above it.
@@ -720,6 +718,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   int BN = tc_bn(KB, 1);
   const int ntt = (a->n_items + BN - 1) / BN;
   int cap = a->n_splits * a->KC < 2048 ? a->n_splits * a->KC : 2048;
+  cap /= 2;                                  // the sample pass keeps one maximum per sampled HALF tile (two epilogue warps per row)
   int sstride = TC_SSTRIDE;
   while ((ntt + sstride - 1) / sstride > cap) sstride *= 2;
   const int nst = (ntt + sstride - 1) / sstride;
@@ -742,7 +741,8 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
     rc = launch_tc_h<2>(KB, BN, tmA, tmB, tmBh, ks, grid, s);
     if (rc) return rc;
     float* tau = a->out_scores;            // U floats of scratch: overwritten by the re-score kernel at the end
-    tau_select_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(a->part_scores, nst, a->U, R, tau);
+    tau_select_kernel<<<(a->U + 7) / 8, 256, 0, s>>>(a->part_scores, 2 * nst, a->U, R, tau);
+    two = true;
     k.tau = tau; k.gthr = nullptr;
     rc = launch_tc_h<1>(KB, BN, tmA, tmB, tmBh, k, grid, s);
   } else {
@@ -755,6 +755,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   r.feats = a->feats; r.E = a->item_emb; r.part_scores = a->part_scores; r.part_ids = a->part_ids; r.part_thr = a->part_thr;
   r.max_normsq = a->max_normsq; r.out_scores = a->out_scores; r.out_ids = a->out_ids; r.flags = a->flags;
   r.U = a->U; r.H = a->H; r.item_offset = a->item_offset; r.K = a->K; r.KC = a->KC; r.n_splits = a->n_splits;
+  if (two) { r.KC = a->KC / 2; r.n_splits = 2 * a->n_splits; }     // every (split, column half) wrote its own list and threshold
   r.answers = a->answers; r.metric_acc = a->metric_acc;
   rescore_select_kernel<<<a->U, RS_NT, 0, s>>>(r);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;

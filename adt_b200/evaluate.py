@@ -161,7 +161,7 @@ class CatalogScorer:
         if key not in self._buf:
             pk = torch.empty(2, U, K, dtype=torch.int32, device=dev)        # [0] scores (float bits), [1] ids: one all-gather payload
             self._buf[key] = (torch.empty(S, U, KC, device=dev), torch.empty(S, U, KC, dtype=torch.int32, device=dev),
-                              torch.empty(S, U, device=dev), pk, torch.empty(U, dtype=torch.int32, device=dev),
+                              torch.empty(2 * S, U, device=dev), pk, torch.empty(U, dtype=torch.int32, device=dev),
                               torch.empty(U, H, dtype=torch.bfloat16, device=dev))
         ps, pi, pt, pk, flags, fb = self._buf[key]
         os_, oi = pk[0].view(torch.float32), pk[1]

@@ -14,6 +14,7 @@ backward, clip + Adam) over one synthetic batch of the C2 shape (configs[1]: ~12
   eval {value, e2e, roofline, cpu_baseline}  the evaluation half (full-catalog top-10 of 512 users per batch, C2)
   fp32 {...}                                 the step with fp32 FFMA GEMM cores (the reference's precision), device + e2e
   c1 {...}                                   configs[0]'s shape (ml-1m: L 200, H 256) through the same trainer
+  c3 {...}                                   configs[2]: Bert4Rec-ADT cloze training step (ml-20m shape), linear layers on tcgen05
   c5 {...}                                   catalog scoring at 1M items (H 64 / 256): tensor-pipe roofline
   reference_gpu_eager {...}                  the unmodified reference in PyTorch eager on the same B200 (the kernel bar)
   evolution {...}                            evolution.py's population evaluation on the supernet, candidates dealt to the ranks
@@ -499,6 +500,56 @@ def c5_section(cx, args):
     return out
 
 
+def c3_section(cx):
+    """configs[2]: Bert4Rec-ADT cloze training step at the ml-20m shape (B 256/GPU, L 200, H 256, 4 heads, inner 1024, 26,744 items,
+    mask_prob 0.2): fused loss (vocabulary head on the labelled positions only) + backward + flat clip/Adam, linear layers on tcgen05
+    (adt_gemm_tc), batches generated on the device (adt_cloze_batch).  Data parallel over the ranks (one all-reduce of the flat gradient)."""
+    import types
+    from adt_b200.bert4rec import BertModel
+    from adt_b200.dp import FlatOptimizer
+    from adt_b200.sampler import ClozeSampler
+    B, L_, H, nh, nl, I, inner = 256, 200, 256, 4, 2, 26744, 1024
+    args = types.SimpleNamespace(device=cx.dev, num_heads=nh, maxlen=L_, num_layers=nl, hidden_units=H, dropout=0.1, attention_dropout=0.1,
+                                 inner_units=inner, type_vocab_size=2)
+    torch.manual_seed(0)
+    m = BertModel(100, I, args).to(cx.dev).train()
+    m.precision = 1
+    rng = np.random.default_rng(23 + cx.rank)
+    n_users = 512
+    hist = {u: [int(x) for x in rng.integers(1, I + 1, size=int(np.clip(rng.geometric(1.0 / 144) + 2, 3, 400)))] for u in range(1, n_users + 1)}
+    cs = ClozeSampler(hist, n_users, I, L_, mask_prob=0.2, dupe_factor=2, prop_sliding_window=0.5, device=cx.dev, seed=23)
+    opt = FlatOptimizer(m, lr=1e-3, clip=5.0)
+    order = torch.from_numpy(rng.permutation(len(cs))).to(cx.dev)
+    state = {"i": 0}
+
+    def step():
+        idx = order[(state["i"] * B) % (len(cs) - B):][:B]
+        state["i"] += 1
+        src, dec, lab = cs.batch(idx, epoch=state["i"])
+        opt.zero_grad()
+        loss = m.fused_loss(src, dec, lab, [0.01, 0.01], [0.001, 0.001])
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(3):
+        step()
+    cx.barrier()
+    K3 = 8
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K3):
+        loss = step()
+    e1.record()
+    cx.barrier()
+    (ms,) = reduce_max(cx, e0.elapsed_time(e1) / K3)
+    out = {"workload": "Bert4Rec-ADT C3: cloze train step (items=26744, maxlen=200, hidden=256, heads=4, inner=1024, blocks=2, batch=256/GPU, mask_prob=0.2)",
+           "value": cx.world * B / (ms / 1e3), "unit": "seqs/s", "ms_per_step": ms, "steps": K3, "dtype": "bf16", "loss": float(loss),
+           "launch": "eager launches (autograd-composed ops); batches from adt_cloze_batch", "round1_ms_per_step_fp32_cores": 86.0}
+    del m, opt, cs
+    torch.cuda.empty_cache()
+    return out
+
+
 def refgpu_section(cx, cfg):
     """the unmodified reference (PyTorch eager, fp32) on the same B200: SURVEY 8d's 'honest kernel bar'"""
     try:
@@ -661,6 +712,14 @@ def main():
         c1 = o
         torch.cuda.empty_cache()
 
+    c3 = None
+    if "c3" not in skip:
+        trace("c3")
+        try:
+            c3 = c3_section(cx)
+        except Exception as e:   # noqa: BLE001
+            c3 = {"error": str(e)[:300]}
+
     c5 = None
     if "c5" not in skip:
         trace("c5")
@@ -717,7 +776,7 @@ def main():
             "loss": main_tr["loss"], "roofline": roofline, "step_roofline": main_tr["step_roofline"],
             "kernels_us": {k_: round(v["avg_us"], 2) for k_, v in sorted(kern.items())},
             "eval_users_per_sec": ev["value"] if ev else None, "eval": ev,
-            ("fp32" if other == "fp32" else "bf16"): other_mode, "c1": c1, "c5": c5, "evolution": evo, "selfcheck": selfcheck, "reference_gpu_eager": refgpu,
+            ("fp32" if other == "fp32" else "bf16"): other_mode, "c1": c1, "c3": c3, "c5": c5, "evolution": evo, "selfcheck": selfcheck, "reference_gpu_eager": refgpu,
             "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

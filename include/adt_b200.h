@@ -274,7 +274,7 @@ typedef struct {
   const float* max_normsq;                                           /* device scalar: max_i |item_emb[i]|^2 */
   const int32_t* seen_indptr; const int32_t* seen_idx;
   int32_t K, KC, n_splits;
-  float* part_scores; int32_t* part_ids; float* part_thr;            /* scratch [n_splits][U][KC], [n_splits][U] */
+  float* part_scores; int32_t* part_ids; float* part_thr;            /* scratch [n_splits][U][KC], [2*n_splits][U] */
   float* out_scores; int32_t* out_ids; int32_t* flags;               /* [U][K], [U][K], [U] */
   const int32_t* answers; double* metric_acc;   /* fused metric epilogue as in adt_score_topk, for the users whose result is proven
                                                    exact (flags[u] == 0); flagged users are accumulated by the exact re-run */
