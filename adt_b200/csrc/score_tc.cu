@@ -662,13 +662,14 @@ extern "C" int adt_score_tc_plan(int32_t U, int32_t H, int32_t n_items, int32_t 
     int R = (tc_target(K) + sstride - 1) / sstride;
     if (R < 6) R = 6;
     const int eff = R * sstride;
-    int best_s = 0, best_kc = 0;
-    for (int kc = 32; kc <= 64; kc *= 2) {      // the capacity that needs the fewest extra splits (ties: the smaller lists)
+    int best_s = 0, best_kc = 0, best_cost = 0;
+    for (int kc = 32; kc <= 64; kc *= 2) {      // keep the split count that fills the SMs when a capacity allows it, else the fewest extra splits
       int s2 = S < RS_MAXC / kc ? S : RS_MAXC / kc;
       if (s2 * kc < nst) s2 = (nst + kc - 1) / kc;
       const int per = kc - 8;               // >= 4x the expected candidates overall; each (split, column half) owns kc/2 of the slots
       if (s2 * per < 4 * eff) s2 = (4 * eff + per - 1) / per;
-      if (s2 * kc <= RS_MAXC && s2 <= ntt && (!best_s || s2 < best_s)) { best_s = s2; best_kc = kc; }
+      const int cost = s2 <= S ? S - s2 : 4096 + s2;
+      if (s2 * kc <= RS_MAXC && s2 <= ntt && (!best_s || cost < best_cost)) { best_s = s2; best_kc = kc; best_cost = cost; }
     }
     if (best_s) { S = best_s; KC = best_kc; mode = 1; } else KC = 64;
   }

@@ -25,6 +25,9 @@ def main():
                 sc.topk_from_feats(feats)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
+            for k, b in sc._buf.items():
+                if len(b) == 6:
+                    print(f"  candidates/user mean {(b[1] >= 0).sum().item() / U:.1f}  max {(b[1] >= 0).sum(dim=(0, 2)).max().item()}  slots {b[1].shape[0] * b[1].shape[2]}")
             print(f"DEBUG={os.environ.get('ADT_TC_DEBUG','0')} U={U} H={H}: {ms:.3f} ms  {2.0*U*(I+1)*H/ms/1e9:.1f} TFLOP/s  {U/ms*1e3:.0f} users/s  fallback={sc.fallback_users}", flush=True)
         del E
 main()
