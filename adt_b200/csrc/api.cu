@@ -190,6 +190,7 @@ extern "C" int adt_workspace_bytes(const adt_workspace_query* q, adt_workspace_s
   out->scatter_rows = 2 * nb * H * f;                                    // head, tail
   out->scatter_flags = nb * (long long)sizeof(int);
   out->score_part = (long long)(q->n_splits > 0 ? q->n_splits : 1) * q->B * (q->K > 0 ? q->K : 1) * 8;
+  out->wgrad_scratch = H >= 128 ? 7 * M * H * 2 : 0;                      // widest user: mid_bwd, 7 bf16 [M,H] operands
   return ADT_OK;
 }
 extern "C" const char* adt_last_error(void) { return g_err; }
@@ -320,6 +321,26 @@ static int launch_pre_bwd(const PreBwdArgs& r, int mma, cudaStream_t s) {
   if (!tm) return fail(ADT_E_SHAPE, "%s", "pre_bwd: tile does not fit shared memory");
   LAUNCH_TM(tm, mma, pre_bwd_kernel, (r.M + tm - 1) / tm, smem, s, r);
   return check_launch("pre_bwd");
+}
+
+// ---- hoisted weight gradients (H >= 128, bf16 mode): see emit_bf16_tile in common.cuh; ADT_WGRAD_HOIST=0 keeps the in-kernel atomics
+static __nv_bfloat16* hoist_ptr(void* scratch, int H, int mma) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_WGRAD_HOIST"); v = e ? (atoi(e) != 0) : 1; }
+  return (v && mma && scratch && H >= 128 && (H & 7) == 0) ? reinterpret_cast<__nv_bfloat16*>(scratch) : nullptr;
+}
+// gW[n_out][k_out] += dY^T X over M rows; dY = [M][ldy] (first n_out columns), X = [M][ldx] bf16 row-major
+static int hoisted_wgrad(const __nv_bfloat16* dy, long long ldy, int n_out, const __nv_bfloat16* x, long long ldx, int k_out, int M, float* gW,
+                         cudaStream_t s) {
+  adt_gemm_tc_args g;
+  memset(&g, 0, sizeof(g));
+  g.a_bf16 = dy; g.lda = ldy; g.b_bf16 = x; g.ldb = ldx; g.c = gW; g.ldc = k_out;
+  g.M = n_out; g.N = k_out; g.K = M; g.accumulate = 1; g.scale = 1.f; g.a_mn = 1; g.b_mn = 1;
+  const int tiles = ((n_out + 127) / 128) * ((k_out + 127) / 128);
+  g.split_k = tiles >= 148 ? 1 : 148 / tiles;
+  TIMED("wgrad_tc", s);
+  if (int e = adt_gemm_tc(&g, (adt_stream_t)s)) return fail(e, "%s", "hoisted weight gradient (adt_gemm_tc)");
+  return ADT_OK;
 }
 
 static adt_dropout row_drop(const adt_dropout& d, int training) {
@@ -509,6 +530,9 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   p.gWsp = a->g_sparse_w; p.gbsp = a->g_sparse_b;
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
+  __nv_bfloat16* hz = hoist_ptr(a->wgrad_scratch, H, mma);
+  const long long hu = (long long)M * H;
+  p.hoist = hz;
   size_t smem;
   int tm = pick_tm(4 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
@@ -521,6 +545,11 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
     TIMED("enc_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, false, (M + tm - 1) / tm, smem, s, p);
   }
   if (int e = check_launch("enc post_bwd")) return e;
+  if (hz) {
+    if (int e = hoisted_wgrad(hz, H, H, hz + hu, H, H, M, a->g_ffn.w2, s)) return e;
+    if (int e = hoisted_wgrad(hz + 2 * hu, H, H, hz + 3 * hu, H, H, M, a->g_ffn.w1, s)) return e;
+    if (int e = hoisted_wgrad(hz + 4 * hu, H, H, hz + 5 * hu, H, H, M, a->g_attn.out_w, s)) return e;
+  }
   if (int e = launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
                               a->drop_attn, a->precision, s))
     return e;
@@ -530,7 +559,13 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   r.ln_g = a->ln1_w; r.ln_b = a->ln1_b; r.Win = a->attn.in_w; r.dx = a->dx;
   r.gWin = a->g_attn.in_w; r.gbin = a->g_attn.in_b; r.gln_g = a->g_ln1_w; r.gln_b = a->g_ln1_b;
   r.M = M; r.H = H; r.qscale = 1.0f / sqrtf((float)(H / a->nh)); r.kv_from_norm = 0;
-  return launch_pre_bwd(r, mma, s);
+  r.hoist = hz;
+  if (int e = launch_pre_bwd(r, mma, s)) return e;
+  if (hz) {   // Wq from LN(x), [Wk; Wv] from x
+    if (int e = hoisted_wgrad(hz, 3 * H, H, hz + 3 * hu, H, H, M, a->g_attn.in_w, s)) return e;
+    if (int e = hoisted_wgrad(hz + H, 3 * H, 2 * H, hz + 4 * hu, H, H, M, a->g_attn.in_w + (long long)H * H, s)) return e;
+  }
+  return ADT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -590,6 +625,8 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
   if (use_seq(a->L, H, a->nh, mma, SEQ_DEC_BWD)) return seq_dec_bwd(a, s);
+  __nv_bfloat16* hz = hoist_ptr(a->wgrad_scratch, H, mma);
+  const long long hu = (long long)M * H;
   size_t smem;
   int tm = pick_tm(4 * (size_t)(H + pad), &smem);
   if (!tm) return fail(ADT_E_SHAPE, "%s", "post_bwd: tile does not fit shared memory");
@@ -602,6 +639,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   p.gWo = a->g_enc.out_w; p.gbo = a->g_enc.out_b; p.gC1 = a->g_ffn.w1; p.gc1 = a->g_ffn.b1; p.gC2 = a->g_ffn.w2; p.gc2 = a->g_ffn.b2;
   p.M = M; p.H = H; p.nh = a->nh;
   p.drop1 = mk_drop(a->drop_ffn1); p.drop2 = mk_drop(a->drop_ffn2);
+  p.hoist = hz;
   if (use_row_small(H, mma)) {
     const size_t sm = PostBwdSmallSmem::TOTAL_BYTES;
     cudaFuncSetAttribute(post_bwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -611,6 +649,11 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
     TIMED("dec_post_bwd", s); LAUNCH_TM2(tm, mma, post_bwd_kernel, true, (M + tm - 1) / tm, smem, s, p);
   }
   if (int e = check_launch("dec post_bwd")) return e;
+  if (hz) {
+    if (int e = hoisted_wgrad(hz, H, H, hz + hu, H, H, M, a->g_ffn.w2, s)) return e;
+    if (int e = hoisted_wgrad(hz + 2 * hu, H, H, hz + 3 * hu, H, H, M, a->g_ffn.w1, s)) return e;
+    if (int e = hoisted_wgrad(hz + 4 * hu, H, H, hz + 5 * hu, H, H, M, a->g_enc.out_w, s)) return e;
+  }
   // cross attention (keys/values from the encoder features)
   if (int e = launch_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,
                               a->drop_enc, a->precision, s))
@@ -621,6 +664,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   m.Wo1 = a->slf.out_w; m.Win2 = a->enc.in_w; m.dfeats = a->dfeats; m.dctx1 = a->dctx;
   m.gWo1 = a->g_slf.out_w; m.gbo1 = a->g_slf.out_b; m.gWin2 = a->g_enc.in_w; m.gbin2 = a->g_enc.in_b;
   m.M = M; m.H = H; m.qscale = qscale;
+  m.hoist = hz;
   if (use_row_small(H, mma)) {
     const size_t sm = MidBwdSmallSmem::TOTAL_BYTES;
     cudaFuncSetAttribute(mid_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -632,6 +676,11 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   { TIMED("mid_bwd", s); LAUNCH_TM(tm, mma, mid_bwd_kernel, (M + tm - 1) / tm, smem, s, m); }
   }
   if (int e = check_launch("mid_bwd")) return e;
+  if (hz) {   // cross-attention in-projection (q rows from a, [k; v] rows from the encoder features) and the self-attention out-projection
+    if (int e = hoisted_wgrad(hz, H, H, hz + hu, H, H, M, a->g_enc.in_w, s)) return e;
+    if (int e = hoisted_wgrad(hz + 2 * hu, 2 * H, 2 * H, hz + 4 * hu, H, H, M, a->g_enc.in_w + (long long)H * H, s)) return e;
+    if (int e = hoisted_wgrad(hz + 5 * hu, H, H, hz + 6 * hu, H, H, M, a->g_slf.out_w, s)) return e;
+  }
   if (a->phase == 2) return ADT_OK;
   }
   if (int e = launch_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
@@ -643,7 +692,12 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   r.ln_g = a->ln_w; r.ln_b = a->ln_b; r.Win = a->slf.in_w; r.dx = a->dx;
   r.gWin = a->g_slf.in_w; r.gbin = a->g_slf.in_b; r.gln_g = a->g_ln_w; r.gln_b = a->g_ln_b;
   r.M = M; r.H = H; r.qscale = qscale; r.kv_from_norm = 1;
-  return launch_pre_bwd(r, mma, s);
+  r.hoist = hz;
+  if (int e = launch_pre_bwd(r, mma, s)) return e;
+  if (hz) {   // q, k and v all read d = LN(x): one [3H x H] product
+    if (int e = hoisted_wgrad(hz, 3 * H, 3 * H, hz + 3 * hu, H, H, M, a->g_slf.in_w, s)) return e;
+  }
+  return ADT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -728,6 +728,21 @@ __device__ __forceinline__ void colsum_atomic(const float* __restrict__ dY, int 
   }
 }
 
+// Hoisted weight gradients (wide models): instead of reducing dY^T X over its few rows and adding H x H partial sums to the global
+// gradient with atomics -- the dominant cost of the backward row-tile kernels at H = 256 -- a CTA only writes the bf16 copies of its
+// dY and X tiles; ONE split-K tcgen05 GEMM per weight (adt_gemm_tc, both operands read MN-major) then reduces over all rows.
+__device__ __forceinline__ void emit_bf16_tile(const float* __restrict__ T, int ld, int C, int rows, __nv_bfloat16* __restrict__ dst,
+                                               long long ldd) {
+  const int c4n = C >> 2;
+  for (int s = threadIdx.x; s < rows * c4n; s += NT) {
+    const int r = s / c4n, c = 4 * (s - r * c4n);
+    const float4 v = *reinterpret_cast<const float4*>(T + r * ld + c);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y); o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + (long long)r * ldd + c) = o;
+  }
+}
+
 // dispatch helper: fp32 FFMA or bf16 tensor-core weight gradient
 template <bool MMA, bool ATOMIC, int TMR>
 __device__ __forceinline__ void wgrad_any(const float* __restrict__ dY, int ldy, int N, const float* __restrict__ X, int ldx, int K,

@@ -2,8 +2,11 @@
 // One GEMM serves the three products of a linear layer (bert4rec/model/modules.py:57-72, :128-139, bert.py:80-90; the wide
 // contractions of the H = 256 shapes):
 //   forward   y  = x W^T        A = x   [M,K]      B = W    [N,K]
-//   dgrad     dx = dy W         A = dy  [M,N]      B = W^T  [K,N]      (transposed bf16 copy made by adt_to_bf16_t)
-//   wgrad     dW = dy^T x       A = dy^T [N,M]     B = x^T  [K,M]
+//   dgrad     dx = dy W         A = dy  [M,N]      B = W read MN-major (b_mn: the operand is stored [K][N], N contiguous)
+//   wgrad     dW = dy^T x       A = dy, B = x, both read MN-major (a_mn, b_mn: stored [K][M] / [K][N]) -- no transposed copies;
+//                               split_k CTAs share one output tile and add their partial sums with vector atomics
+// An MN-major K-slab is loaded as 64-column boxes of 64 K-rows (128-byte rows, SWIZZLE_128B): exactly the canonical MN-major
+// layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with LBO = one box (8 KB) and SBO = 8 K-rows (1 KB).
 // Structure: one 128 x BN output tile per CTA; warp 0 = TMA producer (A and B K-slabs of 64 through an NS-stage ring), warp 1 =
 // tcgen05.mma issuer (accumulator 128 x BN fp32 in TMEM), warps 2-5 = epilogue (tcgen05.ld -> bias / scale / activation -> fp32
 // rows to HBM, thread == output row).  K, M, N are arbitrary: TMA zero-fills out-of-bounds rows / columns, stores are masked.
@@ -26,6 +29,7 @@ constexpr int G_THREADS = 192;
 struct GemmTcArgs {
   float* C; float* pre; const float* bias; long long ldc;
   int M, N, K, act, accumulate; float scale;
+  int a_mn, b_mn, kb_per_split;
 };
 
 __device__ __forceinline__ float g_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -48,7 +52,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM;
-  const int nkb = (a.K + 63) / 64;
+  const int nkb_all = (a.K + 63) / 64;
+  const int kb0 = blockIdx.z * a.kb_per_split;
+  const int nkb = min(a.kb_per_split, nkb_all - kb0);      // K slabs of this split (>= 1 by construction of the grid)
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -69,22 +75,35 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const int st = kb % NS;
         tc::mbar_wait(empty + st, ((kb / NS) & 1) ^ 1);
         tc::mbar_arrive_expect_tx(full + st, A_STAGE + B_STAGE);
-        tc::tma_load_2d(sA + st * A_STAGE, &tmA, kb * 64, m0, full + st);
-        tc::tma_load_2d(sB + st * B_STAGE, &tmB, kb * 64, n0, full + st);
+        const int kc = (kb0 + kb) * 64;
+        if (a.a_mn) {
+#pragma unroll
+          for (int i = 0; i < GM / 64; ++i) tc::tma_load_2d(sA + st * A_STAGE + i * 8192, &tmA, m0 + 64 * i, kc, full + st);
+        } else {
+          tc::tma_load_2d(sA + st * A_STAGE, &tmA, kc, m0, full + st);
+        }
+        if (a.b_mn) {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) tc::tma_load_2d(sB + st * B_STAGE + i * 8192, &tmB, n0 + 64 * i, kc, full + st);
+        } else {
+          tc::tma_load_2d(sB + st * B_STAGE, &tmB, kc, n0, full + st);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::idesc_bf16_f32(GM, BN);
+      const uint32_t idesc = tc::idesc_bf16_f32(GM, BN) | (a.a_mn ? 1u << 15 : 0u) | (a.b_mn ? 1u << 16 : 0u);
+      const uint64_t a_step = a.a_mn ? 128 : 2, b_step = a.b_mn ? 128 : 2;     // 16 K per MMA: 16 rows of 128 B, or 32 B inside a row
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % NS;
         tc::mbar_wait(full + st, (kb / NS) & 1);
         tc::tc_fence_after();
-        const uint64_t ad = tc::smem_desc_k_sw128(tc::smem_u32(sA + st * A_STAGE));
-        const uint64_t bd = tc::smem_desc_k_sw128(tc::smem_u32(sB + st * B_STAGE));
+        const uint32_t sa = tc::smem_u32(sA + st * A_STAGE), sb = tc::smem_u32(sB + st * B_STAGE);
+        const uint64_t ad = a.a_mn ? tc::smem_desc_mn_sw128(sa, 8192) : tc::smem_desc_k_sw128(sa);
+        const uint64_t bd = a.b_mn ? tc::smem_desc_mn_sw128(sb, 8192) : tc::smem_desc_k_sw128(sb);
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
-          tc::mma_bf16_ss(tmem_base, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), idesc, (kb | k4) != 0);
+          tc::mma_bf16_ss(tmem_base, ad + (uint64_t)k4 * a_step, bd + (uint64_t)k4 * b_step, idesc, (kb | k4) != 0);
         tc::mma_commit(empty + st);
       }
       tc::mma_commit(tfull);
@@ -106,7 +125,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         float x = v[c];
-        if (a.bias && nb + c < a.N) x += __ldg(a.bias + nb + c);
+        if (a.bias && blockIdx.z == 0 && nb + c < a.N) x += __ldg(a.bias + nb + c);
         v[c] = x * a.scale;
       }
       if (vec && nb + 32 <= a.N) {
@@ -115,6 +134,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
           float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
           if (prow) *reinterpret_cast<float4*>(prow + c) = o;
           o = make_float4(g_act(o.x, a.act), g_act(o.y, a.act), g_act(o.z, a.act), g_act(o.w, a.act));
+          if (gridDim.z > 1) { atomicAdd(reinterpret_cast<float4*>(crow + c), o); continue; }
           if (a.accumulate) {
             const float4 old = *reinterpret_cast<const float4*>(crow + c);
             o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w);
@@ -127,6 +147,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
           if (nb + c < a.N) {
             if (prow) prow[c] = v[c];
             float o = g_act(v[c], a.act);
+            if (gridDim.z > 1) { atomicAdd(crow + c, o); continue; }
             if (a.accumulate) o += crow[c];
             crow[c] = o;
           }
@@ -200,6 +221,7 @@ EncodeTiledFn g_encode() {
 }
 // bf16 row-major [rows][cols] with row stride ld elements; box = [box_rows][64 cols], 128-byte swizzle, zero fill out of bounds
 int g_make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  // (an MN-major operand passes rows = K, cols = M or N and box_rows = 64: 64 x 64 boxes)
   EncodeTiledFn enc = g_encode();
   if (!enc) return ADT_E_CUDA;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -212,10 +234,10 @@ int g_make_map(CUtensorMap* m, const void* base, long long rows, long long cols,
 }
 
 template <int BN, int NS>
-int g_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& k, cudaStream_t s) {
+int g_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& k, int splits, cudaStream_t s) {
   const size_t smem = 1024 + (size_t)NS * (GM * 128 + BN * 128) + 256;
   cudaFuncSetAttribute(gemm_tc_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((k.N + BN - 1) / BN, (k.M + GM - 1) / GM);
+  dim3 grid((k.N + BN - 1) / BN, (k.M + GM - 1) / GM, splits);
   gemm_tc_kernel<BN, NS><<<grid, G_THREADS, smem, s>>>(tmA, tmB, k);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }
@@ -224,20 +246,31 @@ int g_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& k
 
 extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   cudaStream_t s = (cudaStream_t)s_;
-  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->lda & 7) || (a->ldb & 7) || a->lda < a->K || a->ldb < a->K || a->ldc < a->N) return ADT_E_SHAPE;
+  // an MN-major operand is stored [K][ld] with its M (or N) extent contiguous
+  const long long a_in = a->a_mn ? a->M : a->K, b_in = a->b_mn ? a->N : a->K;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->lda & 7) || (a->ldb & 7) || a->lda < a_in || a->ldb < b_in || a->ldc < a->N) return ADT_E_SHAPE;
   if ((reinterpret_cast<uintptr_t>(a->a_bf16) | reinterpret_cast<uintptr_t>(a->b_bf16)) & 15) return ADT_E_ALIGN;
+  if (a->split_k > 1 && (a->act || a->pre)) return ADT_E_SHAPE;      // partial sums are only linear before the activation
   CUtensorMap tmA, tmB;
   GemmTcArgs k;
   k.C = a->c; k.pre = a->pre; k.bias = a->bias; k.ldc = a->ldc; k.M = a->M; k.N = a->N; k.K = a->K; k.act = a->act; k.accumulate = a->accumulate;
   k.scale = a->scale == 0.f ? 1.f : a->scale;
-  if (int e = g_make_map(&tmA, a->a_bf16, a->M, a->K, a->lda, GM)) return e;
-  // narrow outputs waste less of the tile with 64 columns; wide ones amortise the A slab over 128
-  if (a->N <= 64) {
-    if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, 64)) return e;
-    return g_launch<64, 6>(tmA, tmB, k, s);
+  k.a_mn = a->a_mn ? 1 : 0; k.b_mn = a->b_mn ? 1 : 0;
+  const int nkb = (a->K + 63) / 64;
+  int splits = a->split_k > 1 ? (a->split_k < nkb ? a->split_k : nkb) : 1;
+  k.kb_per_split = (nkb + splits - 1) / splits;
+  splits = (nkb + k.kb_per_split - 1) / k.kb_per_split;
+  if (splits > 1 && !a->accumulate) {
+    if (cudaMemset2DAsync(a->c, (size_t)a->ldc * 4, 0, (size_t)a->N * 4, (size_t)a->M, s) != cudaSuccess) return ADT_E_CUDA;
   }
-  if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, 128)) return e;
-  return g_launch<128, 6>(tmA, tmB, k, s);
+  if (k.a_mn) { if (int e = g_make_map(&tmA, a->a_bf16, a->K, a->M, a->lda, 64)) return e; }
+  else if (int e = g_make_map(&tmA, a->a_bf16, a->M, a->K, a->lda, GM)) return e;
+  // narrow outputs waste less of the tile with 64 columns; wide ones amortise the A slab over 128
+  const int bn = a->N <= 64 ? 64 : 128;
+  if (k.b_mn) { if (int e = g_make_map(&tmB, a->b_bf16, a->K, a->N, a->ldb, 64)) return e; }
+  else if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, bn)) return e;
+  if (bn == 64) return g_launch<64, 6>(tmA, tmB, k, splits, s);
+  return g_launch<128, 6>(tmA, tmB, k, splits, s);
 }
 
 extern "C" int adt_to_bf16_t(const float* x, int64_t ld, void* y_bf16, int64_t ldt, int32_t R, int32_t C, adt_stream_t s_) {

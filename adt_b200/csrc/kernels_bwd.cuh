@@ -60,6 +60,7 @@ struct PostBwdArgs {
   float* gWo; float* gbo; float* gln2_g; float* gln2_b; float* gC1; float* gc1; float* gC2; float* gc2; float* gWsp; float* gbsp;
   int M, H, nh;
   DropDesc drop1, drop2;
+  __nv_bfloat16* hoist;   // nullable: [6][M][H] bf16 operand copies (dh2, a, dh1, z, dy|dc, ctx) for the hoisted weight gradients
 };
 
 template <int TM, bool IS_DEC, bool MMA>
@@ -75,6 +76,8 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   float* Ws = Y + TM * ld;    // weight staging; reused as LN-bwd / sparse-head scratch
   const int row0 = blockIdx.x * TM;
   const int rows = min(TM, M - row0);
+  const long long hu = (long long)M * H;                                        // one hoisted operand
+  __nv_bfloat16* hz = p.hoist ? p.hoist + (long long)row0 * H : nullptr;        // this tile's rows of operand 0
   __shared__ WStreamState wst;
   if (threadIdx.x == 0) {
     wst.g[0] = GemmDesc{p.C2, H, H, H, 1};
@@ -125,7 +128,8 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
   });
   __syncthreads();
   // 3. dC2 += dh2^T a ; dc2 += colsum(dh2)
-  wgrad_any<MMA, true, TM>(Bt, ld, H, A, ld, H, rows, p.gC2, H);
+  if (hz) { emit_bf16_tile(Bt, ld, H, rows, hz, H); emit_bf16_tile(A, ld, H, rows, hz + hu, H); }
+  else wgrad_any<MMA, true, TM>(Bt, ld, H, A, ld, H, rows, p.gC2, H);
   colsum_atomic(Bt, ld, H, rows, p.gc2);
   // 4. da = dh2 C2 ; dh1 = da * [a>0] * m1   (element-wise overwrite of A; A is not this GEMM's operand)
   gemm_stream<TM, true, WS_NST, MMA>(Bt, ld, ws, 0, [&](int, int r, int col, float4 acc) {
@@ -142,7 +146,8 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     __syncthreads();
     Z = Bt;
   }
-  wgrad_any<MMA, true, TM>(A, ld, H, Z, ld, H, rows, p.gC1, H);
+  if (hz) { emit_bf16_tile(A, ld, H, rows, hz + 2 * hu, H); emit_bf16_tile(Z, ld, H, rows, hz + 3 * hu, H); }
+  else wgrad_any<MMA, true, TM>(A, ld, H, Z, ld, H, rows, p.gC1, H);
   colsum_atomic(A, ld, H, rows, p.gc1);
   // 6. dz (enc) / dc (dec) = dO + dh1 C1  -> Bt
   gemm_stream<TM, true, WS_NST, MMA>(A, ld, ws, 1, [&](int, int r, int col, float4 acc) {
@@ -155,7 +160,8 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
     load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
     tile_sync();
-    wgrad_any<MMA, true, TM>(G, ld, H, A, ld, H, rows, p.gWo, H);
+    if (hz) { emit_bf16_tile(G, ld, H, rows, hz + 4 * hu, H); emit_bf16_tile(A, ld, H, rows, hz + 5 * hu, H); }
+    else wgrad_any<MMA, true, TM>(G, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(G, ld, H, rows, p.gbo);
     // 9. dctx = dy Wo (+ independence-head adjoint) -> Bt -> global
     gemm_stream<TM, true, WS_NST, MMA>(G, ld, ws, 2, [&](int, int r, int col, float4 acc) { st4(Bt + r * ld + col, acc); });
@@ -225,7 +231,8 @@ __global__ void __launch_bounds__(NT) post_bwd_kernel(PostBwdArgs p) {
     store_tile<TM>(G, ld, p.dres, H, 0, H, row0, M);
     load_tile<TM>(A, ld, p.ctx, H, 0, H, row0, M);
     tile_sync();
-    wgrad_any<MMA, true, TM>(Bt, ld, H, A, ld, H, rows, p.gWo, H);
+    if (hz) { emit_bf16_tile(Bt, ld, H, rows, hz + 4 * hu, H); emit_bf16_tile(A, ld, H, rows, hz + 5 * hu, H); }
+    else wgrad_any<MMA, true, TM>(Bt, ld, H, A, ld, H, rows, p.gWo, H);
     colsum_atomic(Bt, ld, H, rows, p.gbo);
     gemm_stream<TM, true, WS_NST, MMA>(Bt, ld, ws, 2, [&](int, int r, int col, float4 acc) {
       if (row0 + r < M) st4(p.dctx + (long long)(row0 + r) * H + col, acc);
@@ -357,6 +364,7 @@ struct MidBwdArgs {
   float* dctx1;
   float* gWo1; float* gbo1; float* gWin2; float* gbin2;
   int M, H; float qscale;
+  __nv_bfloat16* hoist;   // nullable: [7][M][H] bf16: dq2*s, a, [dk2|dv2] as one [M][2H], feats, da, ctx1
 };
 
 template <int TM, bool MMA>
@@ -396,14 +404,18 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
     st4(T1 + r * ld + c, v.b);
   });
   __syncthreads();
-  wgrad_any<MMA, true, TM>(T0, ld, H, T1, ld, H, rows, p.gWin2, H);
+  const long long hu = (long long)M * H;
+  __nv_bfloat16* hz = p.hoist ? p.hoist + (long long)row0 * H : nullptr;
+  if (hz) { emit_bf16_tile(T0, ld, H, rows, hz, H); emit_bf16_tile(T1, ld, H, rows, hz + hu, H); }
+  else wgrad_any<MMA, true, TM>(T0, ld, H, T1, ld, H, rows, p.gWin2, H);
   colsum_atomic(T0, ld, H, rows, p.gbin2);
   gemm_stream<TM, true, WS_NST, MMA>(T0, ld, ws, 0, [&](int, int r, int col, float4 acc) { st4(DA + r * ld + col, acc); });
   load_tile<TM>(KV, ld2, p.dk2, H, 0, H, row0, M);
   load_tile<TM>(KV + H, ld2, p.dv2, H, 0, H, row0, M);
   load_tile<TM>(T1, ld, p.feats, H, 0, H, row0, M);
   tile_sync();
-  wgrad_any<MMA, true, TM>(KV, ld2, 2 * H, T1, ld, H, rows, p.gWin2 + (long long)H * H, H);
+  if (hz) { emit_bf16_tile(KV, ld2, 2 * H, rows, p.hoist + 2 * hu + (long long)row0 * 2 * H, 2 * H); emit_bf16_tile(T1, ld, H, rows, hz + 4 * hu, H); }
+  else wgrad_any<MMA, true, TM>(KV, ld2, 2 * H, T1, ld, H, rows, p.gWin2 + (long long)H * H, H);
   colsum_atomic(KV, ld2, 2 * H, rows, p.gbin2 + H);
   gemm_stream<TM, true, WS_NST, MMA>(KV, ld2, ws, 1, [&](int, int r, int col, float4 acc) {
     if (row0 + r < M) {
@@ -413,7 +425,8 @@ __global__ void __launch_bounds__(NT) mid_bwd_kernel(MidBwdArgs p) {
   });
   load_tile<TM>(T1, ld, p.ctx1, H, 0, H, row0, M);
   tile_sync();
-  wgrad_any<MMA, true, TM>(DA, ld, H, T1, ld, H, rows, p.gWo1, H);
+  if (hz) { emit_bf16_tile(DA, ld, H, rows, hz + 5 * hu, H); emit_bf16_tile(T1, ld, H, rows, hz + 6 * hu, H); }
+  else wgrad_any<MMA, true, TM>(DA, ld, H, T1, ld, H, rows, p.gWo1, H);
   colsum_atomic(DA, ld, H, rows, p.gbo1);
   gemm_stream<TM, true, WS_NST, MMA>(DA, ld, ws, 2, [&](int, int r, int col, float4 acc) {
     if (row0 + r < M) st4(p.dctx1 + (long long)(row0 + r) * H + col, acc);
@@ -433,6 +446,7 @@ struct PreBwdArgs {
   float* dx;
   float* gWin; float* gbin; float* gln_g; float* gln_b;
   int M, H; float qscale; int kv_from_norm;
+  __nv_bfloat16* hoist;   // nullable: [5][M][H] bf16: [dq*s | dk | dv] as one [M][3H], LN(x), x
 };
 
 template <int TM, bool MMA>
@@ -477,7 +491,13 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   ln_tile<TM>(X, N, ld, H, p.ln_g, p.ln_b, 1e-8f, row0, M);
   __syncthreads();
   ADT_STAMP(26);
-  wgrad_any<MMA, true, TM>(T, ld, H, N, ld, H, rows, p.gWin, H);
+  const long long hu = (long long)M * H;
+  __nv_bfloat16* hq = p.hoist ? p.hoist + (long long)row0 * 3 * H : nullptr;    // [M][3H] row of this tile
+  if (hq) {
+    emit_bf16_tile(T, ld, H, rows, hq, 3 * H);
+    emit_bf16_tile(N, ld, H, rows, p.hoist + 3 * hu + (long long)row0 * H, H);
+    if (!p.kv_from_norm) emit_bf16_tile(X, ld, H, rows, p.hoist + 4 * hu + (long long)row0 * H, H);
+  } else wgrad_any<MMA, true, TM>(T, ld, H, N, ld, H, rows, p.gWin, H);
   ADT_STAMP(27);
   colsum_atomic(T, ld, H, rows, p.gbin);
   ADT_STAMP(28);
@@ -492,7 +512,8 @@ __global__ void __launch_bounds__(NT) pre_bwd_kernel(PreBwdArgs p) {
   for (int which = 0; which < 2; ++which) {
     load_tile<TM>(T, ld, which == 0 ? p.dk : p.dv, H, 0, H, row0, M);
     tile_sync();
-    wgrad_any<MMA, true, TM>(T, ld, H, Xkv, ld, H, rows, p.gWin + (long long)(1 + which) * H * H, H);
+    if (hq) emit_bf16_tile(T, ld, H, rows, hq + (1 + which) * H, 3 * H);
+    else wgrad_any<MMA, true, TM>(T, ld, H, Xkv, ld, H, rows, p.gWin + (long long)(1 + which) * H * H, H);
     colsum_atomic(T, ld, H, rows, p.gbin + (1 + which) * H);
     gemm_stream<TM, true, WS_NST, MMA>(T, ld, ws, 1 + which, [&](int, int r, int col, float4 acc) {
       st4(D + r * ld + col, f4_add(acc, ld4(D + r * ld + col)));

@@ -418,14 +418,24 @@ struct RescoreArgs {
 
 constexpr int RS_MAXC = 2048;   // candidate slots per user (n_splits * KC)
 constexpr int RS_NT = 256;
+constexpr int RS_STAGES = 2, RS_CW = 32, RS_LD = RS_CW + 4;   // re-score ring: stages per warp, columns per stage, floats per staged row (+4: conflict-free float4 reads)
+constexpr size_t RS_SMEM = (256 + (size_t)(RS_NT / 32) * RS_STAGES * 32 * RS_LD) * sizeof(float);
 
-// One CTA per user: (1) compact the valid candidates of all splits, (2) one THREAD per candidate recomputes its score in fp32 with
+// One CTA per user: (1) compact the valid candidates of all splits, (2) one THREAD per candidate (rows staged through a per-warp cp.async ring) recomputes its score in fp32 with
 // the same sequential fmaf order as the exact kernel (bit-identical scores, so the two paths can be mixed and compared), 16 row
 // loads in flight per thread, (3) rank counting under the total order (score desc, id asc) places the K best, (4) the exactness flag
 // and the fused get_full_sort_score sums.
-__global__ void __launch_bounds__(RS_NT) rescore_select_kernel(RescoreArgs a) {
+// sortable key of a candidate: larger key = better under (score desc, id asc); -0.0 is folded into +0.0 so that equal floats give equal keys
+__device__ __forceinline__ unsigned long long rs_key(float s, int id) {
+  const unsigned u = __float_as_uint(s + 0.f);
+  const unsigned o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)o << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)id);
+}
+
+__global__ void __launch_bounds__(RS_NT, 2) rescore_select_kernel(RescoreArgs a) {
   __shared__ int cid[RS_MAXC];
   __shared__ float csc[RS_MAXC];
+  __shared__ __align__(16) unsigned long long ckey[RS_MAXC];
   __shared__ int cnt_s, first_s;
   __shared__ float red[RS_NT / 32];
   __shared__ float kth_s;
@@ -452,31 +462,67 @@ __global__ void __launch_bounds__(RS_NT) rescore_select_kernel(RescoreArgs a) {
   const int m = cnt_s;
   fn = 0.f; thr_max = -INFINITY;
   for (int i = 0; i < RS_NT / 32; ++i) { fn += fn_s[i]; thr_max = fmaxf(thr_max, tm_s[i]); }
-  for (int c = tid; c < m; c += RS_NT) {
-    const float* e = a.E + (long long)(cid[c] - a.item_offset) * a.H;
-    float acc = 0.f;
-    for (int h0 = 0; h0 < a.H; h0 += 64) {
-      float4 ev[16];
+  // fp32 re-score.  Thread c owns candidate c and keeps the exact kernel's sequential fmaf chain; the rows reach it through a per-warp
+  // cp.async ring (32 rows x RS_CW columns per stage, 16-byte pieces, consecutive lanes per row: every 128-byte row segment is one
+  // coalesced request and a whole stage is in flight at once -- a thread reading its own 1 KB row directly serialises on DRAM latency).
+  {
+    extern __shared__ __align__(16) float rs_dyn[];
+    float* fs = rs_dyn;                                           // [H] user vector
+    float* ring = rs_dyn + 256 + w * (RS_STAGES * 32 * RS_LD);    // this warp's stages
+    for (int c = tid; c < a.H; c += RS_NT) fs[c] = f[c];
+    __syncthreads();
+    const int nch = a.H / RS_CW;
+    for (int base = 0; base < m; base += RS_NT) {
+      const int wbase = base + 32 * w;
+      if (wbase >= m) break;                                      // warp-uniform
+      const int total = nch;
+      auto issue = [&](int ch) {
+        float* st = ring + (ch % RS_STAGES) * (32 * RS_LD);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) ev[j] = __ldg(reinterpret_cast<const float4*>(e + h0) + j);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 fv = *reinterpret_cast<const float4*>(f + h0 + 4 * j);
-        acc = fmaf(fv.x, ev[j].x, acc); acc = fmaf(fv.y, ev[j].y, acc); acc = fmaf(fv.z, ev[j].z, acc); acc = fmaf(fv.w, ev[j].w, acc);
+        for (int i = 0; i < RS_CW / 4; ++i) {
+          const int idx = i * 32 + l, row = idx / (RS_CW / 4), seg = idx % (RS_CW / 4);
+          const int c = wbase + row;
+          const bool ok = c < m;
+          const float* src = a.E + (long long)((ok ? cid[c] : cid[wbase]) - a.item_offset) * a.H + ch * RS_CW + seg * 4;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(st + row * RS_LD + seg * 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0));
+        }
+        asm volatile("cp.async.commit_group;");
+      };
+      for (int ch = 0; ch < RS_STAGES - 1; ++ch) {
+        if (ch < total) issue(ch); else asm volatile("cp.async.commit_group;");
       }
+      float acc = 0.f;
+      for (int ch = 0; ch < total; ++ch) {
+        if (ch + RS_STAGES - 1 < total) issue(ch + RS_STAGES - 1); else asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group %0;" ::"n"(RS_STAGES - 1));
+        __syncwarp();
+        const float* st = ring + (ch % RS_STAGES) * (32 * RS_LD) + l * RS_LD;
+        const float* fv0 = fs + ch * RS_CW;
+#pragma unroll
+        for (int j = 0; j < RS_CW / 4; ++j) {
+          const float4 ev = *reinterpret_cast<const float4*>(st + 4 * j);
+          const float4 fv = *reinterpret_cast<const float4*>(fv0 + 4 * j);
+          acc = fmaf(fv.x, ev.x, acc); acc = fmaf(fv.y, ev.y, acc); acc = fmaf(fv.z, ev.z, acc); acc = fmaf(fv.w, ev.w, acc);
+        }
+        __syncwarp();
+      }
+      if (wbase + l < m) { csc[wbase + l] = acc; ckey[wbase + l] = rs_key(acc, cid[wbase + l]); }
     }
-    csc[c] = acc;
   }
   __syncthreads();
   const int answer = a.answers ? a.answers[u] : -1;
   for (int c = tid; c < m; c += RS_NT) {
     const float s = csc[c];
     const int id = cid[c];
+    const unsigned long long key = ckey[c];
     int rank = 0;
-    for (int j = 0; j < m; ++j) {
-      const float sj = csc[j];
-      rank += (sj > s || (sj == s && cid[j] < id)) ? 1 : 0;
+    int j = 0;
+    for (; j + 4 <= m; j += 4) {                 // branch-free: one 64-bit compare per rival under the total order (score desc, id asc)
+      const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(ckey + j), k23 = *reinterpret_cast<const ulonglong2*>(ckey + j + 2);
+      rank += (k01.x > key) + (k01.y > key) + (k23.x > key) + (k23.y > key);
     }
+    for (; j < m; ++j) rank += ckey[j] > key;
     if (rank < a.K) {
       a.out_scores[(long long)u * a.K + rank] = s;
       a.out_ids[(long long)u * a.K + rank] = id;
@@ -758,6 +804,7 @@ extern "C" int adt_score_topk_tc(const adt_score_topk_tc_args* a, adt_stream_t s
   r.U = a->U; r.H = a->H; r.item_offset = a->item_offset; r.K = a->K; r.KC = a->KC; r.n_splits = a->n_splits;
   if (two) { r.KC = a->KC / 2; r.n_splits = 2 * a->n_splits; }     // every (split, column half) wrote its own list and threshold
   r.answers = a->answers; r.metric_acc = a->metric_acc;
-  rescore_select_kernel<<<a->U, RS_NT, 0, s>>>(r);
+  cudaFuncSetAttribute(rescore_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
+  rescore_select_kernel<<<a->U, RS_NT, RS_SMEM, s>>>(r);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }

@@ -96,7 +96,18 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                         // [61,64) layout type: SWIZZLE_128B
   return d;
 }
-// kind::f16, A/B = bf16 (K-major), D = fp32, shape M x N
+// MN-major operand (its M / N extent is the contiguous one) in 128-byte-swizzled 64-column boxes of K rows: 8 K-rows are 1024 B apart
+// (SBO), consecutive 64-column boxes `box_bytes` apart (LBO).  One MMA (16 K) advances the start address by 16 rows = 2048 B.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t box_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((box_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, A/B = bf16 (K-major; OR bit 15 / 16 for an MN-major A / B), D = fp32, shape M x N
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }

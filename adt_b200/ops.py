@@ -19,6 +19,7 @@ def no_drop():
     return L.adt_dropout()
 
 
+SM_COUNT = 148
 TC_MIN_WORK = 1 << 22     # M*N*K below this: the row-tile kernel's single launch beats convert + GEMM
 
 
@@ -48,9 +49,9 @@ def _bf16(x, transpose=False):
     return y, ld
 
 
-def _gemm_tc(a16, lda, b16, ldb, c, M, N, K, bias=None, act=0, scale=1.0, pre=None, accumulate=False):
+def _gemm_tc(a16, lda, b16, ldb, c, M, N, K, bias=None, act=0, scale=1.0, pre=None, accumulate=False, a_mn=False, b_mn=False, split_k=1):
     a = L.fill(L.adt_gemm_tc_args(), a_bf16=a16, b_bf16=b16, lda=lda, ldb=ldb, c=c, pre=pre, bias=bias, ldc=c.stride(0), M=M, N=N, K=K,
-               act=act, accumulate=int(accumulate), scale=scale)
+               act=act, accumulate=int(accumulate), scale=scale, a_mn=int(a_mn), b_mn=int(b_mn), split_k=split_k)
     L.check(L.lib().adt_gemm_tc(ctypes.byref(a), _st(c.device)), "adt_gemm_tc")
 
 
@@ -102,12 +103,14 @@ class LinearFn(torch.autograd.Function):
         gb = torch.zeros(N, dtype=torch.float32, device=x.device) if has_b else None
         if _use_tc(precision, M, N, K):
             # dx = scale * dy W ; dW = scale * dy^T x ; db = scale * colsum(dy): three more products on the tensor cores
+            # (W, dy and x are read MN-major where the product needs their transpose: no transposed copies)
             dy16, ldd = _bf16(dy)
-            wt16, ldw = _bf16(W, transpose=True)            # [K, N]
-            _gemm_tc(dy16, ldd, wt16, ldw, dx, M, K, N, scale=scale)
-            dyt16, ldt = _bf16(dy, transpose=True)          # [N, M]
-            xt16, ldx = _bf16(x, transpose=True)            # [K, M]
-            _gemm_tc(dyt16, ldt, xt16, ldx, gW, N, K, M, scale=scale)
+            w16, ldw = _bf16(W)
+            x16, ldx = _bf16(x)
+            _gemm_tc(dy16, ldd, w16, ldw, dx, M, K, N, scale=scale, b_mn=True)
+            tiles = ((N + 127) // 128) * ((K + 127) // 128)
+            _gemm_tc(dy16, ldd, x16, ldx, gW, N, K, M, scale=scale, a_mn=True, b_mn=True, accumulate=True,
+                     split_k=max(1, min((M + 63) // 64, SM_COUNT // tiles)))
             if has_b:
                 L.check(lib.adt_colsum(L.ptr(dy), ctypes.c_int64(dy.stride(0)), ctypes.c_int32(M), ctypes.c_int32(N), L.ptr(gb), _st(x.device)),
                         "adt_colsum")

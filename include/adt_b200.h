@@ -45,9 +45,9 @@ const char* adt_last_error(void);
 /* Scratch / saved-activation sizes (bytes) the caller must allocate for one (B, L, H, nh, nl) training step: the library allocates
  * nothing itself.  saved = activations kept from forward for backward; scratch = backward temporaries; sort = keys/vals/tmp/hist of
  * adt_embed_sort; scatter = head/tail/has_tail of adt_embed_bwd; score_part = part_scores + part_ids of adt_score_topk for
- * (U = B, K, n_splits). */
+ * (U = B, K, n_splits); wgrad_scratch = the bf16 operand copies of the hoisted weight gradients (0 when H < 128). */
 typedef struct { int32_t B, L, H, nh, nl, K, n_splits; } adt_workspace_query;
-typedef struct { int64_t saved, scratch, sort_keys, sort_hist, scatter_rows, scatter_flags, score_part; } adt_workspace_sizes;
+typedef struct { int64_t saved, scratch, sort_keys, sort_hist, scatter_rows, scatter_flags, score_part, wgrad_scratch; } adt_workspace_sizes;
 int adt_workspace_bytes(const adt_workspace_query* q, adt_workspace_sizes* out);
 
 /* K1. x = dropout(E[ids]*sqrt(H) + P[t]) * (ids != 0)            -- sasrec/model.py:34-41 and :53-58 */
@@ -110,6 +110,8 @@ typedef struct {
   adt_dropout drop_attn, drop_ffn1, drop_ffn2;
   int32_t precision;
   adt_wmirror wm;
+  void* wgrad_scratch;        /* optional, adt_workspace_sizes.wgrad_scratch bytes (precision 1, H >= 128): the row-tile kernels then only write
+                                 bf16 copies of their dY / X tiles and every weight gradient becomes ONE split-K tcgen05 GEMM over all rows */
 } adt_enc_block_bwd_args;
 int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t stream);
 
@@ -149,6 +151,7 @@ typedef struct {
   int32_t phase;   /* 0: whole block; 2: FFN + cross-attention adjoints (produce dfeats, dctx, dd); 1: self-attention + LN adjoints
                     * (produce dx; nothing the encoder backward needs -> may run beside it on another stream) */
   adt_wmirror wm;
+  void* wgrad_scratch;        /* as in adt_enc_block_bwd_args */
 } adt_dec_block_bwd_args;
 int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t stream);
 
@@ -315,6 +318,9 @@ typedef struct {
   const void* a_bf16; const void* b_bf16; int64_t lda, ldb;
   float* c; float* pre; const float* bias; int64_t ldc;
   int32_t M, N, K, act, accumulate; float scale;
+  int32_t a_mn, b_mn;                          /* != 0: the operand is stored MN-major, i.e. as [K][ld] with its M (or N) extent contiguous:
+                                                  dgrad reads W [N,K] as b_mn, wgrad reads dy [M,N] and x [M,K] as a_mn / b_mn -- no transposes */
+  int32_t split_k;                             /* > 1: that many CTAs share an output tile and add partial sums atomically (act 0, pre NULL) */
 } adt_gemm_tc_args;
 int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t stream);
 /* operand copies for adt_gemm_tc: fp32 [R][C] (row stride ld) -> bf16 [R][ldy], or -> its bf16 transpose [C][ldt] */

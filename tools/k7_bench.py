@@ -9,6 +9,7 @@ def main():
     I = 1_000_000
     only = os.environ.get("K7_ONLY")           # e.g. "512,64"
     for H in (64, 256):
+        torch.manual_seed(H)
         E = (torch.randn(I + 1, H, device="cuda") * 0.1)
         fake = types.SimpleNamespace(item_emb=types.SimpleNamespace(weight=E))
         for U in (512, 4096):
