@@ -52,6 +52,11 @@ def _f(ref, *shape):
     return torch.empty(*shape, dtype=torch.float32, device=ref.device)
 
 
+def _wg(ref, M, H, prec):
+    """bf16 operand scratch of the hoisted weight gradients (adt_workspace_sizes.wgrad_scratch: 7 [M,H] bf16 matrices), wide bf16 models only"""
+    return torch.empty(7 * M * H * 2, dtype=torch.uint8, device=ref.device) if (prec and H >= 128) else None
+
+
 class EmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ids, E, P, drop):
@@ -132,12 +137,13 @@ class EncBlockFn(torch.autograd.Function):
         M, H = x.shape
         g = [torch.zeros_like(t) for t in p]
         sc = {k: _f(x, M, H) for k in ("dq", "dk", "dv", "dctx", "dy", "dx")}
+        wg = _wg(x, M, H, prec)
         a = L.fill(L.adt_enc_block_bwd_args(), x=x, ids=ids, ln1_w=p[0], ln1_b=p[1], attn=_mha_w(p[2], p[3], p[4], p[5]), ln2_w=p[6],
                    ln2_b=p[7], ffn=L.fill(L.adt_ffn_w(), w1=p[8], b1=p[9], w2=p[10], b2=p[11]), sparse_w=p[12], sparse_b=p[13],
                    q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"],
                    dout=dout.contiguous() if dout is not None else None, dx_extra=None,
                    drec=drec.contiguous() if drec is not None else None, nll_coef=0.0,
-                   dq=sc["dq"], dk=sc["dk"], dv=sc["dv"], dctx=sc["dctx"], dy=sc["dy"], dx=sc["dx"],
+                   dq=sc["dq"], dk=sc["dk"], dv=sc["dv"], dctx=sc["dctx"], dy=sc["dy"], dx=sc["dx"], wgrad_scratch=wg,
                    g_ln1_w=g[0], g_ln1_b=g[1], g_attn=_mha_g(g[2], g[3], g[4], g[5]), g_ln2_w=g[6], g_ln2_b=g[7],
                    g_ffn=L.fill(L.adt_ffn_g(), w1=g[8], b1=g[9], w2=g[10], b2=g[11]), g_sparse_w=g[12], g_sparse_b=g[13],
                    B=B, L=Lq, H=H, nh=nh, mask_mode=0, drop_attn=d_attn, drop_ffn1=d_f1, drop_ffn2=d_f2, precision=int(prec))
@@ -174,12 +180,13 @@ class DecBlockFn(torch.autograd.Function):
         M, H = x.shape
         g = [torch.zeros_like(t) for t in p]
         sc = {k: _f(x, M, H) for k in ("dq", "dk", "dv", "dctx", "dd", "dq2", "dk2", "dv2", "dctx2", "dx")}
+        wg = _wg(x, M, H, prec)
         dfeats = torch.zeros_like(feats)
         a = L.fill(L.adt_dec_block_bwd_args(), x=x, feats=feats, ids=ids, ln_w=p[0], ln_b=p[1], slf=_mha_w(p[2], p[3], p[4], p[5]),
                    enc=_mha_w(p[6], p[7], p[8], p[9]), ffn=L.fill(L.adt_ffn_w(), w1=p[10], b1=p[11], w2=p[12], b2=p[13]),
                    out=sv["out"], enc_in=None, mse_coef=0.0, dout=dout.contiguous(), denc=None,
                    dq=sc["dq"], dk=sc["dk"], dv=sc["dv"], dctx=sc["dctx"], dd=sc["dd"], dq2=sc["dq2"], dk2=sc["dk2"], dv2=sc["dv2"],
-                   dctx2=sc["dctx2"], dfeats=dfeats, dx=sc["dx"], g_ln_w=g[0], g_ln_b=g[1], g_slf=_mha_g(g[2], g[3], g[4], g[5]),
+                   dctx2=sc["dctx2"], dfeats=dfeats, dx=sc["dx"], wgrad_scratch=wg, g_ln_w=g[0], g_ln_b=g[1], g_slf=_mha_g(g[2], g[3], g[4], g[5]),
                    g_enc=_mha_g(g[6], g[7], g[8], g[9]), g_ffn=L.fill(L.adt_ffn_g(), w1=g[10], b1=g[11], w2=g[12], b2=g[13]),
                    B=B, L=Lq, H=H, nh=nh, mask_mode=0, drop_slf=d_s, drop_enc=d_e, drop_ffn1=d_f1, drop_ffn2=d_f2, precision=int(prec),
                    lse1=sv["lse1"], lse2=sv["lse2"], **{k: sv[k] for k in DecBlockFn.SAVED})

@@ -222,6 +222,10 @@ class Engine:
         w["denc"] = [f(M, H) for _ in range(nl)]
         w["side"] = {k: f(M, H) for k in ("dq", "dk", "dv", "dctx", "dres")}   # decoder block 0 backward, run beside the encoder backward
         w["cpos"], w["cneg"] = f(M), f(M)
+        # bf16 operand copies of the hoisted weight gradients (H >= 128 in the bf16 mode; one more for the side-stream half of decoder block 0)
+        nwg = w["sizes"]["wgrad_scratch"] if self.precision else 0
+        w["wg"] = torch.empty(nwg, dtype=torch.uint8, device=dev) if nwg else None
+        w["side"]["wg"] = torch.empty(nwg, dtype=torch.uint8, device=dev) if nwg else None
         N = 4 * M
         i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
         w["keys"], w["vals"], w["keys_tmp"], w["vals_tmp"] = i32(N), i32(N), i32(N), i32(N)
@@ -426,7 +430,7 @@ class Engine:
                        dout=dout, denc=w["denc"][i_enc] if fused else None,
                        dq=sb["dq"] if split else w["dq"], dk=sb["dk"] if split else z4[0], dv=sb["dv"] if split else z4[1],
                        dctx=sb["dctx"] if split else w["dctx"], dd=sb["dres"] if split else w["dres"],
-                       dq2=w["dq2"], dk2=z4[2], dv2=z4[3], dctx2=w["dctx2"], phase=2 if split else 0,
+                       dq2=w["dq2"], dk2=z4[2], dv2=z4[3], dctx2=w["dctx2"], phase=2 if split else 0, wgrad_scratch=w["wg"],
                        dfeats=w["dfeats"], dx=out_dx, g_ln_w=g[pre + "layer_norm.weight"], g_ln_b=g[pre + "layer_norm.bias"],
                        g_slf=mg(pre + "slf_attn."), g_enc=mg(pre + "enc_attn."), g_ffn=fg(pre + "pos_ffn."),
                        B=B, L=Lq, H=H, nh=nh, mask_mode=0, precision=self.precision,
@@ -439,6 +443,7 @@ class Engine:
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     a.phase = 1
+                    a.wgrad_scratch = sb["wg"].data_ptr() if sb["wg"] is not None else None
                     L.check(self.lib.adt_dec_block_bwd(L.ctypes.byref(a), self._stream()), "adt_dec_block_bwd")
             dxd = out_dx
         dx_dec_emb = dxd
@@ -469,7 +474,7 @@ class Engine:
                        q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"],
                        dout=dout, dx_extra=dx_extra, drec=dr[l] if dr is not None else None,
                        nll_coef=(float(lambdas2[nl - 1]) / (Mg * nh)) if (fused and nh > 1) else 0.0,
-                       dq=w["dq"], dk=z4[0], dv=z4[1], dctx=w["dctx"], dy=w["dres"], dx=other,
+                       dq=w["dq"], dk=z4[0], dv=z4[1], dctx=w["dctx"], dy=w["dres"], dx=other, wgrad_scratch=w["wg"],
                        g_ln1_w=g[pre + "attention_layernorm.weight"], g_ln1_b=g[pre + "attention_layernorm.bias"],
                        g_attn=mg(pre + "attention_layer."), g_ln2_w=g[pre + "forward_layernorm.weight"],
                        g_ln2_b=g[pre + "forward_layernorm.bias"], g_ffn=fg(pre + "forward_layer."),

@@ -1,5 +1,6 @@
 """A/B of the sequence-resident block kernels against the three/five-kernel row-tile path on the C2 shape (run twice, with
-ADT_SEQ_FUSED=0 and =1; tests/test_round2_gpu.py compares the two JSON lines).   python tools/seq_ab.py [nh] [L]"""
+ADT_SEQ_FUSED=0 and =1; tests/test_round2_gpu.py compares the two JSON lines), and -- with a hidden size >= 128 -- of the hoisted tcgen05
+weight gradients against the in-kernel ones (ADT_WGRAD_HOIST=1 / 0).   python tools/seq_ab.py [nh] [L] [hidden]"""
 import json, os, sys, types
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, torch
@@ -10,9 +11,10 @@ from adt_b200.evaluate import CatalogScorer
 
 nh = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 Lq = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-cfg = dict(synth.CONFIGS["C2"], nh=nh, L=Lq, B=64)
+Hd = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+cfg = dict(synth.CONFIGS["C2"], nh=nh, L=Lq, B=64, H=Hd)
 torch.manual_seed(0)
-args = types.SimpleNamespace(device="cuda", num_heads=nh, maxlen=Lq, num_layers=2, hidden_units=64, dropout=0.5)
+args = types.SimpleNamespace(device="cuda", num_heads=nh, maxlen=Lq, num_layers=2, hidden_units=Hd, dropout=0.5)
 m = SASRecADT(1, cfg["items"], args)
 for _, prm in m.named_parameters():
     if prm.dim() >= 2:
@@ -29,6 +31,8 @@ for k in range(3):
     tr.step(*synth.make_batch(rng, cfg))
     out["loss"].append(tr.loss()); out["gnorm"].append(tr.grad_norm())
     out["gsum"].append(float(m.engine.gflat.double().abs().sum()))
+    if k == 0:
+        out["gnorms"] = {n: float(m.engine.grad_view(n).double().norm()) for n, _ in m.engine.order}
 m.eval()
 seq, ans, ip, ix = synth.make_eval_batch(rng, cfg, 100)
 s, ids = CatalogScorer(m, K=10).topk(seq, ip, ix)
