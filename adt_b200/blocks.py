@@ -52,9 +52,14 @@ def _f(ref, *shape):
     return torch.empty(*shape, dtype=torch.float32, device=ref.device)
 
 
+def _fs(ref, M, H, prec):
+    """bf16 operand scratch of the tcgen05 forward path (adt_workspace_sizes.fwd_scratch), wide bf16 models only"""
+    return torch.empty(9 * M * H * 2 + 10 * H * H * 2, dtype=torch.uint8, device=ref.device) if (prec and H >= 128) else None
+
+
 def _wg(ref, M, H, prec):
-    """bf16 operand scratch of the hoisted weight gradients (adt_workspace_sizes.wgrad_scratch: 7 [M,H] bf16 matrices), wide bf16 models only"""
-    return torch.empty(7 * M * H * 2, dtype=torch.uint8, device=ref.device) if (prec and H >= 128) else None
+    """bf16 operand scratch of the tcgen05 backward path / hoisted weight gradients (adt_workspace_sizes.wgrad_scratch), wide bf16 models only"""
+    return torch.empty(12 * M * H * 2 + 10 * H * H * 2, dtype=torch.uint8, device=ref.device) if (prec and H >= 128) else None
 
 
 class EmbedFn(torch.autograd.Function):
@@ -120,11 +125,12 @@ class EncBlockFn(torch.autograd.Function):
         x = x.contiguous()
         sv = {k: _f(x, M, H) for k in ("q", "k", "v", "ctx", "y", "h1", "out")}
         sv["lse"], sv["rec"] = _f(x, B, nh, Lq), _f(x, M, nh, nh)
+        fs = _fs(x, M, H, prec)
         a = L.fill(L.adt_enc_block_fwd_args(), x=x, ids=ids, ln1_w=p[0], ln1_b=p[1], attn=_mha_w(p[2], p[3], p[4], p[5]), ln2_w=p[6],
                    ln2_b=p[7], ffn=L.fill(L.adt_ffn_w(), w1=p[8], b1=p[9], w2=p[10], b2=p[11]), sparse_w=p[12], sparse_b=p[13],
                    q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"], out=sv["out"], rec=sv["rec"],
                    nll_acc=None, B=B, L=Lq, H=H, nh=nh, training=int(training), mask_mode=0, drop_attn=d_attn, drop_ffn1=d_f1,
-                   drop_ffn2=d_f2, precision=int(prec))
+                   drop_ffn2=d_f2, precision=int(prec), tc_scratch=fs)
         L.check(L.lib().adt_enc_block_fwd(ctypes.byref(a), _stream(x.device)), "adt_enc_block_fwd")
         ctx.sv, ctx.x, ctx.ids, ctx.cfg, ctx.p = sv, x, ids, cfg, p
         return sv["out"], sv["rec"]
@@ -164,10 +170,11 @@ class DecBlockFn(torch.autograd.Function):
         x, feats = x.contiguous(), feats.contiguous()
         sv = {k: _f(x, M, H) for k in DecBlockFn.SAVED + ("out",)}
         sv["lse1"], sv["lse2"] = _f(x, B, nh, Lq), _f(x, B, nh, Lq)
+        fs = _fs(x, M, H, prec)
         a = L.fill(L.adt_dec_block_fwd_args(), x=x, feats=feats, ids=ids, ln_w=p[0], ln_b=p[1], slf=_mha_w(p[2], p[3], p[4], p[5]),
                    enc=_mha_w(p[6], p[7], p[8], p[9]), ffn=L.fill(L.adt_ffn_w(), w1=p[10], b1=p[11], w2=p[12], b2=p[13]), enc_in=None,
                    out=sv["out"], mse_acc=None, B=B, L=Lq, H=H, nh=nh, training=int(training), mask_mode=0, drop_slf=d_s, drop_enc=d_e,
-                   drop_ffn1=d_f1, drop_ffn2=d_f2, precision=int(prec), lse1=sv["lse1"], lse2=sv["lse2"], **{k: sv[k] for k in DecBlockFn.SAVED})
+                   drop_ffn1=d_f1, drop_ffn2=d_f2, precision=int(prec), tc_scratch=fs, lse1=sv["lse1"], lse2=sv["lse2"], **{k: sv[k] for k in DecBlockFn.SAVED})
         L.check(L.lib().adt_dec_block_fwd(ctypes.byref(a), _stream(x.device)), "adt_dec_block_fwd")
         ctx.sv, ctx.x, ctx.feats, ctx.ids, ctx.cfg, ctx.p = sv, x, feats, ids, cfg, p
         return sv["out"]

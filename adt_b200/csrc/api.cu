@@ -14,6 +14,7 @@
 #include "kernels_attn_small.cuh"
 #include "kernels_rowtile_small.cuh"
 #include "kernels_seq.cuh"
+#include "block_tc.cuh"
 
 using namespace adt;
 
@@ -190,7 +191,8 @@ extern "C" int adt_workspace_bytes(const adt_workspace_query* q, adt_workspace_s
   out->scatter_rows = 2 * nb * H * f;                                    // head, tail
   out->scatter_flags = nb * (long long)sizeof(int);
   out->score_part = (long long)(q->n_splits > 0 ? q->n_splits : 1) * q->B * (q->K > 0 ? q->K : 1) * 8;
-  out->wgrad_scratch = H >= 128 ? 7 * M * H * 2 : 0;                      // widest user: mid_bwd, 7 bf16 [M,H] operands
+  out->wgrad_scratch = H >= 128 ? 12 * M * H * 2 + 10 * H * H * 2 : 0;    // tcgen05 backward: <= 10 bf16 [M,H] operand slots + weights
+  out->fwd_scratch = H >= 128 ? 9 * M * H * 2 + 10 * H * H * 2 : 0;       // decoder block: 7 bf16 operands + fp32 h2 + 10 H^2 bf16 weights
   return ADT_OK;
 }
 extern "C" const char* adt_last_error(void) { return g_err; }
@@ -337,7 +339,7 @@ static int hoisted_wgrad(const __nv_bfloat16* dy, long long ldy, int n_out, cons
   g.a_bf16 = dy; g.lda = ldy; g.b_bf16 = x; g.ldb = ldx; g.c = gW; g.ldc = k_out;
   g.M = n_out; g.N = k_out; g.K = M; g.accumulate = 1; g.scale = 1.f; g.a_mn = 1; g.b_mn = 1;
   const int tiles = ((n_out + 127) / 128) * ((k_out + 127) / 128);
-  g.split_k = tiles >= 148 ? 1 : 148 / tiles;
+  g.split_k = tiles >= 296 ? 1 : 296 / tiles;     // two CTAs per SM (11 K slabs each at C1: the 3-stage ring)
   TIMED("wgrad_tc", s);
   if (int e = adt_gemm_tc(&g, (adt_stream_t)s)) return fail(e, "%s", "hoisted weight gradient (adt_gemm_tc)");
   return ADT_OK;
@@ -475,6 +477,296 @@ static int seq_dec_bwd(const adt_dec_block_bwd_args* a, cudaStream_t s) {
   return ADT_OK;
 }
 
+
+// ---- tcgen05 forward path for wide models (block_tc.cuh); ADT_FWD_TC=0 keeps the row-tile kernels ---------------------------------
+static bool use_fwd_tc(const void* scratch, int M, int H, int nh, int mma) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_FWD_TC"); v = e ? (atoi(e) != 0) : 1; }
+  return v && mma && scratch && H >= 128 && H <= 256 && (H & 7) == 0 && M >= 512 && nh <= 8;
+}
+struct TcScratch {
+  __nv_bfloat16* base; long long mh; __nv_bfloat16* wb;     // M*H elements per operand; weights after 9 operands
+  __nv_bfloat16* op(int i) const { return base + i * mh; }
+};
+static TcScratch mk_tcs(void* p, int M, int H) {
+  TcScratch t;
+  t.base = reinterpret_cast<__nv_bfloat16*>(p); t.mh = (long long)M * H; t.wb = t.base + 9 * t.mh;
+  return t;
+}
+static int ew_grid(long long n4) { const long long b = (n4 + 255) / 256; return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16); }
+static int row_grid(int M) { const int b = (M + 7) / 8; return b < 148 * 8 ? b : 148 * 8; }
+// bf16 copy of a weight: from the mirror when the caller keeps one, else converted into `dst`
+static const __nv_bfloat16* tc_weight(const float* W, long long n, const adt_wmirror& wm, __nv_bfloat16* dst, cudaStream_t s) {
+  if (wm.bf16 && wm.base32) return reinterpret_cast<const __nv_bfloat16*>(wm.bf16) + (W - wm.base32);
+  cast_bf16_kernel<<<ew_grid(n / 4), 256, 0, s>>>(W, dst, n / 4);
+  return dst;
+}
+static void tc_cast(const float* x, __nv_bfloat16* dst, long long n, cudaStream_t s) { cast_bf16_kernel<<<ew_grid(n / 4), 256, 0, s>>>(x, dst, n / 4); }
+// c (and c2 for columns >= n_split) = (A W^T + bias) * scale, optionally added to what c holds
+static int tc_linear(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, float* c, float* c2, int n_split, int M, int N, int K,
+                     float scale, int accumulate, cudaStream_t s) {
+  adt_gemm_tc_args g;
+  memset(&g, 0, sizeof(g));
+  g.a_bf16 = A; g.lda = K; g.b_bf16 = W; g.ldb = K; g.c = c; g.ldc = c2 ? n_split : N; g.bias = bias;
+  g.M = M; g.N = N; g.K = K; g.scale = scale; g.accumulate = accumulate; g.c2 = c2; g.n_split = n_split;
+  TIMED("linear_tc", s);
+  if (int e = adt_gemm_tc(&g, (adt_stream_t)s)) return fail(e, "%s", "tcgen05 forward path (adt_gemm_tc)");
+  return ADT_OK;
+}
+// shared tail of both blocks: h1 = z C1^T + c1 (saved) ; a = relu(h1 m1) ; h2 = a C2^T + c2 ; block output
+static int tc_ffn_out(const TcScratch& t, const __nv_bfloat16* zb, int a_op, int h2_op, const adt_ffn_w& ffn, const __nv_bfloat16* C1b,
+                      const __nv_bfloat16* C2b, float* h1, const adt_dropout& d1, const adt_dropout& d2, int training, RowOutArgs o, int M,
+                      int H, cudaStream_t s) {
+  if (int e = tc_linear(zb, C1b, ffn.b1, h1, nullptr, 0, M, H, H, 1.f, 0, s)) return e;
+  { TIMED("row_tc", s); relu_drop_cast_kernel<<<ew_grid((long long)M * H / 4), 256, 0, s>>>(h1, t.op(a_op), (long long)M * H / 4, mk_drop(row_drop(d1, training))); }
+  float* h2 = reinterpret_cast<float*>(t.op(h2_op));
+  if (int e = tc_linear(t.op(a_op), C2b, ffn.b2, h2, nullptr, 0, M, H, H, 1.f, 0, s)) return e;
+  o.h2 = h2; o.M = M; o.H = H; o.drop2 = mk_drop(row_drop(d2, training));
+  { TIMED("row_tc", s); row_out_kernel<<<row_grid(M), 256, 0, s>>>(o); }
+  return check_launch("tcgen05 forward path");
+}
+
+static int tc_enc_fwd(const adt_enc_block_fwd_args* a, cudaStream_t s) {
+  const int M = a->B * a->L, H = a->H;
+  const TcScratch t = mk_tcs(a->tc_scratch, M, H);
+  const long long hh = (long long)H * H;
+  const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  if (a->phase != 2) {
+    const __nv_bfloat16* Winb = tc_weight(a->attn.in_w, 3 * hh, a->wm, t.wb, s);
+    RowLnArgs r;
+    memset(&r, 0, sizeof(r));
+    r.x = a->x; r.g = a->ln1_w; r.b = a->ln1_b; r.yb = t.op(0); r.xb = t.op(1); r.M = M; r.H = H;
+    { TIMED("row_tc", s); row_ln_cast_kernel<<<row_grid(M), 256, 0, s>>>(r); }
+    // q = (LN1(x) Wq^T + bq) * scale ; [k | v] = x [Wk; Wv]^T + [bk | bv]
+    if (int e = tc_linear(t.op(0), Winb, a->attn.in_b, a->q, nullptr, 0, M, H, H, qscale, 0, s)) return e;
+    if (int e = tc_linear(t.op(1), Winb + hh, a->attn.in_b + H, a->k, a->v, H, M, 2 * H, H, 1.f, 0, s)) return e;
+    if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))
+      return e;
+    if (a->phase == 1) return ADT_OK;
+  }
+  const __nv_bfloat16* Wob = tc_weight(a->attn.out_w, hh, a->wm, t.wb + 3 * hh, s);
+  const __nv_bfloat16* C1b = tc_weight(a->ffn.w1, hh, a->wm, t.wb + 4 * hh, s);
+  const __nv_bfloat16* C2b = tc_weight(a->ffn.w2, hh, a->wm, t.wb + 5 * hh, s);
+  // y = LN1(x) + ctx Wo^T + bo : LN1(x) is written into y, the out-projection accumulates on top
+  RowLnArgs r;
+  memset(&r, 0, sizeof(r));
+  r.x = a->x; r.g = a->ln1_w; r.b = a->ln1_b; r.y = a->y; r.M = M; r.H = H;
+  { TIMED("row_tc", s); row_ln_cast_kernel<<<row_grid(M), 256, 0, s>>>(r); }
+  tc_cast(a->ctx, t.op(2), (long long)M * H, s);
+  if (a->rec || a->nll_acc) {
+    TIMED("row_tc", s);
+    sparse_head_fwd_kernel<<<row_grid(M), 256, 0, s>>>(a->ctx, a->sparse_w, a->sparse_b, a->rec, a->nll_acc, M, H, a->nh);
+  }
+  if (int e = tc_linear(t.op(2), Wob, a->attn.out_b, a->y, nullptr, 0, M, H, H, 1.f, 1, s)) return e;
+  memset(&r, 0, sizeof(r));
+  r.x = a->y; r.g = a->ln2_w; r.b = a->ln2_b; r.yb = t.op(3); r.M = M; r.H = H;
+  { TIMED("row_tc", s); row_ln_cast_kernel<<<row_grid(M), 256, 0, s>>>(r); }
+  RowOutArgs o;
+  memset(&o, 0, sizeof(o));
+  o.u = a->y; o.ln_g = a->ln2_w; o.ln_b = a->ln2_b; o.ids = a->ids; o.out = a->out; o.is_dec = 0;
+  return tc_ffn_out(t, t.op(3), 4, 5, a->ffn, C1b, C2b, a->h1, a->drop_ffn1, a->drop_ffn2, a->training, o, M, H, s);
+}
+
+static int tc_dec_fwd(const adt_dec_block_fwd_args* a, cudaStream_t s) {
+  const int M = a->B * a->L, H = a->H;
+  const TcScratch t = mk_tcs(a->tc_scratch, M, H);
+  const long long hh = (long long)H * H;
+  const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  if (a->phase != 2) {
+    const __nv_bfloat16* W1b = tc_weight(a->slf.in_w, 3 * hh, a->wm, t.wb, s);
+    RowLnArgs r;
+    memset(&r, 0, sizeof(r));
+    r.x = a->x; r.g = a->ln_w; r.b = a->ln_b; r.y = a->d; r.yb = t.op(0); r.M = M; r.H = H;
+    { TIMED("row_tc", s); row_ln_cast_kernel<<<row_grid(M), 256, 0, s>>>(r); }
+    if (int e = tc_linear(t.op(0), W1b, a->slf.in_b, a->q1, nullptr, 0, M, H, H, qscale, 0, s)) return e;
+    if (int e = tc_linear(t.op(0), W1b + hh, a->slf.in_b + H, a->k1, a->v1, H, M, 2 * H, H, 1.f, 0, s)) return e;
+    if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
+      return e;
+    if (a->phase == 1) return ADT_OK;
+  }
+  const __nv_bfloat16* Wo1b = tc_weight(a->slf.out_w, hh, a->wm, t.wb + 3 * hh, s);
+  const __nv_bfloat16* W2b = tc_weight(a->enc.in_w, 3 * hh, a->wm, t.wb + 4 * hh, s);
+  const __nv_bfloat16* Wo2b = tc_weight(a->enc.out_w, hh, a->wm, t.wb + 7 * hh, s);
+  const __nv_bfloat16* C1b = tc_weight(a->ffn.w1, hh, a->wm, t.wb + 8 * hh, s);
+  const __nv_bfloat16* C2b = tc_weight(a->ffn.w2, hh, a->wm, t.wb + 9 * hh, s);
+  // a = ctx1 Wo1^T + bo1 ; q2 = (a Wq2^T + bq2) * scale ; [k2 | v2] from the encoder features
+  tc_cast(a->ctx1, t.op(1), (long long)M * H, s);
+  if (int e = tc_linear(t.op(1), Wo1b, a->slf.out_b, a->a, nullptr, 0, M, H, H, 1.f, 0, s)) return e;
+  tc_cast(a->a, t.op(2), (long long)M * H, s);
+  tc_cast(a->feats, t.op(3), (long long)M * H, s);
+  if (int e = tc_linear(t.op(2), W2b, a->enc.in_b, a->q2, nullptr, 0, M, H, H, qscale, 0, s)) return e;
+  if (int e = tc_linear(t.op(3), W2b + hh, a->enc.in_b + H, a->k2, a->v2, H, M, 2 * H, H, 1.f, 0, s)) return e;
+  if (int e = launch_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, a->precision, s))
+    return e;
+  // c = ctx2 Wo2^T + bo2 ; out = (d + FFN(c) + c) * keep
+  tc_cast(a->ctx2, t.op(4), (long long)M * H, s);
+  if (int e = tc_linear(t.op(4), Wo2b, a->enc.out_b, a->c, nullptr, 0, M, H, H, 1.f, 0, s)) return e;
+  tc_cast(a->c, t.op(5), (long long)M * H, s);
+  RowOutArgs o;
+  memset(&o, 0, sizeof(o));
+  o.u = a->c; o.resid = a->d; o.ids = a->ids; o.enc_in = a->enc_in; o.out = a->out; o.acc = a->mse_acc; o.is_dec = 1;
+  return tc_ffn_out(t, t.op(5), 6, 7, a->ffn, C1b, C2b, a->h1, a->drop_ffn1, a->drop_ffn2, a->training, o, M, H, s);
+}
+
+// ---- tcgen05 backward path for wide models (block_tc.cuh); ADT_BWD_TC=0 keeps the row-tile kernels (with hoisted weight gradients) -----
+static bool use_bwd_tc(const void* scratch, int M, int H, int nh, int mma) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_BWD_TC"); v = e ? (atoi(e) != 0) : 1; }
+  return v && mma && scratch && H >= 128 && H <= 256 && (H & 7) == 0 && M >= 512 && nh <= 8 && ((H / nh) & 31) == 0;
+}
+struct TcBwdScratch {
+  __nv_bfloat16* base; long long mh; __nv_bfloat16* wb;     // 12 operand slots of M*H bf16, then the bf16 weights
+  __nv_bfloat16* op(int i) const { return base + i * mh; }
+  float* f32(int i) const { return reinterpret_cast<float*>(base + i * mh); }   // an fp32 [M,H] matrix takes slots i, i+1
+};
+static TcBwdScratch mk_tcb(void* p, int M, int H) {
+  TcBwdScratch t;
+  t.base = reinterpret_cast<__nv_bfloat16*>(p); t.mh = (long long)M * H; t.wb = t.base + 12 * t.mh;
+  return t;
+}
+static int rows_grid2(int M) { const int b = (M + 7) / 8; return b < 148 * 4 ? b : 148 * 4; }
+// c (+)= A W : A bf16 [M][lda] (first Kred columns), W bf16 [Kred][N_out] row-major read MN-major
+static int tc_dgrad(const __nv_bfloat16* A, long long lda, int Kred, const __nv_bfloat16* W, int N_out, float* c, int accumulate, int M, cudaStream_t s) {
+  adt_gemm_tc_args g;
+  memset(&g, 0, sizeof(g));
+  g.a_bf16 = A; g.lda = lda; g.b_bf16 = W; g.ldb = N_out; g.b_mn = 1; g.c = c; g.ldc = N_out;
+  g.M = M; g.N = N_out; g.K = Kred; g.scale = 1.f; g.accumulate = accumulate;
+  TIMED("dgrad_tc", s);
+  if (int e = adt_gemm_tc(&g, (adt_stream_t)s)) return fail(e, "%s", "tcgen05 backward path (dgrad)");
+  return ADT_OK;
+}
+static void tc_pack(const float* s0, float sc0, float* gb0, const float* s1, float* gb1, const float* s2, float* gb2, __nv_bfloat16* dst, long long ld,
+                    int M, int H, cudaStream_t s) {
+  RowPackArgs p;
+  memset(&p, 0, sizeof(p));
+  p.src[0] = s0; p.scale[0] = sc0; p.gb[0] = gb0; p.src[1] = s1; p.scale[1] = 1.f; p.gb[1] = gb1; p.src[2] = s2; p.scale[2] = 1.f; p.gb[2] = gb2;
+  p.n = s2 ? 3 : (s1 ? 2 : 1); p.dst = dst; p.ld = ld; p.M = M; p.H = H;
+  TIMED("row_tc", s);
+  row_pack_kernel<<<rows_grid2(M), 256, 0, s>>>(p);
+}
+// FFN adjoint shared by both blocks.  In: dO etc. through `pp`.  Out: slots 6-7 hold dz (enc) / dc (dec) = dO + dh1 C1.
+static int tc_ffn_bwd(const TcBwdScratch& t, RowPostPrepArgs pp, const adt_ffn_w& ffn, const adt_ffn_g& gf, const __nv_bfloat16* C1b,
+                      const __nv_bfloat16* C2b, const __nv_bfloat16* zb, int M, int H, cudaStream_t s) {
+  pp.g = t.f32(6); pp.dh2b = t.op(0); pp.ab = t.op(1); pp.gc2 = gf.b2; pp.M = M; pp.H = H;
+  { TIMED("row_tc", s); row_post_prep_kernel<<<rows_grid2(M), 256, 0, s>>>(pp); }
+  if (int e = hoisted_wgrad(t.op(0), H, H, t.op(1), H, H, M, gf.w2, s)) return e;
+  if (int e = tc_dgrad(t.op(0), H, H, C2b, H, t.f32(8), 0, M, s)) return e;                       // da = dh2 C2
+  { TIMED("row_tc", s); row_dh1_kernel<<<rows_grid2(M), 256, 0, s>>>(t.f32(8), pp.h1, t.op(2), gf.b1, M, H, pp.drop1); }
+  if (int e = hoisted_wgrad(t.op(2), H, H, zb, H, H, M, gf.w1, s)) return e;
+  return tc_dgrad(t.op(2), H, H, C1b, H, t.f32(6), 1, M, s);                                      // dz / dc = dO + dh1 C1
+}
+
+static int tc_enc_bwd(const adt_enc_block_bwd_args* a, cudaStream_t s) {
+  const int M = a->B * a->L, H = a->H;
+  const TcBwdScratch t = mk_tcb(a->wgrad_scratch, M, H);
+  const long long hh = (long long)H * H;
+  const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  const __nv_bfloat16* Winb = tc_weight(a->attn.in_w, 3 * hh, a->wm, t.wb, s);
+  const __nv_bfloat16* Wob = tc_weight(a->attn.out_w, hh, a->wm, t.wb + 3 * hh, s);
+  const __nv_bfloat16* C1b = tc_weight(a->ffn.w1, hh, a->wm, t.wb + 4 * hh, s);
+  const __nv_bfloat16* C2b = tc_weight(a->ffn.w2, hh, a->wm, t.wb + 5 * hh, s);
+  // z = LN2(y) as the wgrad operand of C1
+  RowLnArgs r;
+  memset(&r, 0, sizeof(r));
+  r.x = a->y; r.g = a->ln2_w; r.b = a->ln2_b; r.yb = t.op(3); r.M = M; r.H = H;
+  { TIMED("row_tc", s); row_ln_cast_kernel<<<row_grid(M), 256, 0, s>>>(r); }
+  RowPostPrepArgs pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.dout = a->dout; pp.ids = a->ids; pp.h1 = a->h1; pp.is_dec = 0;
+  pp.drop1 = mk_drop(a->drop_ffn1); pp.drop2 = mk_drop(a->drop_ffn2);
+  if (int e = tc_ffn_bwd(t, pp, a->ffn, a->g_ffn, C1b, C2b, t.op(3), M, H, s)) return e;
+  // dy = LN2^T(dz) ; gbo += colsum(dy) ; gWo += dy^T ctx ; dctx = dy Wo (+ independence head)
+  RowLnBwdArgs lb;
+  memset(&lb, 0, sizeof(lb));
+  lb.x = a->y; lb.g = t.f32(6); lb.ln_g = a->ln2_w; lb.dx = a->dy; lb.dxb = t.op(4); lb.gln_g = a->g_ln2_w; lb.gln_b = a->g_ln2_b;
+  lb.gb = a->g_attn.out_b; lb.M = M; lb.H = H;
+  { TIMED("row_tc", s); row_ln_bwd_kernel<<<rows_grid2(M), 256, 0, s>>>(lb); }
+  tc_cast(a->ctx, t.op(5), (long long)M * H, s);
+  if (int e = hoisted_wgrad(t.op(4), H, H, t.op(5), H, H, M, a->g_attn.out_w, s)) return e;
+  if (int e = tc_dgrad(t.op(4), H, H, Wob, H, a->dctx, 0, M, s)) return e;
+  if (a->nll_coef != 0.f || a->drec) {
+    TIMED("row_tc", s);
+    sparse_head_bwd_kernel<<<rows_grid2(M), 256, 0, s>>>(a->ctx, a->sparse_w, a->sparse_b, a->drec, a->nll_coef, a->dctx, a->g_sparse_w,
+                                                        a->g_sparse_b, M, H, a->nh);
+  }
+  if (int e = check_launch("tcgen05 backward path (enc post)")) return e;
+  if (int e = launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
+                              a->drop_attn, a->precision, s))
+    return e;
+  // in-projection: [dq*s | dk | dv] packed ; q rows read LN1(x), k / v rows read x
+  tc_pack(a->dq, qscale, a->g_attn.in_b, a->dk, a->g_attn.in_b + H, a->dv, a->g_attn.in_b + 2 * H, t.op(0), 3 * H, M, H, s);
+  memset(&r, 0, sizeof(r));
+  r.x = a->x; r.g = a->ln1_w; r.b = a->ln1_b; r.yb = t.op(3); r.xb = t.op(4); r.M = M; r.H = H;
+  { TIMED("row_tc", s); row_ln_cast_kernel<<<row_grid(M), 256, 0, s>>>(r); }
+  if (int e = hoisted_wgrad(t.op(0), 3 * H, H, t.op(3), H, H, M, a->g_attn.in_w, s)) return e;
+  if (int e = hoisted_wgrad(t.op(0) + H, 3 * H, 2 * H, t.op(4), H, H, M, a->g_attn.in_w + hh, s)) return e;
+  if (int e = tc_dgrad(t.op(0), 3 * H, H, Winb, H, a->dy, 1, M, s)) return e;                    // dN = dy + dq*s Wq
+  memset(&lb, 0, sizeof(lb));
+  lb.x = a->x; lb.g = a->dy; lb.ln_g = a->ln1_w; lb.extra = a->dx_extra; lb.dx = a->dx; lb.gln_g = a->g_ln1_w; lb.gln_b = a->g_ln1_b;
+  lb.M = M; lb.H = H;
+  { TIMED("row_tc", s); row_ln_bwd_kernel<<<rows_grid2(M), 256, 0, s>>>(lb); }
+  if (int e = tc_dgrad(t.op(0) + H, 3 * H, 2 * H, Winb + hh, H, a->dx, 1, M, s)) return e;       // dx += dk Wk + dv Wv
+  return check_launch("tcgen05 backward path (enc pre)");
+}
+
+static int tc_dec_bwd(const adt_dec_block_bwd_args* a, cudaStream_t s) {
+  const int M = a->B * a->L, H = a->H;
+  const TcBwdScratch t = mk_tcb(a->wgrad_scratch, M, H);
+  const long long hh = (long long)H * H;
+  const float qscale = 1.0f / sqrtf((float)(H / a->nh));
+  if (a->phase != 1) {
+    const __nv_bfloat16* Wo1b = tc_weight(a->slf.out_w, hh, a->wm, t.wb + 3 * hh, s);
+    const __nv_bfloat16* W2b = tc_weight(a->enc.in_w, 3 * hh, a->wm, t.wb + 4 * hh, s);
+    const __nv_bfloat16* Wo2b = tc_weight(a->enc.out_w, hh, a->wm, t.wb + 7 * hh, s);
+    const __nv_bfloat16* C1b = tc_weight(a->ffn.w1, hh, a->wm, t.wb + 8 * hh, s);
+    const __nv_bfloat16* C2b = tc_weight(a->ffn.w2, hh, a->wm, t.wb + 9 * hh, s);
+    tc_cast(a->c, t.op(3), (long long)M * H, s);
+    RowPostPrepArgs pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.dout = a->dout; pp.out = a->out; pp.enc_in = a->enc_in; pp.mse_coef = a->mse_coef; pp.denc = a->denc; pp.ids = a->ids; pp.h1 = a->h1;
+    pp.g_copy = a->dd; pp.is_dec = 1;
+    pp.drop1 = mk_drop(a->drop_ffn1); pp.drop2 = mk_drop(a->drop_ffn2);
+    if (int e = tc_ffn_bwd(t, pp, a->ffn, a->g_ffn, C1b, C2b, t.op(3), M, H, s)) return e;
+    // dc (slots 6-7): gbo2 += colsum ; gWo2 += dc^T ctx2 ; dctx2 = dc Wo2
+    tc_pack(t.f32(6), 1.f, a->g_enc.out_b, nullptr, nullptr, nullptr, nullptr, t.op(4), H, M, H, s);
+    tc_cast(a->ctx2, t.op(5), (long long)M * H, s);
+    if (int e = hoisted_wgrad(t.op(4), H, H, t.op(5), H, H, M, a->g_enc.out_w, s)) return e;
+    if (int e = tc_dgrad(t.op(4), H, H, Wo2b, H, a->dctx2, 0, M, s)) return e;
+    if (int e = check_launch("tcgen05 backward path (dec post)")) return e;
+    if (int e = launch_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,
+                                a->drop_enc, a->precision, s))
+      return e;
+    // cross-attention in-projection (q rows from a, k / v rows from the encoder features), then the self-attention out-projection
+    tc_pack(a->dq2, qscale, a->g_enc.in_b, a->dk2, a->g_enc.in_b + H, a->dv2, a->g_enc.in_b + 2 * H, t.op(0), 3 * H, M, H, s);
+    tc_cast(a->a, t.op(3), (long long)M * H, s);
+    tc_cast(a->feats, t.op(4), (long long)M * H, s);
+    if (int e = hoisted_wgrad(t.op(0), 3 * H, H, t.op(3), H, H, M, a->g_enc.in_w, s)) return e;
+    if (int e = hoisted_wgrad(t.op(0) + H, 3 * H, 2 * H, t.op(4), H, H, M, a->g_enc.in_w + hh, s)) return e;
+    if (int e = tc_dgrad(t.op(0), 3 * H, H, W2b, H, t.f32(8), 0, M, s)) return e;                  // da = dq2*s Wq2
+    if (int e = tc_dgrad(t.op(0) + H, 3 * H, 2 * H, W2b + hh, H, a->dfeats, 1, M, s)) return e;    // dfeats += dk2 Wk2 + dv2 Wv2
+    tc_pack(t.f32(8), 1.f, a->g_slf.out_b, nullptr, nullptr, nullptr, nullptr, t.op(5), H, M, H, s);
+    tc_cast(a->ctx1, t.op(6), (long long)M * H, s);
+    if (int e = hoisted_wgrad(t.op(5), H, H, t.op(6), H, H, M, a->g_slf.out_w, s)) return e;
+    if (int e = tc_dgrad(t.op(5), H, H, Wo1b, H, a->dctx, 0, M, s)) return e;
+    if (int e = check_launch("tcgen05 backward path (dec mid)")) return e;
+    if (a->phase == 2) return ADT_OK;
+  }
+  const __nv_bfloat16* W1b = tc_weight(a->slf.in_w, 3 * hh, a->wm, t.wb, s);
+  if (int e = launch_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
+                              a->drop_slf, a->precision, s))
+    return e;
+  // q, k and v all read d = LN(x): one [3H x H] weight gradient, one K = 3H dgrad on top of dd
+  tc_pack(a->dq, qscale, a->g_slf.in_b, a->dk, a->g_slf.in_b + H, a->dv, a->g_slf.in_b + 2 * H, t.op(0), 3 * H, M, H, s);
+  tc_cast(a->d, t.op(3), (long long)M * H, s);
+  if (int e = hoisted_wgrad(t.op(0), 3 * H, 3 * H, t.op(3), H, H, M, a->g_slf.in_w, s)) return e;
+  if (int e = tc_dgrad(t.op(0), 3 * H, 3 * H, W1b, H, a->dd, 1, M, s)) return e;
+  RowLnBwdArgs lb;
+  memset(&lb, 0, sizeof(lb));
+  lb.x = a->x; lb.g = a->dd; lb.ln_g = a->ln_w; lb.dx = a->dx; lb.gln_g = a->g_ln_w; lb.gln_b = a->g_ln_b; lb.M = M; lb.H = H;
+  { TIMED("row_tc", s); row_ln_bwd_kernel<<<rows_grid2(M), 256, 0, s>>>(lb); }
+  return check_launch("tcgen05 backward path (dec pre)");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s_) {
   cudaStream_t s = (cudaStream_t)s_;
@@ -483,6 +775,7 @@ extern "C" int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t s
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   if (a->phase < 0 || a->phase > 2) return fail(ADT_E_SHAPE, "%s", "enc_block_fwd: phase must be 0, 1 or 2");
   if (a->phase == 0 && use_seq(a->L, H, a->nh, mma, a->training ? SEQ_ENC_FWD_TRAIN : SEQ_ENC_FWD)) return seq_enc_fwd(a, s);
+  if (a->y && a->h1 && a->out && use_fwd_tc(a->tc_scratch, M, H, a->nh, mma)) return tc_enc_fwd(a, s);
   if (a->phase != 2) {
     if (int e = launch_pre_fwd(a->x, a->ln1_w, a->ln1_b, a->attn, a->q, a->k, a->v, nullptr, M, H, a->nh, 0, a->precision, s)) return e;
     if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))
@@ -519,6 +812,7 @@ extern "C" int adt_enc_block_bwd(const adt_enc_block_bwd_args* a, adt_stream_t s
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   if (use_seq(a->L, H, a->nh, mma, SEQ_ENC_BWD)) return seq_enc_bwd(a, s);
+  if (use_bwd_tc(a->wgrad_scratch, M, H, a->nh, mma)) return tc_enc_bwd(a, s);
   PostBwdArgs p;
   memset(&p, 0, sizeof(p));
   p.dout = a->dout; p.ids = a->ids; p.ctx = a->ctx; p.u = a->y; p.h1 = a->h1;
@@ -575,6 +869,7 @@ extern "C" int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t s
   const int M = a->B * a->L, H = a->H;
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   if (use_seq(a->L, H, a->nh, mma, SEQ_DEC_FWD)) return seq_dec_fwd(a, s);
+  if (a->d && a->a && a->c && a->h1 && use_fwd_tc(a->tc_scratch, M, H, a->nh, mma)) return tc_dec_fwd(a, s);
   if (a->phase != 2) {
     if (int e = launch_pre_fwd(a->x, a->ln_w, a->ln_b, a->slf, a->q1, a->k1, a->v1, a->d, M, H, a->nh, 1, a->precision, s)) return e;
     if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
@@ -625,6 +920,7 @@ extern "C" int adt_dec_block_bwd(const adt_dec_block_bwd_args* a, adt_stream_t s
   const int mma = a->precision ? 1 : 0, pad = mma ? 8 : 4;
   const float qscale = 1.0f / sqrtf((float)(H / a->nh));
   if (use_seq(a->L, H, a->nh, mma, SEQ_DEC_BWD)) return seq_dec_bwd(a, s);
+  if (use_bwd_tc(a->wgrad_scratch, M, H, a->nh, mma)) return tc_dec_bwd(a, s);
   __nv_bfloat16* hz = hoist_ptr(a->wgrad_scratch, H, mma);
   const long long hu = (long long)M * H;
   size_t smem;

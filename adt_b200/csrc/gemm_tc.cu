@@ -30,6 +30,7 @@ struct GemmTcArgs {
   float* C; float* pre; const float* bias; long long ldc;
   int M, N, K, act, accumulate; float scale;
   int a_mn, b_mn, kb_per_split;
+  float* C2; int n_split;     // columns >= n_split (a multiple of 32) are written to C2 at column (col - n_split)
 };
 
 __device__ __forceinline__ float g_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
       tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + c0, v);
       const int nb = n0 + c0;
       if (row >= a.M || nb >= a.N) continue;
-      float* crow = a.C + (long long)row * a.ldc + nb;
+      float* crow = (a.C2 && nb >= a.n_split ? a.C2 - a.n_split : a.C) + (long long)row * a.ldc + nb;
       float* prow = a.pre ? a.pre + (long long)row * a.ldc + nb : nullptr;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
@@ -248,7 +249,7 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   cudaStream_t s = (cudaStream_t)s_;
   // an MN-major operand is stored [K][ld] with its M (or N) extent contiguous
   const long long a_in = a->a_mn ? a->M : a->K, b_in = a->b_mn ? a->N : a->K;
-  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->lda & 7) || (a->ldb & 7) || a->lda < a_in || a->ldb < b_in || a->ldc < a->N) return ADT_E_SHAPE;
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->lda & 7) || (a->ldb & 7) || a->lda < a_in || a->ldb < b_in || (!a->c2 && a->ldc < a->N)) return ADT_E_SHAPE;
   if ((reinterpret_cast<uintptr_t>(a->a_bf16) | reinterpret_cast<uintptr_t>(a->b_bf16)) & 15) return ADT_E_ALIGN;
   if (a->split_k > 1 && (a->act || a->pre)) return ADT_E_SHAPE;      // partial sums are only linear before the activation
   CUtensorMap tmA, tmB;
@@ -256,6 +257,8 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   k.C = a->c; k.pre = a->pre; k.bias = a->bias; k.ldc = a->ldc; k.M = a->M; k.N = a->N; k.K = a->K; k.act = a->act; k.accumulate = a->accumulate;
   k.scale = a->scale == 0.f ? 1.f : a->scale;
   k.a_mn = a->a_mn ? 1 : 0; k.b_mn = a->b_mn ? 1 : 0;
+  k.C2 = a->c2; k.n_split = a->n_split;
+  if (k.C2 && (k.n_split <= 0 || (k.n_split & 31) || a->ldc < k.n_split || a->ldc < a->N - k.n_split)) return ADT_E_SHAPE;
   const int nkb = (a->K + 63) / 64;
   int splits = a->split_k > 1 ? (a->split_k < nkb ? a->split_k : nkb) : 1;
   k.kb_per_split = (nkb + splits - 1) / splits;
@@ -269,8 +272,11 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   const int bn = a->N <= 64 ? 64 : 128;
   if (k.b_mn) { if (int e = g_make_map(&tmB, a->b_bf16, a->K, a->N, a->ldb, 64)) return e; }
   else if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, bn)) return e;
-  if (bn == 64) return g_launch<64, 6>(tmA, tmB, k, splits, s);
-  return g_launch<128, 6>(tmA, tmB, k, splits, s);
+  // short K ranges (the H x H layers of a block: 4 slabs) leave the ring idle: a shallow ring lets 2-3 CTAs share an SM, so one CTA's
+  // epilogue and prologue overlap another's main loop
+  const int slabs = k.kb_per_split;
+  if (bn == 64) return slabs <= 4 ? g_launch<64, 2>(tmA, tmB, k, splits, s) : slabs <= 16 ? g_launch<64, 3>(tmA, tmB, k, splits, s) : g_launch<64, 6>(tmA, tmB, k, splits, s);
+  return slabs <= 4 ? g_launch<128, 2>(tmA, tmB, k, splits, s) : slabs <= 16 ? g_launch<128, 3>(tmA, tmB, k, splits, s) : g_launch<128, 6>(tmA, tmB, k, splits, s);
 }
 
 extern "C" int adt_to_bf16_t(const float* x, int64_t ld, void* y_bf16, int64_t ldt, int32_t R, int32_t C, adt_stream_t s_) {

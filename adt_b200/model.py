@@ -187,6 +187,11 @@ class Engine:
         m = self.m
         return bool(self.lib.adt_seq_kernels_apply(int(Lq), int(m.hidden), int(m.num_heads), int(self.precision)))
 
+    def mirror_kernels(self, Lq):
+        """kernels that read the bf16 weight mirror serve this shape: the sequence-resident block kernels, or the tcgen05 forward path of
+        wide models (which otherwise converts every weight per call)"""
+        return self.seq_kernels(Lq) or (bool(self.precision) and self.m.hidden >= 128)
+
     def grad_view(self, name):
         p = dict(self.order)[name]
         o = self.offs[name]
@@ -226,6 +231,10 @@ class Engine:
         nwg = w["sizes"]["wgrad_scratch"] if self.precision else 0
         w["wg"] = torch.empty(nwg, dtype=torch.uint8, device=dev) if nwg else None
         w["side"]["wg"] = torch.empty(nwg, dtype=torch.uint8, device=dev) if nwg else None
+        # bf16 operands of the tcgen05 forward path (same condition; the side-stream half of decoder block 0 owns a second one)
+        nfs = w["sizes"]["fwd_scratch"] if self.precision else 0
+        w["fs"] = torch.empty(nfs, dtype=torch.uint8, device=dev) if nfs else None
+        w["side"]["fs"] = torch.empty(nfs, dtype=torch.uint8, device=dev) if nfs else None
         N = 4 * M
         i32 = lambda n: torch.empty(n, dtype=torch.int32, device=dev)
         w["keys"], w["vals"], w["keys_tmp"], w["vals_tmp"] = i32(N), i32(N), i32(N), i32(N)
@@ -284,7 +293,7 @@ class Engine:
             sa, s1, s2 = sites[("enc", l)]
             last = l == m.num_layers - 1
             a = L.fill(L.adt_enc_block_fwd_args(), x=w["x"][l], ids=seq, phase=(last_phase if l == m.num_layers - 1 else 0),
-                       wm=wm, out_last=(out_last if last else None),
+                       wm=wm, out_last=(out_last if last else None), tc_scratch=w.get("fs"),
                        ln1_w=layer.attention_layernorm.weight, ln1_b=layer.attention_layernorm.bias, attn=_mha_w(layer.attention_layer),
                        ln2_w=layer.forward_layernorm.weight, ln2_b=layer.forward_layernorm.bias, ffn=_ffn_w(layer.forward_layer),
                        sparse_w=layer.sparse.weight, sparse_b=layer.sparse.bias,
@@ -349,6 +358,7 @@ class Engine:
             sv = w["dec"][j]
             ss, se, s1, s2 = sites[("dec", j)]
             a = L.fill(L.adt_dec_block_fwd_args(), x=w["xd"][j], feats=w["feats"], ids=dec, wm=self.wm(),
+                       tc_scratch=(w["side"]["fs"] if phases[0] == 1 else w["fs"]),     # phase 1 runs beside the encoder on the side stream
                        ln_w=layer.layer_norm.weight, ln_b=layer.layer_norm.bias, slf=_mha_w(layer.slf_attn), enc=_mha_w(layer.enc_attn),
                        ffn=_ffn_w(layer.pos_ffn), enc_in=w["x"][nl - 1 - j] if fused_mse else None,
                        out=w["xd"][j + 1], mse_acc=(w["acc"][3 + j:] if fused_mse else None),
@@ -628,7 +638,7 @@ class SASRecADT(nn.Module):
         eng = self.engine
         B, Lq = seq.shape
         w = eng.workspace(B, Lq)
-        if eng.precision and eng.seq_kernels(Lq) and not torch.cuda.is_current_stream_capturing():
+        if eng.precision and eng.mirror_kernels(Lq) and not torch.cuda.is_current_stream_capturing():
             eng.ensure_mirror()
         if Lq > 1 and self.num_layers >= 1:
             return eng.encode_last(seq, w).clone()

@@ -131,7 +131,7 @@ class FusedTrainer:
         dev = eng.dev()
         eng.ensure_flat()
         # bf16 weight mirror for the sequence-resident block kernels: refreshed here, then rewritten by every Adam launch
-        self._mirror_on = bool(eng.use_mirror and eng.precision and eng.seq_kernels(Lq))
+        self._mirror_on = bool(eng.use_mirror and eng.precision and eng.mirror_kernels(Lq))
         if self._mirror_on:
             eng.refresh_mirror()
         if self.step_dev is None or self.step_dev.device != dev:

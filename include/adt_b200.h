@@ -45,9 +45,10 @@ const char* adt_last_error(void);
 /* Scratch / saved-activation sizes (bytes) the caller must allocate for one (B, L, H, nh, nl) training step: the library allocates
  * nothing itself.  saved = activations kept from forward for backward; scratch = backward temporaries; sort = keys/vals/tmp/hist of
  * adt_embed_sort; scatter = head/tail/has_tail of adt_embed_bwd; score_part = part_scores + part_ids of adt_score_topk for
- * (U = B, K, n_splits); wgrad_scratch = the bf16 operand copies of the hoisted weight gradients (0 when H < 128). */
+ * (U = B, K, n_splits); wgrad_scratch = the bf16 operand copies of the hoisted weight gradients, fwd_scratch = the bf16 operands of the
+ * tcgen05 forward path (both 0 when H < 128). */
 typedef struct { int32_t B, L, H, nh, nl, K, n_splits; } adt_workspace_query;
-typedef struct { int64_t saved, scratch, sort_keys, sort_hist, scatter_rows, scatter_flags, score_part, wgrad_scratch; } adt_workspace_sizes;
+typedef struct { int64_t saved, scratch, sort_keys, sort_hist, scatter_rows, scatter_flags, score_part, wgrad_scratch, fwd_scratch; } adt_workspace_sizes;
 int adt_workspace_bytes(const adt_workspace_query* q, adt_workspace_sizes* out);
 
 /* K1. x = dropout(E[ids]*sqrt(H) + P[t]) * (ids != 0)            -- sasrec/model.py:34-41 and :53-58 */
@@ -90,6 +91,8 @@ typedef struct {
   float* out_last; /* optional [B][H]: the block output of the LAST position of every sequence (predict reads nothing else,
                       sasrec/model.py:89); `out` may then be NULL.  Only honoured by the sequence-resident kernels (phase 0, precision 1,
                       H == 64, L <= 64, nh in {1,2,4}); otherwise ignored, so callers must check adt_seq_kernels_apply() first */
+  void* tc_scratch; /* optional, adt_workspace_sizes.fwd_scratch bytes (precision 1, H >= 128, H % 64 == 0, phase 0): every linear layer
+                       then runs as one tcgen05 GEMM over all rows (block_tc.cuh) instead of inside the row-tile kernels */
 } adt_enc_block_fwd_args;
 int adt_enc_block_fwd(const adt_enc_block_fwd_args* a, adt_stream_t stream);
 
@@ -130,6 +133,7 @@ typedef struct {
   int32_t phase;   /* 0: whole block; 1: only LN + self-attention (independent of the encoder -> may run beside it on another
                     * stream); 2: the rest (cross-attention on `feats`, FFN) */
   adt_wmirror wm;
+  void* tc_scratch; /* as in adt_enc_block_fwd_args (phases 0, 1 and 2) */
 } adt_dec_block_fwd_args;
 int adt_dec_block_fwd(const adt_dec_block_fwd_args* a, adt_stream_t stream);
 
@@ -321,6 +325,8 @@ typedef struct {
   int32_t a_mn, b_mn;                          /* != 0: the operand is stored MN-major, i.e. as [K][ld] with its M (or N) extent contiguous:
                                                   dgrad reads W [N,K] as b_mn, wgrad reads dy [M,N] and x [M,K] as a_mn / b_mn -- no transposes */
   int32_t split_k;                             /* > 1: that many CTAs share an output tile and add partial sums atomically (act 0, pre NULL) */
+  float* c2; int32_t n_split;                  /* optional second output: columns >= n_split (multiple of 32) go to c2[:, col - n_split] (row stride ldc):
+                                                  one product fills the separate k and v buffers of a packed in-projection */
 } adt_gemm_tc_args;
 int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t stream);
 /* operand copies for adt_gemm_tc: fp32 [R][C] (row stride ld) -> bf16 [R][ldy], or -> its bf16 transpose [C][ldt] */

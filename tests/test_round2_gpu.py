@@ -313,26 +313,60 @@ def test_sequence_resident_block_kernels_match_row_tile_kernels(nh, Lq):
     assert np.abs(np.array(a["scores"]) - np.array(b["scores"])).max() < 1e-2
 
 
+def _ab_wide(env_name, nh, Lq, Hd):
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for v in ("0", "1"):
+        env = dict(os.environ, **{env_name: v})
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "seq_ab.py"), str(nh), str(Lq), str(Hd)], capture_output=True, text=True,
+                           env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    return res
+
+
 @pytest.mark.parametrize("nh,Lq,Hd", [(2, 50, 128), (2, 40, 256), (3, 33, 192)])
 def test_hoisted_tcgen05_weight_gradients_match_in_kernel_ones(nh, Lq, Hd):
     """wide models in the bf16 mode: the backward row-tile kernels write bf16 copies of their dY / X tiles and each weight gradient is one
     split-K tcgen05 GEMM reading both MN-major (ADT_WGRAD_HOIST=1, the default) -- against the in-kernel mma.sync + atomics path (=0):
     same bf16 operand rounding, so every parameter's gradient norm, the losses and the updated parameters agree to accumulation order."""
-    import json, os, subprocess, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = []
-    for hoist in ("0", "1"):
-        env = dict(os.environ, ADT_WGRAD_HOIST=hoist)
-        r = subprocess.run([sys.executable, os.path.join(root, "tools", "seq_ab.py"), str(nh), str(Lq), str(Hd)], capture_output=True, text=True,
-                           env=env, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
-    a, b = res
+    a, b = _ab_wide("ADT_WGRAD_HOIST", nh, Lq, Hd)
     for n, v in a["gnorms"].items():
         assert abs(v - b["gnorms"][n]) <= 2e-4 * max(v, 1e-6) + 1e-9, (n, v, b["gnorms"][n])
     for k in range(3):
         assert abs(a["loss"][k] - b["loss"][k]) / abs(a["loss"][k]) < 2e-5, (k, a["loss"], b["loss"])
         assert abs(a["gnorm"][k] - b["gnorm"][k]) / a["gnorm"][k] < 1e-3, (k, a["gnorm"], b["gnorm"])
+    assert abs(a["psum"] - b["psum"]) / a["psum"] < 1e-4
+
+
+@pytest.mark.parametrize("nh,Lq,Hd", [(2, 50, 128), (2, 40, 256), (3, 33, 192)])
+def test_tcgen05_forward_path_matches_row_tile_kernels(nh, Lq, Hd):
+    """wide models in the bf16 mode: forward of the encoder / decoder blocks as tcgen05 GEMMs + warp-per-row kernels (block_tc.cuh,
+    ADT_FWD_TC=1, the default) against the row-tile kernels (=0): same bf16 operand rounding, same Philox dropout streams, same saved
+    activations -> losses, gradient norms, updated parameters and the evaluation top-10 agree to bf16-flip level."""
+    a, b = _ab_wide("ADT_FWD_TC", nh, Lq, Hd)
+    for k in range(3):
+        assert abs(a["loss"][k] - b["loss"][k]) / abs(a["loss"][k]) < 2e-4, (k, a["loss"], b["loss"])
+        assert abs(a["gnorm"][k] - b["gnorm"][k]) / a["gnorm"][k] < 5e-3, (k, a["gnorm"], b["gnorm"])
+    for n, v in a["gnorms"].items():
+        assert abs(v - b["gnorms"][n]) <= 5e-3 * max(v, 1e-6) + 1e-8, (n, v, b["gnorms"][n])
+    assert abs(a["psum"] - b["psum"]) / a["psum"] < 1e-4
+    assert np.mean(np.array(a["ids"]) == np.array(b["ids"])) > 0.8      # near-ties of the 12k-item catalog swap after three bf16 steps
+    assert np.abs(np.array(a["scores"]) - np.array(b["scores"])).max() < 2e-2
+
+
+@pytest.mark.parametrize("nh,Lq,Hd", [(2, 50, 128), (2, 40, 256), (3, 33, 192)])
+def test_tcgen05_backward_path_matches_row_tile_kernels(nh, Lq, Hd):
+    """wide models in the bf16 mode: backward of the encoder / decoder blocks as tcgen05 dgrad / wgrad GEMMs + warp-per-row adjoint kernels
+    (block_tc.cuh, ADT_BWD_TC=1, the default) against the row-tile kernels (=0, with hoisted weight gradients): per-parameter gradient
+    norms, losses, global gradient norms and updated parameters agree to bf16-flip level."""
+    a, b = _ab_wide("ADT_BWD_TC", nh, Lq, Hd)
+    for n, v in a["gnorms"].items():
+        assert abs(v - b["gnorms"][n]) <= 5e-3 * max(v, 1e-6) + 1e-8, (n, v, b["gnorms"][n])
+    for k in range(3):
+        assert abs(a["loss"][k] - b["loss"][k]) / abs(a["loss"][k]) < 2e-4, (k, a["loss"], b["loss"])
+        assert abs(a["gnorm"][k] - b["gnorm"][k]) / a["gnorm"][k] < 5e-3, (k, a["gnorm"], b["gnorm"])
     assert abs(a["psum"] - b["psum"]) / a["psum"] < 1e-4
 
 
