@@ -396,44 +396,72 @@ __global__ void __launch_bounds__(256) sparse_head_bwd_kernel(const float* __res
                                                               int H, int nh) {
   __shared__ float gw[256];
   __shared__ float gbv[8];
-  const int lane = threadIdx.x & 31, hd = H / nh;
+  __shared__ float dls[8][8];          // per warp: dl[j] of the (row, head) being processed
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, hd = H / nh, tpd = hd >> 5, nflat = H >> 5;
   for (int c = threadIdx.x; c < H; c += 256) gw[c] = 0.f;
   if (threadIdx.x < 8) gbv[threadIdx.x] = 0.f;
   __syncthreads();
-  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += gridDim.x * 8) {
+  // this lane's share of gWs: flat slot i <-> (class j = i / tpd, column d = lane + 32 (i % tpd)); slots are compile-time indices
+  float accw[8], accb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) accw[i] = accb[i] = 0.f;
+  for (int row = blockIdx.x * 8 + w; row < M; row += gridDim.x * 8) {
     const float* xr = ctx + (long long)row * H;
     float* dr_out = dctx + (long long)row * H;
     for (int c = 0; c < nh; ++c) {
       float lg[8];
       float mx = -INFINITY;
-      for (int j = 0; j < nh; ++j) {
-        float s = 0.f;
-        for (int d = lane; d < hd; d += 32) s = fmaf(xr[c * hd + d], __ldg(Wsp + j * hd + d), s);
-        lg[j] = warp_sum(s) + bsp[j];
-        mx = fmaxf(mx, lg[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        lg[j] = -INFINITY;
+        if (j < nh) {
+          float s = 0.f;
+          for (int d = lane; d < hd; d += 32) s = fmaf(xr[c * hd + d], __ldg(Wsp + j * hd + d), s);
+          lg[j] = warp_sum(s) + bsp[j];
+          mx = fmaxf(mx, lg[j]);
+        }
       }
       float se = 0.f;
-      for (int j = 0; j < nh; ++j) se += expf(lg[j] - mx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nh) se += expf(lg[j] - mx);
       const float* dr = drec ? drec + ((long long)row * nh + c) * nh : nullptr;
       float gsum = 0.f;
       if (dr) for (int j = 0; j < nh; ++j) gsum += dr[j];
-      for (int j = 0; j < nh; ++j) {
-        const float pj = expf(lg[j] - mx) / se;
-        float dl = nll_coef * (pj - (j == c ? 1.f : 0.f));
-        if (dr) dl += dr[j] - pj * gsum;
-        lg[j] = dl;
-        if (lane == 0) atomicAdd(gbv + j, dl);
-      }
-      for (int d = lane; d < hd; d += 32) {
-        const float x = xr[c * hd + d];
-        float add = 0.f;
-        for (int j = 0; j < nh; ++j) {
-          add = fmaf(lg[j], __ldg(Wsp + j * hd + d), add);
-          atomicAdd(gw + j * hd + d, lg[j] * x);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nh) {
+          const float pj = expf(lg[j] - mx) / se;
+          float dl = nll_coef * (pj - (j == c ? 1.f : 0.f));
+          if (dr) dl += dr[j] - pj * gsum;
+          accb[j] += dl;                       // identical in every lane; lane 0's copy is used
+          if (lane == 0) dls[w][j] = dl;
         }
+      __syncwarp();
+      for (int d = lane; d < hd; d += 32) {
+        float add = 0.f;
+        for (int j = 0; j < nh; ++j) add = fmaf(dls[w][j], __ldg(Wsp + j * hd + d), add);
         dr_out[c * hd + d] += add;
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nflat) {
+          const int j = i / tpd, t = i - j * tpd;
+          accw[i] = fmaf(dls[w][j], xr[c * hd + lane + 32 * t], accw[i]);
+        }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < nflat) {
+      const int j = i / tpd, t = i - j * tpd;
+      atomicAdd(gw + j * hd + lane + 32 * t, accw[i]);
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nh) atomicAdd(gbv + j, accb[j]);
   }
   __syncthreads();
   smem_cols_to_global(gw, gWsp, H);

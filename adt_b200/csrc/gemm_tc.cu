@@ -269,6 +269,7 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   if (k.a_mn) { if (int e = g_make_map(&tmA, a->a_bf16, a->K, a->M, a->lda, 64)) return e; }
   else if (int e = g_make_map(&tmA, a->a_bf16, a->M, a->K, a->lda, GM)) return e;
   // narrow outputs waste less of the tile with 64 columns; wide ones amortise the A slab over 128
+  // (256-column tiles were measured SLOWER at the C1 shapes: fewer, longer CTAs, two per SM instead of three)
   const int bn = a->N <= 64 ? 64 : 128;
   if (k.b_mn) { if (int e = g_make_map(&tmB, a->b_bf16, a->K, a->N, a->ldb, 64)) return e; }
   else if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, bn)) return e;
