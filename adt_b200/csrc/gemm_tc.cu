@@ -38,6 +38,38 @@ __device__ __forceinline__ float g_act(float x, int act) {
   return act == 1 ? fmaxf(x, 0.f) : act == 2 ? g_gelu(x) : act == 3 ? (x > 0.f ? x : expm1f(x)) : act == 4 ? (x > 0.f ? x : expm1f(x)) + 1.f : x;
 }
 
+// one 32-column chunk of a row: pre-activation copy, activation (compiled out for act == 0: a per-element switch on a run-time `act`
+// cost a constant-bank jump per element), then store / accumulate / atomic add (split K)
+template <bool ACT>
+__device__ __forceinline__ void epi_chunk(const GemmTcArgs& a, float (&v)[32], float* __restrict__ crow, float* __restrict__ prow, int nb, bool vec,
+                                          bool atomic) {
+  if (vec) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      if (prow) *reinterpret_cast<float4*>(prow + c) = o;
+      if (ACT) o = make_float4(g_act(o.x, a.act), g_act(o.y, a.act), g_act(o.z, a.act), g_act(o.w, a.act));
+      if (atomic) { atomicAdd(reinterpret_cast<float4*>(crow + c), o); continue; }
+      if (a.accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(crow + c);
+        o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w);
+      }
+      *reinterpret_cast<float4*>(crow + c) = o;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (nb + c < a.N) {
+        if (prow) prow[c] = v[c];
+        float o = ACT ? g_act(v[c], a.act) : v[c];
+        if (atomic) { atomicAdd(crow + c, o); continue; }
+        if (a.accumulate) o += crow[c];
+        crow[c] = o;
+      }
+    }
+  }
+}
+
 template <int BN, int NS>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                GemmTcArgs a) {
@@ -129,31 +161,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         if (a.bias && blockIdx.z == 0 && nb + c < a.N) x += __ldg(a.bias + nb + c);
         v[c] = x * a.scale;
       }
-      if (vec && nb + 32 <= a.N) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-          if (prow) *reinterpret_cast<float4*>(prow + c) = o;
-          o = make_float4(g_act(o.x, a.act), g_act(o.y, a.act), g_act(o.z, a.act), g_act(o.w, a.act));
-          if (gridDim.z > 1) { atomicAdd(reinterpret_cast<float4*>(crow + c), o); continue; }
-          if (a.accumulate) {
-            const float4 old = *reinterpret_cast<const float4*>(crow + c);
-            o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w);
-          }
-          *reinterpret_cast<float4*>(crow + c) = o;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (nb + c < a.N) {
-            if (prow) prow[c] = v[c];
-            float o = g_act(v[c], a.act);
-            if (gridDim.z > 1) { atomicAdd(crow + c, o); continue; }
-            if (a.accumulate) o += crow[c];
-            crow[c] = o;
-          }
-        }
-      }
+      if (a.act == 0) epi_chunk<false>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1);
+      else epi_chunk<true>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1);
     }
   }
   tc::tc_fence_before();
