@@ -625,7 +625,26 @@ def selfcheck_section(cx):
                             "fixture": "tests/golden/sasrec_c2mini_p5.npz (unmodified reference; its 6 sequences split across the ranks, "
                                        "loss and global gradient norm of the all-reduced step against the reference's)"}
     else:
-        res["dp_parity"] = {"skipped": f"fixture batch {B} not divisible by {cx.world}"}
+        # the fixture's 6 sequences do not split over this many ranks: tile them cyclically to world * per sequences and compare the
+        # N-rank step with the SINGLE-rank step (a one-member process group) on the same global batch -- same Philox streams, because
+        # a rank's dropout counters start at its global row offset
+        per = -(-B // cx.world)
+        idx = [(cx.rank * per + i) % B for i in range(per)]
+        gidx = [(r * per + i) % B for r in range(cx.world) for i in range(per)]
+        solo = [torch.distributed.new_group(ranks=[r]) for r in range(cx.world)][cx.rank]
+        l1, l2, wd = [float(x) for x in g["lambdas1"]], [float(x) for x in g["lambdas2"]], float(g["wd"])
+        out = []
+        for pg, ii in ((None, idx), (solo, gidx)):
+            m = T.model_from_golden(g).train()
+            tr = FusedTrainer(m, l1, l2, weight_decay=wd, seed=int(g["drop_seed"]), process_group=pg)
+            tr.t = int(g["drop_step"])
+            tr.step(g["seq"][ii], g["dec"][ii], g["pos"][ii], g["neg"][ii])
+            out.append((tr.loss(), tr.grad_norm()))
+        (loss, gn), (loss1, gn1) = out
+        e_loss, e_gn = abs(loss - loss1) / abs(loss1), abs(gn - gn1) / abs(gn1)
+        res["dp_parity"] = {"loss_rel_err": e_loss, "grad_norm_rel_err": e_gn, "ok": bool(e_loss < 1e-5 and e_gn < 1e-4), "ranks": cx.world,
+                            "fixture": f"tests/golden/sasrec_c2mini_p5.npz tiled to {len(gidx)} sequences ({per} per rank): loss and global gradient "
+                                       "norm of the all-reduced N-rank step against the single-rank step on the same global batch"}
     # item-sharded top-K: every rank scores the same users against its shard; merged ids must equal the unsharded exact result
     import types
     gen = torch.Generator(device="cpu").manual_seed(11)
