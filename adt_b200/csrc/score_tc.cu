@@ -88,8 +88,12 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int A_BYTES = ATM ? 0 : KB * BM * 128;
-  constexpr int TM_COLS = ATM ? 512 : 2 * BN;                 // accumulators 2 x BN (+ KB*32 columns of A behind them)
-  constexpr uint32_t A_COL = 2 * BN;
+  // accumulator ring in tensor memory: MMA(t + NACC - 1) may be issued while tile t is still being read out.  The per-tile chain
+  // (commit -> barrier -> tcgen05.ld -> filter -> arrive -> next MMA) costs ~2k cycles against ~130 of MMA at H = 64, so the depth of
+  // this ring, not the tensor pipe, sets the tile rate: three buffers when they fit beside the A tile (BN 128: 384 + KB*32 <= 512)
+  constexpr int NACC = (ATM && 3 * BN + KB * 32 <= 512) ? 3 : 2;
+  constexpr int TM_COLS = ATM ? 512 : 2 * BN;                 // accumulators NACC x BN (+ KB*32 columns of A behind them)
+  constexpr uint32_t A_COL = NACC * BN;
   constexpr int B_STAGE = KB * BN * 128;
   uint8_t* sA = smem;
   uint8_t* sB = sA + A_BYTES;
@@ -101,10 +105,10 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(vsm + 4 * 1024);
   uint64_t* full = bars;               // [NS] B stage filled (TMA tx)
   uint64_t* empty = bars + NS;         // [NS] B stage consumed (tcgen05.commit)
-  uint64_t* tfull = bars + 2 * NS;     // [2] accumulator ready (tcgen05.commit)
-  uint64_t* tempty = bars + 2 * NS + 2;  // [2] accumulator drained (4 epilogue warps)
-  uint64_t* abar = bars + 2 * NS + 4;  // A tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
+  uint64_t* tfull = bars + 2 * NS;     // [NACC] accumulator ready (tcgen05.commit)
+  uint64_t* tempty = bars + 2 * NS + NACC;  // [NACC] accumulator drained (epilogue warps)
+  uint64_t* abar = bars + 2 * NS + 2 * NACC;  // A tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2 * NACC + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = MC ? blockIdx.y : blockIdx.x, u0 = (MC ? blockIdx.x : blockIdx.y) * BM;
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
       tc::mbar_init(full + i, 1);
       tc::mbar_init(empty + i, MC ? 2 : 1);      // multicast ring: both CTAs of the pair must have consumed a stage
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       tc::mbar_init(tfull + i, 1);
       tc::mbar_init(tempty + i, MODE == 0 ? 4 : 8);
     }
@@ -158,8 +162,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
       constexpr uint32_t idesc = tc::idesc_bf16_f32(BM, BN);
       tc::mbar_wait(abar, 0);
       for (int t = 0; t < ntiles; ++t) {
-        const int st = t % NS, acc = t & 1;
-        tc::mbar_wait(tempty + acc, ((t >> 1) & 1) ^ 1);
+        const int st = t % NS, acc = t % NACC;
+        tc::mbar_wait(tempty + acc, ((t / NACC) & 1) ^ 1);
         tc::mbar_wait(full + st, (t / NS) & 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
     const int u = u0 + row;
     const int KC = MODE == 0 ? a.KC : a.KC / 2;      // two-pass: every (row, column half) owns KC/2 candidate slots = one virtual split
     const int CB = MODE == 0 ? 0 : half * (BN / 2), CE = MODE == 0 ? BN : CB + BN / 2;
+    constexpr int CW = (MODE != 0 && (BN / 2) % 64 == 0) ? 64 : 32;      // columns per tcgen05.ld of the two-pass epilogues
     if (ATM && half == 0) {     // this thread's feature row (bf16, KB*32 words) -> TMEM columns A_COL.. of its lane
       const uint4* frow = reinterpret_cast<const uint4*>(a.feats_bf16 + (long long)(u < a.U ? u : 0) * (KB * 64));
 #pragma unroll 1
@@ -233,34 +238,34 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
       const long long vsplit = (long long)split * 2 + half;
       const long long obase = (vsplit * a.U + (u < a.U ? u : 0)) * KC;
       for (int t = 0; t < ntiles; ++t) {
-        const int st = t & 1;
-        tc::mbar_wait(tfull + st, (t >> 1) & 1);
+        const int st = t % NACC;
+        tc::mbar_wait(tfull + st, (t / NACC) & 1);
         tc::tc_fence_after();
         const int tb = (tfirst + t * tstep) * BN;
 #pragma unroll 1
-        for (int c0 = CB; c0 < CE; c0 += 32) {
-          float v[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
-          if (c0 + 32 == CE) {               // accumulator fully read: hand it back to the MMA warp
+        for (int c0 = CB; c0 < CE; c0 += CW) {
+          float v[CW];
+          tc::tmem_ldw<CW>(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
+          if (c0 + CW == CE) {               // accumulator fully read: hand it back to the MMA warp
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty + st);
           }
           const int ib = tb + c0;
           const int nvalid = a.n_items - ib;
-          if (nvalid < 32) {
+          if (nvalid < CW) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
+            for (int c = 0; c < CW; ++c)
               if (c >= nvalid) v[c] = -INFINITY;
           }
           if (a.debug == 1) continue;
           float mx = v[0];
 #pragma unroll
-          for (int c = 1; c < 32; ++c) mx = fmaxf(mx, v[c]);
+          for (int c = 1; c < CW; ++c) mx = fmaxf(mx, v[c]);
           if (a.debug == 2) continue;
-          if (mx > thr) {                    // rare (about one row in 150 per chunk): walk the 32 registers, no staging through smem
+          if (mx > thr) {                    // rare (about one row in 75 per chunk): walk the registers, no staging through smem
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
+            for (int c = 0; c < CW; ++c) {
               if (v[c] > thr) {
                 const int item = a.item_offset + ib + c;
                 if (!tc_is_seen(a, sb, se, item)) {       // candidates go straight to HBM, no list on chip
@@ -282,23 +287,23 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
       // R-th largest of them): no lists, no shared memory, one store per (row, tile)
       thr = 0.f;
       for (int t = 0; t < ntiles; ++t) {
-        const int st = t & 1;
-        tc::mbar_wait(tfull + st, (t >> 1) & 1);
+        const int st = t % NACC;
+        tc::mbar_wait(tfull + st, (t / NACC) & 1);
         tc::tc_fence_after();
         const int tb = (tfirst + t * tstep) * BN;
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c0 = CB; c0 < CE; c0 += 32) {
-          float v[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
-          if (c0 + 32 == CE) {
+        for (int c0 = CB; c0 < CE; c0 += CW) {
+          float v[CW];
+          tc::tmem_ldw<CW>(tmem_base + ((uint32_t)(32 * q) << 16) + st * BN + c0, v);
+          if (c0 + CW == CE) {
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tempty + st);
           }
           const int nvalid = a.n_items - (tb + c0);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, c < nvalid ? v[c] : -INFINITY);
+          for (int c = 0; c < CW; ++c) mx = fmaxf(mx, c < nvalid ? v[c] : -INFINITY);
         }
         if (u < a.U) a.part_scores[((long long)(split + t * a.n_splits) * 2 + half) * a.U + u] = mx;
       }
@@ -326,10 +331,10 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
       if (nm > rej) { rej = nm; thr = unkey(nm); }
     };
     for (int t = 0; t < ntiles; ++t) {
-      const int st = t & 1;
+      const int st = t % NACC;
       // thresholds of the other splits: issue the (L2) load now, consume it after this tile
       const uint32_t gnext = (MODE == 0 && a.gthr && u < a.U) ? __ldcg(a.gthr + u) : 0u;
-      tc::mbar_wait(tfull + st, (t >> 1) & 1);
+      tc::mbar_wait(tfull + st, (t / NACC) & 1);
       tc::tc_fence_after();
       const int tb = (tfirst + t * tstep) * BN;
 #pragma unroll 1

@@ -32,10 +32,24 @@ def test_benched_c2_configuration_against_live_oracle(precision, use_graph):
     evaluated live on the host with the same Philox streams: loss within 2e-2 (bf16) / 1e-5 (fp32), embedding gather bit exact,
     global gradient norm, and every parameter's gradient direction (cosine)."""
     from adt_b200 import synth
+    _against_live_oracle(synth.CONFIGS["C2"], precision, use_graph)
+
+
+@pytest.mark.parametrize("H,nh,use_graph", [(128, 2, False), (256, 2, True), (192, 3, False)])
+def test_wide_model_tcgen05_block_path_against_live_oracle(H, nh, use_graph):
+    """wide models (H >= 128) in the bf16 mode take the tcgen05 block path (block_tc.cuh: every linear layer one adt_gemm_tc launch,
+    warp-per-row kernels in between, forward AND backward): the same check as the benched configuration -- loss, gradient norm,
+    bit-exact embedding gather, per-parameter gradient cosine -- against the oracle evaluated live on the host."""
+    from adt_b200 import synth
+    cfg = dict(synth.CONFIGS["C2"], H=H, nh=nh, L=40, B=32, items=3000)
+    _against_live_oracle(cfg, "bf16", use_graph)
+
+
+def _against_live_oracle(cfg, precision, use_graph):
+    from adt_b200 import synth
     from adt_b200.lambdas import get_lambdas
     from adt_b200.trainer import FusedTrainer
     from oracle import sasrec_oracle as O
-    cfg = synth.CONFIGS["C2"]
     m = _c2_model(cfg).train()
     sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     l1, l2 = get_lambdas(cfg["dataset"])
