@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
   // accumulator ring in tensor memory: MMA(t + NACC - 1) may be issued while tile t is still being read out.  The per-tile chain
   // (commit -> barrier -> tcgen05.ld -> filter -> arrive -> next MMA) costs ~2k cycles against ~130 of MMA at H = 64, so the depth of
   // this ring, not the tensor pipe, sets the tile rate: three buffers when they fit beside the A tile (BN 128: 384 + KB*32 <= 512)
-  constexpr int NACC = (ATM && 3 * BN + KB * 32 <= 512) ? 3 : 2;
-  constexpr int TM_COLS = ATM ? 512 : 2 * BN;                 // accumulators NACC x BN (+ KB*32 columns of A behind them)
+  constexpr int NACC = (3 * BN + (ATM ? KB * 32 : 0) <= 512) ? 3 : 2;
+  constexpr int TM_COLS = (ATM || NACC * BN > 256) ? 512 : (NACC * BN > 128 ? 256 : 128);   // accumulators NACC x BN (+ KB*32 columns of A behind them)
   constexpr uint32_t A_COL = NACC * BN;
   constexpr int B_STAGE = KB * BN * 128;
   uint8_t* sA = smem;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) score_tc_kernel(const __grid_c
     const int u = u0 + row;
     const int KC = MODE == 0 ? a.KC : a.KC / 2;      // two-pass: every (row, column half) owns KC/2 candidate slots = one virtual split
     const int CB = MODE == 0 ? 0 : half * (BN / 2), CE = MODE == 0 ? BN : CB + BN / 2;
-    constexpr int CW = (MODE != 0 && (BN / 2) % 64 == 0) ? 64 : 32;      // columns per tcgen05.ld of the two-pass epilogues
+    constexpr int CW = 32;      // columns per tcgen05.ld (64-column loads were measured 2x SLOWER: 0.38 -> 0.82 ms at 512 x 1M x 256)
     if (ATM && half == 0) {     // this thread's feature row (bf16, KB*32 words) -> TMEM columns A_COL.. of its lane
       const uint4* frow = reinterpret_cast<const uint4*>(a.feats_bf16 + (long long)(u < a.U ? u : 0) * (KB * 64));
 #pragma unroll 1
