@@ -52,14 +52,23 @@ def _f(ref, *shape):
     return torch.empty(*shape, dtype=torch.float32, device=ref.device)
 
 
-def _fs(ref, M, H, prec):
+def _ws_sizes(B, Lq, H, nh):
+    q = L.fill(L.adt_workspace_query(), B=B, L=Lq, H=H, nh=nh, nl=1, K=1, n_splits=1)
+    sz = L.adt_workspace_sizes()
+    L.check(L.lib().adt_workspace_bytes(ctypes.byref(q), ctypes.byref(sz)), "adt_workspace_bytes")
+    return sz
+
+
+def _fs(ref, B, Lq, H, nh, prec):
     """bf16 operand scratch of the tcgen05 forward path (adt_workspace_sizes.fwd_scratch), wide bf16 models only"""
-    return torch.empty(9 * M * H * 2 + 10 * H * H * 2, dtype=torch.uint8, device=ref.device) if (prec and H >= 128) else None
+    n = int(_ws_sizes(B, Lq, H, nh).fwd_scratch) if (prec and H >= 128) else 0
+    return torch.empty(n, dtype=torch.uint8, device=ref.device) if n else None
 
 
-def _wg(ref, M, H, prec):
+def _wg(ref, B, Lq, H, nh, prec):
     """bf16 operand scratch of the tcgen05 backward path / hoisted weight gradients (adt_workspace_sizes.wgrad_scratch), wide bf16 models only"""
-    return torch.empty(12 * M * H * 2 + 10 * H * H * 2, dtype=torch.uint8, device=ref.device) if (prec and H >= 128) else None
+    n = int(_ws_sizes(B, Lq, H, nh).wgrad_scratch) if (prec and H >= 128) else 0
+    return torch.empty(n, dtype=torch.uint8, device=ref.device) if n else None
 
 
 class EmbedFn(torch.autograd.Function):
@@ -125,7 +134,7 @@ class EncBlockFn(torch.autograd.Function):
         x = x.contiguous()
         sv = {k: _f(x, M, H) for k in ("q", "k", "v", "ctx", "y", "h1", "out")}
         sv["lse"], sv["rec"] = _f(x, B, nh, Lq), _f(x, M, nh, nh)
-        fs = _fs(x, M, H, prec)
+        fs = _fs(x, B, Lq, H, nh, prec)
         a = L.fill(L.adt_enc_block_fwd_args(), x=x, ids=ids, ln1_w=p[0], ln1_b=p[1], attn=_mha_w(p[2], p[3], p[4], p[5]), ln2_w=p[6],
                    ln2_b=p[7], ffn=L.fill(L.adt_ffn_w(), w1=p[8], b1=p[9], w2=p[10], b2=p[11]), sparse_w=p[12], sparse_b=p[13],
                    q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"], out=sv["out"], rec=sv["rec"],
@@ -143,7 +152,7 @@ class EncBlockFn(torch.autograd.Function):
         M, H = x.shape
         g = [torch.zeros_like(t) for t in p]
         sc = {k: _f(x, M, H) for k in ("dq", "dk", "dv", "dctx", "dy", "dx")}
-        wg = _wg(x, M, H, prec)
+        wg = _wg(x, B, Lq, H, nh, prec)
         a = L.fill(L.adt_enc_block_bwd_args(), x=x, ids=ids, ln1_w=p[0], ln1_b=p[1], attn=_mha_w(p[2], p[3], p[4], p[5]), ln2_w=p[6],
                    ln2_b=p[7], ffn=L.fill(L.adt_ffn_w(), w1=p[8], b1=p[9], w2=p[10], b2=p[11]), sparse_w=p[12], sparse_b=p[13],
                    q=sv["q"], k=sv["k"], v=sv["v"], ctx=sv["ctx"], lse=sv["lse"], y=sv["y"], h1=sv["h1"],
@@ -170,7 +179,7 @@ class DecBlockFn(torch.autograd.Function):
         x, feats = x.contiguous(), feats.contiguous()
         sv = {k: _f(x, M, H) for k in DecBlockFn.SAVED + ("out",)}
         sv["lse1"], sv["lse2"] = _f(x, B, nh, Lq), _f(x, B, nh, Lq)
-        fs = _fs(x, M, H, prec)
+        fs = _fs(x, B, Lq, H, nh, prec)
         a = L.fill(L.adt_dec_block_fwd_args(), x=x, feats=feats, ids=ids, ln_w=p[0], ln_b=p[1], slf=_mha_w(p[2], p[3], p[4], p[5]),
                    enc=_mha_w(p[6], p[7], p[8], p[9]), ffn=L.fill(L.adt_ffn_w(), w1=p[10], b1=p[11], w2=p[12], b2=p[13]), enc_in=None,
                    out=sv["out"], mse_acc=None, B=B, L=Lq, H=H, nh=nh, training=int(training), mask_mode=0, drop_slf=d_s, drop_enc=d_e,
@@ -187,7 +196,7 @@ class DecBlockFn(torch.autograd.Function):
         M, H = x.shape
         g = [torch.zeros_like(t) for t in p]
         sc = {k: _f(x, M, H) for k in ("dq", "dk", "dv", "dctx", "dd", "dq2", "dk2", "dv2", "dctx2", "dx")}
-        wg = _wg(x, M, H, prec)
+        wg = _wg(x, B, Lq, H, nh, prec)
         dfeats = torch.zeros_like(feats)
         a = L.fill(L.adt_dec_block_bwd_args(), x=x, feats=feats, ids=ids, ln_w=p[0], ln_b=p[1], slf=_mha_w(p[2], p[3], p[4], p[5]),
                    enc=_mha_w(p[6], p[7], p[8], p[9]), ffn=L.fill(L.adt_ffn_w(), w1=p[10], b1=p[11], w2=p[12], b2=p[13]),

@@ -191,8 +191,10 @@ extern "C" int adt_workspace_bytes(const adt_workspace_query* q, adt_workspace_s
   out->scatter_rows = 2 * nb * H * f;                                    // head, tail
   out->scatter_flags = nb * (long long)sizeof(int);
   out->score_part = (long long)(q->n_splits > 0 ? q->n_splits : 1) * q->B * (q->K > 0 ? q->K : 1) * 8;
-  out->wgrad_scratch = H >= 128 ? 12 * M * H * 2 + 10 * H * H * 2 : 0;    // tcgen05 backward: <= 10 bf16 [M,H] operand slots + weights
-  out->fwd_scratch = H >= 128 ? 9 * M * H * 2 + 10 * H * H * 2 : 0;       // decoder block: 7 bf16 operands + fp32 h2 + 10 H^2 bf16 weights
+  // + the attention area of long sequences: packed bf16 [q|k|v] (+ dctx), scores (+ dP) in fp32 and P (+ dS) in bf16, [B*nh][L][Lp]
+  const long long Lp = (q->L + 7) / 8 * 8, zll = M * nh * Lp;
+  out->wgrad_scratch = H >= 128 ? 12 * M * H * 2 + 10 * H * H * 2 + 1024 + 4 * M * H * 2 + zll * 12 : 0;   // tcgen05 backward: <= 10 operand slots + weights
+  out->fwd_scratch = H >= 128 ? 9 * M * H * 2 + 10 * H * H * 2 + 1024 + 3 * M * H * 2 + zll * 6 : 0;       // decoder block: 7 operands + fp32 h2 + weights
   return ADT_OK;
 }
 extern "C" const char* adt_last_error(void) { return g_err; }
@@ -478,6 +480,10 @@ static int seq_dec_bwd(const adt_dec_block_bwd_args* a, cudaStream_t s) {
 }
 
 
+static int blk_attn_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, const int* ids, int B, int L, int H, int nh,
+                        int mask_mode, const adt_dropout& d, int training, int precision, void* area, cudaStream_t s);
+static int blk_attn_bwd(const float* q, const float* k, const float* v, const float* dctx, const float* lse, const int* ids, float* dq, float* dk,
+                        float* dv, int B, int L, int H, int nh, int mask_mode, const adt_dropout& d, int precision, void* area, cudaStream_t s);
 // ---- tcgen05 forward path for wide models (block_tc.cuh); ADT_FWD_TC=0 keeps the row-tile kernels ---------------------------------
 static bool use_fwd_tc(const void* scratch, int M, int H, int nh, int mma) {
   static int v = -1;
@@ -540,7 +546,8 @@ static int tc_enc_fwd(const adt_enc_block_fwd_args* a, cudaStream_t s) {
     // q = (LN1(x) Wq^T + bq) * scale ; [k | v] = x [Wk; Wv]^T + [bk | bv]
     if (int e = tc_linear(t.op(0), Winb, a->attn.in_b, a->q, nullptr, 0, M, H, H, qscale, 0, s)) return e;
     if (int e = tc_linear(t.op(1), Winb + hh, a->attn.in_b + H, a->k, a->v, H, M, 2 * H, H, 1.f, 0, s)) return e;
-    if (int e = launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision, s))
+    if (int e = blk_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_attn, a->training, a->precision,
+                             t.wb + 10 * hh, s))
       return e;
     if (a->phase == 1) return ADT_OK;
   }
@@ -580,7 +587,8 @@ static int tc_dec_fwd(const adt_dec_block_fwd_args* a, cudaStream_t s) {
     { TIMED("row_tc", s); row_ln_cast_kernel<<<row_grid(M), 256, 0, s>>>(r); }
     if (int e = tc_linear(t.op(0), W1b, a->slf.in_b, a->q1, nullptr, 0, M, H, H, qscale, 0, s)) return e;
     if (int e = tc_linear(t.op(0), W1b + hh, a->slf.in_b + H, a->k1, a->v1, H, M, 2 * H, H, 1.f, 0, s)) return e;
-    if (int e = launch_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision, s))
+    if (int e = blk_attn_fwd(a->q1, a->k1, a->v1, a->ctx1, a->lse1, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_slf, a->training, a->precision,
+                             t.wb + 10 * hh, s))
       return e;
     if (a->phase == 1) return ADT_OK;
   }
@@ -596,7 +604,8 @@ static int tc_dec_fwd(const adt_dec_block_fwd_args* a, cudaStream_t s) {
   tc_cast(a->feats, t.op(3), (long long)M * H, s);
   if (int e = tc_linear(t.op(2), W2b, a->enc.in_b, a->q2, nullptr, 0, M, H, H, qscale, 0, s)) return e;
   if (int e = tc_linear(t.op(3), W2b + hh, a->enc.in_b + H, a->k2, a->v2, H, M, 2 * H, H, 1.f, 0, s)) return e;
-  if (int e = launch_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, a->precision, s))
+  if (int e = blk_attn_fwd(a->q2, a->k2, a->v2, a->ctx2, a->lse2, a->ids, a->B, a->L, H, a->nh, a->mask_mode, a->drop_enc, a->training, a->precision,
+                           t.wb + 10 * hh, s))
     return e;
   // c = ctx2 Wo2^T + bo2 ; out = (d + FFN(c) + c) * keep
   tc_cast(a->ctx2, t.op(4), (long long)M * H, s);
@@ -644,6 +653,87 @@ static void tc_pack(const float* s0, float sc0, float* gb0, const float* s1, flo
   TIMED("row_tc", s);
   row_pack_kernel<<<rows_grid2(M), 256, 0, s>>>(p);
 }
+// ---- attention of long sequences as strided-batch tcgen05 GEMMs (block_tc.cuh); ADT_ATTN_TC=0 keeps the generic row-tile attention ------
+static bool use_attn_tc(int B, int L, int H, int nh) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("ADT_ATTN_TC"); v = e ? (atoi(e) != 0) : 1; }
+  return v && L > 64 && L <= 256 && ((H / nh) & 7) == 0 && (long long)B * nh <= 65535;
+}
+static int attn_rows_grid(long long rows) { const long long b = (rows + 7) / 8; return (int)(b < 148 * 16 ? b : 148 * 16); }
+static uint8_t* align256(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255); }
+struct AttnWs {
+  __nv_bfloat16* qkv; __nv_bfloat16* dcb; float* S; float* dP; __nv_bfloat16* Pb; __nv_bfloat16* dSb; long long Lp;
+};
+static AttnWs mk_attn_ws(void* area, int M, int H, int nh, int L, bool bwd) {
+  AttnWs w;
+  w.Lp = (L + 7) / 8 * 8;
+  const long long zll = (long long)M * nh * w.Lp;          // Z * L * Lp
+  uint8_t* p = align256(area);
+  w.qkv = reinterpret_cast<__nv_bfloat16*>(p); p += (long long)M * 3 * H * 2;
+  w.dcb = reinterpret_cast<__nv_bfloat16*>(p); if (bwd) p += (long long)M * H * 2;
+  w.S = reinterpret_cast<float*>(p); p += zll * 4;
+  w.dP = reinterpret_cast<float*>(p); if (bwd) p += zll * 4;
+  w.Pb = reinterpret_cast<__nv_bfloat16*>(p); p += zll * 2;
+  w.dSb = reinterpret_cast<__nv_bfloat16*>(p);
+  return w;
+}
+static int tc_bgemm(const __nv_bfloat16* A, long long lda, long long a_so, long long a_si, int a_mn, const __nv_bfloat16* Bm, long long ldb,
+                    long long b_so, long long b_si, int b_mn, float* C, long long ldc, long long c_so, long long c_si, int M, int N, int K, int nh,
+                    int B, cudaStream_t s, int causal_skip = 0) {
+  adt_gemm_tc_args g;
+  memset(&g, 0, sizeof(g));
+  g.a_bf16 = A; g.lda = lda; g.a_so = a_so; g.a_si = a_si; g.a_mn = a_mn; g.b_bf16 = Bm; g.ldb = ldb; g.b_so = b_so; g.b_si = b_si; g.b_mn = b_mn;
+  g.c = C; g.ldc = ldc; g.c_so = c_so; g.c_si = c_si; g.M = M; g.N = N; g.K = K; g.scale = 1.f; g.batch_inner = nh; g.batch_outer = B; g.causal_skip = causal_skip;
+  TIMED("attn_gemm_tc", s);
+  if (int e = adt_gemm_tc(&g, (adt_stream_t)s)) return fail(e, "%s", "tcgen05 attention (batched adt_gemm_tc)");
+  return ADT_OK;
+}
+static int tc_attn_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, const int* key_ids, int B, int L, int H, int nh,
+                       int mask_mode, const adt_dropout& d, int training, void* area, cudaStream_t s) {
+  const int M = B * L, hd = H / nh;
+  const AttnWs w = mk_attn_ws(area, M, H, nh, L, false);
+  const long long Lp = w.Lp, q_so = (long long)L * 3 * H, s_so = (long long)nh * L * Lp, s_si = (long long)L * Lp;
+  tc_pack(q, 1.f, nullptr, k, nullptr, v, nullptr, w.qkv, 3 * H, M, H, s);
+  if (int e = tc_bgemm(w.qkv, 3 * H, q_so, hd, 0, w.qkv + H, 3 * H, q_so, hd, 0, w.S, Lp, s_so, s_si, L, L, hd, nh, B, s, mask_mode == 0)) return e;   // S = q k^T
+  AttnRowArgs r;
+  memset(&r, 0, sizeof(r));
+  r.S = w.S; r.lse_out = lse; r.Pb = w.Pb; r.key_ids = key_ids; r.Z = B * nh; r.L = L; r.Lp = (int)Lp; r.nh = nh; r.mask_mode = mask_mode; r.bwd = 0;
+  r.drop = mk_drop(row_drop(d, training));
+  { TIMED("attn_row_tc", s); attn_row_kernel<<<attn_rows_grid(B * nh * L), 256, 0, s>>>(r); }
+  // ctx = P v  (v read MN-major from the packed copy)
+  if (int e = tc_bgemm(w.Pb, Lp, s_so, s_si, 0, w.qkv + 2 * H, 3 * H, q_so, hd, 1, ctx, H, (long long)L * H, hd, L, hd, L, nh, B, s)) return e;
+  return check_launch("tcgen05 attention fwd");
+}
+static int tc_attn_bwd(const float* q, const float* k, const float* v, const float* dctx, const float* lse, const int* key_ids, float* dq, float* dk,
+                       float* dv, int B, int L, int H, int nh, int mask_mode, const adt_dropout& d, void* area, cudaStream_t s) {
+  const int M = B * L, hd = H / nh;
+  const AttnWs w = mk_attn_ws(area, M, H, nh, L, true);
+  const long long Lp = w.Lp, q_so = (long long)L * 3 * H, s_so = (long long)nh * L * Lp, s_si = (long long)L * Lp, c_so = (long long)L * H;
+  tc_pack(q, 1.f, nullptr, k, nullptr, v, nullptr, w.qkv, 3 * H, M, H, s);
+  tc_cast(dctx, w.dcb, (long long)M * H, s);
+  if (int e = tc_bgemm(w.qkv, 3 * H, q_so, hd, 0, w.qkv + H, 3 * H, q_so, hd, 0, w.S, Lp, s_so, s_si, L, L, hd, nh, B, s, mask_mode == 0)) return e;        // S = q k^T
+  if (int e = tc_bgemm(w.dcb, H, c_so, hd, 0, w.qkv + 2 * H, 3 * H, q_so, hd, 0, w.dP, Lp, s_so, s_si, L, L, hd, nh, B, s, mask_mode == 0)) return e;       // dP = dctx v^T
+  AttnRowArgs r;
+  memset(&r, 0, sizeof(r));
+  r.S = w.S; r.dP = w.dP; r.lse_in = lse; r.Pb = w.Pb; r.dSb = w.dSb; r.key_ids = key_ids; r.Z = B * nh; r.L = L; r.Lp = (int)Lp; r.nh = nh;
+  r.mask_mode = mask_mode; r.bwd = 1; r.drop = mk_drop(d);
+  { TIMED("attn_row_tc", s); attn_row_kernel<<<attn_rows_grid(B * nh * L), 256, 0, s>>>(r); }
+  if (int e = tc_bgemm(w.dSb, Lp, s_so, s_si, 0, w.qkv + H, 3 * H, q_so, hd, 1, dq, H, c_so, hd, L, hd, L, nh, B, s)) return e;             // dq = dS k
+  if (int e = tc_bgemm(w.dSb, Lp, s_so, s_si, 1, w.qkv, 3 * H, q_so, hd, 1, dk, H, c_so, hd, L, hd, L, nh, B, s)) return e;                 // dk = dS^T q
+  if (int e = tc_bgemm(w.Pb, Lp, s_so, s_si, 1, w.dcb, H, c_so, hd, 1, dv, H, c_so, hd, L, hd, L, nh, B, s)) return e;                      // dv = (P m)^T dctx
+  return check_launch("tcgen05 attention bwd");
+}
+// attention of the tcgen05 block path: long sequences through the batched GEMMs, short ones through the row-tile / small kernels
+static int blk_attn_fwd(const float* q, const float* k, const float* v, float* ctx, float* lse, const int* ids, int B, int L, int H, int nh,
+                        int mask_mode, const adt_dropout& d, int training, int precision, void* area, cudaStream_t s) {
+  if (area && use_attn_tc(B, L, H, nh)) return tc_attn_fwd(q, k, v, ctx, lse, ids, B, L, H, nh, mask_mode, d, training, area, s);
+  return launch_attn_fwd(q, k, v, ctx, lse, ids, B, L, H, nh, mask_mode, d, training, precision, s);
+}
+static int blk_attn_bwd(const float* q, const float* k, const float* v, const float* dctx, const float* lse, const int* ids, float* dq, float* dk,
+                        float* dv, int B, int L, int H, int nh, int mask_mode, const adt_dropout& d, int precision, void* area, cudaStream_t s) {
+  if (area && use_attn_tc(B, L, H, nh)) return tc_attn_bwd(q, k, v, dctx, lse, ids, dq, dk, dv, B, L, H, nh, mask_mode, d, area, s);
+  return launch_attn_bwd(q, k, v, dctx, lse, ids, dq, dk, dv, B, L, H, nh, mask_mode, d, precision, s);
+}
 // FFN adjoint shared by both blocks.  In: dO etc. through `pp`.  Out: slots 6-7 hold dz (enc) / dc (dec) = dO + dh1 C1.
 static int tc_ffn_bwd(const TcBwdScratch& t, RowPostPrepArgs pp, const adt_ffn_w& ffn, const adt_ffn_g& gf, const __nv_bfloat16* C1b,
                       const __nv_bfloat16* C2b, const __nv_bfloat16* zb, int M, int H, cudaStream_t s) {
@@ -690,8 +780,8 @@ static int tc_enc_bwd(const adt_enc_block_bwd_args* a, cudaStream_t s) {
                                                         a->g_sparse_b, M, H, a->nh);
   }
   if (int e = check_launch("tcgen05 backward path (enc post)")) return e;
-  if (int e = launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
-                              a->drop_attn, a->precision, s))
+  if (int e = blk_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
+                           a->drop_attn, a->precision, t.wb + 10 * hh, s))
     return e;
   // in-projection: [dq*s | dk | dv] packed ; q rows read LN1(x), k / v rows read x
   tc_pack(a->dq, qscale, a->g_attn.in_b, a->dk, a->g_attn.in_b + H, a->dv, a->g_attn.in_b + 2 * H, t.op(0), 3 * H, M, H, s);
@@ -733,8 +823,8 @@ static int tc_dec_bwd(const adt_dec_block_bwd_args* a, cudaStream_t s) {
     if (int e = hoisted_wgrad(t.op(4), H, H, t.op(5), H, H, M, a->g_enc.out_w, s)) return e;
     if (int e = tc_dgrad(t.op(4), H, H, Wo2b, H, a->dctx2, 0, M, s)) return e;
     if (int e = check_launch("tcgen05 backward path (dec post)")) return e;
-    if (int e = launch_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,
-                                a->drop_enc, a->precision, s))
+    if (int e = blk_attn_bwd(a->q2, a->k2, a->v2, a->dctx2, a->lse2, a->ids, a->dq2, a->dk2, a->dv2, a->B, a->L, H, a->nh, a->mask_mode,
+                             a->drop_enc, a->precision, t.wb + 10 * hh, s))
       return e;
     // cross-attention in-projection (q rows from a, k / v rows from the encoder features), then the self-attention out-projection
     tc_pack(a->dq2, qscale, a->g_enc.in_b, a->dk2, a->g_enc.in_b + H, a->dv2, a->g_enc.in_b + 2 * H, t.op(0), 3 * H, M, H, s);
@@ -752,8 +842,8 @@ static int tc_dec_bwd(const adt_dec_block_bwd_args* a, cudaStream_t s) {
     if (a->phase == 2) return ADT_OK;
   }
   const __nv_bfloat16* W1b = tc_weight(a->slf.in_w, 3 * hh, a->wm, t.wb, s);
-  if (int e = launch_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
-                              a->drop_slf, a->precision, s))
+  if (int e = blk_attn_bwd(a->q1, a->k1, a->v1, a->dctx, a->lse1, a->ids, a->dq, a->dk, a->dv, a->B, a->L, H, a->nh, a->mask_mode,
+                           a->drop_slf, a->precision, t.wb + 10 * hh, s))
     return e;
   // q, k and v all read d = LN(x): one [3H x H] weight gradient, one K = 3H dgrad on top of dd
   tc_pack(a->dq, qscale, a->g_slf.in_b, a->dk, a->g_slf.in_b + H, a->dv, a->g_slf.in_b + 2 * H, t.op(0), 3 * H, M, H, s);

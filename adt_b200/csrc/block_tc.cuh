@@ -469,3 +469,97 @@ __global__ void __launch_bounds__(256) sparse_head_bwd_kernel(const float* __res
 }
 
 }  // namespace adt
+
+// =====================================================================================================================
+// Attention for long sequences (64 < L <= 256) as strided-batch tcgen05 GEMMs over (sequence, head) + one warp-per-row
+// softmax kernel.  S = q k^T and P, dS live in HBM as [B*nh][L][Lp] matrices (82 MB fp32 at C1: HBM-cheap next to the
+// generic kernel's 14 TFLOP/s) -- same masks, same Philox dropout stream, same lse as attn_fwd_kernel / attn_bwd_kernel.
+// =====================================================================================================================
+namespace adt {
+
+struct AttnRowArgs {
+  const float* S;              // [Z][L][Lp] scores (q pre-scaled)
+  const float* dP;             // bwd: dctx v^T, same layout
+  const float* lse_in;         // bwd: saved row log-sum-exp [Z][L]
+  float* lse_out;              // fwd (nullable)
+  __nv_bfloat16* Pb;           // fwd: dropout(softmax) ; bwd: softmax * mask  (operand of ctx / dv)
+  __nv_bfloat16* dSb;          // bwd: p * (dp - delta)                          (operand of dq / dk)
+  const int* key_ids;          // mask_mode 1
+  int Z, L, Lp, nh, mask_mode, bwd;
+  DropDesc drop;
+};
+
+// one warp per (z, i) row; lane owns keys 8*lane .. 8*lane+7 (L <= 256)
+__global__ void __launch_bounds__(256) attn_row_kernel(AttnRowArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long nrows = (long long)a.Z * a.L;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < nrows; row += (long long)gridDim.x * 8) {
+    const int z = (int)(row / a.L), i = (int)(row - (long long)z * a.L), b = z / a.nh;
+    const int nj = a.mask_mode == 0 ? i + 1 : a.L;
+    const int j0 = 8 * lane;
+    const float* srow = a.S + row * a.Lp;
+    float sv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sv[c] = -INFINITY;
+    if (j0 < nj) {
+      const float4 s0 = *reinterpret_cast<const float4*>(srow + j0), s1 = *reinterpret_cast<const float4*>(srow + j0 + 4);
+      sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (j0 + c >= nj) sv[c] = -INFINITY;
+      else if (a.mask_mode == 1 && a.key_ids[b * a.L + j0 + c] == 0) sv[c] = -1e9f;
+    }
+    float mv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mv[c] = 1.f;
+    if (a.drop.enabled && j0 < nj) drop_mul8_attn(a.drop, a.drop.base + (unsigned long long)row, ((a.L + 7) & ~7) >> 3, lane, mv);
+    float out0[8], out1[8];
+    if (!a.bwd) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) mx = fmaxf(mx, sv[c]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { sv[c] = sv[c] == -INFINITY ? 0.f : expf(sv[c] - mx); sum += sv[c]; }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      if (a.lse_out && lane == 0) a.lse_out[row] = mx + logf(sum);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out0[c] = sv[c] * mv[c] * inv;
+    } else {
+      const float ls = a.lse_in[row];
+      float dv8[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dv8[c] = 0.f;
+      if (j0 < nj) {
+        const float4 d0 = *reinterpret_cast<const float4*>(a.dP + row * a.Lp + j0), d1 = *reinterpret_cast<const float4*>(a.dP + row * a.Lp + j0 + 4);
+        dv8[0] = d0.x; dv8[1] = d0.y; dv8[2] = d0.z; dv8[3] = d0.w; dv8[4] = d1.x; dv8[5] = d1.y; dv8[6] = d1.z; dv8[7] = d1.w;
+      }
+      float delta = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float pj = sv[c] == -INFINITY ? 0.f : expf(sv[c] - ls);
+        const float dp = sv[c] == -INFINITY ? 0.f : dv8[c] * mv[c];
+        delta = fmaf(dp, pj, delta);
+        sv[c] = pj; dv8[c] = dp;
+      }
+      delta = warp_sum(delta);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { out0[c] = sv[c] * mv[c]; out1[c] = sv[c] * (dv8[c] - delta); }
+    }
+    // every column up to Lp is written (zeros beyond the visible keys): the following GEMMs reduce over all L columns
+    if (j0 < a.Lp) {
+      uint4 o;
+      o.x = pack_bf16(out0[0], out0[1]); o.y = pack_bf16(out0[2], out0[3]); o.z = pack_bf16(out0[4], out0[5]); o.w = pack_bf16(out0[6], out0[7]);
+      *reinterpret_cast<uint4*>(a.Pb + row * a.Lp + j0) = o;
+      if (a.bwd) {
+        o.x = pack_bf16(out1[0], out1[1]); o.y = pack_bf16(out1[2], out1[3]); o.z = pack_bf16(out1[4], out1[5]); o.w = pack_bf16(out1[6], out1[7]);
+        *reinterpret_cast<uint4*>(a.dSb + row * a.Lp + j0) = o;
+      }
+    }
+  }
+}
+
+}  // namespace adt

@@ -31,6 +31,9 @@ struct GemmTcArgs {
   int M, N, K, act, accumulate; float scale;
   int a_mn, b_mn, kb_per_split;
   float* C2; int n_split;     // columns >= n_split (a multiple of 32) are written to C2 at column (col - n_split)
+  int causal_skip;            // output tiles entirely above the diagonal (n0 > m0 + 127) are never read by the caller: skip them
+  int batch_inner, nbatch;    // strided batch: blockIdx.z = zo * batch_inner + zi selects the matrices (nbatch <= 1: blockIdx.z = K split)
+  long long c_so, c_si;       // element offsets of C per outer / inner batch index
 };
 
 __device__ __forceinline__ float g_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
@@ -85,9 +88,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM;
+  if (a.causal_skip && n0 > m0 + GM - 1) return;      // whole CTA, before any barrier / TMEM allocation
   const int nkb_all = (a.K + 63) / 64;
-  const int kb0 = blockIdx.z * a.kb_per_split;
-  const int nkb = min(a.kb_per_split, nkb_all - kb0);      // K slabs of this split (>= 1 by construction of the grid)
+  const bool batched = a.nbatch > 1;
+  const int zi = batched ? (int)blockIdx.z % a.batch_inner : 0, zo = batched ? (int)blockIdx.z / a.batch_inner : 0;
+  const int kb0 = batched ? 0 : blockIdx.z * a.kb_per_split;
+  const int nkb = batched ? nkb_all : min(a.kb_per_split, nkb_all - kb0);      // K slabs of this CTA (>= 1 by construction of the grid)
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmA);
@@ -111,15 +117,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
         const int kc = (kb0 + kb) * 64;
         if (a.a_mn) {
 #pragma unroll
-          for (int i = 0; i < GM / 64; ++i) tc::tma_load_2d(sA + st * A_STAGE + i * 8192, &tmA, m0 + 64 * i, kc, full + st);
+          for (int i = 0; i < GM / 64; ++i) tc::tma_load_4d(sA + st * A_STAGE + i * 8192, &tmA, m0 + 64 * i, kc, zi, zo, full + st);
         } else {
-          tc::tma_load_2d(sA + st * A_STAGE, &tmA, kc, m0, full + st);
+          tc::tma_load_4d(sA + st * A_STAGE, &tmA, kc, m0, zi, zo, full + st);
         }
         if (a.b_mn) {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tc::tma_load_2d(sB + st * B_STAGE + i * 8192, &tmB, n0 + 64 * i, kc, full + st);
+          for (int i = 0; i < BN / 64; ++i) tc::tma_load_4d(sB + st * B_STAGE + i * 8192, &tmB, n0 + 64 * i, kc, zi, zo, full + st);
         } else {
-          tc::tma_load_2d(sB + st * B_STAGE, &tmB, kc, n0, full + st);
+          tc::tma_load_4d(sB + st * B_STAGE, &tmB, kc, n0, zi, zo, full + st);
         }
       }
     }
@@ -153,16 +159,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
       tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + c0, v);
       const int nb = n0 + c0;
       if (row >= a.M || nb >= a.N) continue;
-      float* crow = (a.C2 && nb >= a.n_split ? a.C2 - a.n_split : a.C) + (long long)row * a.ldc + nb;
+      float* crow = (a.C2 && nb >= a.n_split ? a.C2 - a.n_split : a.C) + zo * a.c_so + zi * a.c_si + (long long)row * a.ldc + nb;
       float* prow = a.pre ? a.pre + (long long)row * a.ldc + nb : nullptr;
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         float x = v[c];
-        if (a.bias && blockIdx.z == 0 && nb + c < a.N) x += __ldg(a.bias + nb + c);
+        if (a.bias && (batched || blockIdx.z == 0) && nb + c < a.N) x += __ldg(a.bias + nb + c);
         v[c] = x * a.scale;
       }
-      if (a.act == 0) epi_chunk<false>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1);
-      else epi_chunk<true>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1);
+      if (a.act == 0) epi_chunk<false>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1 && !batched);
+      else epi_chunk<true>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1 && !batched);
     }
   }
   tc::tc_fence_before();
@@ -230,15 +236,21 @@ EncodeTiledFn g_encode() {
   return fn;
 }
 // bf16 row-major [rows][cols] with row stride ld elements; box = [box_rows][64 cols], 128-byte swizzle, zero fill out of bounds
-int g_make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+int g_make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows, long long n_inner = 1,
+               long long s_inner = 0, long long n_outer = 1, long long s_outer = 0) {
   // (an MN-major operand passes rows = K, cols = M or N and box_rows = 64: 64 x 64 boxes)
+  // always 4-D {cols, rows, inner batch, outer batch}; a plain matrix is a batch of one (the batch strides are then never used, but
+  // must still be multiples of 16 bytes)
   EncodeTiledFn enc = g_encode();
   if (!enc) return ADT_E_CUDA;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (n_inner <= 1 && n_outer <= 1) { s_inner = ld * rows; s_outer = ld * rows; }
+  if (s_inner == 0) s_inner = ld * rows;
+  if (s_outer == 0) s_outer = s_inner * n_inner;
+  cuuint64_t gdim[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(n_inner > 0 ? n_inner : 1), (cuuint64_t)(n_outer > 0 ? n_outer : 1)};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s_inner * 2, (cuuint64_t)s_outer * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? ADT_OK : ADT_E_CUDA;
 }
@@ -261,27 +273,34 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->lda & 7) || (a->ldb & 7) || a->lda < a_in || a->ldb < b_in || (!a->c2 && a->ldc < a->N)) return ADT_E_SHAPE;
   if ((reinterpret_cast<uintptr_t>(a->a_bf16) | reinterpret_cast<uintptr_t>(a->b_bf16)) & 15) return ADT_E_ALIGN;
   if (a->split_k > 1 && (a->act || a->pre)) return ADT_E_SHAPE;      // partial sums are only linear before the activation
+  const long long bi = a->batch_inner > 0 ? a->batch_inner : 1, bo = a->batch_outer > 0 ? a->batch_outer : 1;
+  const bool batched = bi * bo > 1;
+  if (batched && (a->split_k > 1 || a->pre || a->c2 || bi * bo > 65535 || ((a->a_si | a->a_so | a->b_si | a->b_so) & 7) || ((a->c_si | a->c_so) & 3)))
+    return ADT_E_SHAPE;
   CUtensorMap tmA, tmB;
   GemmTcArgs k;
   k.C = a->c; k.pre = a->pre; k.bias = a->bias; k.ldc = a->ldc; k.M = a->M; k.N = a->N; k.K = a->K; k.act = a->act; k.accumulate = a->accumulate;
   k.scale = a->scale == 0.f ? 1.f : a->scale;
   k.a_mn = a->a_mn ? 1 : 0; k.b_mn = a->b_mn ? 1 : 0;
   k.C2 = a->c2; k.n_split = a->n_split;
+  k.batch_inner = (int)bi; k.nbatch = (int)(bi * bo); k.c_so = a->c_so; k.c_si = a->c_si;
+  k.causal_skip = a->causal_skip ? 1 : 0;
   if (k.C2 && (k.n_split <= 0 || (k.n_split & 31) || a->ldc < k.n_split || a->ldc < a->N - k.n_split)) return ADT_E_SHAPE;
   const int nkb = (a->K + 63) / 64;
   int splits = a->split_k > 1 ? (a->split_k < nkb ? a->split_k : nkb) : 1;
   k.kb_per_split = (nkb + splits - 1) / splits;
   splits = (nkb + k.kb_per_split - 1) / k.kb_per_split;
+  if (batched) splits = (int)(bi * bo);          // grid.z walks the batch instead of K splits
   if (splits > 1 && !a->accumulate) {
     if (cudaMemset2DAsync(a->c, (size_t)a->ldc * 4, 0, (size_t)a->N * 4, (size_t)a->M, s) != cudaSuccess) return ADT_E_CUDA;
   }
-  if (k.a_mn) { if (int e = g_make_map(&tmA, a->a_bf16, a->K, a->M, a->lda, 64)) return e; }
-  else if (int e = g_make_map(&tmA, a->a_bf16, a->M, a->K, a->lda, GM)) return e;
+  if (k.a_mn) { if (int e = g_make_map(&tmA, a->a_bf16, a->K, a->M, a->lda, 64, bi, a->a_si, bo, a->a_so)) return e; }
+  else if (int e = g_make_map(&tmA, a->a_bf16, a->M, a->K, a->lda, GM, bi, a->a_si, bo, a->a_so)) return e;
   // narrow outputs waste less of the tile with 64 columns; wide ones amortise the A slab over 128
   // (256-column tiles were measured SLOWER at the C1 shapes: fewer, longer CTAs, two per SM instead of three)
   const int bn = a->N <= 64 ? 64 : 128;
-  if (k.b_mn) { if (int e = g_make_map(&tmB, a->b_bf16, a->K, a->N, a->ldb, 64)) return e; }
-  else if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, bn)) return e;
+  if (k.b_mn) { if (int e = g_make_map(&tmB, a->b_bf16, a->K, a->N, a->ldb, 64, bi, a->b_si, bo, a->b_so)) return e; }
+  else if (int e = g_make_map(&tmB, a->b_bf16, a->N, a->K, a->ldb, bn, bi, a->b_si, bo, a->b_so)) return e;
   // short K ranges (the H x H layers of a block: 4 slabs) leave the ring idle: a shallow ring lets 2-3 CTAs share an SM, so one CTA's
   // epilogue and prologue overlap another's main loop
   const int slabs = k.kb_per_split;

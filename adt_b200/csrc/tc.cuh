@@ -52,6 +52,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
                : "memory");
 }
 
+// 4-D tile load (columns, rows, inner batch, outer batch): one [rows x 64] box of one matrix of a strided batch
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 // 2-D tile load delivered to the same shared-memory offset of EVERY CTA of the cluster named in cta_mask; each destination CTA's
 // mbarrier (same offset) receives the complete_tx of the bytes written into it
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {

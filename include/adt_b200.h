@@ -327,6 +327,10 @@ typedef struct {
   int32_t split_k;                             /* > 1: that many CTAs share an output tile and add partial sums atomically (act 0, pre NULL) */
   float* c2; int32_t n_split;                  /* optional second output: columns >= n_split (multiple of 32) go to c2[:, col - n_split] (row stride ldc):
                                                   one product fills the separate k and v buffers of a packed in-projection */
+  int32_t batch_inner, batch_outer;            /* > 1: a strided batch of batch_outer x batch_inner independent products in ONE launch (attention: heads x
+                                                  sequences); matrix (zo, zi) of an operand starts at base + zo * x_so + zi * x_si elements */
+  int64_t a_so, a_si, b_so, b_si, c_so, c_si;  /* batch strides in elements (a / b: multiples of 8, c: multiples of 4); split_k, pre, c2 unavailable */
+  int32_t causal_skip;                         /* != 0: output tiles entirely above the diagonal are left untouched (causal attention scores) */
 } adt_gemm_tc_args;
 int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t stream);
 /* operand copies for adt_gemm_tc: fp32 [R][C] (row stride ld) -> bf16 [R][ldy], or -> its bf16 transpose [C][ldt] */

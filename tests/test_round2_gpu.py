@@ -35,13 +35,16 @@ def test_benched_c2_configuration_against_live_oracle(precision, use_graph):
     _against_live_oracle(synth.CONFIGS["C2"], precision, use_graph)
 
 
-@pytest.mark.parametrize("H,nh,use_graph", [(128, 2, False), (256, 2, True), (192, 3, False)])
-def test_wide_model_tcgen05_block_path_against_live_oracle(H, nh, use_graph):
+@pytest.mark.parametrize("H,nh,use_graph,Lq", [(128, 2, False, 40), (256, 2, True, 40), (192, 3, False, 40), (128, 2, False, 100), (256, 2, True, 200)])
+def test_wide_model_tcgen05_block_path_against_live_oracle(H, nh, use_graph, Lq):
     """wide models (H >= 128) in the bf16 mode take the tcgen05 block path (block_tc.cuh: every linear layer one adt_gemm_tc launch,
-    warp-per-row kernels in between, forward AND backward): the same check as the benched configuration -- loss, gradient norm,
-    bit-exact embedding gather, per-parameter gradient cosine -- against the oracle evaluated live on the host."""
+    warp-per-row kernels in between, forward AND backward; sequences longer than 64 also run attention as strided-batch tcgen05 GEMMs
+    + a softmax row kernel): the same check as the benched configuration -- loss, gradient norm, bit-exact embedding gather,
+    per-parameter gradient cosine -- against the oracle evaluated live on the host."""
     from adt_b200 import synth
-    cfg = dict(synth.CONFIGS["C2"], H=H, nh=nh, L=40, B=32, items=3000)
+    cfg = dict(synth.CONFIGS["C2"], H=H, nh=nh, L=Lq, B=32, items=3000)
+    if Lq > 64:
+        cfg.update(geo=1.0 / 60, lo=8, add=6)      # longer histories, so that the long rows are not mostly padding
     _against_live_oracle(cfg, "bf16", use_graph)
 
 
@@ -384,6 +387,19 @@ def test_tcgen05_backward_path_matches_row_tile_kernels(nh, Lq, Hd):
     assert abs(a["psum"] - b["psum"]) / a["psum"] < 1e-4
 
 
+@pytest.mark.parametrize("nh,Lq,Hd", [(2, 100, 128), (2, 200, 256), (3, 70, 192)])
+def test_tcgen05_batched_attention_matches_row_tile_attention(nh, Lq, Hd):
+    """sequences longer than 64 on the tcgen05 block path: attention as strided-batch GEMMs over (sequence, head) with the scores in HBM
+    (ADT_ATTN_TC=1, the default) against the generic row-tile attention kernels (=0): same masks, same Philox dropout stream."""
+    a, b = _ab_wide("ADT_ATTN_TC", nh, Lq, Hd)
+    for k in range(3):
+        assert abs(a["loss"][k] - b["loss"][k]) / abs(a["loss"][k]) < 2e-4, (k, a["loss"], b["loss"])
+        assert abs(a["gnorm"][k] - b["gnorm"][k]) / a["gnorm"][k] < 5e-3, (k, a["gnorm"], b["gnorm"])
+    for n, v in a["gnorms"].items():
+        assert abs(v - b["gnorms"][n]) <= 5e-3 * max(v, 1e-6) + 1e-8, (n, v, b["gnorms"][n])
+    assert abs(a["psum"] - b["psum"]) / a["psum"] < 1e-4
+
+
 @pytest.mark.parametrize("M,N,K,act", [(256, 256, 256, 0), (1000, 768, 256, 2), (333, 200, 1024, 1), (2048, 26844, 256, 0), (130, 64, 72, 3)])
 def test_tcgen05_linear_matches_fp32_linear(M, N, K, act):
     """adt_gemm_tc (TMA + tcgen05.mma, bf16 operands, fp32 accumulate) behind ops.linear(precision=1): forward, input gradient,
@@ -417,3 +433,45 @@ def test_tcgen05_linear_matches_fp32_linear(M, N, K, act):
     for got, ref, name in ((gx, gx_ref, "dx"), (gW, gW_ref, "dW"), (gb, gb_ref, "db")):
         err = float((got - ref).abs().max() / (ref.abs().max() + 1e-12))
         assert err < 5e-3, (name, err)
+
+
+@pytest.mark.parametrize("B,nh,Lq,hd", [(3, 2, 200, 128), (2, 4, 70, 64), (2, 3, 129, 32)])
+def test_tcgen05_batched_gemm_over_heads_and_sequences(B, nh, Lq, hd):
+    """adt_gemm_tc as a strided batch (4-D TMA maps: columns, rows, head, sequence): the two products of attention on head slices of
+    [B, L, H] tensors -- S = Q K^T (both K-major) and ctx = P V (V read MN-major), plus dK = dS^T Q (both MN-major) -- against torch
+    on the same bf16-rounded operands."""
+    import ctypes
+    from adt_b200 import _lib as L
+    lib = L.lib()
+    H = nh * hd
+    g = torch.Generator().manual_seed(B * 1000 + Lq)
+    r = lambda *s: (torch.randn(*s, generator=g) * 0.3).cuda()
+    q, k, v = r(B, Lq, H), r(B, Lq, H), r(B, Lq, H)
+    qb, kb, vb = q.bfloat16().contiguous(), k.bfloat16().contiguous(), v.bfloat16().contiguous()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Lp = (Lq + 7) // 8 * 8
+    S = torch.zeros(B, nh, Lq, Lp, device="cuda")
+    a = L.fill(L.adt_gemm_tc_args(), a_bf16=qb, b_bf16=kb, lda=H, ldb=H, c=S, ldc=Lp, M=Lq, N=Lq, K=hd, scale=1.0, batch_inner=nh, batch_outer=B,
+               a_so=Lq * H, a_si=hd, b_so=Lq * H, b_si=hd, c_so=nh * Lq * Lp, c_si=Lq * Lp)
+    L.check(lib.adt_gemm_tc(ctypes.byref(a), st), "adt_gemm_tc")
+    qh = qb.float().view(B, Lq, nh, hd).permute(0, 2, 1, 3)
+    kh = kb.float().view(B, Lq, nh, hd).permute(0, 2, 1, 3)
+    vh = vb.float().view(B, Lq, nh, hd).permute(0, 2, 1, 3)
+    S_ref = qh @ kh.transpose(-1, -2)
+    assert torch.allclose(S[..., :Lq], S_ref, rtol=1e-3, atol=1e-3), float((S[..., :Lq] - S_ref).abs().max())
+    # ctx = P V with P [B, nh, L, Lp] bf16 (zero beyond L) and V read MN-major from its [B, L, H] home
+    P = torch.zeros(B, nh, Lq, Lp, device="cuda", dtype=torch.bfloat16)
+    P[..., :Lq] = torch.softmax(S_ref, -1).bfloat16()
+    ctx = torch.zeros(B, Lq, H, device="cuda")
+    a = L.fill(L.adt_gemm_tc_args(), a_bf16=P, b_bf16=vb, lda=Lp, ldb=H, c=ctx, ldc=H, M=Lq, N=hd, K=Lq, scale=1.0, b_mn=1, batch_inner=nh,
+               batch_outer=B, a_so=nh * Lq * Lp, a_si=Lq * Lp, b_so=Lq * H, b_si=hd, c_so=Lq * H, c_si=hd)
+    L.check(lib.adt_gemm_tc(ctypes.byref(a), st), "adt_gemm_tc")
+    ctx_ref = (P[..., :Lq].float() @ vh).permute(0, 2, 1, 3).reshape(B, Lq, H)
+    assert torch.allclose(ctx, ctx_ref, rtol=2e-3, atol=2e-3), float((ctx - ctx_ref).abs().max())
+    # dK = dS^T Q: both operands MN-major (dS as [K = query][M = key], Q as [K = query][N = d])
+    dk = torch.zeros(B, Lq, H, device="cuda")
+    a = L.fill(L.adt_gemm_tc_args(), a_bf16=P, b_bf16=qb, lda=Lp, ldb=H, c=dk, ldc=H, M=Lq, N=hd, K=Lq, scale=1.0, a_mn=1, b_mn=1, batch_inner=nh,
+               batch_outer=B, a_so=nh * Lq * Lp, a_si=Lq * Lp, b_so=Lq * H, b_si=hd, c_so=Lq * H, c_si=hd)
+    L.check(lib.adt_gemm_tc(ctypes.byref(a), st), "adt_gemm_tc")
+    dk_ref = (P[..., :Lq].float().transpose(-1, -2) @ qh).permute(0, 2, 1, 3).reshape(B, Lq, H)
+    assert torch.allclose(dk, dk_ref, rtol=2e-3, atol=2e-3), float((dk - dk_ref).abs().max())
