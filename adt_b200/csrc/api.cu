@@ -1321,15 +1321,20 @@ extern "C" int adt_small_table_grad(const int32_t* ids, const float* dx, float* 
   return check_launch("small_table_grad");
 }
 
+extern "C" int64_t adt_attention_scratch_bytes(int32_t B, int32_t L, int32_t H, int32_t nh, int32_t backward) {
+  if (B <= 0 || L <= 0 || H <= 0 || nh <= 0 || !use_attn_tc(B, L, H, nh)) return 0;
+  const long long M = (long long)B * L, Lp = (L + 7) / 8 * 8, zll = M * nh * Lp;
+  return 1024 + (backward ? 4 : 3) * M * H * 2 + zll * (backward ? 12 : 6);
+}
 extern "C" int adt_attention_fwd(const adt_attention_args* a, adt_stream_t s_) {
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
-  return launch_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->key_ids, a->B, a->L, a->H, a->nh, a->mask_mode, a->drop, a->training,
-                         a->precision ? 1 : 0, (cudaStream_t)s_);
+  return blk_attn_fwd(a->q, a->k, a->v, a->ctx, a->lse, a->key_ids, a->B, a->L, a->H, a->nh, a->mask_mode, a->drop, a->training,
+                      a->precision ? 1 : 0, a->precision ? a->tc_scratch : nullptr, (cudaStream_t)s_);
 }
 extern "C" int adt_attention_bwd(const adt_attention_args* a, adt_stream_t s_) {
   if (int e = check_dims(a->B, a->L, a->H, a->nh)) return e;
-  return launch_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->key_ids, a->dq, a->dk, a->dv, a->B, a->L, a->H, a->nh, a->mask_mode, a->drop,
-                         a->precision ? 1 : 0, (cudaStream_t)s_);
+  return blk_attn_bwd(a->q, a->k, a->v, a->dctx, a->lse, a->key_ids, a->dq, a->dk, a->dv, a->B, a->L, a->H, a->nh, a->mask_mode, a->drop,
+                      a->precision ? 1 : 0, a->precision ? a->tc_scratch : nullptr, (cudaStream_t)s_);
 }
 
 extern "C" int adt_softmax_ce_fwd(const float* logits, const int32_t* labels, float* lse, double* loss_acc, int32_t R, int32_t V,

@@ -59,6 +59,16 @@ def _use_tc(precision, M, N, K):
     return bool(precision) and M >= 128 and M * N * K >= TC_MIN_WORK and torch.cuda.get_device_capability()[0] >= 10
 
 
+def _attn_scratch(ref, B, Lq, H, nh, precision, backward):
+    """scratch of the tcgen05 attention path (bf16 mode, 65..256 positions): packed bf16 operands, scores and probabilities in HBM"""
+    if not precision or torch.cuda.get_device_capability()[0] < 10:
+        return None
+    f = L.lib().adt_attention_scratch_bytes
+    f.restype = ctypes.c_int64
+    n = int(f(ctypes.c_int32(B), ctypes.c_int32(Lq), ctypes.c_int32(H), ctypes.c_int32(nh), ctypes.c_int32(backward)))
+    return torch.empty(n, dtype=torch.uint8, device=ref.device) if n else None
+
+
 class LinearFn(torch.autograd.Function):
     """y = act((x W^T + b) * scale), x [M,K], W [N,K]  (act: 0 none, 1 relu, 2 gelu)."""
 
@@ -170,8 +180,9 @@ class AttnFn(torch.autograd.Function):
         H = q.shape[1]
         out = torch.empty_like(q)
         lse = torch.empty(B, nh, Lq, dtype=torch.float32, device=q.device)
+        ws = _attn_scratch(q, B, Lq, H, nh, precision, 0)
         a = L.fill(L.adt_attention_args(), q=q, k=k, v=v, ctx=out, lse=lse, key_ids=key_ids, dctx=None, dq=None, dk=None, dv=None, B=B,
-                   L=Lq, H=H, nh=nh, mask_mode=mask_mode, training=int(training), drop=drop, precision=precision)
+                   L=Lq, H=H, nh=nh, mask_mode=mask_mode, training=int(training), drop=drop, precision=precision, tc_scratch=ws)
         L.check(L.lib().adt_attention_fwd(ctypes.byref(a), _st(q.device)), "adt_attention_fwd")
         ctx.save_for_backward(q, k, v, lse)
         ctx.cfg = (key_ids, dims, drop, training, precision)
@@ -186,8 +197,9 @@ class AttnFn(torch.autograd.Function):
         d = drop
         if not training:
             d = no_drop()
+        ws = _attn_scratch(q, B, Lq, H, nh, precision, 1)
         a = L.fill(L.adt_attention_args(), q=q, k=k, v=v, ctx=None, lse=lse, key_ids=key_ids, dctx=dctx.contiguous(), dq=dq, dk=dk, dv=dv,
-                   B=B, L=Lq, H=H, nh=nh, mask_mode=mask_mode, training=int(training), drop=d, precision=precision)
+                   B=B, L=Lq, H=H, nh=nh, mask_mode=mask_mode, training=int(training), drop=d, precision=precision, tc_scratch=ws)
         L.check(L.lib().adt_attention_bwd(ctypes.byref(a), _st(q.device)), "adt_attention_bwd")
         return dq, dk, dv, None, None, None, None, None
 

@@ -357,7 +357,10 @@ typedef struct {
   const float* q; const float* k; const float* v; float* ctx; float* lse; const int32_t* key_ids;
   const float* dctx; float* dq; float* dk; float* dv;                       /* backward only */
   int32_t B, L, H, nh, mask_mode, training; adt_dropout drop; int32_t precision;
+  void* tc_scratch;   /* optional, adt_attention_scratch_bytes(B, L, H, nh, backward) bytes: sequences of 65..256 positions in the bf16 mode then run as
+                         strided-batch tcgen05 GEMMs (q k^T, P v, and the three backward products) + one softmax / dropout row kernel */
 } adt_attention_args;
+int64_t adt_attention_scratch_bytes(int32_t B, int32_t L, int32_t H, int32_t nh, int32_t backward);
 int adt_attention_fwd(const adt_attention_args* a, adt_stream_t stream);
 int adt_attention_bwd(const adt_attention_args* a, adt_stream_t stream);
 /* softmax cross-entropy over logits rows [R,V] (nn.CrossEntropyLoss on the rows that carry a label, trainer.py:113-115).

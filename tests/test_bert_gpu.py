@@ -99,9 +99,12 @@ def test_bert_fused_masked_loss_and_predict(name):
     assert rel_err(pred, g["pred"]) < 5e-5
 
 
-def test_bert_ml20m_like_shape_vs_oracle():
+@pytest.mark.parametrize("precision", [0, 1])
+def test_bert_ml20m_like_shape_vs_oracle(precision):
     """template shape of bert4rec/templates/ml-1m.json (maxlen 200, hidden 256, 4 heads, inner 1024) with a vocabulary wide
-    enough (V = 1600) to need two column blocks of the tied head; fused masked-CE loss and all gradients vs the oracle."""
+    enough (V = 1600) to need two column blocks of the tied head; fused masked-CE loss and all gradients vs the oracle.
+    precision 1 = the bf16 mode: linear layers on adt_gemm_tc, attention (200 positions, key-padding mask) as strided-batch tcgen05
+    GEMMs + the softmax row kernel -- loss within 2e-2, every gradient's direction (cosine) against the fp32 oracle."""
     from adt_b200.bert4rec import BertModel
     from oracle import bert_oracle as BO
     from oracle.sasrec_oracle import Drop
@@ -129,11 +132,17 @@ def test_bert_ml20m_like_shape_vs_oracle():
     ref.backward()
     m = m.cuda().train()
     m.drop_seed, m.drop_step = 77, 5
+    m.precision = precision
     loss = m.fused_loss(seq, dec, lab, l1, l2)
-    assert abs(float(loss) - float(ref)) / abs(float(ref)) < 1e-5
+    assert abs(float(loss) - float(ref)) / abs(float(ref)) < (2e-2 if precision else 1e-5)
     loss.backward()
     for k, prm in m.named_parameters():
-        assert grad_close(prm.grad, sd[k].grad.numpy()), k
+        if precision:
+            a, b = prm.grad.detach().cpu().numpy().ravel().astype(np.float64), sd[k].grad.numpy().ravel().astype(np.float64)
+            if np.linalg.norm(b) > 1e-7:
+                assert a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30) > 0.98, k
+        else:
+            assert grad_close(prm.grad, sd[k].grad.numpy()), k
 
 
 @pytest.mark.parametrize("name", NAMES[:2])
