@@ -32,6 +32,8 @@ struct GemmTcArgs {
   int a_mn, b_mn, kb_per_split;
   float* C2; int n_split;     // columns >= n_split (a multiple of 32) are written to C2 at column (col - n_split)
   int causal_skip;            // output tiles entirely above the diagonal (n0 > m0 + 127) are never read by the caller: skip them
+  int tiles_n, tiles_m, n_work, n_split_k;   // work items = tiles_n x tiles_m x (batch | K splits)
+  int stage;                                 // the launch reserved the chunk staging area of the coalesced epilogue
   int batch_inner, nbatch;    // strided batch: blockIdx.z = zo * batch_inner + zi selects the matrices (nbatch <= 1: blockIdx.z = K split)
   long long c_so, c_si;       // element offsets of C per outer / inner batch index
 };
@@ -73,6 +75,55 @@ __device__ __forceinline__ void epi_chunk(const GemmTcArgs& a, float (&v)[32], f
   }
 }
 
+// Coalesced variant for full 32-column chunks: the warp parks its 32 x 32 chunk in shared memory (thread == row while reading TMEM) and
+// writes it back four rows per instruction, 128 contiguous bytes per row -- a thread-per-row store touches 32 different lines with
+// 16 bytes each, twice the L2 write requests for the same bytes.
+template <bool ACT>
+__device__ __forceinline__ void epi_chunk_staged(const GemmTcArgs& a, float (&v)[32], float* __restrict__ stage, float* __restrict__ cbase, int row0,
+                                                 bool atomic) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 32; c += 4) {
+    float4 o = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    if (ACT) o = make_float4(g_act(o.x, a.act), g_act(o.y, a.act), g_act(o.z, a.act), g_act(o.w, a.act));
+    *reinterpret_cast<float4*>(stage + lane * 36 + c) = o;
+  }
+  __syncwarp();
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int r = 0; r < 32; r += 4) {
+    const int rr = r + sub;
+    if (row0 + rr < a.M) {
+      float4 o = *reinterpret_cast<const float4*>(stage + rr * 36 + c4);
+      float* dst = cbase + (long long)rr * a.ldc + c4;
+      if (atomic) { atomicAdd(reinterpret_cast<float4*>(dst), o); continue; }
+      if (a.accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(dst);
+        o = make_float4(o.x + old.x, o.y + old.y, o.z + old.z, o.w + old.w);
+      }
+      *reinterpret_cast<float4*>(dst) = o;
+    }
+  }
+  __syncwarp();
+}
+
+// Persistent: a CTA walks work items w = blockIdx.x, blockIdx.x + gridDim.x, ... where an item is one 128 x BN output tile of one
+// matrix of the batch (or one K split of it).  The TMA ring and the two TMEM accumulators run ACROSS items: while the epilogue warps
+// drain item i, the producer is already loading item i+1 and the MMA warp fills the other accumulator -- the H x H layers and the
+// attention products of a block are thousands of 2-4-slab items whose per-CTA set-up (barriers, TMEM allocation, first TMA round trip)
+// otherwise costs more than their math.
+struct WorkItem { int m0, n0, zi, zo, kb0, nkb; bool skip; };
+__device__ __forceinline__ WorkItem g_item(const GemmTcArgs& a, int w, int BN) {
+  WorkItem it;
+  const int tn = w % a.tiles_n, r = w / a.tiles_n, tm = r % a.tiles_m, z = r / a.tiles_m;
+  it.n0 = tn * BN; it.m0 = tm * GM;
+  const int nkb_all = (a.K + 63) / 64;
+  if (a.nbatch > 1) { it.zi = z % a.batch_inner; it.zo = z / a.batch_inner; it.kb0 = 0; it.nkb = nkb_all; }
+  else { it.zi = it.zo = 0; it.kb0 = z * a.kb_per_split; it.nkb = min(a.kb_per_split, nkb_all - it.kb0); }
+  it.skip = a.causal_skip && it.n0 > it.m0 + GM - 1;       // tile entirely above the diagonal: never read by the caller
+  return it;
+}
+
 template <int BN, int NS>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                GemmTcArgs a) {
@@ -84,25 +135,21 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NS * B_STAGE);
   uint64_t* full = bars;
   uint64_t* empty = bars + NS;
-  uint64_t* tfull = bars + 2 * NS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
+  uint64_t* tfull = bars + 2 * NS;        // [2] accumulator ready
+  uint64_t* tempty = bars + 2 * NS + 2;   // [2] accumulator drained (one arrival per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+  float* stage_all = reinterpret_cast<float*>(sB + NS * B_STAGE + 256);     // [4 epilogue warps][32][36] chunk staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM;
-  if (a.causal_skip && n0 > m0 + GM - 1) return;      // whole CTA, before any barrier / TMEM allocation
-  const int nkb_all = (a.K + 63) / 64;
-  const bool batched = a.nbatch > 1;
-  const int zi = batched ? (int)blockIdx.z % a.batch_inner : 0, zo = batched ? (int)blockIdx.z / a.batch_inner : 0;
-  const int kb0 = batched ? 0 : blockIdx.z * a.kb_per_split;
-  const int nkb = batched ? nkb_all : min(a.kb_per_split, nkb_all - kb0);      // K slabs of this CTA (>= 1 by construction of the grid)
+  const bool split = a.nbatch <= 1 && a.n_split_k > 1;
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
     for (int i = 0; i < NS; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
-    tc::mbar_init(tfull, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tc::tmem_alloc<2 * BN>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -110,22 +157,27 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % NS;
-        tc::mbar_wait(empty + st, ((kb / NS) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(full + st, A_STAGE + B_STAGE);
-        const int kc = (kb0 + kb) * 64;
-        if (a.a_mn) {
+      int g = 0;                                             // slabs issued so far (ring position)
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+        const WorkItem it = g_item(a, w, BN);
+        if (it.skip) continue;
+        for (int kb = 0; kb < it.nkb; ++kb, ++g) {
+          const int st = g % NS;
+          tc::mbar_wait(empty + st, ((g / NS) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(full + st, A_STAGE + B_STAGE);
+          const int kc = (it.kb0 + kb) * 64;
+          if (a.a_mn) {
 #pragma unroll
-          for (int i = 0; i < GM / 64; ++i) tc::tma_load_4d(sA + st * A_STAGE + i * 8192, &tmA, m0 + 64 * i, kc, zi, zo, full + st);
-        } else {
-          tc::tma_load_4d(sA + st * A_STAGE, &tmA, kc, m0, zi, zo, full + st);
-        }
-        if (a.b_mn) {
+            for (int i = 0; i < GM / 64; ++i) tc::tma_load_4d(sA + st * A_STAGE + i * 8192, &tmA, it.m0 + 64 * i, kc, it.zi, it.zo, full + st);
+          } else {
+            tc::tma_load_4d(sA + st * A_STAGE, &tmA, kc, it.m0, it.zi, it.zo, full + st);
+          }
+          if (a.b_mn) {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tc::tma_load_4d(sB + st * B_STAGE + i * 8192, &tmB, n0 + 64 * i, kc, zi, zo, full + st);
-        } else {
-          tc::tma_load_4d(sB + st * B_STAGE, &tmB, kc, n0, zi, zo, full + st);
+            for (int i = 0; i < BN / 64; ++i) tc::tma_load_4d(sB + st * B_STAGE + i * 8192, &tmB, it.n0 + 64 * i, kc, it.zi, it.zo, full + st);
+          } else {
+            tc::tma_load_4d(sB + st * B_STAGE, &tmB, kc, it.n0, it.zi, it.zo, full + st);
+          }
         }
       }
     }
@@ -133,47 +185,79 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_tc_kernel(const __grid_cons
     if (lane == 0) {
       const uint32_t idesc = tc::idesc_bf16_f32(GM, BN) | (a.a_mn ? 1u << 15 : 0u) | (a.b_mn ? 1u << 16 : 0u);
       const uint64_t a_step = a.a_mn ? 128 : 2, b_step = a.b_mn ? 128 : 2;     // 16 K per MMA: 16 rows of 128 B, or 32 B inside a row
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % NS;
-        tc::mbar_wait(full + st, (kb / NS) & 1);
+      int g = 0, n = 0;                                      // slabs consumed, items done
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+        const WorkItem it = g_item(a, w, BN);
+        if (it.skip) continue;
+        const int acc = n & 1;
+        tc::mbar_wait(tempty + acc, ((n >> 1) & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t sa = tc::smem_u32(sA + st * A_STAGE), sb = tc::smem_u32(sB + st * B_STAGE);
-        const uint64_t ad = a.a_mn ? tc::smem_desc_mn_sw128(sa, 8192) : tc::smem_desc_k_sw128(sa);
-        const uint64_t bd = a.b_mn ? tc::smem_desc_mn_sw128(sb, 8192) : tc::smem_desc_k_sw128(sb);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < it.nkb; ++kb, ++g) {
+          const int st = g % NS;
+          tc::mbar_wait(full + st, (g / NS) & 1);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(sA + st * A_STAGE), sb = tc::smem_u32(sB + st * B_STAGE);
+          const uint64_t ad = a.a_mn ? tc::smem_desc_mn_sw128(sa, 8192) : tc::smem_desc_k_sw128(sa);
+          const uint64_t bd = a.b_mn ? tc::smem_desc_mn_sw128(sb, 8192) : tc::smem_desc_k_sw128(sb);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          tc::mma_bf16_ss(tmem_base, ad + (uint64_t)k4 * a_step, bd + (uint64_t)k4 * b_step, idesc, (kb | k4) != 0);
-        tc::mma_commit(empty + st);
+          for (int k4 = 0; k4 < 4; ++k4)
+            tc::mma_bf16_ss(d_tmem, ad + (uint64_t)k4 * a_step, bd + (uint64_t)k4 * b_step, idesc, (kb | k4) != 0);
+          tc::mma_commit(empty + st);
+        }
+        tc::mma_commit(tfull + acc);
+        ++n;
       }
-      tc::mma_commit(tfull);
     }
   } else {
     const int q = warp & 3;
-    const int row = m0 + 32 * q + lane;
-    tc::mbar_wait(tfull, 0);
-    tc::tc_fence_after();
     const bool vec = ((a.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) && (!a.pre || (reinterpret_cast<uintptr_t>(a.pre) & 15) == 0);
+    int n = 0;
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+      const WorkItem it = g_item(a, w, BN);
+      if (it.skip) continue;
+      const int acc = n & 1;
+      tc::mbar_wait(tfull + acc, (n >> 1) & 1);
+      tc::tc_fence_after();
+      const int row = it.m0 + 32 * q + lane;
+      const bool first_split = !split || it.kb0 == 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + c0, v);
-      const int nb = n0 + c0;
-      if (row >= a.M || nb >= a.N) continue;
-      float* crow = (a.C2 && nb >= a.n_split ? a.C2 - a.n_split : a.C) + zo * a.c_so + zi * a.c_si + (long long)row * a.ldc + nb;
-      float* prow = a.pre ? a.pre + (long long)row * a.ldc + nb : nullptr;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * BN + c0, v);
+        if (c0 + 32 == BN) {                 // accumulator fully read: hand it back to the MMA warp
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(tempty + acc);
+        }
+        const int nb = it.n0 + c0;
+        if (nb >= a.N) continue;             // warp-uniform
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float x = v[c];
-        if (a.bias && (batched || blockIdx.z == 0) && nb + c < a.N) x += __ldg(a.bias + nb + c);
-        v[c] = x * a.scale;
+        for (int c = 0; c < 32; ++c) {
+          float x = v[c];
+          if (a.bias && first_split && nb + c < a.N) x += __ldg(a.bias + nb + c);
+          v[c] = x * a.scale;
+        }
+        float* cmat = (a.C2 && nb >= a.n_split ? a.C2 - a.n_split : a.C) + it.zo * a.c_so + it.zi * a.c_si;
+        if (a.stage && vec && nb + 32 <= a.N && !a.pre) {          // warp-uniform: full chunk, no pre-activation copy -> coalesced rows
+          const int row0 = it.m0 + 32 * q;
+          float* cbase = cmat + (long long)row0 * a.ldc + nb;
+          if (a.act == 0) epi_chunk_staged<false>(a, v, stage_all + q * (32 * 36), cbase, row0, split);
+          else epi_chunk_staged<true>(a, v, stage_all + q * (32 * 36), cbase, row0, split);
+          continue;
+        }
+        if (row >= a.M) continue;
+        float* crow = cmat + (long long)row * a.ldc + nb;
+        float* prow = a.pre ? a.pre + (long long)row * a.ldc + nb : nullptr;
+        if (a.act == 0) epi_chunk<false>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, split);
+        else epi_chunk<true>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, split);
       }
-      if (a.act == 0) epi_chunk<false>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1 && !batched);
-      else epi_chunk<true>(a, v, crow, prow, nb, vec && nb + 32 <= a.N, gridDim.z > 1 && !batched);
+      ++n;
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<2 * BN>(tmem_base);
 }
 
 // fp32 [R][C] (row stride ld) -> bf16 TRANSPOSE [C][ldt] (ldt >= R, multiple of 8), through a 32 x 32 smem tile
@@ -256,10 +340,20 @@ int g_make_map(CUtensorMap* m, const void* base, long long rows, long long cols,
 }
 
 template <int BN, int NS>
-int g_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& k, int splits, cudaStream_t s) {
-  const size_t smem = 1024 + (size_t)NS * (GM * 128 + BN * 128) + 256;
+int g_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmTcArgs k, int splits, cudaStream_t s, bool stage = false) {
+  k.stage = stage ? 1 : 0;
+  const size_t smem = 1024 + (size_t)NS * (GM * 128 + BN * 128) + 256 + (stage ? 4 * 32 * 36 * 4 : 0);
   cudaFuncSetAttribute(gemm_tc_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((k.N + BN - 1) / BN, (k.M + GM - 1) / GM, splits);
+  k.tiles_n = (k.N + BN - 1) / BN; k.tiles_m = (k.M + GM - 1) / GM;
+  k.n_split_k = k.nbatch > 1 ? 1 : splits;
+  const long long work = (long long)k.tiles_n * k.tiles_m * splits;
+  if (work > 0x7fffffff) return ADT_E_SHAPE;
+  k.n_work = (int)work;
+  // resident CTAs: the two accumulators take 2 * BN of the 512 TMEM columns, the ring its shared memory
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > 512 / (2 * BN)) per_sm = 512 / (2 * BN);
+  if (per_sm < 1) per_sm = 1;
+  const int grid = (int)(work < 148ll * per_sm ? work : 148ll * per_sm);
   gemm_tc_kernel<BN, NS><<<grid, G_THREADS, smem, s>>>(tmA, tmB, k);
   return cudaGetLastError() == cudaSuccess ? ADT_OK : ADT_E_CUDA;
 }
@@ -290,7 +384,7 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   int splits = a->split_k > 1 ? (a->split_k < nkb ? a->split_k : nkb) : 1;
   k.kb_per_split = (nkb + splits - 1) / splits;
   splits = (nkb + k.kb_per_split - 1) / k.kb_per_split;
-  if (batched) splits = (int)(bi * bo);          // grid.z walks the batch instead of K splits
+  if (batched) splits = (int)(bi * bo);          // the third work dimension walks the batch instead of K splits
   if (splits > 1 && !a->accumulate) {
     if (cudaMemset2DAsync(a->c, (size_t)a->ldc * 4, 0, (size_t)a->N * 4, (size_t)a->M, s) != cudaSuccess) return ADT_E_CUDA;
   }
@@ -304,8 +398,9 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   // short K ranges (the H x H layers of a block: 4 slabs) leave the ring idle: a shallow ring lets 2-3 CTAs share an SM, so one CTA's
   // epilogue and prologue overlap another's main loop
   const int slabs = k.kb_per_split;
-  if (bn == 64) return slabs <= 4 ? g_launch<64, 2>(tmA, tmB, k, splits, s) : slabs <= 16 ? g_launch<64, 3>(tmA, tmB, k, splits, s) : g_launch<64, 6>(tmA, tmB, k, splits, s);
-  return slabs <= 4 ? g_launch<128, 2>(tmA, tmB, k, splits, s) : slabs <= 16 ? g_launch<128, 3>(tmA, tmB, k, splits, s) : g_launch<128, 6>(tmA, tmB, k, splits, s);
+  // (the output-bound short-K launches also stage their chunks for 128-byte-row stores; two CTAs per SM either way)
+  if (bn == 64) return slabs <= 16 ? g_launch<64, 4>(tmA, tmB, k, splits, s, slabs <= 4) : g_launch<64, 6>(tmA, tmB, k, splits, s);
+  return slabs <= 4 ? g_launch<128, 2>(tmA, tmB, k, splits, s, true) : slabs <= 16 ? g_launch<128, 3>(tmA, tmB, k, splits, s) : g_launch<128, 6>(tmA, tmB, k, splits, s);
 }
 
 extern "C" int adt_to_bf16_t(const float* x, int64_t ld, void* y_bf16, int64_t ldt, int32_t R, int32_t C, adt_stream_t s_) {
