@@ -633,7 +633,7 @@ static TcBwdScratch mk_tcb(void* p, int M, int H) {
   t.base = reinterpret_cast<__nv_bfloat16*>(p); t.mh = (long long)M * H; t.wb = t.base + 12 * t.mh;
   return t;
 }
-static int rows_grid2(int M) { const int b = (M + 7) / 8; return b < 148 * 4 ? b : 148 * 4; }
+static int rows_grid2(int M) { const int b = (M + 7) / 8; return b < 148 * 8 ? b : 148 * 8; }
 // c (+)= A W : A bf16 [M][lda] (first Kred columns), W bf16 [Kred][N_out] row-major read MN-major
 static int tc_dgrad(const __nv_bfloat16* A, long long lda, int Kred, const __nv_bfloat16* W, int N_out, float* c, int accumulate, int M, cudaStream_t s) {
   adt_gemm_tc_args g;
@@ -776,7 +776,7 @@ static int tc_enc_bwd(const adt_enc_block_bwd_args* a, cudaStream_t s) {
   if (int e = tc_dgrad(t.op(4), H, H, Wob, H, a->dctx, 0, M, s)) return e;
   if (a->nll_coef != 0.f || a->drec) {
     TIMED("row_tc", s);
-    sparse_head_bwd_kernel<<<rows_grid2(M), 256, 0, s>>>(a->ctx, a->sparse_w, a->sparse_b, a->drec, a->nll_coef, a->dctx, a->g_sparse_w,
+    sparse_head_bwd_kernel<<<attn_rows_grid(M), 256, 0, s>>>(a->ctx, a->sparse_w, a->sparse_b, a->drec, a->nll_coef, a->dctx, a->g_sparse_w,
                                                         a->g_sparse_b, M, H, a->nh);
   }
   if (int e = check_launch("tcgen05 backward path (enc post)")) return e;
