@@ -400,6 +400,7 @@ extern "C" int adt_gemm_tc(const adt_gemm_tc_args* a, adt_stream_t s_) {
   const int slabs = k.kb_per_split;
   // (the output-bound short-K launches also stage their chunks for 128-byte-row stores; two CTAs per SM either way)
   if (bn == 64) return slabs <= 16 ? g_launch<64, 4>(tmA, tmB, k, splits, s, slabs <= 4) : g_launch<64, 6>(tmA, tmB, k, splits, s);
+  // (eight epilogue warps -- two per lane quarter -- were measured slower too: 8.5 -> 8.9 ms/step)
   // (a 4-stage ring with one CTA per SM was measured slower: 8.5 -> 10.3 ms/step at C1 -- two resident CTAs hide more latency than a deeper ring)
   return slabs <= 4 ? g_launch<128, 2>(tmA, tmB, k, splits, s, true) : slabs <= 16 ? g_launch<128, 3>(tmA, tmB, k, splits, s) : g_launch<128, 6>(tmA, tmB, k, splits, s);
 }
