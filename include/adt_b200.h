@@ -315,8 +315,11 @@ int adt_linear_bwd(const adt_linear_bwd_args* a, adt_stream_t stream);
 int adt_act_bwd(const float* dy, const float* pre, float* dpre, int64_t n, int32_t act, adt_stream_t stream);
 /* nn.Linear on tcgen05 (bert4rec/model/modules.py:57-72, :128-139, bert.py:80-90 and their autograd): c[M,N] (fp32, row stride ldc)
  * (+)= act((A[M,K] . B[N,K]^T + bias[N]) * scale), A / B bf16 row-major with row strides lda / ldb (multiples of 8 elements; use
- * adt_to_bf16_ld / adt_to_bf16_t to make the operand copies: forward A = x, B = W; dgrad A = dy, B = W^T; wgrad A = dy^T, B = x^T).
- * TMA-fed 128 x 128 (or x 64) tiles, fp32 accumulators in TMEM; M, N, K arbitrary (zero-filled edges, masked stores).
+ * adt_to_bf16_ld to make the operand copies: forward A = x, B = W; dgrad A = dy, B = W with b_mn; wgrad A = dy with a_mn, B = x with
+ * b_mn -- see a_mn / b_mn below; transposed copies from adt_to_bf16_t work too).  Also every linear layer and the attention products of
+ * the wide SASRec-ADT blocks (sasrec/modules.py:644-655, :666-677; vendored MHA :270-527).
+ * Persistent CTAs walk 128 x 128 (or x 64) output tiles: TMA-fed ring, fp32 accumulators double-buffered in TMEM; M, N, K arbitrary
+ * (zero-filled edges, masked stores).
  * pre (optional, same layout as c) receives the pre-activation values; accumulate != 0 adds into c. */
 typedef struct {
   const void* a_bf16; const void* b_bf16; int64_t lda, ldb;
